@@ -1,0 +1,255 @@
+#!/usr/bin/env python
+"""Headline benchmark: INN train-step patches/sec (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N --steps K --warmup W]          one process per GPU (torchrun for N > 1)
+  python bench.py --impl reference ...                     the reference's CPU path (oracle port) on host cores
+
+Workload = BASELINE.json configs[1]/[2]: UncondSRFlow scale 4, 4 couplings, lr_window 10 (84 + 108 latent
+channels), 256x256 patches, batch 32 PER GPU (weak scaling), synthetic U[0,1) frames and N(0,1) latents,
+random-init weights (seed 0).  One step = zero_grad + forward + L2 + backward + inverse + L2 + backward
++ gradient all-reduce (N > 1) + Adam (lit_wrapper.py:36-56,76; loss.mmd excluded, lambda 0).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(arch="SRF", scale=4, num_coupling=4, lr_window=10, patch=256, batch_per_gpu=32)
+
+
+def conv_macs_per_patch(P, scale=4, num_coupling=4, hidden=256):
+    """Algorithmic MACs of the coupling subnets for one PxP patch, one direction:
+    per GLOW block at C channels both subnets together do hidden*C*k^2*(1/2+1)... = 3/2*... -> 768*C*k^2 at hidden 256."""
+    total = 0
+    C, px = 12, (P // 2) ** 2
+    for _ in range((scale - 1).bit_length()):
+        C, px = C * 4, px // 4
+        for k in range(num_coupling):
+            kk = 9 if k % 2 == 0 else 1
+            total += px * 3 * hidden * C * kk
+    return total
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 6:
+                reasons |= {n for n, v in zip(names, r[2:6]) if v.lower().startswith("active")}
+        mx = max((int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference / CPU arm
+def cpu_reference_run(steps, warmup, batch, threads=None, patch=WORKLOAD["patch"]):
+    """The reference's own CPU implementation of the path: its archs.py restated in oracle/ref_torch.py
+    (the reference cannot travel to the GPU box and needs the un-installable FrEIA), fp32, all host threads."""
+    from oracle import ref_torch as R
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    opt = R.make_opt(scale=WORKLOAD["scale"], num_coupling=WORKLOAD["num_coupling"], lr_window=WORKLOAD["lr_window"])
+    torch.manual_seed(0)
+    net = R.build_srf(3, patch, patch, opt)
+    optim = R.make_optimizer(net, opt)
+    hr, lr, z = R.synthetic_batch(opt, batch, patch, patch, seed=0)
+    for _ in range(warmup):
+        R.train_step(net, optim, hr, lr, z, opt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        R.train_step(net, optim, hr, lr, z, opt)
+    dt = time.perf_counter() - t0
+    return dict(value=batch * steps / dt, ms_per_step=1e3 * dt / steps, cores=threads, batch=batch)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 2
+    r = cpu_reference_run(args.steps, args.warmup, batch)
+    sample = f"{args.steps} steps x {batch} patches of 256x256 (same model/config as the GPU arm, bounded batch)"
+    line = {
+        "impl": "reference", "metric": "INN train-step patches/sec", "value": r["value"], "unit": "patches/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SRF scale4 c4 lr_window10 256x256 train step, CPU, batch 2 per step", **WORKLOAD},
+        "cpu_baseline": {"value": r["value"], "unit": "patches/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    from oracle import ref_torch as R            # only for make_opt/synthetic_batch helpers + cpu_baseline leg
+    from sin_inn_b200 import archs, kernels, train
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P, B = WORKLOAD["patch"], args.batch
+    opt = R.make_opt(scale=WORKLOAD["scale"], num_coupling=WORKLOAD["num_coupling"], lr_window=WORKLOAD["lr_window"],
+                     precision=args.precision, tensor_core=not args.no_tensor_core)
+    torch.manual_seed(0)
+    net = archs.UncondSRFlow(3, P, P, opt).to(dev)
+    trainer = train.SingleVideoTrainer(net, opt, world_size=world)
+    trainer.broadcast_params()
+    # synthetic data: a pool of pinned host batches (per-rank seed), copied H2D inside the e2e region
+    pool = []
+    for i in range(2):
+        hr, lr, z = R.synthetic_batch(opt, B, P, P, seed=1000 * rank + i)
+        pool.append(tuple(t.pin_memory() for t in (hr, lr, z)))
+    dev_batches = [tuple(t.to(dev, non_blocking=True) for t in b) for b in pool]
+    h2d = sum(t.numel() * 4 for t in pool[0])
+    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        return trainer.training_step(*dev_batches[i % 2])
+
+    def step_e2e(i):
+        hr, lr, z = (t.to(dev, non_blocking=True) for t in pool[i % 2])
+        lf, lb = trainer.training_step(hr, lr, z)
+        return float(lf.item() + lb.item())          # D2H read of the step's result
+
+    for i in range(args.warmup):
+        step_resident(i)
+    kernels.LAUNCHES = 0
+    kernels.profile_begin()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step_resident(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    sampler.stop_flag = True
+    launches = kernels.LAUNCHES
+    prof = kernels.profile_end()
+    # end-to-end: pinned host inputs -> device, step, loss back to host, every step
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank == 0:
+        pk = peaks()
+        value = world * B * args.steps / (ms / 1e3)
+        e2e = world * B * args.steps / (ms_e2e / 1e3)
+        # roofline of the dominant kernel family (subnet convolutions): algorithmic FLOPs of the launches
+        # timed with CUDA events inside the timed region / their summed duration
+        conv = prof.get("conv", {"ms": 0.0, "flops": 0.0, "n": 0})
+        wg = prof.get("wgrad", {"ms": 0.0, "flops": 0.0, "n": 0})
+        tc_ms, tc_fl = conv["ms"] + wg["ms"], conv["flops"] + wg["flops"]
+        achieved = tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
+        alg_flops_step = 6 * 2 * conv_macs_per_patch(P) * B
+        line = {
+            "metric": "INN train-step patches/sec", "value": value, "unit": "patches/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": f"SRF scale4 c4 lr_window10 {P}x{P} train step, batch {B}/GPU", **WORKLOAD,
+                       "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision, "tensor_core": not args.no_tensor_core,
+                       "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2",
+                       "backward": "recompute-from-inverse"},
+            "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
+                         "kernel": "subnet conv implicit GEMMs (fprop+dgrad+wgrad launches)",
+                         "kernel_ms_per_step": tc_ms / args.steps, "kernel_launches": conv["n"] + wg["n"],
+                         "whole_step_algorithmic_tflops": alg_flops_step / (ms / args.steps / 1e3) / 1e12},
+            "clocks": sampler.summary(),
+            "profile_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(steps=3, warmup=1, batch=2)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "patches/s", "cores": r["cores"], "kind": "port",
+                                    "sample": "3 steps x 2 patches of 256x256, same model, oracle port of archs.py on host cores"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=WORKLOAD["batch_per_gpu"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tensor-core", action="store_true", help="route the subnet GEMMs to the CUDA-core kernels")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

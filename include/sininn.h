@@ -1,0 +1,181 @@
+/*
+ * sininn.h -- C ABI of libsininn.so: the sm_100a (B200) kernels behind the
+ * invertible-network hot path of paramhanji/sin-inn.
+ *
+ * The reference has no native boundary: its hot path is Python that calls
+ * ATen/cuDNN (archs.py) and the un-vendored FrEIA package.  Each entry point
+ * below names the reference code it replaces (paths relative to the reference
+ * repository root).  Host bindings: sin_inn_b200/_lib.py (ctypes);
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless said otherwise
+ *   - nothing allocates, synchronises or takes ownership; kernels are launched on
+ *     the stream passed in (a cudaStream_t, passed as void*)
+ *   - return value 0 = ok, negative = SININN_E*; sininn_last_error() gives text
+ *   - "NHWC" = channels-last activation matrix [B*H*W pixels][C], addressed with an
+ *     explicit pixel stride (in elements) so channel slices of a wider tensor work
+ *   - dtype codes: SININN_F32 / SININN_BF16
+ */
+#ifndef SININN_H
+#define SININN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SININN_OK            0
+#define SININN_EINVAL       -1
+#define SININN_ECUDA        -2
+#define SININN_EUNSUPPORTED -3
+#define SININN_EWORKSPACE   -4
+
+#define SININN_F32  0
+#define SININN_BF16 1
+
+/* coupling kinds */
+#define SININN_GLOW 0   /* log-scale g(s) = clamp*0.636*atan(s/clamp)   (FrEIA GLOWCouplingBlock, call site archs.py:61-64) */
+#define SININN_IRN  1   /* log-scale g(h) = clamp*(2*sigmoid(h)-1)      (InvBlockExp, archs.py:153,156) */
+
+/* activations fused into conv epilogues */
+#define SININN_ACT_NONE  0
+#define SININN_ACT_RELU  1   /* nn.ReLU in subnet_conv / subnet_conv_1x1, archs.py:11-17 */
+#define SININN_ACT_LRELU 2   /* LeakyReLU(0.2) in DenseBlock, archs.py:82,89-93 */
+
+typedef void* sininn_stream_t;
+
+int         sininn_version(void);
+const char* sininn_last_error(void);
+/* sm count / compute capability of the current device; any pointer may be NULL */
+int         sininn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- resampling
+ * Replaces FrEIA IRevNetDownsampling (call sites archs.py:28-31,35-38):
+ *   out[b,(dy*2+dx)*C+c,i,j] = in[b,c,2i+dy,2j+dx]
+ * and HaarDownsampling.forward (archs.py:183-199): the four +-1 2x2 patterns of
+ * archs.py:167-176, band-major output channel k*C+c; `scale` multiplies the
+ * result (0.25 = reference forward, 1 = reference reverse; other values give
+ * the transposes needed by the backward pass).
+ * C,H,W always describe the FULL-resolution side.  rev=0: [B,C,H,W] ->
+ * [B,4C,H/2,W/2]; rev=1: the inverse mapping.  mode 0 = squeeze, 1 = Haar. */
+int sininn_resample_nchw(const float* in, float* out, int B, int C, int H, int W,
+                         int mode, int rev, float scale, sininn_stream_t stream);
+/* Same maps on channels-last tensors: full-res [B,H,W,C] <-> [B,H/2,W/2,4C]. */
+int sininn_resample_nhwc(const float* in, float* out, int B, int C, int H, int W,
+                         int mode, int rev, float scale, sininn_stream_t stream);
+
+/* Layout changes at the API boundary (the reference API is NCHW-contiguous,
+ * loss.py:16-17).  chan_map (device int32[C], may be NULL): out channel i takes
+ * in channel chan_map[i] -- folds FrEIA PermuteRandom (archs.py:65-68) into the
+ * copy.  bf16_out (may be NULL): additionally writes out[:, c0:c1] as a compact
+ * bf16 [npix][c1-c0] matrix (operand copy for the tensor-core subnets). */
+int sininn_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, const int32_t* chan_map,
+                        void* bf16_out, int c0, int c1, sininn_stream_t stream);
+int sininn_nhwc_to_nchw(const float* in, float* out, int B, int C, int HW, const int32_t* chan_map,
+                        sininn_stream_t stream);
+/* FrEIA PermuteRandom on channels-last data: out[p][i] = in[p][chan_map[i]] */
+int sininn_permute_nhwc(const float* in, float* out, long long npix, int C, const int32_t* chan_map,
+                        void* bf16_out, int c0, int c1, sininn_stream_t stream);
+
+/* ---------------------------------------------------------------- coupling
+ * One half of an affine coupling, in place on a channel slice u[npix][L]
+ * (pixel stride u_stride) of the fp32 trunk:
+ *   inverse=0:  u <- exp(g(s)) * u + t        (GLOW y = e(s)*x + t; IRN y2 = x2*exp(s) + G, archs.py:154)
+ *   inverse=1:  u <- (u - t) / exp(g(s))      (archs.py:157 and GLOW rev)
+ * s,t: fp32 [npix][L] with their own strides (GLOW: both halves of one subnet
+ * output; IRN: outputs of H and G).  u_bf16 (may be NULL): compact bf16 copy of
+ * the updated slice. */
+int sininn_coupling_apply(float* u, int u_stride, const float* s, int s_stride, const float* t, int t_stride,
+                          long long npix, int L, int kind, float clamp, int inverse,
+                          void* u_bf16, sininn_stream_t stream);
+/* Backward of one coupling half from its OUTPUT (recompute-from-inverse, the
+ * equations of SURVEY.md section 8a).  On entry u holds y and du holds dL/dy;
+ * on exit u holds the reconstructed input x and du holds dL/dx.  Writes
+ * dL/d(raw s) and dL/dt ([npix][L] each, dtype out_dtype, own strides).
+ * `inverse` says which direction produced y (0: y=e*x+t, 1: y=(x-t)/e). */
+int sininn_coupling_bwd(float* u, int u_stride, float* du, int du_stride,
+                        const float* s, int s_stride, const float* t, int t_stride,
+                        long long npix, int L, int kind, float clamp, int inverse,
+                        void* ds_out, int ds_stride, void* dt_out, int dt_stride, int out_dtype,
+                        void* x_bf16, sininn_stream_t stream);
+
+/* small helpers around the subnets */
+/* out[p][c] = scale * in[p][c] converted to out_dtype */
+int sininn_cast_slice(const float* in, int in_stride, long long npix, int L, float scale, void* out, int out_dtype,
+                      int out_stride, sininn_stream_t stream);
+/* out <- d * act'(y) where y is the activation OUTPUT (sign-preserving activations); d fp32, y and out
+ * in their own dtypes (out may alias d when out_dtype is fp32) */
+int sininn_act_bwd(const float* d, int d_stride, const void* y, int y_dtype, int y_stride,
+                   void* out, int out_dtype, int out_stride, long long npix, int L,
+                   int act, float slope, sininn_stream_t stream);
+/* out[j] (+)= sum_p in[p][j]; deterministic two-pass; workspace >= sininn_colsum_workspace_bytes */
+size_t sininn_colsum_workspace_bytes(long long npix, int N);
+int sininn_colsum(const void* in, int dtype, int in_stride, long long npix, int N, float* out, int accumulate,
+                  void* workspace, size_t workspace_bytes, sininn_stream_t stream);
+/* out (+)= alpha*a  over a [npix][L] slice (IRN additive half y1 = x1 +- F(x2), archs.py:152,158) */
+int sininn_axpy_slice(float* out, int out_stride, const void* a, int a_dtype, int a_stride, long long npix, int L,
+                      float alpha, sininn_stream_t stream);
+
+/* ---------------------------------------------------------------- convolutions
+ * Stride-1 "same" convolution with 1x1 or 3x3 taps on channels-last data as an
+ * implicit GEMM  out[p][co] = sum_{tap,ci} in[p+off(tap)][ci] * wpack[tap][co][ci]
+ * with a fused epilogue.  Replaces nn.Conv2d inside subnet_conv / subnet_conv_1x1
+ * (archs.py:11-17) and DenseBlock (archs.py:77-81, 88-95); with dgrad-packed
+ * weights the same call is the data gradient. */
+typedef struct {
+  int B, H, W;
+  int Cin, Cout, taps;            /* taps = 1 or 9 */
+  const void* in;  int in_dtype;  int in_stride;
+  const void* wpack;              /* [taps][rows_pad][k_pad], dtype = in_dtype, zero padded */
+  int rows_pad, k_pad;
+  const float* bias;              /* [Cout] or NULL */
+  void* out;       int out_dtype; int out_stride;
+  int act; float slope;           /* activation applied to acc+bias */
+  const void* mask; int mask_stride; /* NULL, or activation OUTPUT (dtype=out_dtype): result *= act'(mask) */
+  int mask_act;
+  int accumulate; float alpha;    /* out = (accumulate ? out : 0) + alpha * f(acc + bias) */
+} sininn_conv_desc;
+
+int sininn_conv_simt(const sininn_conv_desc* d, sininn_stream_t stream);   /* fp32-accurate CUDA-core path */
+int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream);     /* tcgen05/TMEM/TMA bf16 path */
+
+/* Re-layout nn.Conv2d OIHW fp32 weights for the implicit GEMMs above.
+ *   mode 0 (fprop): out[tap][co][ci] = w[co][ci][tap]           rows = Cout, k = Cin
+ *   mode 1 (dgrad): out[tap][ci][co] = w[co][ci][taps-1-tap]    rows = Cin,  k = Cout */
+int sininn_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, int mode,
+                            void* out, int out_dtype, int rows_pad, int k_pad, sininn_stream_t stream);
+
+/* Weight gradient  dw[co][ci][tap] (+)= sum_p dy[p][co] * x[p+off(tap)][ci]  (OIHW fp32),
+ * deterministic split over pixels + fixed-order reduction (no float atomics). */
+typedef struct {
+  int B, H, W;
+  int Cin, Cout, taps;
+  const void* x;  int x_dtype;  int x_stride;
+  const void* dy; int dy_dtype; int dy_stride;
+  float* dw;      int accumulate;
+  void* workspace; size_t workspace_bytes;
+} sininn_wgrad_desc;
+
+size_t sininn_wgrad_workspace_bytes(const sininn_wgrad_desc* d, int tensor_core);
+int sininn_wgrad_simt(const sininn_wgrad_desc* d, sininn_stream_t stream);
+int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream);
+
+/* ---------------------------------------------------------------- caller-side fusions
+ * sum((a[:, :L]-b)^2) over a strided slice -> out[0] (+ optional gradient 2*scale*(a-b)); used for
+ * loss.reconstruction (loss.py:3-5) and latent_nll (loss.py:38-39, b = NULL). */
+size_t sininn_sqdiff_workspace_bytes(long long n);
+int sininn_sqdiff_nchw(const float* a, const float* b, long long n, float scale, float* loss_out,
+                       float* grad_out, void* workspace, size_t workspace_bytes, sininn_stream_t stream);
+/* torch.optim.Adam semantics (lit_wrapper.py:134-137: L2 weight decay folded into the gradient) over a
+ * flat fp32 arena; step is the 1-based step count. */
+int sininn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                     float grad_scale, sininn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SININN_H */

@@ -1,0 +1,89 @@
+// Shared helpers for libsininn (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/sininn.h"
+
+namespace sininn {
+
+void set_error(const char* fmt, ...);
+
+#define SININN_CHECK_ARG(cond, ...)                         \
+  do {                                                      \
+    if (!(cond)) {                                          \
+      ::sininn::set_error(__VA_ARGS__);                     \
+      return SININN_EINVAL;                                 \
+    }                                                       \
+  } while (0)
+
+#define SININN_CHECK_LAUNCH(name)                                               \
+  do {                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                       \
+    if (e__ != cudaSuccess) {                                                   \
+      ::sininn::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return SININN_ECUDA;                                                      \
+    }                                                                           \
+  } while (0)
+
+static inline cudaStream_t as_stream(sininn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+int sm_count();
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 consecutive elements -> fp32 (pointer must be 16 B / 8 B aligned for float / bf16)
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+// ---- coupling log-scales (fp32, accurate libm variants: the fp32 path must match the reference to 1e-4)
+// GLOW: g(s) = clamp*0.636*atan(s/clamp), g'(s) = 0.636/(1+(s/clamp)^2)      (FrEIA pre-v0.2, literal 0.636)
+// IRN : g(h) = clamp*(2*sigmoid(h)-1),   g'(h) = 2*clamp*sig*(1-sig)         (archs.py:153)
+__device__ __forceinline__ void log_scale(int kind, float clamp, float raw, float& g, float& dg) {
+  if (kind == SININN_GLOW) {
+    float r = raw / clamp;
+    g = clamp * 0.636f * atanf(r);
+    dg = 0.636f / (1.0f + r * r);
+  } else {
+    float sg = 1.0f / (1.0f + expf(-raw));
+    g = clamp * (2.0f * sg - 1.0f);
+    dg = 2.0f * clamp * sg * (1.0f - sg);
+  }
+}
+
+__device__ __forceinline__ float act_fwd(int act, float slope, float v) {
+  if (act == SININN_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == SININN_ACT_LRELU) return v > 0.f ? v : slope * v;
+  return v;
+}
+// derivative from the activation OUTPUT y (both activations preserve sign)
+__device__ __forceinline__ float act_grad(int act, float slope, float y) {
+  if (act == SININN_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == SININN_ACT_LRELU) return y > 0.f ? 1.f : slope;
+  return 1.f;
+}
+
+}  // namespace sininn

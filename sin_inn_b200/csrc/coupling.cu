@@ -1,0 +1,397 @@
+// Affine-coupling elementwise kernels (forward, inverse, backward-from-output) and small
+// bandwidth-bound helpers around the subnets.  All operate on channels-last [npix][L] slices
+// addressed with explicit pixel strides, 128-bit accesses when L and the strides allow.
+//
+// Reference semantics:
+//   GLOW  y = exp(g(s))*x + t / x = (y-t)/exp(g(s)), g(s)=clamp*0.636*atan(s/clamp)
+//         (FrEIA GLOWCouplingBlock pre-v0.2; call site /root/reference/archs.py:61-64)
+//   IRN   y2 = x2*exp(s) + G(y1), s = clamp*(2*sigmoid(H(y1))-1)   (/root/reference/archs.py:152-158)
+// Backward-from-output equations: SURVEY.md section 8a.
+#include "common.cuh"
+
+namespace sininn {
+
+template <int VEC>
+struct Pack {
+  float v[VEC];
+};
+
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> ldv(const float* p) {
+  Pack<VEC> r;
+  if constexpr (VEC == 4) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    r.v[0] = *p;
+  }
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void stv(float* p, const Pack<VEC>& r) {
+  if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  else *p = r.v[0];
+}
+template <int VEC>
+__device__ __forceinline__ void stv(__nv_bfloat16* p, const Pack<VEC>& r) {
+  if constexpr (VEC == 4) store4(p, make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+  else *p = __float2bfloat16_rn(r.v[0]);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) coupling_apply_kernel(float* __restrict__ u, int u_stride, const float* __restrict__ s,
+                                                             int s_stride, const float* __restrict__ t, int t_stride,
+                                                             long long npix, int L, int kind, float clamp, int inverse,
+                                                             __nv_bfloat16* __restrict__ ubf) {
+  const int Lv = L / VEC;
+  const long long total = npix * Lv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % Lv) * VEC;
+    long long p = idx / Lv;
+    Pack<VEC> x = ldv<VEC>(u + p * u_stride + c);
+    Pack<VEC> sv = ldv<VEC>(s + p * s_stride + c);
+    Pack<VEC> tv = ldv<VEC>(t + p * t_stride + c);
+    Pack<VEC> y;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float g, dg;
+      log_scale(kind, clamp, sv.v[e], g, dg);
+      float ex = expf(g);
+      y.v[e] = inverse ? (x.v[e] - tv.v[e]) / ex : ex * x.v[e] + tv.v[e];
+    }
+    stv<VEC>(u + p * u_stride + c, y);
+    if (ubf != nullptr) stv<VEC>(ubf + p * L + c, y);
+  }
+}
+
+template <int VEC, typename TO>
+__global__ void __launch_bounds__(256) coupling_bwd_kernel(float* __restrict__ u, int u_stride, float* __restrict__ du, int du_stride,
+                                                           const float* __restrict__ s, int s_stride, const float* __restrict__ t,
+                                                           int t_stride, long long npix, int L, int kind, float clamp, int inverse,
+                                                           TO* __restrict__ ds, int ds_stride, TO* __restrict__ dt, int dt_stride,
+                                                           __nv_bfloat16* __restrict__ xbf) {
+  const int Lv = L / VEC;
+  const long long total = npix * Lv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % Lv) * VEC;
+    long long p = idx / Lv;
+    Pack<VEC> y = ldv<VEC>(u + p * u_stride + c);
+    Pack<VEC> dy = ldv<VEC>(du + p * du_stride + c);
+    Pack<VEC> sv = ldv<VEC>(s + p * s_stride + c);
+    Pack<VEC> tv = ldv<VEC>(t + p * t_stride + c);
+    Pack<VEC> x, dx, dsv, dtv;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float g, dg;
+      log_scale(kind, clamp, sv.v[e], g, dg);
+      float ex = expf(g);
+      if (!inverse) {            // y = ex*x + t
+        x.v[e] = (y.v[e] - tv.v[e]) / ex;
+        dx.v[e] = dy.v[e] * ex;
+        dsv.v[e] = dy.v[e] * x.v[e] * ex * dg;
+        dtv.v[e] = dy.v[e];
+      } else {                   // y = (x - t)/ex
+        x.v[e] = y.v[e] * ex + tv.v[e];
+        float q = dy.v[e] / ex;
+        dx.v[e] = q;
+        dsv.v[e] = -dy.v[e] * y.v[e] * dg;
+        dtv.v[e] = -q;
+      }
+    }
+    stv<VEC>(u + p * u_stride + c, x);
+    stv<VEC>(du + p * du_stride + c, dx);
+    stv<VEC>(ds + p * ds_stride + c, dsv);
+    stv<VEC>(dt + p * dt_stride + c, dtv);
+    if (xbf != nullptr) stv<VEC>(xbf + p * L + c, x);
+  }
+}
+
+template <int VEC, typename TO>
+__global__ void __launch_bounds__(256) cast_slice_kernel(const float* __restrict__ in, int in_stride, long long npix, int L,
+                                                         float scale, TO* __restrict__ out, int out_stride) {
+  const int Lv = L / VEC;
+  const long long total = npix * Lv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % Lv) * VEC;
+    long long p = idx / Lv;
+    Pack<VEC> v = ldv<VEC>(in + p * in_stride + c);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v.v[e] *= scale;
+    stv<VEC>(out + p * out_stride + c, v);
+  }
+}
+
+template <typename TY, typename TO>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* d, int d_stride, const TY* __restrict__ y, int y_stride,
+                                                      TO* out, int out_stride, long long npix, int L, int act, float slope) {
+  const long long total = npix * L;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % L);
+    long long p = idx / L;
+    float g = act_grad(act, slope, to_f32(y[p * y_stride + c]));
+    out[p * out_stride + c] = from_f32<TO>(d[p * d_stride + c] * g);
+  }
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(256) axpy_slice_kernel(float* __restrict__ out, int out_stride, const TA* __restrict__ a,
+                                                         int a_stride, long long npix, int L, float alpha) {
+  const long long total = npix * L;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % L);
+    long long p = idx / L;
+    out[p * out_stride + c] += alpha * to_f32(a[p * a_stride + c]);
+  }
+}
+
+// ---- column sums (bias gradients): partial[chunk][N] then fixed-order finish
+constexpr int CS_COLS = 64, CS_ROWS = 4;
+template <typename T>
+__global__ void __launch_bounds__(CS_COLS* CS_ROWS) colsum_partial_kernel(const T* __restrict__ in, int in_stride, long long npix,
+                                                                          int N, long long rows_per_chunk, float* __restrict__ partial) {
+  __shared__ float red[CS_ROWS][CS_COLS];
+  const int col = blockIdx.y * CS_COLS + threadIdx.x;
+  const long long r0 = blockIdx.x * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > npix) r1 = npix;
+  float acc = 0.f;
+  if (col < N)
+    for (long long r = r0 + threadIdx.y; r < r1; r += CS_ROWS) acc += to_f32(in[r * in_stride + col]);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    float sum = red[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < CS_ROWS; ++k) sum += red[k][threadIdx.x];
+    partial[(long long)blockIdx.x * N + col] = sum;
+  }
+}
+__global__ void colsum_finish_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out, int accumulate) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  float sum = 0.f;
+  for (int k = 0; k < chunks; ++k) sum += partial[(long long)k * N + col];
+  out[col] = accumulate ? out[col] + sum : sum;
+}
+
+static inline long long colsum_chunks(long long npix) {
+  long long chunks = (npix + 255) / 256;          // >= 256 rows per chunk
+  long long cap = (long long)sm_count() * 8;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
+// ---- sum of squared differences with optional gradient (loss.reconstruction / latent_nll)
+__global__ void __launch_bounds__(256) sqdiff_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                                             float gscale, float* __restrict__ grad, float* __restrict__ partial) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d = a[i] - (b ? b[i] : 0.f);
+    acc += d * d;
+    if (grad) grad[i] = gscale * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < 8; ++k) s += red[k];
+    partial[blockIdx.x] = s;
+  }
+}
+__global__ void sqdiff_finish_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int k = 0; k < n; ++k) s += (double)partial[k];
+    out[0] = (float)(s * (double)scale);
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                   float wd, float bc1, float bc2_sqrt, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float w = p[i];
+    float gr = g[i] * gscale + wd * w;             // torch.optim.Adam: L2 weight decay folded into the gradient
+    float mi = b1 * m[i] + (1.f - b1) * gr;
+    float vi = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = w - (lr / bc1) * (mi / denom);
+  }
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  long long cap = (long long)sm_count() * 32;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace sininn
+
+using namespace sininn;
+
+extern "C" {
+
+int sininn_coupling_apply(float* u, int u_stride, const float* s, int s_stride, const float* t, int t_stride,
+                          long long npix, int L, int kind, float clamp, int inverse, void* u_bf16,
+                          sininn_stream_t stream) {
+  SININN_CHECK_ARG(u && s && t && npix > 0 && L > 0, "coupling_apply: bad arguments");
+  SININN_CHECK_ARG(kind == SININN_GLOW || kind == SININN_IRN, "coupling_apply: unknown kind %d", kind);
+  SININN_CHECK_ARG(clamp > 0.f, "coupling_apply: clamp must be positive");
+  __nv_bfloat16* bf = reinterpret_cast<__nv_bfloat16*>(u_bf16);
+  bool v4 = (L % 4) == 0 && (u_stride % 4) == 0 && (s_stride % 4) == 0 && (t_stride % 4) == 0 && aligned16(u) &&
+            aligned16(s) && aligned16(t) && (!bf || aligned8(bf));
+  const long long total = npix * (v4 ? L / 4 : L);
+  const int block = 256, grid = grid_for(total, block);
+  if (v4) coupling_apply_kernel<4><<<grid, block, 0, as_stream(stream)>>>(u, u_stride, s, s_stride, t, t_stride, npix, L, kind, clamp, inverse, bf);
+  else coupling_apply_kernel<1><<<grid, block, 0, as_stream(stream)>>>(u, u_stride, s, s_stride, t, t_stride, npix, L, kind, clamp, inverse, bf);
+  SININN_CHECK_LAUNCH("coupling_apply");
+  return SININN_OK;
+}
+
+int sininn_coupling_bwd(float* u, int u_stride, float* du, int du_stride, const float* s, int s_stride, const float* t,
+                        int t_stride, long long npix, int L, int kind, float clamp, int inverse, void* ds_out,
+                        int ds_stride, void* dt_out, int dt_stride, int out_dtype, void* x_bf16, sininn_stream_t stream) {
+  SININN_CHECK_ARG(u && du && s && t && ds_out && dt_out && npix > 0 && L > 0, "coupling_bwd: bad arguments");
+  SININN_CHECK_ARG(kind == SININN_GLOW || kind == SININN_IRN, "coupling_bwd: unknown kind %d", kind);
+  SININN_CHECK_ARG(out_dtype == SININN_F32 || out_dtype == SININN_BF16, "coupling_bwd: bad out_dtype");
+  __nv_bfloat16* bf = reinterpret_cast<__nv_bfloat16*>(x_bf16);
+  const bool f32 = out_dtype == SININN_F32;
+  bool v4 = (L % 4) == 0 && (u_stride % 4) == 0 && (du_stride % 4) == 0 && (s_stride % 4) == 0 && (t_stride % 4) == 0 &&
+            (ds_stride % 4) == 0 && (dt_stride % 4) == 0 && aligned16(u) && aligned16(du) && aligned16(s) && aligned16(t) &&
+            (f32 ? (aligned16(ds_out) && aligned16(dt_out)) : (aligned8(ds_out) && aligned8(dt_out))) && (!bf || aligned8(bf));
+  const long long total = npix * (v4 ? L / 4 : L);
+  const int block = 256, grid = grid_for(total, block);
+  cudaStream_t st = as_stream(stream);
+#define LAUNCH(V, T)                                                                                                    \
+  coupling_bwd_kernel<V, T><<<grid, block, 0, st>>>(u, u_stride, du, du_stride, s, s_stride, t, t_stride, npix, L, kind, \
+                                                    clamp, inverse, reinterpret_cast<T*>(ds_out), ds_stride,            \
+                                                    reinterpret_cast<T*>(dt_out), dt_stride, bf)
+  if (f32) { if (v4) LAUNCH(4, float); else LAUNCH(1, float); }
+  else     { if (v4) LAUNCH(4, __nv_bfloat16); else LAUNCH(1, __nv_bfloat16); }
+#undef LAUNCH
+  SININN_CHECK_LAUNCH("coupling_bwd");
+  return SININN_OK;
+}
+
+int sininn_cast_slice(const float* in, int in_stride, long long npix, int L, float scale, void* out, int out_dtype,
+                      int out_stride, sininn_stream_t stream) {
+  SININN_CHECK_ARG(in && out && npix > 0 && L > 0, "cast_slice: bad arguments");
+  SININN_CHECK_ARG(out_dtype == SININN_F32 || out_dtype == SININN_BF16, "cast_slice: bad out_dtype");
+  const bool f32 = out_dtype == SININN_F32;
+  bool v4 = (L % 4) == 0 && (in_stride % 4) == 0 && (out_stride % 4) == 0 && aligned16(in) && (f32 ? aligned16(out) : aligned8(out));
+  const long long total = npix * (v4 ? L / 4 : L);
+  const int block = 256, grid = grid_for(total, block);
+  cudaStream_t st = as_stream(stream);
+  if (f32) {
+    if (v4) cast_slice_kernel<4, float><<<grid, block, 0, st>>>(in, in_stride, npix, L, scale, (float*)out, out_stride);
+    else cast_slice_kernel<1, float><<<grid, block, 0, st>>>(in, in_stride, npix, L, scale, (float*)out, out_stride);
+  } else {
+    if (v4) cast_slice_kernel<4, __nv_bfloat16><<<grid, block, 0, st>>>(in, in_stride, npix, L, scale, (__nv_bfloat16*)out, out_stride);
+    else cast_slice_kernel<1, __nv_bfloat16><<<grid, block, 0, st>>>(in, in_stride, npix, L, scale, (__nv_bfloat16*)out, out_stride);
+  }
+  SININN_CHECK_LAUNCH("cast_slice");
+  return SININN_OK;
+}
+
+int sininn_act_bwd(const float* d, int d_stride, const void* y, int y_dtype, int y_stride, void* out, int out_dtype,
+                   int out_stride, long long npix, int L, int act, float slope, sininn_stream_t stream) {
+  SININN_CHECK_ARG(d && y && out && npix > 0 && L > 0, "act_bwd: bad arguments");
+  SININN_CHECK_ARG((y_dtype == SININN_F32 || y_dtype == SININN_BF16) && (out_dtype == SININN_F32 || out_dtype == SININN_BF16),
+                   "act_bwd: bad dtype");
+  const long long total = npix * L;
+  const int block = 256, grid = grid_for(total, block);
+  cudaStream_t st = as_stream(stream);
+#define LAUNCH(TY, TO) act_bwd_kernel<TY, TO><<<grid, block, 0, st>>>(d, d_stride, (const TY*)y, y_stride, (TO*)out, out_stride, npix, L, act, slope)
+  if (y_dtype == SININN_F32) { if (out_dtype == SININN_F32) LAUNCH(float, float); else LAUNCH(float, __nv_bfloat16); }
+  else                       { if (out_dtype == SININN_F32) LAUNCH(__nv_bfloat16, float); else LAUNCH(__nv_bfloat16, __nv_bfloat16); }
+#undef LAUNCH
+  SININN_CHECK_LAUNCH("act_bwd");
+  return SININN_OK;
+}
+
+int sininn_axpy_slice(float* out, int out_stride, const void* a, int a_dtype, int a_stride, long long npix, int L,
+                      float alpha, sininn_stream_t stream) {
+  SININN_CHECK_ARG(out && a && npix > 0 && L > 0, "axpy_slice: bad arguments");
+  SININN_CHECK_ARG(a_dtype == SININN_F32 || a_dtype == SININN_BF16, "axpy_slice: bad dtype");
+  const long long total = npix * L;
+  const int block = 256, grid = grid_for(total, block);
+  if (a_dtype == SININN_F32) axpy_slice_kernel<float><<<grid, block, 0, as_stream(stream)>>>(out, out_stride, (const float*)a, a_stride, npix, L, alpha);
+  else axpy_slice_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>(out, out_stride, (const __nv_bfloat16*)a, a_stride, npix, L, alpha);
+  SININN_CHECK_LAUNCH("axpy_slice");
+  return SININN_OK;
+}
+
+size_t sininn_colsum_workspace_bytes(long long npix, int N) {
+  if (npix <= 0 || N <= 0) return 0;
+  return (size_t)colsum_chunks(npix) * (size_t)N * sizeof(float);
+}
+
+int sininn_colsum(const void* in, int dtype, int in_stride, long long npix, int N, float* out, int accumulate,
+                  void* workspace, size_t workspace_bytes, sininn_stream_t stream) {
+  SININN_CHECK_ARG(in && out && npix > 0 && N > 0, "colsum: bad arguments");
+  SININN_CHECK_ARG(dtype == SININN_F32 || dtype == SININN_BF16, "colsum: bad dtype");
+  const long long chunks = colsum_chunks(npix);
+  if (!workspace || workspace_bytes < (size_t)chunks * N * sizeof(float)) {
+    set_error("colsum: workspace too small (%zu < %zu)", workspace_bytes, (size_t)chunks * N * sizeof(float));
+    return SININN_EWORKSPACE;
+  }
+  const long long rows_per_chunk = (npix + chunks - 1) / chunks;
+  dim3 grid((unsigned)chunks, (N + CS_COLS - 1) / CS_COLS), block(CS_COLS, CS_ROWS);
+  cudaStream_t st = as_stream(stream);
+  float* partial = reinterpret_cast<float*>(workspace);
+  if (dtype == SININN_F32) colsum_partial_kernel<float><<<grid, block, 0, st>>>((const float*)in, in_stride, npix, N, rows_per_chunk, partial);
+  else colsum_partial_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, in_stride, npix, N, rows_per_chunk, partial);
+  colsum_finish_kernel<<<(N + 127) / 128, 128, 0, st>>>(partial, (int)chunks, N, out, accumulate);
+  SININN_CHECK_LAUNCH("colsum");
+  return SININN_OK;
+}
+
+size_t sininn_sqdiff_workspace_bytes(long long n) {
+  (void)n;
+  return (size_t)sm_count() * 8 * sizeof(float);
+}
+
+int sininn_sqdiff_nchw(const float* a, const float* b, long long n, float scale, float* loss_out, float* grad_out,
+                       void* workspace, size_t workspace_bytes, sininn_stream_t stream) {
+  SININN_CHECK_ARG(a && loss_out && n > 0, "sqdiff: bad arguments");
+  int grid = grid_for(n, 256);
+  int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  if (!workspace || workspace_bytes < (size_t)grid * sizeof(float)) {
+    set_error("sqdiff: workspace too small");
+    return SININN_EWORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  sqdiff_partial_kernel<<<grid, 256, 0, st>>>(a, b, n, 2.f * scale, grad_out, (float*)workspace);
+  sqdiff_finish_kernel<<<1, 32, 0, st>>>((const float*)workspace, grid, scale, loss_out);
+  SININN_CHECK_LAUNCH("sqdiff");
+  return SININN_OK;
+}
+
+int sininn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                     sininn_stream_t stream) {
+  SININN_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  const int block = 256, grid = grid_for(n, block);
+  adam_kernel<<<grid, block, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                     weight_decay, bc1, sqrtf(bc2), grad_scale);
+  SININN_CHECK_LAUNCH("adam_step");
+  return SININN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,352 @@
+// Squeeze (i-RevNet order) and Haar down/up-sampling, layout changes, channel permutation.
+// All HBM-bound: one read + one write of the tensor, 128-bit accesses where alignment allows.
+//
+// Reference semantics:
+//   squeeze  FrEIA IRevNetDownsampling (call sites /root/reference/archs.py:28-31,35-38)
+//            out[b,(dy*2+dx)*C+c,i,j] = in[b,c,2i+dy,2j+dx]
+//   Haar     HaarDownsampling.forward /root/reference/archs.py:183-199, patterns :167-176,
+//            band-major channel order out[k*C+c] (:188-190)
+#include "common.cuh"
+
+namespace sininn {
+
+// a=(0,0) b=(0,1) c=(1,0) d=(1,1) of one 2x2 block  ->  four output planes
+template <bool HAAR>
+__device__ __forceinline__ void fwd4(float a, float b, float c, float d, float scale, float o[4]) {
+  if (HAAR) {
+    o[0] = (a + b + c + d) * scale;
+    o[1] = (a - b + c - d) * scale;
+    o[2] = (a + b - c - d) * scale;
+    o[3] = (a - b - c + d) * scale;
+  } else {
+    o[0] = a; o[1] = b; o[2] = c; o[3] = d;
+  }
+}
+// inverse of the reference forward is the transpose of the same +-1 patterns (H*H^T = 4I)
+template <bool HAAR>
+__device__ __forceinline__ void inv4(const float o[4], float scale, float& a, float& b, float& c, float& d) {
+  if (HAAR) {
+    a = (o[0] + o[1] + o[2] + o[3]) * scale;
+    b = (o[0] - o[1] + o[2] - o[3]) * scale;
+    c = (o[0] + o[1] - o[2] - o[3]) * scale;
+    d = (o[0] - o[1] - o[2] + o[3]) * scale;
+  } else {
+    a = o[0]; b = o[1]; c = o[2]; d = o[3];
+  }
+}
+
+template <int N> struct VecT;
+template <> struct VecT<1> { typedef float type; };
+template <> struct VecT<2> { typedef float2 type; };
+template <> struct VecT<4> { typedef float4 type; };
+
+// ---------------------------------------------------------------- NCHW <-> NCHW
+// One thread = VEC output columns of one (plane, output row): reads 2 rows x 2*VEC floats,
+// writes VEC floats to each of 4 planes.  Consecutive threads walk the row => coalesced both ways.
+template <int VEC, bool HAAR>
+__global__ void __launch_bounds__(256) resample_nchw_fwd_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                int C, int H, int W, float scale, long long total) {
+  const int Ho = H >> 1, Wo = W >> 1, Wv = Wo / VEC;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int jv = (int)(idx % Wv);
+    long long r = idx / Wv;
+    int i = (int)(r % Ho);
+    long long plane = r / Ho;          // b*C + c
+    int c = (int)(plane % C);
+    long long b = plane / C;
+    const float* r0 = in + (plane * H + 2 * i) * (long long)W + 2 * jv * VEC;
+    const float* r1 = r0 + W;
+    __align__(16) float x0[2 * VEC], x1[2 * VEC];
+    typedef typename VecT<VEC == 1 ? 2 : 4>::type LT;   // VEC=1: float2, VEC>=2: float4 chunks
+    constexpr int LN = (VEC == 1 ? 2 : 4);
+#pragma unroll
+    for (int q = 0; q < 2 * VEC / LN; ++q) {
+      *reinterpret_cast<LT*>(&x0[q * LN]) = __ldcs(reinterpret_cast<const LT*>(r0) + q);
+      *reinterpret_cast<LT*>(&x1[q * LN]) = __ldcs(reinterpret_cast<const LT*>(r1) + q);
+    }
+    __align__(16) float o[4][VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float t[4];
+      fwd4<HAAR>(x0[2 * v], x0[2 * v + 1], x1[2 * v], x1[2 * v + 1], scale, t);
+      o[0][v] = t[0]; o[1][v] = t[1]; o[2][v] = t[2]; o[3][v] = t[3];
+    }
+    typedef typename VecT<VEC>::type ST;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float* dst = out + (((b * 4 + k) * C + c) * Ho + i) * (long long)Wo + jv * VEC;
+      __stcs(reinterpret_cast<ST*>(dst), *reinterpret_cast<ST*>(&o[k][0]));
+    }
+  }
+}
+
+template <int VEC, bool HAAR>
+__global__ void __launch_bounds__(256) resample_nchw_inv_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                int C, int H, int W, float scale, long long total) {
+  const int Ho = H >> 1, Wo = W >> 1, Wv = Wo / VEC;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int jv = (int)(idx % Wv);
+    long long r = idx / Wv;
+    int i = (int)(r % Ho);
+    long long plane = r / Ho;
+    int c = (int)(plane % C);
+    long long b = plane / C;
+    typedef typename VecT<VEC>::type ST;
+    __align__(16) float o[4][VEC];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float* src = in + (((b * 4 + k) * C + c) * Ho + i) * (long long)Wo + jv * VEC;
+      *reinterpret_cast<ST*>(&o[k][0]) = __ldcs(reinterpret_cast<const ST*>(src));
+    }
+    __align__(16) float x0[2 * VEC], x1[2 * VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float t[4] = {o[0][v], o[1][v], o[2][v], o[3][v]};
+      inv4<HAAR>(t, scale, x0[2 * v], x0[2 * v + 1], x1[2 * v], x1[2 * v + 1]);
+    }
+    float* r0 = out + (plane * H + 2 * i) * (long long)W + 2 * jv * VEC;
+    float* r1 = r0 + W;
+    typedef typename VecT<VEC == 1 ? 2 : 4>::type LT;
+    constexpr int LN = (VEC == 1 ? 2 : 4);
+#pragma unroll
+    for (int q = 0; q < 2 * VEC / LN; ++q) {
+      __stcs(reinterpret_cast<LT*>(r0) + q, *reinterpret_cast<LT*>(&x0[q * LN]));
+      __stcs(reinterpret_cast<LT*>(r1) + q, *reinterpret_cast<LT*>(&x1[q * LN]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------- NHWC <-> NHWC
+// full-res [B,H,W,C] <-> [B,H/2,W/2,4C]; one thread = VEC channels of one low-res pixel.
+template <int VEC, bool HAAR, bool REV>
+__global__ void __launch_bounds__(256) resample_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                            int C, int H, int W, float scale, long long total) {
+  const int Ho = H >> 1, Wo = W >> 1, Cv = C / VEC;
+  typedef typename VecT<VEC>::type VT;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(idx % Cv);
+    long long r = idx / Cv;
+    int j = (int)(r % Wo);
+    r /= Wo;
+    int i = (int)(r % Ho);
+    long long b = r / Ho;
+    int c = cv * VEC;
+    long long hi = ((b * H + 2 * i) * (long long)W + 2 * j) * C + c;   // full-res (2i,2j)
+    long long lo = ((b * Ho + i) * (long long)Wo + j) * 4 * C + c;     // low-res pixel, band 0
+    __align__(16) float v[4][VEC];
+    if (!REV) {
+      *reinterpret_cast<VT*>(v[0]) = *reinterpret_cast<const VT*>(in + hi);
+      *reinterpret_cast<VT*>(v[1]) = *reinterpret_cast<const VT*>(in + hi + C);
+      *reinterpret_cast<VT*>(v[2]) = *reinterpret_cast<const VT*>(in + hi + (long long)W * C);
+      *reinterpret_cast<VT*>(v[3]) = *reinterpret_cast<const VT*>(in + hi + (long long)W * C + C);
+      __align__(16) float o[4][VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        float t[4];
+        fwd4<HAAR>(v[0][e], v[1][e], v[2][e], v[3][e], scale, t);
+        o[0][e] = t[0]; o[1][e] = t[1]; o[2][e] = t[2]; o[3][e] = t[3];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<VT*>(out + lo + (long long)k * C) = *reinterpret_cast<VT*>(o[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<VT*>(v[k]) = *reinterpret_cast<const VT*>(in + lo + (long long)k * C);
+      __align__(16) float o[4][VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        float t[4] = {v[0][e], v[1][e], v[2][e], v[3][e]};
+        inv4<HAAR>(t, scale, o[0][e], o[1][e], o[2][e], o[3][e]);
+      }
+      *reinterpret_cast<VT*>(out + hi) = *reinterpret_cast<VT*>(o[0]);
+      *reinterpret_cast<VT*>(out + hi + C) = *reinterpret_cast<VT*>(o[1]);
+      *reinterpret_cast<VT*>(out + hi + (long long)W * C) = *reinterpret_cast<VT*>(o[2]);
+      *reinterpret_cast<VT*>(out + hi + (long long)W * C + C) = *reinterpret_cast<VT*>(o[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- NCHW <-> NHWC (32x32 smem transpose)
+// TO_NHWC: in [B][C][HW] -> out [B][HW][C], out channel i <- in channel map[i]
+// else   : in [B][HW][C] -> out [B][C][HW], out channel i <- in channel map[i]
+template <bool TO_NHWC>
+__global__ void __launch_bounds__(256) layout_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW,
+                                                     const int32_t* __restrict__ map, __nv_bfloat16* __restrict__ bf,
+                                                     int bc0, int bc1) {
+  __shared__ float tile[32][33];
+  const long long b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  if (TO_NHWC) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int c = c0 + ty + 8 * r, p = p0 + tx;
+      if (c < C && p < HW) {
+        int cs = map ? map[c] : c;
+        tile[ty + 8 * r][tx] = __ldcs(in + (b * C + cs) * (long long)HW + p);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int p = p0 + ty + 8 * r, c = c0 + tx;
+      if (c < C && p < HW) {
+        float v = tile[tx][ty + 8 * r];
+        out[(b * HW + p) * (long long)C + c] = v;
+        if (bf != nullptr && c >= bc0 && c < bc1) bf[(b * HW + p) * (long long)(bc1 - bc0) + (c - bc0)] = __float2bfloat16_rn(v);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int p = p0 + ty + 8 * r, c = c0 + tx;
+      if (c < C && p < HW) {
+        int cs = map ? map[c] : c;
+        tile[ty + 8 * r][tx] = in[(b * HW + p) * (long long)C + cs];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int c = c0 + ty + 8 * r, p = p0 + tx;
+      if (c < C && p < HW) __stcs(out + (b * C + c) * (long long)HW + p, tile[tx][ty + 8 * r]);
+    }
+  }
+}
+
+// out[p][i] = in[p][map[i]]  (+ optional compact bf16 copy of out[:, bc0:bc1])
+template <int VEC>
+__global__ void __launch_bounds__(256) permute_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, long long npix,
+                                                           int C, const int32_t* __restrict__ map,
+                                                           __nv_bfloat16* __restrict__ bf, int bc0, int bc1) {
+  const int Cv = C / VEC;
+  const long long total = npix * Cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(idx % Cv);
+    long long p = idx / Cv;
+    int c = cv * VEC;
+    float v[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v[e] = in[p * C + __ldg(map + c + e)];
+    if (VEC == 4) {
+      store4(out + p * C + c, make_float4(v[0], v[1], v[2], v[3]));
+      if (bf != nullptr && c >= bc0 && c < bc1)   // bc0, bc1 multiples of 4 on this path
+        store4(bf + p * (long long)(bc1 - bc0) + (c - bc0), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        out[p * C + c + e] = v[e];
+        if (bf != nullptr && c + e >= bc0 && c + e < bc1)
+          bf[p * (long long)(bc1 - bc0) + (c + e - bc0)] = __float2bfloat16_rn(v[e]);
+      }
+    }
+  }
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  long long cap = (long long)sm_count() * 32;   // grid-stride beyond ~32 CTAs per SM
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace sininn
+
+using namespace sininn;
+
+extern "C" {
+
+int sininn_resample_nchw(const float* in, float* out, int B, int C, int H, int W, int mode, int rev, float scale,
+                         sininn_stream_t stream) {
+  SININN_CHECK_ARG(in && out, "resample_nchw: null pointer");
+  SININN_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, "resample_nchw: bad shape");
+  SININN_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "resample_nchw: H and W must be even (got %dx%d)", H, W);
+  SININN_CHECK_ARG(mode == 0 || mode == 1, "resample_nchw: mode must be 0 (squeeze) or 1 (haar)");
+  cudaStream_t st = as_stream(stream);
+  const int Wo = W / 2;
+  int vec = 1;
+  if ((Wo % 4) == 0 && aligned16(in) && aligned16(out)) vec = 4;
+  else if ((Wo % 2) == 0 && aligned16(in) && aligned16(out)) vec = 2;
+  else SININN_CHECK_ARG(aligned8(in) && aligned8(out), "resample_nchw: pointers must be 8-byte aligned");
+  const long long total = (long long)B * C * (H / 2) * (Wo / vec);
+  const int block = 256, grid = grid_for(total, block);
+#define LAUNCH(V, HA)                                                                                   \
+  do {                                                                                                  \
+    if (!rev) resample_nchw_fwd_kernel<V, HA><<<grid, block, 0, st>>>(in, out, C, H, W, scale, total);  \
+    else resample_nchw_inv_kernel<V, HA><<<grid, block, 0, st>>>(in, out, C, H, W, scale, total);       \
+  } while (0)
+  if (mode == 1) {
+    if (vec == 4) LAUNCH(4, true); else if (vec == 2) LAUNCH(2, true); else LAUNCH(1, true);
+  } else {
+    if (vec == 4) LAUNCH(4, false); else if (vec == 2) LAUNCH(2, false); else LAUNCH(1, false);
+  }
+#undef LAUNCH
+  SININN_CHECK_LAUNCH("resample_nchw");
+  return SININN_OK;
+}
+
+int sininn_resample_nhwc(const float* in, float* out, int B, int C, int H, int W, int mode, int rev, float scale,
+                         sininn_stream_t stream) {
+  SININN_CHECK_ARG(in && out, "resample_nhwc: null pointer");
+  SININN_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, "resample_nhwc: bad shape");
+  SININN_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "resample_nhwc: H and W must be even (got %dx%d)", H, W);
+  SININN_CHECK_ARG(mode == 0 || mode == 1, "resample_nhwc: mode must be 0 (squeeze) or 1 (haar)");
+  cudaStream_t st = as_stream(stream);
+  const int vec = ((C % 4) == 0 && aligned16(in) && aligned16(out)) ? 4 : 1;
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / vec);
+  const int block = 256, grid = grid_for(total, block);
+#define LAUNCH(V, HA, RV) resample_nhwc_kernel<V, HA, RV><<<grid, block, 0, st>>>(in, out, C, H, W, scale, total)
+  if (vec == 4) {
+    if (mode == 1) { if (rev) LAUNCH(4, true, true); else LAUNCH(4, true, false); }
+    else           { if (rev) LAUNCH(4, false, true); else LAUNCH(4, false, false); }
+  } else {
+    if (mode == 1) { if (rev) LAUNCH(1, true, true); else LAUNCH(1, true, false); }
+    else           { if (rev) LAUNCH(1, false, true); else LAUNCH(1, false, false); }
+  }
+#undef LAUNCH
+  SININN_CHECK_LAUNCH("resample_nhwc");
+  return SININN_OK;
+}
+
+int sininn_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, const int32_t* chan_map, void* bf16_out,
+                        int c0, int c1, sininn_stream_t stream) {
+  SININN_CHECK_ARG(in && out && B > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad arguments");
+  SININN_CHECK_ARG(B <= 65535, "nchw_to_nhwc: batch too large for grid.z");
+  if (bf16_out) SININN_CHECK_ARG(0 <= c0 && c0 < c1 && c1 <= C, "nchw_to_nhwc: bad bf16 channel range");
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  layout_kernel<true><<<grid, block, 0, as_stream(stream)>>>(in, out, C, HW, chan_map,
+                                                             reinterpret_cast<__nv_bfloat16*>(bf16_out), c0, c1);
+  SININN_CHECK_LAUNCH("nchw_to_nhwc");
+  return SININN_OK;
+}
+
+int sininn_nhwc_to_nchw(const float* in, float* out, int B, int C, int HW, const int32_t* chan_map,
+                        sininn_stream_t stream) {
+  SININN_CHECK_ARG(in && out && B > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad arguments");
+  SININN_CHECK_ARG(B <= 65535, "nhwc_to_nchw: batch too large for grid.z");
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  layout_kernel<false><<<grid, block, 0, as_stream(stream)>>>(in, out, C, HW, chan_map, nullptr, 0, 0);
+  SININN_CHECK_LAUNCH("nhwc_to_nchw");
+  return SININN_OK;
+}
+
+int sininn_permute_nhwc(const float* in, float* out, long long npix, int C, const int32_t* chan_map, void* bf16_out,
+                        int c0, int c1, sininn_stream_t stream) {
+  SININN_CHECK_ARG(in && out && chan_map && npix > 0 && C > 0, "permute_nhwc: bad arguments");
+  SININN_CHECK_ARG(in != out, "permute_nhwc: cannot run in place");
+  if (bf16_out) SININN_CHECK_ARG(0 <= c0 && c0 < c1 && c1 <= C, "permute_nhwc: bad bf16 channel range");
+  __nv_bfloat16* bf = reinterpret_cast<__nv_bfloat16*>(bf16_out);
+  bool v4 = (C % 4) == 0 && aligned16(out) && (!bf || ((c0 % 4) == 0 && (c1 % 4) == 0 && aligned8(bf)));
+  const long long total = npix * (v4 ? C / 4 : C);
+  const int block = 256, grid = grid_for(total, block);
+  if (v4) permute_nhwc_kernel<4><<<grid, block, 0, as_stream(stream)>>>(in, out, npix, C, chan_map, bf, c0, c1);
+  else permute_nhwc_kernel<1><<<grid, block, 0, as_stream(stream)>>>(in, out, npix, C, chan_map, bf, c0, c1);
+  SININN_CHECK_LAUNCH("permute_nhwc");
+  return SININN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,600 @@
+"""Plan executor for invertible networks on the libsininn kernels.
+
+A network is compiled into a list of plan ops (resample / coupling block /
+channel permutation).  The executor keeps the activations ("trunk") as ONE fp32
+channels-last tensor that every coupling half-step updates in place, and runs
+
+  * forward            net(x)            (reference: FrEIA ReversibleGraphNet.forward,
+  * inverse            net(x, rev=True)   call site archs.py:71; InvRescaleNet.forward archs.py:223-233)
+  * backward           from the OUTPUT only: each block's input is reconstructed with
+                       the exact inverse while gradients flow,
+                       so no activation is stored between forward and backward.
+
+The only tensors that cross the API are NCHW-contiguous fp32 (loss.py:16-17 needs
+`.view(b, c*h*w)` to work on the result).
+"""
+import os
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, GLOW, IRN, SininnError, require_cuda
+
+
+@dataclass(frozen=True)
+class EngineConfig:
+    precision: str = "bf16"      # "fp32": CUDA-core fp32 subnets (1e-4 parity); "bf16": bf16 operands, fp32 accumulate
+    tensor_core: bool = True     # tcgen05 kernels for the subnets (bf16 only)
+
+    @property
+    def act_dtype(self):
+        return torch.bfloat16 if self.precision == "bf16" else torch.float32
+
+    @property
+    def tc(self):
+        return self.tensor_core and self.precision == "bf16"
+
+
+def default_config():
+    prec = os.environ.get("SININN_PRECISION", "bf16")
+    if prec not in ("bf16", "fp32"):
+        raise SininnError(f"SININN_PRECISION must be bf16 or fp32, got {prec!r}")
+    tc = os.environ.get("SININN_TENSOR_CORE", "1") != "0"
+    return EngineConfig(precision=prec, tensor_core=tc)
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+# ----------------------------------------------------------------------------- packed-weight cache
+_pack_cache = {}
+
+
+def invalidate_packs():
+    """Forget packed weights (call after parameters were modified outside torch's version tracking)."""
+    _pack_cache.clear()
+
+
+def packed(w, mode, dtype):
+    """Implicit-GEMM layout of an OIHW weight, cached until the parameter changes."""
+    key = (w.data_ptr(), mode, dtype)
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == w._version and hit[2] == tuple(w.shape):
+        return hit[1]
+    co, ci = w.shape[0], w.shape[1]
+    rows, k = (co, ci) if mode == 0 else (ci, co)
+    p = K.pack_weight(w, mode, dtype, _round_up(rows, 16), _round_up(k, 16))
+    _pack_cache[key] = (w._version, p, tuple(w.shape))
+    return p
+
+
+# ----------------------------------------------------------------------------- trunk state
+class Trunk:
+    """fp32 channels-last activations [B,h,w,C] (+ gradient of the same shape during backward)
+    and a cache of compact bf16 copies of channel ranges (tensor-core operands)."""
+
+    def __init__(self, U, dU=None):
+        self.U, self.dU = U, dU
+        self.bf = {}
+
+    @property
+    def geom(self):
+        return tuple(self.U.shape[:3])
+
+    @property
+    def C(self):
+        return self.U.shape[3]
+
+    @property
+    def npix(self):
+        s = self.U.shape
+        return s[0] * s[1] * s[2]
+
+    def mat(self):
+        return self.U.view(self.npix, self.C)
+
+    def dmat(self):
+        return self.dU.view(self.npix, self.C)
+
+    def set(self, U, dU=None, bf=None):
+        self.U, self.dU = U, dU
+        self.bf = bf or {}
+
+    def invalidate(self, c0, c1):
+        for key in [k for k in self.bf if not (k[1] <= c0 or k[0] >= c1)]:
+            del self.bf[key]
+
+    def operand(self, rng, dtype):
+        """Channel range as a GEMM operand of `dtype` ([npix, L] view)."""
+        c0, c1 = rng
+        if dtype == torch.float32:
+            return self.mat()[:, c0:c1]
+        hit = self.bf.get((c0, c1))
+        if hit is None:
+            hit = torch.empty(self.npix, _round_up(c1 - c0, 8), dtype=dtype, device=self.U.device)[:, :c1 - c0]
+            K.cast_slice(self.mat()[:, c0:c1], hit)
+            self.bf[(c0, c1)] = hit
+        return hit
+
+
+class RunCtx:
+    def __init__(self, cfg, want_grads=False):
+        self.cfg = cfg
+        self.adt = cfg.act_dtype
+        self.tc = cfg.tc
+        self.grads = {} if want_grads else None
+
+    def add_grad(self, param, g):
+        if param is None or not param.requires_grad:
+            return
+        cur = self.grads.get(id(param))
+        self.grads[id(param)] = g if cur is None else cur + g
+
+
+# ----------------------------------------------------------------------------- subnets
+def _is_conv(m, k=None):
+    return (isinstance(m, nn.Conv2d) and m.kernel_size[0] == m.kernel_size[1] and m.kernel_size[0] in (1, 3)
+            and m.stride == (1, 1) and m.dilation == (1, 1) and m.groups == 1
+            and m.padding == (m.kernel_size[0] // 2,) * 2 and m.padding_mode == "zeros"
+            and (k is None or m.kernel_size[0] == k))
+
+
+class ConvSubnet:
+    """conv(k) -> ReLU -> conv(k): subnet_conv / subnet_conv_1x1 (archs.py:11-17)."""
+
+    def __init__(self, seq):
+        mods = list(seq.children()) if isinstance(seq, nn.Sequential) else []
+        if not (len(mods) == 3 and _is_conv(mods[0]) and isinstance(mods[1], nn.ReLU) and _is_conv(mods[2], mods[0].kernel_size[0])):
+            raise SininnError("unsupported coupling subnet: expected nn.Sequential(Conv2d(k), ReLU, Conv2d(k)) with "
+                              f"k in (1,3), stride 1, 'same' zero padding; got {seq}")
+        self.c1, self.c2 = mods[0], mods[2]
+        self.taps = self.c1.kernel_size[0] ** 2
+        self.cin, self.hidden, self.cout = self.c1.in_channels, self.c1.out_channels, self.c2.out_channels
+
+    def parameters(self):
+        return [p for p in (self.c1.weight, self.c1.bias, self.c2.weight, self.c2.bias) if p is not None]
+
+    def fwd(self, ctx, tr, src):
+        x = tr.operand(src, ctx.adt)
+        dev = x.device
+        h = torch.empty(tr.npix, self.hidden, dtype=ctx.adt, device=dev)
+        K.conv(x, packed(self.c1.weight, 0, ctx.adt), tr.geom, self.hidden, h, bias=self.c1.bias, act=ACT_RELU,
+               tensor_core=ctx.tc)
+        a = torch.empty(tr.npix, self.cout, dtype=torch.float32, device=dev)
+        K.conv(h, packed(self.c2.weight, 0, ctx.adt), tr.geom, self.cout, a, bias=self.c2.bias, tensor_core=ctx.tc)
+        return a, (x, h)
+
+    def bwd(self, ctx, tr, saved, da, dsrc):
+        """da: dL/d(output) [npix, cout] in the activation dtype; accumulates dL/d(input) into dsrc (fp32 view)."""
+        x, h = saved
+        dev = x.device
+        dh = torch.empty_like(h)
+        K.conv(da, packed(self.c2.weight, 1, ctx.adt), tr.geom, self.hidden, dh, mask=h, mask_act=ACT_RELU,
+               tensor_core=ctx.tc)
+        if self.c2.weight.requires_grad:
+            ctx.add_grad(self.c2.weight, K.wgrad(h, da, tr.geom, self.taps, torch.empty_like(self.c2.weight),
+                                                 tensor_core=ctx.tc))
+        if self.c2.bias is not None and self.c2.bias.requires_grad:
+            ctx.add_grad(self.c2.bias, K.colsum(da, torch.empty(self.cout, dtype=torch.float32, device=dev)))
+        K.conv(dh, packed(self.c1.weight, 1, ctx.adt), tr.geom, self.cin, dsrc, accumulate=True, tensor_core=ctx.tc)
+        if self.c1.weight.requires_grad:
+            ctx.add_grad(self.c1.weight, K.wgrad(x, dh, tr.geom, self.taps, torch.empty_like(self.c1.weight),
+                                                 tensor_core=ctx.tc))
+        if self.c1.bias is not None and self.c1.bias.requires_grad:
+            ctx.add_grad(self.c1.bias, K.colsum(dh, torch.empty(self.hidden, dtype=torch.float32, device=dev)))
+
+
+class DenseSubnet:
+    """DenseBlock (archs.py:74-95): five 3x3 convs over a growing channel concatenation, LeakyReLU(0.2)
+    after the first four.  The concatenation is one channels-last buffer; conv j reads its first
+    cin+32(j-1) channels and writes its 32 outputs right behind them, so torch.cat costs nothing."""
+
+    SLOPE = 0.2
+
+    def __init__(self, block):
+        self.convs = [block.conv1, block.conv2, block.conv3, block.conv4, block.conv5]
+        for c in self.convs:
+            if not _is_conv(c, 3):
+                raise SininnError(f"unsupported DenseBlock conv {c}")
+        self.cin = self.convs[0].in_channels
+        self.gc = self.convs[0].out_channels
+        self.cout = self.convs[4].out_channels
+        self.ctot = self.cin + 4 * self.gc
+
+    def parameters(self):
+        out = []
+        for c in self.convs:
+            out += [p for p in (c.weight, c.bias) if p is not None]
+        return out
+
+    def fwd(self, ctx, tr, src):
+        dev = tr.U.device
+        cat = torch.empty(tr.npix, _round_up(self.ctot, 8), dtype=ctx.adt, device=dev)
+        K.cast_slice(tr.mat()[:, src[0]:src[1]], cat[:, :self.cin])
+        for j in range(4):
+            lo = self.cin + self.gc * j
+            K.conv(cat[:, :lo], packed(self.convs[j].weight, 0, ctx.adt), tr.geom, self.gc, cat[:, lo:lo + self.gc],
+                   bias=self.convs[j].bias, act=ACT_LRELU, slope=self.SLOPE, tensor_core=ctx.tc)
+        out = torch.empty(tr.npix, self.cout, dtype=torch.float32, device=dev)
+        K.conv(cat[:, :self.ctot], packed(self.convs[4].weight, 0, ctx.adt), tr.geom, self.cout, out,
+               bias=self.convs[4].bias, tensor_core=ctx.tc)
+        return out, (cat,)
+
+    def bwd(self, ctx, tr, saved, dout, dsrc):
+        (cat,) = saved
+        dev = cat.device
+        # gradient of the concatenation buffer accumulates in fp32; each conv's upstream gradient is
+        # cast to the operand dtype (compact, aligned) after the LeakyReLU derivative is applied
+        dcat = torch.empty(tr.npix, self.ctot, dtype=torch.float32, device=dev)
+        c5 = self.convs[4]
+        K.conv(dout, packed(c5.weight, 1, ctx.adt), tr.geom, self.ctot, dcat, tensor_core=ctx.tc)
+        if c5.weight.requires_grad:
+            ctx.add_grad(c5.weight, K.wgrad(cat[:, :self.ctot], dout, tr.geom, 9, torch.empty_like(c5.weight),
+                                            tensor_core=ctx.tc))
+        if c5.bias is not None and c5.bias.requires_grad:
+            ctx.add_grad(c5.bias, K.colsum(dout, torch.empty(self.cout, dtype=torch.float32, device=dev)))
+        for j in (3, 2, 1, 0):
+            lo = self.cin + self.gc * j
+            g = torch.empty(tr.npix, self.gc, dtype=ctx.adt, device=dev)
+            K.act_bwd(dcat[:, lo:lo + self.gc], cat[:, lo:lo + self.gc], g, ACT_LRELU, self.SLOPE)
+            cj = self.convs[j]
+            K.conv(g, packed(cj.weight, 1, ctx.adt), tr.geom, lo, dcat[:, :lo], accumulate=True, tensor_core=ctx.tc)
+            if cj.weight.requires_grad:
+                ctx.add_grad(cj.weight, K.wgrad(cat[:, :lo], g, tr.geom, 9, torch.empty_like(cj.weight),
+                                                tensor_core=ctx.tc))
+            if cj.bias is not None and cj.bias.requires_grad:
+                ctx.add_grad(cj.bias, K.colsum(g, torch.empty(self.gc, dtype=torch.float32, device=dev)))
+        K.axpy_slice(dsrc, dcat[:, :self.cin], 1.0)
+
+
+# ----------------------------------------------------------------------------- plan ops
+class ResampleOp:
+    """mode 0: FrEIA IRevNetDownsampling (archs.py:28-31,35-38); mode 1: HaarDownsampling (archs.py:162-199)."""
+    kind = "resample"
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def fwd_scale(self):
+        return 0.25 if self.mode == 1 else 1.0
+
+    # value maps: forward scale s_f, inverse scale 1.  Gradient maps are the transposes:
+    #   grad of forward  = inverse map * s_f ; grad of inverse = forward map / s_f  (H H^T = 4 I for Haar)
+    def apply_nchw(self, x, rev, grad=False):
+        if not grad:
+            return K.resample_nchw(x, self.mode, rev, 1.0 if rev else self.fwd_scale())
+        if not rev:   # gradient of the forward map: [B,4C,h,w] -> [B,C,2h,2w]
+            return K.resample_nchw(x, self.mode, 1, self.fwd_scale())
+        return K.resample_nchw(x, self.mode, 0, 1.0 if self.mode == 0 else 1.0)
+
+    def apply_nhwc(self, x, rev, grad=False):
+        if not grad:
+            return K.resample_nhwc(x, self.mode, rev, 1.0 if rev else self.fwd_scale())
+        if not rev:
+            return K.resample_nhwc(x, self.mode, 1, self.fwd_scale())
+        return K.resample_nhwc(x, self.mode, 0, 1.0)
+
+    def parameters(self):
+        return []
+
+
+class PermOp:
+    """FrEIA PermuteRandom (archs.py:65-68): fwd x[:, perm], rev x[:, perm_inv]."""
+    kind = "perm"
+
+    def __init__(self, perm):
+        self.perm_cpu = torch.as_tensor(perm, dtype=torch.int32).clone()
+        inv = torch.empty_like(self.perm_cpu)
+        inv[self.perm_cpu.long()] = torch.arange(len(self.perm_cpu), dtype=torch.int32)
+        self.inv_cpu = inv
+        self._dev = {}
+
+    def maps(self, device):
+        key = (device.type, device.index)
+        if key not in self._dev:
+            self._dev[key] = (self.perm_cpu.to(device), self.inv_cpu.to(device))
+        return self._dev[key]
+
+    def gather_map(self, device, rev, grad=False):
+        """Index map m with out[:, i] = in[:, m[i]] for the value pass (or its gradient pass)."""
+        perm, inv = self.maps(device)
+        use_inv = bool(rev) != bool(grad)     # gradient of a gather with perm is a gather with perm_inv
+        return inv if use_inv else perm
+
+    def parameters(self):
+        return []
+
+
+class HalfStep:
+    """dst <- affine(dst; nets(src)).  kind: 'glow' (one net, output = [s | t]), 'irn_affine' (s from
+    nets[0], t from nets[1]), 'irn_add' (dst <- dst + sign * nets[0](src))."""
+
+    def __init__(self, kind, nets, src, dst, clamp):
+        self.kind, self.nets, self.src, self.dst, self.clamp = kind, nets, src, dst, clamp
+
+
+class CouplingOp:
+    kind = "coupling"
+
+    def __init__(self, steps_fwd, channels):
+        self.steps = steps_fwd          # execution order for rev=False; rev=True runs them reversed + inverted
+        self.channels = channels
+
+    def parameters(self):
+        out = []
+        seen = set()
+        for st in self.steps:
+            for n in st.nets:
+                if id(n) not in seen:
+                    seen.add(id(n))
+                    out += n.parameters()
+        return out
+
+    def first_src(self, rev):
+        return (self.steps[-1] if rev else self.steps[0]).src
+
+    # ---- value pass
+    def run(self, ctx, tr, rev):
+        steps = self.steps[::-1] if rev else self.steps
+        for i, st in enumerate(steps):
+            L = st.dst[1] - st.dst[0]
+            nxt = steps[i + 1].src if i + 1 < len(steps) else None
+            want_bf = ctx.adt == torch.bfloat16 and nxt == st.dst and L % 8 == 0
+            u = tr.mat()[:, st.dst[0]:st.dst[1]]
+            if st.kind == "glow":
+                a, _ = st.nets[0].fwd(ctx, tr, st.src)
+                tr.invalidate(*st.dst)
+                bf = K.coupling_apply(u, a[:, :L], a[:, L:], GLOW, st.clamp, rev, want_bf)
+            elif st.kind == "irn_affine":
+                s, _ = st.nets[0].fwd(ctx, tr, st.src)
+                t, _ = st.nets[1].fwd(ctx, tr, st.src)
+                tr.invalidate(*st.dst)
+                bf = K.coupling_apply(u, s, t, IRN, st.clamp, rev, want_bf)
+            else:
+                f, _ = st.nets[0].fwd(ctx, tr, st.src)
+                tr.invalidate(*st.dst)
+                K.axpy_slice(u, f, -1.0 if rev else 1.0)
+                bf = None
+            if bf is not None:
+                tr.bf[st.dst] = bf
+
+    # ---- backward from the output: restores the block input in tr.U and turns tr.dU into dL/d(input)
+    def backward(self, ctx, tr, rev):
+        executed = self.steps[::-1] if rev else self.steps
+        undo = executed[::-1]
+        for i, st in enumerate(undo):
+            L = st.dst[1] - st.dst[0]
+            nxt = undo[i + 1].src if i + 1 < len(undo) else None
+            want_bf = ctx.adt == torch.bfloat16 and nxt == st.dst and L % 8 == 0
+            u = tr.mat()[:, st.dst[0]:st.dst[1]]
+            du = tr.dmat()[:, st.dst[0]:st.dst[1]]
+            dsrc = tr.dmat()[:, st.src[0]:st.src[1]]
+            dev = u.device
+            if st.kind == "glow":
+                a, saved = st.nets[0].fwd(ctx, tr, st.src)
+                da = torch.empty(tr.npix, 2 * L, dtype=ctx.adt, device=dev)
+                tr.invalidate(*st.dst)
+                bf = K.coupling_bwd(u, du, a[:, :L], a[:, L:], GLOW, st.clamp, rev, da[:, :L], da[:, L:], want_bf)
+                st.nets[0].bwd(ctx, tr, saved, da, dsrc)
+            elif st.kind == "irn_affine":
+                s, saved_s = st.nets[0].fwd(ctx, tr, st.src)
+                t, saved_t = st.nets[1].fwd(ctx, tr, st.src)
+                Lp = _round_up(L, 8)
+                ds = torch.empty(tr.npix, Lp, dtype=ctx.adt, device=dev)[:, :L]
+                dt = torch.empty(tr.npix, Lp, dtype=ctx.adt, device=dev)[:, :L]
+                tr.invalidate(*st.dst)
+                bf = K.coupling_bwd(u, du, s, t, IRN, st.clamp, rev, ds, dt, want_bf)
+                st.nets[0].bwd(ctx, tr, saved_s, ds, dsrc)
+                st.nets[1].bwd(ctx, tr, saved_t, dt, dsrc)
+            else:
+                sign = -1.0 if rev else 1.0
+                f, saved = st.nets[0].fwd(ctx, tr, st.src)
+                tr.invalidate(*st.dst)
+                K.axpy_slice(u, f, -sign)                       # restore dst
+                df = torch.empty(tr.npix, _round_up(L, 8), dtype=ctx.adt, device=dev)[:, :L]
+                K.cast_slice(du, df, sign)
+                st.nets[0].bwd(ctx, tr, saved, df, dsrc)
+                bf = None
+            if bf is not None:
+                tr.bf[st.dst] = bf
+
+
+def glow_op(channels, s1, s2, clamp):
+    """FrEIA GLOWCouplingBlock (call site archs.py:61-64): forward runs s2 on x2 to update x1, then s1 on
+    y1 to update x2; rev undoes them in the opposite order."""
+    l1 = channels // 2
+    h1, h2 = (0, l1), (l1, channels)
+    n1, n2 = ConvSubnet(s1), ConvSubnet(s2)
+    if n1.cin != l1 or n1.cout != 2 * (channels - l1) or n2.cin != channels - l1 or n2.cout != 2 * l1:
+        raise SininnError("GLOW subnet channel counts do not match the split")
+    return CouplingOp([HalfStep("glow", [n2], h2, h1, clamp), HalfStep("glow", [n1], h1, h2, clamp)], channels)
+
+
+def irn_op(channels, split1, F, G, H, clamp):
+    """InvBlockExp (archs.py:135-160): y1 = x1 + F(x2); y2 = x2*exp(clamp*(2*sigmoid(H(y1))-1)) + G(y1)."""
+    h1, h2 = (0, split1), (split1, channels)
+    nF, nG, nH = DenseSubnet(F), DenseSubnet(G), DenseSubnet(H)
+    return CouplingOp([HalfStep("irn_add", [nF], h2, h1, clamp), HalfStep("irn_affine", [nH, nG], h1, h2, clamp)],
+                      channels)
+
+
+# ----------------------------------------------------------------------------- the plan
+class Plan:
+    """Ops in forward order.  Resamples ahead of the first coupling run on NCHW data (few channels);
+    from the first coupling on, everything is channels-last.  A trailing permutation is folded into the
+    layout change at the API boundary."""
+
+    def __init__(self, ops, in_dims):
+        self.ops = ops
+        self.in_dims = tuple(in_dims)
+        first = next((i for i, o in enumerate(ops) if o.kind == "coupling"), len(ops))
+        self.prefix = ops[:first]
+        self.body = ops[first:]
+        if any(o.kind != "resample" for o in self.prefix):
+            first = next(i for i, o in enumerate(ops) if o.kind != "resample")
+            self.prefix, self.body = ops[:first], ops[first:]
+        self.tail_perm = self.body[-1] if self.body and self.body[-1].kind == "perm" else None
+        self.core = self.body[:-1] if self.tail_perm is not None else self.body
+        c, h, w = self.in_dims
+        for o in ops:
+            if o.kind == "resample":
+                c, h, w = c * 4, h // 2, w // 2
+        self.out_dims = (c, h, w)
+
+    def parameters(self):
+        out, seen = [], set()
+        for o in self.ops:
+            for p in o.parameters():
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    out.append(p)
+        return out
+
+    def _check_input(self, x, rev):
+        require_cuda(x, "network input")
+        if x.dtype != torch.float32 or x.dim() != 4:
+            raise SininnError(f"network input must be a 4-D fp32 NCHW tensor, got {x.dtype} {tuple(x.shape)}")
+        want = self.out_dims if rev else self.in_dims
+        if x.shape[1] != want[0]:
+            raise SininnError(f"expected {want[0]} channels for rev={rev}, got {x.shape[1]}")
+        f = 1
+        for o in self.ops:
+            if o.kind == "resample":
+                f *= 2
+        if not rev and (x.shape[2] % f or x.shape[3] % f):
+            raise SininnError(f"input height/width must be multiples of {f}, got {tuple(x.shape[2:])}")
+
+    def _hint(self, op, rev, ctx):
+        """bf16 operand range the next coupling will read first (so the producer can emit it)."""
+        if op is None or op.kind != "coupling" or ctx.adt != torch.bfloat16:
+            return None
+        src = op.first_src(rev)
+        return src if (src[1] - src[0]) % 8 == 0 and not isinstance(
+            (op.steps[-1] if rev else op.steps[0]).nets[0], DenseSubnet) else None
+
+    # ---- value pass ---------------------------------------------------------------------------
+    def execute(self, x, rev, cfg):
+        self._check_input(x, rev)
+        ctx = RunCtx(cfg)
+        if not self.body:
+            seq = self.prefix[::-1] if rev else self.prefix
+            for op in seq:
+                x = op.apply_nchw(x, rev)
+            return x
+        dev = x.device
+        if not rev:
+            for op in self.prefix:
+                x = op.apply_nchw(x, False)
+            seq = self.core
+            hint = self._hint(seq[0] if seq else None, rev, ctx)
+            U, bf = K.nchw_to_nhwc(x, None, hint)
+        else:
+            seq = self.core[::-1]
+            cmap = self.tail_perm.gather_map(dev, True) if self.tail_perm is not None else None
+            hint = self._hint(seq[0] if seq else None, rev, ctx)
+            U, bf = K.nchw_to_nhwc(x, cmap, hint)
+        tr = Trunk(U)
+        if bf is not None:
+            tr.bf[hint] = bf
+        for i, op in enumerate(seq):
+            nxt = seq[i + 1] if i + 1 < len(seq) else None
+            if op.kind == "coupling":
+                op.run(ctx, tr, rev)
+            elif op.kind == "perm":
+                hint = self._hint(nxt, rev, ctx)
+                U, bf = K.permute_nhwc(tr.U, op.gather_map(dev, rev), hint)
+                tr.set(U, None, {hint: bf} if bf is not None else None)
+            else:
+                tr.set(op.apply_nhwc(tr.U, rev))
+        if not rev:
+            cmap = self.tail_perm.gather_map(dev, False) if self.tail_perm is not None else None
+            return K.nhwc_to_nchw(tr.U, cmap)
+        y = K.nhwc_to_nchw(tr.U, None)
+        for op in self.prefix[::-1]:
+            y = op.apply_nchw(y, True)
+        return y
+
+    # ---- backward from the output ----------------------------------------------------------------
+    def backward(self, y, dy, rev, cfg, need_dx=True):
+        """y: the output execute(x, rev) produced; dy: dL/dy.  Returns (dL/dx or None, {id(param): grad})."""
+        require_cuda(dy, "grad_output")
+        ctx = RunCtx(cfg, want_grads=True)
+        dy = dy.contiguous()
+        if dy.dtype != torch.float32:
+            raise SininnError("grad_output must be fp32")
+        if not self.body:
+            seq = self.prefix if rev else self.prefix[::-1]
+            for op in seq:
+                dy = op.apply_nchw(dy, rev, grad=True)
+            return dy, ctx.grads
+        dev = y.device
+        # 1. bring (y, dy) back into the channels-last trunk the value pass ended with
+        if not rev:
+            cmap = self.tail_perm.gather_map(dev, True) if self.tail_perm is not None else None   # undo perm
+            U, _ = K.nchw_to_nhwc(y, cmap, None)
+            dU, _ = K.nchw_to_nhwc(dy, cmap, None)
+            undo = self.core[::-1]
+        else:
+            for op in self.prefix:                 # the value pass ended with inverse resamples on NCHW
+                y = op.apply_nchw(y, False)        # re-apply forward map to get back to the trunk
+                dy = op.apply_nchw(dy, True, grad=True)
+            U, _ = K.nchw_to_nhwc(y, None, None)
+            dU, _ = K.nchw_to_nhwc(dy, None, None)
+            undo = self.core                       # executed order was reversed(core)
+        tr = Trunk(U, dU)
+        # 2. walk the executed ops backwards
+        for op in undo:
+            if op.kind == "coupling":
+                op.backward(ctx, tr, rev)
+            elif op.kind == "perm":
+                m_val = op.gather_map(dev, not rev)            # inverse of the executed value map
+                m_grad = op.gather_map(dev, rev, grad=True)
+                U, _ = K.permute_nhwc(tr.U, m_val, None)
+                dU, _ = K.permute_nhwc(tr.dU, m_grad, None)
+                tr.set(U, dU)
+            else:
+                U = op.apply_nhwc(tr.U, not rev)
+                dU = op.apply_nhwc(tr.dU, rev, grad=True)
+                tr.set(U, dU)
+        if not need_dx:
+            return None, ctx.grads
+        # 3. gradient back out through the API-side layout change and the NCHW resamples
+        if not rev:
+            dx = K.nhwc_to_nchw(tr.dU, None)
+            for op in self.prefix[::-1]:
+                dx = op.apply_nchw(dx, False, grad=True)
+        else:
+            cmap = self.tail_perm.gather_map(dev, True, grad=True) if self.tail_perm is not None else None
+            dx = K.nhwc_to_nchw(tr.dU, cmap)
+        return dx, ctx.grads
+
+
+class _INNFunction(torch.autograd.Function):
+    """Differentiable net(x) / net(x, rev=True) that keeps only its output for backward."""
+
+    @staticmethod
+    def forward(ctx, x, plan, rev, cfg, *params):
+        y = plan.execute(x.detach(), rev, cfg)
+        ctx.plan, ctx.rev, ctx.cfg = plan, rev, cfg
+        ctx.params = params
+        ctx.need_dx = x.requires_grad
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dx, grads = ctx.plan.backward(y, dy, ctx.rev, ctx.cfg, need_dx=ctx.need_dx)
+        gl = [grads.get(id(p)) if p.requires_grad else None for p in ctx.params]
+        return (dx, None, None, None, *gl)
+
+
+def run_network(plan, x, rev, cfg):
+    params = plan.parameters()
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+    if not needs_grad:
+        return plan.execute(x, rev, cfg)
+    return _INNFunction.apply(x, plan, bool(rev), cfg, *params)

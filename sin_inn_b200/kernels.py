@@ -1,0 +1,295 @@
+"""Thin typed wrappers: torch tensors / 2-D strided views -> libsininn C-ABI calls.
+
+Every function launches on torch's current CUDA stream and returns immediately.
+A "view" is a 2-D fp32/bf16 tensor [npix, L] with unit channel stride and an
+arbitrary row stride (a channel slice of a wider channels-last matrix).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import F32, BF16, ConvDesc, WgradDesc, check, dtype_code, load, stream_ptr
+
+_workspaces = {}
+
+# ---- launch accounting / optional CUDA-event profiling (used by bench.py; off by default)
+LAUNCHES = 0          # kernels launched through this module since last reset
+_prof = None
+
+
+def profile_begin():
+    """Start timing every launch with CUDA events on the launching stream, grouped by kernel family."""
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """Stop profiling; returns {family: {"ms", "flops", "bytes", "n"}} (algorithmic flops/bytes as passed in)."""
+    global _prof
+    rec, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for fam, e0, e1, nk, flops, nbytes in rec:
+        d = out.setdefault(fam, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += flops
+        d["bytes"] += nbytes
+        d["n"] += nk
+    return out
+
+
+def _run(family, fn, nk=1, flops=0.0, nbytes=0.0):
+    global LAUNCHES
+    LAUNCHES += nk
+    if _prof is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn()
+    e1.record()
+    _prof.append((family, e0, e1, nk, flops, nbytes))
+    return rc
+
+
+def _workspace(dev, name, nbytes):
+    key = (dev.index, name)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
+        _workspaces[key] = buf
+    return buf
+
+
+def _view2d(t):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise _lib.SininnError(f"expected a 2-D view with unit channel stride, got shape {tuple(t.shape)} stride {t.stride()}")
+    _lib.require_cuda(t)
+    return t
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+# ----------------------------------------------------------------------------- resampling / layout
+def resample_nchw(x, mode, rev, scale=1.0):
+    """mode 0 squeeze / 1 Haar on NCHW fp32.  rev=0: [B,C,H,W]->[B,4C,H/2,W/2]."""
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    B, c, h, w = x.shape
+    if not rev:
+        C_, H, W = c, h, w
+        out = torch.empty(B, 4 * c, h // 2, w // 2, dtype=torch.float32, device=x.device)
+    else:
+        if c % 4:
+            raise _lib.SininnError(f"inverse resample needs channels % 4 == 0, got {c}")
+        C_, H, W = c // 4, 2 * h, 2 * w
+        out = torch.empty(B, c // 4, 2 * h, 2 * w, dtype=torch.float32, device=x.device)
+    check(_run("resample", lambda: load().sininn_resample_nchw(x.data_ptr(), out.data_ptr(), B, C_, H, W, mode, int(rev), float(scale),
+                                      stream_ptr()), 1, 0.0, 8.0 * x.numel()), "resample_nchw")
+    return out
+
+
+def resample_nhwc(x, mode, rev, scale=1.0):
+    """Same maps on channels-last [B,H,W,C] fp32 tensors."""
+    _lib.require_cuda(x)
+    B, h, w, c = x.shape
+    if not rev:
+        C_, H, W = c, h, w
+        out = torch.empty(B, h // 2, w // 2, 4 * c, dtype=torch.float32, device=x.device)
+    else:
+        C_, H, W = c // 4, 2 * h, 2 * w
+        out = torch.empty(B, 2 * h, 2 * w, c // 4, dtype=torch.float32, device=x.device)
+    check(_run("resample", lambda: load().sininn_resample_nhwc(x.data_ptr(), out.data_ptr(), B, C_, H, W, mode, int(rev), float(scale),
+                                      stream_ptr()), 1, 0.0, 8.0 * x.numel()), "resample_nhwc")
+    return out
+
+
+def nchw_to_nhwc(x, chan_map=None, bf16_range=None):
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    B, c, h, w = x.shape
+    out = torch.empty(B, h, w, c, dtype=torch.float32, device=x.device)
+    bf = None
+    c0 = c1 = 0
+    if bf16_range is not None:
+        c0, c1 = bf16_range
+        bf = torch.empty(B * h * w, c1 - c0, dtype=torch.bfloat16, device=x.device)
+    check(_run("layout", lambda: load().sininn_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, c, h * w, _p(chan_map), _p(bf), c0, c1,
+                                     stream_ptr()), 1, 0.0, 8.0 * x.numel()), "nchw_to_nhwc")
+    return out, bf
+
+
+def nhwc_to_nchw(x, chan_map=None):
+    _lib.require_cuda(x)
+    B, h, w, c = x.shape
+    out = torch.empty(B, c, h, w, dtype=torch.float32, device=x.device)
+    check(_run("layout", lambda: load().sininn_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), B, c, h * w, _p(chan_map), stream_ptr()), 1, 0.0, 8.0 * x.numel()),
+          "nhwc_to_nchw")
+    return out
+
+
+def permute_nhwc(x, chan_map, bf16_range=None):
+    """x: channels-last tensor [..., C]; out[..., i] = x[..., chan_map[i]]."""
+    _lib.require_cuda(x)
+    c = x.shape[-1]
+    npix = x.numel() // c
+    out = torch.empty_like(x)
+    bf = None
+    c0 = c1 = 0
+    if bf16_range is not None:
+        c0, c1 = bf16_range
+        bf = torch.empty(npix, c1 - c0, dtype=torch.bfloat16, device=x.device)
+    check(_run("permute", lambda: load().sininn_permute_nhwc(x.data_ptr(), out.data_ptr(), npix, c, chan_map.data_ptr(), _p(bf), c0, c1,
+                                     stream_ptr()), 1, 0.0, 8.0 * x.numel()), "permute_nhwc")
+    return out, bf
+
+
+# ----------------------------------------------------------------------------- coupling
+def coupling_apply(u, s, t, kind, clamp, inverse, want_bf16=False):
+    u, s, t = _view2d(u), _view2d(s), _view2d(t)
+    npix, L = u.shape
+    bf = torch.empty(npix, L, dtype=torch.bfloat16, device=u.device) if want_bf16 else None
+    check(_run("coupling", lambda: load().sininn_coupling_apply(u.data_ptr(), u.stride(0), s.data_ptr(), s.stride(0), t.data_ptr(), t.stride(0),
+                                       npix, L, kind, float(clamp), int(inverse), _p(bf), stream_ptr()), 1, 0.0, 16.0 * npix * L),
+          "coupling_apply")
+    return bf
+
+
+def coupling_bwd(u, du, s, t, kind, clamp, inverse, ds, dt, want_bf16=False):
+    u, du, s, t, ds, dt = map(_view2d, (u, du, s, t, ds, dt))
+    npix, L = u.shape
+    if ds.dtype != dt.dtype:
+        raise _lib.SininnError("coupling_bwd: ds and dt must share a dtype")
+    bf = torch.empty(npix, L, dtype=torch.bfloat16, device=u.device) if want_bf16 else None
+    check(_run("coupling_bwd", lambda: load().sininn_coupling_bwd(u.data_ptr(), u.stride(0), du.data_ptr(), du.stride(0), s.data_ptr(), s.stride(0),
+                                     t.data_ptr(), t.stride(0), npix, L, kind, float(clamp), int(inverse),
+                                     ds.data_ptr(), ds.stride(0), dt.data_ptr(), dt.stride(0), dtype_code(ds), _p(bf),
+                                     stream_ptr()), 1, 0.0, (24.0 + 2.0 * ds.element_size()) * npix * L), "coupling_bwd")
+    return bf
+
+
+def cast_slice(src, out, scale=1.0):
+    """out[p][c] = scale*src[p][c]; src fp32 view, out fp32/bf16 view of the same shape."""
+    src, out = _view2d(src), _view2d(out)
+    npix, L = src.shape
+    check(_run("misc", lambda: load().sininn_cast_slice(src.data_ptr(), src.stride(0), npix, L, float(scale), out.data_ptr(),
+                                   dtype_code(out), out.stride(0), stream_ptr()), 1, 0.0, (4.0 + out.element_size()) * npix * L), "cast_slice")
+    return out
+
+
+def act_bwd(d, y, out, act, slope=0.0):
+    """out = d * act'(y); d fp32 view, y the activation output, out fp32/bf16 view (may be d itself)."""
+    d, y, out = _view2d(d), _view2d(y), _view2d(out)
+    npix, L = d.shape
+    check(_run("misc", lambda: load().sininn_act_bwd(d.data_ptr(), d.stride(0), y.data_ptr(), dtype_code(y), y.stride(0), out.data_ptr(),
+                                dtype_code(out), out.stride(0), npix, L, act, float(slope), stream_ptr()), 1, 0.0, 0.0), "act_bwd")
+    return out
+
+
+def colsum(src, out, accumulate=False):
+    src = _view2d(src)
+    npix, N = src.shape
+    lib = load()
+    nbytes = lib.sininn_colsum_workspace_bytes(npix, N)
+    ws = _workspace(src.device, "colsum", nbytes)
+    check(_run("colsum", lambda: lib.sininn_colsum(src.data_ptr(), dtype_code(src), src.stride(0), npix, N,
+                                                   out.data_ptr(), int(accumulate), ws.data_ptr(), ws.numel(),
+                                                   stream_ptr()), 2, 0.0, float(src.element_size()) * npix * N), "colsum")
+    return out
+
+
+def axpy_slice(out, a, alpha):
+    out, a = _view2d(out), _view2d(a)
+    npix, L = out.shape
+    check(_run("misc", lambda: load().sininn_axpy_slice(out.data_ptr(), out.stride(0), a.data_ptr(), dtype_code(a), a.stride(0), npix, L,
+                                   float(alpha), stream_ptr()), 1, 0.0, 0.0), "axpy_slice")
+
+
+# ----------------------------------------------------------------------------- convolutions
+def pack_weight(w, mode, dtype, rows_pad, k_pad):
+    """w: OIHW fp32 parameter.  mode 0 fprop [tap][co][ci]; mode 1 dgrad [tap][ci][co] (flipped)."""
+    _lib.require_cuda(w, "weight")
+    co, ci, kh, kw = w.shape
+    taps = kh * kw
+    out = torch.empty(taps, rows_pad, k_pad, dtype=dtype, device=w.device)
+    wc = w.detach().contiguous()
+    check(_run("pack", lambda: load().sininn_pack_conv_weight(wc.data_ptr(), co, ci, taps, mode, out.data_ptr(), dtype_code(out), rows_pad,
+                                         k_pad, stream_ptr()), 1, 0.0, 0.0), "pack_conv_weight")
+    return out
+
+
+def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask_act=0, accumulate=False, alpha=1.0,
+         tensor_core=False):
+    """Implicit-GEMM 1x1 / 3x3 convolution on channels-last views.
+    x: [npix, Cin] view; wpack: [taps, rows_pad, k_pad]; geom = (B, H, W); out: [npix, cout] view."""
+    x, out = _view2d(x), _view2d(out)
+    B, H, W = geom
+    d = ConvDesc()
+    d.B, d.H, d.W = B, H, W
+    d.Cin, d.Cout, d.taps = x.shape[1], cout, wpack.shape[0]
+    d.inp, d.in_dtype, d.in_stride = x.data_ptr(), dtype_code(x), x.stride(0)
+    if wpack.dtype != x.dtype:
+        raise _lib.SininnError("conv: packed weights and input must share a dtype")
+    d.wpack, d.rows_pad, d.k_pad = wpack.data_ptr(), wpack.shape[1], wpack.shape[2]
+    d.bias = _p(bias)
+    d.out, d.out_dtype, d.out_stride = out.data_ptr(), dtype_code(out), out.stride(0)
+    d.act, d.slope = act, float(slope)
+    if mask is not None:
+        mask = _view2d(mask)
+        if mask.dtype != out.dtype:
+            raise _lib.SininnError("conv: mask dtype must equal out dtype")
+        d.mask, d.mask_stride, d.mask_act = mask.data_ptr(), mask.stride(0), mask_act
+    else:
+        d.mask, d.mask_stride, d.mask_act = 0, 0, 0
+    d.accumulate, d.alpha = int(accumulate), float(alpha)
+    lib = load()
+    fn = lib.sininn_conv_tc if tensor_core else lib.sininn_conv_simt
+    flops = 2.0 * B * H * W * d.Cin * d.Cout * d.taps
+    check(_run("conv", lambda: fn(C.byref(d), stream_ptr()), 1, flops), "conv_tc" if tensor_core else "conv_simt")
+    return out
+
+
+def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False):
+    """dw[co][ci][tap] (+)= sum_p dy[p][co] * x[p+off(tap)][ci];  dw: OIHW fp32 contiguous."""
+    x, dy = _view2d(x), _view2d(dy)
+    B, H, W = geom
+    d = WgradDesc()
+    d.B, d.H, d.W = B, H, W
+    d.Cin, d.Cout, d.taps = x.shape[1], dy.shape[1], taps
+    d.x, d.x_dtype, d.x_stride = x.data_ptr(), dtype_code(x), x.stride(0)
+    d.dy, d.dy_dtype, d.dy_stride = dy.data_ptr(), dtype_code(dy), dy.stride(0)
+    d.dw, d.accumulate = dw.data_ptr(), int(accumulate)
+    lib = load()
+    nbytes = lib.sininn_wgrad_workspace_bytes(C.byref(d), int(tensor_core))
+    ws = _workspace(x.device, "wgrad", nbytes)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+    fn = lib.sininn_wgrad_tc if tensor_core else lib.sininn_wgrad_simt
+    flops = 2.0 * B * H * W * d.Cin * d.Cout * d.taps
+    check(_run("wgrad", lambda: fn(C.byref(d), stream_ptr()), 2, flops), "wgrad_tc" if tensor_core else "wgrad_simt")
+    return dw
+
+
+# ----------------------------------------------------------------------------- caller-side fusions
+def sqdiff(a, b, scale, want_grad=False):
+    """scale * sum((a-b)^2) -> 0-dim tensor; optional gradient 2*scale*(a-b)."""
+    _lib.require_cuda(a)
+    a = a.contiguous()
+    n = a.numel()
+    lib = load()
+    ws = _workspace(a.device, "sqdiff", lib.sininn_sqdiff_workspace_bytes(n))
+    out = torch.empty((), dtype=torch.float32, device=a.device)
+    grad = torch.empty_like(a) if want_grad else None
+    if b is not None:
+        b = b.contiguous()
+    check(_run("loss", lambda: lib.sininn_sqdiff_nchw(a.data_ptr(), _p(b), n, float(scale), out.data_ptr(), _p(grad),
+                                                      ws.data_ptr(), ws.numel(), stream_ptr()), 2), "sqdiff")
+    return out, grad
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step, grad_scale=1.0):
+    n = param.numel()
+    check(_run("adam", lambda: load().sininn_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n,
+                                  float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                  int(step), float(grad_scale), stream_ptr()), 1, 0.0, 28.0 * n), "adam_step")

@@ -1,0 +1,138 @@
+"""Lightning-free restatement of the reference's training / validation / inference steps
+(lit_wrapper.py:29-77, 79-89, 91-128) on top of the drop-in nets, plus the data-parallel plumbing.
+
+Differences from the reference, all outside the INN kernels:
+  * loss.mmd is not evaluated (its lambdas default to 0, main.py:53,56, and the reference code
+    hard-codes .to('cuda'), loss.py:27-29);
+  * parameters and gradients live in two flat fp32 arenas so that the optimizer is ONE fused Adam
+    launch and data parallelism is ONE NCCL all-reduce per step (the reference gets an implicit DDP
+    all-reduce inside each of its two manual_backward calls);
+  * the TCR branch (lit_wrapper.py:58-72) is off by default and not reproduced.
+"""
+import torch
+import torch.distributed as dist
+
+from . import engine
+from . import kernels as K
+
+
+def reconstruction(x, y):
+    """loss.py:3-5 (L2)."""
+    return torch.mean((x - y) ** 2)
+
+
+def latent_nll(z):
+    """loss.py:38-39."""
+    return torch.mean(z ** 2)
+
+
+class FlatParams:
+    """Re-homes a module's trainable parameters (and their .grad) into two contiguous fp32 arenas.
+    Parameter objects, names and shapes are untouched, so state_dict()/load_state_dict() keep working."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError("module has no trainable parameters")
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            m = p.numel()
+            self.flat[off:off + m].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + m].view(p.shape)
+            p.grad = self.grad[off:off + m].view(p.shape)
+            off += m
+        self.numel = n
+
+    def zero_grad(self):
+        self.grad.zero_()
+        off = 0
+        for p in self.params:          # re-attach in case something replaced .grad
+            m = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
+                p.grad = self.grad[off:off + m].view(p.shape)
+            off += m
+
+
+class FusedAdam:
+    """torch.optim.Adam semantics (lit_wrapper.py:134-137: lr, betas, L2 weight decay in the gradient)
+    as one kernel over the flat arenas."""
+
+    def __init__(self, flat, lr=1e-4, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-5):
+        self.fp = flat
+        self.lr, self.betas, self.eps, self.wd = lr, tuple(betas), eps, weight_decay
+        self.exp_avg = torch.zeros_like(flat.flat)
+        self.exp_avg_sq = torch.zeros_like(flat.flat)
+        self.steps = 0
+
+    def zero_grad(self):
+        self.fp.zero_grad()
+
+    def step(self, grad_scale=1.0):
+        self.steps += 1
+        K.adam_step(self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas, self.eps, self.wd,
+                    self.steps, grad_scale)
+        # the kernel wrote the parameters through raw pointers (no tensor version bump): drop the packed copies
+        engine.invalidate_packs()
+
+
+class SingleVideoTrainer:
+    """Mirror of SingleVideoINN's step logic (lit_wrapper.py:12-89) for one process / one GPU; with
+    torch.distributed initialised it is the data-parallel step (patch batches sharded by rank)."""
+
+    def __init__(self, inn, opt, world_size=1):
+        self.inn, self.opt = inn, opt
+        self.flat = FlatParams(inn)
+        self.optim = FusedAdam(self.flat, lr=opt.learning_rate, betas=opt.adam_betas, weight_decay=opt.weight_decay)
+        self.world_size = world_size
+
+    def broadcast_params(self):
+        if self.world_size > 1:
+            dist.broadcast(self.flat.flat, src=0)
+
+    def training_step(self, hr, lr, z):
+        """hr (b,3,H,W), lr (b,lr_dims,h,w), z (b,z_dims,h,w) on the GPU.  Returns the two loss tensors."""
+        o = self.opt
+        self.optim.zero_grad()
+        lr_z = torch.cat((lr, z), dim=1)
+        # forward pass HR -> (LR, z)                                   lit_wrapper.py:45-49
+        lr_z_hat = self.inn(hr)
+        fwd_loss = o.lambda_fwd_rec * reconstruction(lr_z_hat[:, :o.lr_dims], lr)
+        if o.lambda_latent_nll:
+            fwd_loss = fwd_loss + o.lambda_latent_nll * latent_nll(lr_z_hat[:, o.lr_dims:])
+        fwd_loss.backward()
+        # reverse pass (LR, z) -> HR                                    lit_wrapper.py:53-56
+        hr_hat = self.inn(lr_z, rev=True)
+        bwd_loss = o.lambda_bwd_rec * reconstruction(hr_hat, hr)
+        bwd_loss.backward()
+        if self.world_size > 1:
+            dist.all_reduce(self.flat.grad)                            # one NCCL all-reduce per step
+        self.optim.step(grad_scale=1.0 / self.world_size)              # lit_wrapper.py:76
+        return fwd_loss.detach(), bwd_loss.detach()
+
+    @torch.no_grad()
+    def validation_step(self, hr, lr, z):
+        """lit_wrapper.py:79-89: lr_acc, hr_acc, z_nll."""
+        o = self.opt
+        lr_z_hat = self.inn(hr)
+        hr_hat = self.inn(torch.cat((lr, z), dim=1), rev=True)
+        return (reconstruction(lr_z_hat[:, :o.lr_dims], lr), reconstruction(hr_hat, hr),
+                latent_nll(lr_z_hat[:, o.lr_dims:]))
+
+    @torch.no_grad()
+    def infer(self, lr, temp=None, generator=None):
+        """lit_wrapper.py:105-115: z = temp*N(0,1); hr_hat = inn(cat(lr, z), rev=True)."""
+        o = self.opt
+        b, _, h, w = lr.shape
+        z = (o.temp if temp is None else temp) * torch.randn(b, o.z_dims, h, w, device=lr.device, generator=generator)
+        return self.inn(torch.cat((lr, z), dim=1), rev=True)
+
+
+def shard_frames(n_frames, rank, world_size):
+    """Frame-sharded inference (no communication): contiguous block of frames per rank."""
+    per = (n_frames + world_size - 1) // world_size
+    lo = min(rank * per, n_frames)
+    return range(lo, min(lo + per, n_frames))

@@ -1,0 +1,189 @@
+"""TEST-ONLY stand-in for sin_inn_b200.kernels: the same call signatures implemented with plain
+torch ops on CPU tensors.  It lets the `-m "not gpu"` suite exercise the host-side logic (plan
+compilation, in-place half-steps, permutation folding, backward-by-inverse bookkeeping, gradient
+plumbing) where no GPU exists.  It is never imported by the package; GPU tests use the real library.
+"""
+import torch
+import torch.nn.functional as F
+
+GLOW, IRN = 0, 1
+
+
+def _haar_fwd(a, b, c, d, scale):
+    return ((a + b + c + d) * scale, (a - b + c - d) * scale, (a + b - c - d) * scale, (a - b - c + d) * scale)
+
+
+def resample_nchw(x, mode, rev, scale=1.0):
+    B, c, h, w = x.shape
+    if not rev:
+        a, b = x[:, :, 0::2, 0::2], x[:, :, 0::2, 1::2]
+        cc, d = x[:, :, 1::2, 0::2], x[:, :, 1::2, 1::2]
+        o = _haar_fwd(a, b, cc, d, scale) if mode == 1 else (a, b, cc, d)
+        return torch.cat(o, 1).contiguous()
+    C = c // 4
+    o = [x[:, k * C:(k + 1) * C] for k in range(4)]
+    if mode == 1:
+        a, b, cc, d = _haar_fwd(o[0], o[1], o[2], o[3], scale)
+    else:
+        a, b, cc, d = o
+    out = x.new_empty(B, C, 2 * h, 2 * w)
+    out[:, :, 0::2, 0::2], out[:, :, 0::2, 1::2] = a, b
+    out[:, :, 1::2, 0::2], out[:, :, 1::2, 1::2] = cc, d
+    return out
+
+
+def resample_nhwc(x, mode, rev, scale=1.0):
+    return resample_nchw(x.permute(0, 3, 1, 2), mode, rev, scale).permute(0, 2, 3, 1).contiguous()
+
+
+def _bf(t2d, rng):
+    if rng is None:
+        return None
+    return t2d[:, rng[0]:rng[1]].to(torch.bfloat16).contiguous()
+
+
+def nchw_to_nhwc(x, chan_map=None, bf16_range=None):
+    if chan_map is not None:
+        x = x[:, chan_map.long()]
+    out = x.permute(0, 2, 3, 1).contiguous()
+    return out, _bf(out.view(-1, out.shape[3]), bf16_range)
+
+
+def nhwc_to_nchw(x, chan_map=None):
+    if chan_map is not None:
+        x = x[..., chan_map.long()]
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def permute_nhwc(x, chan_map, bf16_range=None):
+    out = x[..., chan_map.long()].contiguous()
+    return out, _bf(out.view(-1, out.shape[-1]), bf16_range)
+
+
+def _log_scale(kind, clamp, raw):
+    if kind == GLOW:
+        r = raw / clamp
+        return clamp * 0.636 * torch.atan(r), 0.636 / (1 + r * r)
+    sg = torch.sigmoid(raw)
+    return clamp * (2 * sg - 1), 2 * clamp * sg * (1 - sg)
+
+
+def coupling_apply(u, s, t, kind, clamp, inverse, want_bf16=False):
+    g, _ = _log_scale(kind, clamp, s)
+    e = torch.exp(g)
+    u.copy_((u - t) / e if inverse else e * u + t)
+    return u.to(torch.bfloat16).contiguous() if want_bf16 else None
+
+
+def coupling_bwd(u, du, s, t, kind, clamp, inverse, ds, dt, want_bf16=False):
+    g, dg = _log_scale(kind, clamp, s)
+    e = torch.exp(g)
+    y, dy = u.clone(), du.clone()
+    if not inverse:
+        x = (y - t) / e
+        du.copy_(dy * e)
+        ds.copy_((dy * x * e * dg).to(ds.dtype))
+        dt.copy_(dy.to(dt.dtype))
+    else:
+        x = y * e + t
+        du.copy_(dy / e)
+        ds.copy_((-dy * y * dg).to(ds.dtype))
+        dt.copy_((-dy / e).to(dt.dtype))
+    u.copy_(x)
+    return x.to(torch.bfloat16).contiguous() if want_bf16 else None
+
+
+def cast_slice(src, out, scale=1.0):
+    out.copy_((src * scale).to(out.dtype))
+    return out
+
+
+def act_bwd(d, y, out, act, slope=0.0):
+    yf = y.float()
+    g = torch.where(yf > 0, torch.ones_like(yf), torch.full_like(yf, slope if act == 2 else 0.0)) if act else 1.0
+    out.copy_((d.float() * g).to(out.dtype))
+    return out
+
+
+def colsum(src, out, accumulate=False):
+    s = src.float().sum(0)
+    out.copy_(out + s if accumulate else s)
+    return out
+
+
+def axpy_slice(out, a, alpha):
+    out.add_(a.float() * alpha)
+
+
+def pack_weight(w, mode, dtype, rows_pad, k_pad):
+    co, ci, kh, kw = w.shape
+    taps = kh * kw
+    wt = w.detach().reshape(co, ci, taps)
+    out = torch.zeros(taps, rows_pad, k_pad, dtype=torch.float32, device=w.device)
+    if mode == 0:
+        out[:, :co, :ci] = wt.permute(2, 0, 1)
+    else:
+        out[:, :ci, :co] = wt.flip(2).permute(2, 1, 0)
+    return out.to(dtype)
+
+
+def _shift(x4, dy, dx):
+    """x4: [B,H,W,C]; result[b,h,w] = x4[b,h+dy,w+dx] with zero fill."""
+    B, H, W, C = x4.shape
+    xp = F.pad(x4, (0, 0, 1, 1, 1, 1))
+    return xp[:, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W]
+
+
+def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask_act=0, accumulate=False, alpha=1.0,
+         tensor_core=False):
+    B, H, W = geom
+    cin = x.shape[1]
+    taps = wpack.shape[0]
+    x4 = x.float().reshape(B, H, W, cin)
+    acc = torch.zeros(B * H * W, cout, dtype=torch.float32)
+    for tap in range(taps):
+        dy, dx = (tap // 3 - 1, tap % 3 - 1) if taps == 9 else (0, 0)
+        xs = _shift(x4, dy, dx).reshape(B * H * W, cin)
+        acc += xs @ wpack[tap, :cout, :cin].float().t()
+    if bias is not None:
+        acc = acc + bias.detach().float()
+    if act == 1:
+        acc = torch.relu(acc)
+    elif act == 2:
+        acc = F.leaky_relu(acc, slope)
+    if mask is not None:
+        m = mask.float()
+        acc = acc * torch.where(m > 0, torch.ones_like(m), torch.full_like(m, slope if mask_act == 2 else 0.0))
+    acc = acc * alpha
+    if accumulate:
+        acc = acc + out.float()
+    out.copy_(acc.to(out.dtype))
+    return out
+
+
+def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False):
+    B, H, W = geom
+    cin, cout = x.shape[1], dy.shape[1]
+    x4 = x.float().reshape(B, H, W, cin)
+    dyf = dy.float()
+    res = torch.zeros(cout, cin, taps)
+    for tap in range(taps):
+        oy, ox = (tap // 3 - 1, tap % 3 - 1) if taps == 9 else (0, 0)
+        xs = _shift(x4, oy, ox).reshape(B * H * W, cin)
+        res[:, :, tap] = dyf.t() @ xs
+    res = res.reshape(dw.shape)
+    dw.copy_(dw + res if accumulate else res)
+    return dw
+
+
+def sqdiff(a, b, scale, want_grad=False):
+    d = a - (b if b is not None else 0)
+    return (d * d).sum() * scale, (2 * scale * d if want_grad else None)
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step, grad_scale=1.0):
+    g = grad * grad_scale + weight_decay * param
+    exp_avg.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+    exp_avg_sq.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+    bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
+    param.sub_((lr / bc1) * exp_avg / (exp_avg_sq.sqrt() / bc2 ** 0.5 + eps))

@@ -1,0 +1,129 @@
+"""Host-side logic (plan compilation, half-step bookkeeping, permutation folding, backward-by-inverse)
+checked on CPU against the oracle with the torch stand-in kernels.  The real kernels are checked by
+the `-m gpu` tests."""
+import types
+
+import pytest
+import torch
+
+from oracle import ref_torch as R
+from sin_inn_b200 import archs, engine as E
+
+
+def _pair(arch, scale, nc, lr_window, H, W, seed=5):
+    opt = R.make_opt(scale=scale, num_coupling=nc, lr_window=lr_window, architecture=arch, precision="fp32")
+    torch.manual_seed(seed)
+    ora = R.build(arch, 3, H, W, opt)
+    torch.manual_seed(seed)
+    net = {"SRF": archs.UncondSRFlow, "IRN": archs.InvRescaleNet}[arch](3, H, W, opt)
+    if arch == "IRN":
+        R.randomize_irn_conv5(ora, 1)
+        R.randomize_irn_conv5(net, 1)
+    return opt, ora, net
+
+
+@pytest.mark.parametrize("arch,scale,nc,lrw", [("SRF", 2, 2, 1), ("SRF", 4, 2, 10), ("IRN", 2, 1, 1), ("IRN", 4, 1, 10)])
+def test_same_seed_same_init_and_keys(arch, scale, nc, lrw):
+    _, ora, net = _pair(arch, scale, nc, lrw, 16, 16)
+    sa, sb = ora.state_dict(), net.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    net.load_state_dict(sa)
+
+
+@pytest.mark.parametrize("arch,scale,nc,lrw,H,W", [("SRF", 2, 2, 1, 16, 24), ("SRF", 4, 2, 10, 16, 32),
+                                                   ("IRN", 2, 1, 1, 16, 16), ("IRN", 4, 1, 10, 16, 24)])
+def test_forward_inverse_backward_match_oracle(fake_kernels, arch, scale, nc, lrw, H, W):
+    opt, ora, net = _pair(arch, scale, nc, lrw, H, W)
+    hr, lr, z = R.synthetic_batch(opt, 2, H, W, seed=3)
+    lrz = torch.cat((lr, z), 1)
+    res = {}
+    for tag, m in (("ora", ora), ("net", net)):
+        for p in m.parameters():
+            p.grad = None
+        x = hr.clone().requires_grad_(True)
+        y = m(x)
+        (R.reconstruction(y[:, :opt.lr_dims], lr) + 0.3 * R.latent_nll(y[:, opt.lr_dims:])).backward()
+        u = lrz.clone().requires_grad_(True)
+        xr = m(u, rev=True)
+        R.reconstruction(xr, hr).backward()
+        with torch.no_grad():
+            rt = m(y.detach(), rev=True)
+        res[tag] = dict(y=y.detach(), dx=x.grad, xr=xr.detach(), du=u.grad, rt=rt,
+                        g={n: p.grad.clone() for n, p in m.named_parameters() if p.requires_grad})
+    a, b = res["ora"], res["net"]
+    for k in ("y", "dx", "xr", "du", "rt"):
+        scale_ = max(1.0, a[k].abs().max().item())
+        assert (a[k] - b[k]).abs().max().item() <= 2e-4 * scale_, k
+    assert set(a["g"]) == set(b["g"])
+    for n in a["g"]:
+        ref = a["g"][n]
+        tol = 2e-4 * max(ref.abs().max().item(), 1e-3)
+        assert (ref - b["g"][n]).abs().max().item() <= tol, n
+    assert (b["rt"] - hr).abs().max().item() < 1e-4
+    assert b["y"].is_contiguous() and b["xr"].is_contiguous()
+
+
+def test_standalone_freia_modules(fake_kernels):
+    from sin_inn_b200.freia import modules as Fm
+    Ff_o, Fm_o = R._freia()
+    x = torch.randn(2, 12, 8, 12)
+    sq, sq_o = Fm.IRevNetDownsampling([(12, 8, 12)]), Fm_o.IRevNetDownsampling([(12, 8, 12)])
+    y = sq([x])[0]
+    assert torch.equal(y, sq_o([x])[0]) and torch.equal(sq([y], rev=True)[0], x)
+    assert sq.output_dims([(12, 8, 12)]) == [(48, 4, 6)]
+    pm, pm_o = Fm.PermuteRandom([(12, 8, 12)], seed=3), Fm_o.PermuteRandom([(12, 8, 12)], seed=3)
+    assert torch.equal(pm.perm, pm_o.perm)
+    assert torch.equal(pm([x])[0], pm_o([x])[0]) and torch.equal(pm([x], rev=True)[0], pm_o([x], rev=True)[0])
+    torch.manual_seed(0)
+    gl = Fm.GLOWCouplingBlock([(12, 8, 12)], subnet_constructor=archs.subnet_conv, clamp=1.2)
+    torch.manual_seed(0)
+    gl_o = Fm_o.GLOWCouplingBlock([(12, 8, 12)], subnet_constructor=R.subnet_conv, clamp=1.2)
+    gl.engine_config = None
+    import os
+    os.environ["SININN_PRECISION"] = "fp32"
+    try:
+        xg = x.clone().requires_grad_(True)
+        yg = gl([xg])[0]
+        yo = gl_o([x])[0]
+        assert (yg - yo).abs().max() < 1e-4
+        assert (gl([yg.detach()], rev=True)[0] - x).abs().max() < 1e-4
+        yg.square().mean().backward()
+        xo = x.clone().requires_grad_(True)
+        gl_o([xo])[0].square().mean().backward()
+        assert (xg.grad - xo.grad).abs().max() < 1e-5
+    finally:
+        del os.environ["SININN_PRECISION"]
+
+
+def test_cpu_input_fails_loudly():
+    opt = R.make_opt(scale=2, num_coupling=1, lr_window=1)
+    net = archs.UncondSRFlow(3, 16, 16, opt)
+    with pytest.raises(E.SininnError):
+        net(torch.rand(1, 3, 16, 16))
+
+
+@pytest.mark.parametrize("arch,scale,nc,lrw", [("SRF", 4, 2, 10), ("IRN", 4, 1, 10)])
+def test_bf16_operand_path_bookkeeping(fake_kernels, arch, scale, nc, lrw):
+    """bf16 operand copies (cached per channel range, emitted by producer kernels) must stay coherent with
+    the fp32 trunk: outputs/gradients stay within the bf16 tolerance of the fp32 oracle."""
+    opt, ora, net = _pair(arch, scale, nc, lrw, 16, 32)
+    net.engine_config = E.EngineConfig(precision="bf16", tensor_core=False)
+    hr, lr, z = R.synthetic_batch(opt, 2, 16, 32, seed=4)
+    lrz = torch.cat((lr, z), 1)
+    out = {}
+    for tag, m in (("ora", ora), ("net", net)):
+        for p in m.parameters():
+            p.grad = None
+        y = m(hr)
+        R.reconstruction(y[:, :opt.lr_dims], lr).backward()
+        xr = m(lrz, rev=True)
+        R.reconstruction(xr, hr).backward()
+        out[tag] = (y.detach(), xr.detach(), {n: p.grad for n, p in m.named_parameters() if p.requires_grad})
+    for i in (0, 1):
+        ref = out["ora"][i]
+        assert (ref - out["net"][i]).abs().max() <= 2e-2 * max(1.0, ref.abs().max().item())
+    for n, g in out["ora"][2].items():
+        rel = (g - out["net"][2][n]).norm() / (g.norm() + 1e-12)
+        assert rel < 1e-1, (n, float(rel))   # tiny 2x4-pixel grids: little averaging of bf16 rounding

@@ -1,0 +1,237 @@
+"""Per-kernel parity: each libsininn entry point (through the ctypes C-ABI wrappers) against the plain-torch
+restatement in tests/fake_kernels.py on the same seeded inputs, including ragged / unaligned shapes."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import fake_kernels as FK  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def K():
+    from sin_inn_b200 import kernels
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return kernels
+
+
+def rnd(*shape, seed=0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g).to(dtype)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("shape", [(2, 3, 16, 32), (1, 12, 6, 10), (3, 5, 4, 12), (1, 3, 270, 480)])
+def test_resample_nchw(K, mode, shape):
+    x = rnd(*shape, seed=1)
+    scale = 0.25 if mode else 1.0
+    y = K.resample_nchw(x.to(DEV), mode, 0, scale)
+    ref = FK.resample_nchw(x, mode, 0, scale)
+    if mode == 0:
+        assert torch.equal(y.cpu(), ref)                      # pure permutation: bit exact
+    else:
+        assert (y.cpu() - ref).abs().max() <= 1e-6 * ref.abs().max()
+    xr = K.resample_nchw(y, mode, 1, 1.0)
+    assert (xr.cpu() - x).abs().max() <= (0 if mode == 0 else 1e-6 * x.abs().max())
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("shape", [(2, 8, 12, 48), (1, 6, 10, 12), (2, 4, 4, 5)])
+def test_resample_nhwc(K, mode, shape):
+    x = rnd(*shape, seed=2)
+    scale = 0.25 if mode else 1.0
+    y = K.resample_nhwc(x.to(DEV), mode, 0, scale)
+    ref = FK.resample_nhwc(x, mode, 0, scale)
+    assert (y.cpu() - ref).abs().max() <= 1e-6 * ref.abs().max()
+    xr = K.resample_nhwc(y, mode, 1, 1.0)
+    assert (xr.cpu() - x).abs().max() <= 1e-6 * x.abs().max()
+
+
+@pytest.mark.parametrize("C,hw", [(48, (8, 8)), (192, (5, 9)), (7, (3, 11))])
+def test_layout_and_permute(K, C, hw):
+    x = rnd(2, C, *hw, seed=3)
+    perm = torch.randperm(C, generator=torch.Generator().manual_seed(4)).to(torch.int32)
+    rng = (C // 2, C) if C % 8 == 0 else None
+    y, bf = K.nchw_to_nhwc(x.to(DEV), perm.to(DEV), rng)
+    ry, rbf = FK.nchw_to_nhwc(x, perm, rng)
+    assert torch.equal(y.cpu(), ry)
+    if rng:
+        assert torch.equal(bf.cpu(), rbf)
+    back = K.nhwc_to_nchw(y, None)
+    assert torch.equal(back.cpu(), x[:, perm.long()])
+    z, zbf = K.permute_nhwc(y, perm.to(DEV), rng)
+    rz, rzbf = FK.permute_nhwc(ry, perm, rng)
+    assert torch.equal(z.cpu(), rz)
+    if rng:
+        assert torch.equal(zbf.cpu(), rzbf)
+
+
+@pytest.mark.parametrize("kind,clamp", [(0, 1.2), (1, 1.0)])
+@pytest.mark.parametrize("npix,C,L", [(1000, 48, 24), (333, 192, 108), (77, 10, 3)])
+def test_coupling_apply_and_bwd(K, kind, clamp, npix, C, L):
+    U = rnd(npix, C, seed=5)
+    A = rnd(npix, 2 * L, seed=6) * 2
+    for inverse in (0, 1):
+        u_ref = U.clone()
+        FK.coupling_apply(u_ref[:, :L], A[:, :L], A[:, L:], kind, clamp, inverse)
+        u = U.clone().to(DEV)
+        a = A.to(DEV)
+        bf = K.coupling_apply(u[:, :L], a[:, :L], a[:, L:], kind, clamp, inverse, want_bf16=True)
+        assert (u.cpu() - u_ref).abs().max() <= 2e-6 * u_ref.abs().max()
+        assert torch.equal(u.cpu()[:, L:], U[:, L:])                    # untouched half
+        assert (bf.float().cpu() - u_ref[:, :L]).abs().max() <= 8e-3 * u_ref[:, :L].abs().max()
+        # backward from the output restores the input and matches autograd
+        x0 = U[:, :L].clone().double().requires_grad_(True)
+        s0 = A[:, :L].clone().double().requires_grad_(True)
+        t0 = A[:, L:].clone().double().requires_grad_(True)
+        g, _ = FK._log_scale(kind, clamp, s0)
+        y0 = (x0 - t0) / torch.exp(g) if inverse else torch.exp(g) * x0 + t0
+        dy = rnd(npix, L, seed=7)
+        y0.backward(dy.double())
+        du = torch.zeros(npix, C)
+        du[:, :L] = dy
+        du = du.to(DEV)
+        ds = torch.empty(npix, L, device=DEV)
+        dt = torch.empty(npix, L, device=DEV)
+        K.coupling_bwd(u[:, :L], du[:, :L], a[:, :L], a[:, L:], kind, clamp, inverse, ds, dt)
+        tol = lambda r: 1e-5 * max(1.0, r.abs().max().item())
+        assert (u.cpu()[:, :L] - U[:, :L]).abs().max() <= tol(U)
+        assert (du.cpu()[:, :L] - x0.grad.float()).abs().max() <= tol(x0.grad)
+        assert (ds.cpu() - s0.grad.float()).abs().max() <= tol(s0.grad)
+        assert (dt.cpu() - t0.grad.float()).abs().max() <= tol(t0.grad)
+
+
+def test_small_helpers(K):
+    src = rnd(500, 40, seed=8)
+    out = torch.empty(500, 24, dtype=torch.bfloat16, device=DEV)
+    K.cast_slice(src.to(DEV)[:, 8:32], out, -0.5)
+    assert torch.equal(out.cpu(), (src[:, 8:32] * -0.5).to(torch.bfloat16))
+    d, y = rnd(500, 40, seed=9), rnd(500, 40, seed=10)
+    o = torch.empty(500, 16, dtype=torch.bfloat16, device=DEV)
+    K.act_bwd(d.to(DEV)[:, 4:20], y.to(torch.bfloat16).to(DEV)[:, 4:20], o, 2, 0.2)
+    ref = torch.empty(500, 16, dtype=torch.bfloat16)
+    FK.act_bwd(d[:, 4:20], y.to(torch.bfloat16)[:, 4:20], ref, 2, 0.2)
+    assert torch.equal(o.cpu(), ref)
+    big = rnd(70000, 50, seed=11)
+    cs = torch.empty(50, device=DEV)
+    K.colsum(big.to(DEV), cs)
+    assert (cs.cpu() - big.double().sum(0).float()).abs().max() <= 1e-4 * big.abs().sum(0).max()
+    cs2 = cs.clone()
+    K.colsum(big.to(torch.bfloat16).to(DEV)[:, 3:20], cs2[3:20], accumulate=True)
+    ref2 = cs.cpu()[3:20] + big.to(torch.bfloat16)[:, 3:20].double().sum(0).float()
+    assert (cs2.cpu()[3:20] - ref2).abs().max() <= 1e-3 * ref2.abs().max()
+    a = rnd(500, 12, seed=12)
+    tgt = src.clone().to(DEV)
+    K.axpy_slice(tgt[:, 4:16], a.to(DEV), -1.0)
+    assert torch.allclose(tgt.cpu()[:, 4:16], src[:, 4:16] - a) and torch.equal(tgt.cpu()[:, 16:], src[:, 16:])
+    loss, grad = K.sqdiff(src.to(DEV), d.to(DEV), 0.01, want_grad=True)
+    assert abs(loss.item() - 0.01 * ((src - d) ** 2).sum().item()) <= 1e-4 * abs(loss.item())
+    assert torch.allclose(grad.cpu(), 0.02 * (src - d), atol=1e-6)
+
+
+def test_adam_matches_torch(K):
+    p0, g = rnd(10000, seed=13), rnd(10000, seed=14)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.99), weight_decay=1e-5)
+    p = p0.clone().to(DEV)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in (1, 2, 3):
+        ref.grad = g * step
+        opt.step()
+        K.adam_step(p, (g * step).to(DEV), m, v, 1e-3, (0.9, 0.99), 1e-8, 1e-5, step)
+    assert (p.cpu() - ref.detach()).abs().max() < 1e-6
+
+
+def _conv_case(K, taps, cin, cout, geom, in_dtype, out_dtype, tensor_core, flags=None, seed=20, in_pad=0):
+    B, H, W = geom
+    npix = B * H * W
+    k = 3 if taps == 9 else 1
+    w = rnd(cout, cin, k, k, seed=seed) * 0.1
+    bias = rnd(cout, seed=seed + 1)
+    xw = rnd(npix, cin + in_pad, seed=seed + 2)
+    if in_dtype == torch.bfloat16:
+        w = w.to(torch.bfloat16).float()
+        xw = xw.to(torch.bfloat16).float()
+    flags = flags or {}
+    rp, kp = (cout + 15) // 16 * 16, (cin + 15) // 16 * 16
+    wp_ref = FK.pack_weight(w, 0, in_dtype, rp, kp)
+    wp = K.pack_weight(w.to(DEV), 0, in_dtype, rp, kp)
+    assert torch.equal(wp.cpu(), wp_ref)
+    out_w = cout + 8
+    base = rnd(npix, out_w, seed=seed + 3).to(out_dtype)
+    mask = rnd(npix, cout, seed=seed + 4).to(out_dtype) if flags.get("mask") else None
+    ref = base.clone()
+    FK.conv(xw.to(in_dtype)[:, :cin], wp_ref, geom, cout, ref[:, :cout], bias=bias, act=flags.get("act", 0), slope=0.2,
+            mask=mask, mask_act=flags.get("mask_act", 0), accumulate=flags.get("accumulate", False),
+            alpha=flags.get("alpha", 1.0))
+    got = base.clone().to(DEV)
+    K.conv(xw.to(in_dtype).to(DEV)[:, :cin], wp, geom, cout, got[:, :cout], bias=bias.to(DEV), act=flags.get("act", 0),
+           slope=0.2, mask=None if mask is None else mask.to(DEV), mask_act=flags.get("mask_act", 0),
+           accumulate=flags.get("accumulate", False), alpha=flags.get("alpha", 1.0), tensor_core=tensor_core)
+    got = got.cpu().float()
+    ref = ref.float()
+    assert torch.equal(got[:, cout:], base.float()[:, cout:]), "conv wrote outside its channel slice"
+    tol = (2e-5 if out_dtype == torch.float32 else 1e-2) * max(1.0, ref.abs().max().item())
+    err = (got[:, :cout] - ref[:, :cout]).abs().max().item()
+    assert err <= tol, f"conv mismatch {err} > {tol}"
+
+
+CONV_SHAPES = [(9, 24, 256, (2, 16, 16)), (9, 256, 48, (1, 8, 24)), (1, 24, 256, (2, 8, 8)), (1, 256, 192, (1, 5, 9)),
+               (9, 96, 256, (1, 5, 9)), (9, 56, 32, (1, 12, 20)), (9, 20, 10, (2, 3, 5))]
+
+
+@pytest.mark.parametrize("taps,cin,cout,geom", CONV_SHAPES)
+@pytest.mark.parametrize("dt", ["fp32", "bf16"])
+def test_conv_simt(K, taps, cin, cout, geom, dt):
+    idt = torch.float32 if dt == "fp32" else torch.bfloat16
+    _conv_case(K, taps, cin, cout, geom, idt, torch.float32, False, in_pad=4)
+    _conv_case(K, taps, cin, cout, geom, idt, idt, False, {"act": 1})
+    _conv_case(K, taps, cin, cout, geom, idt, idt, False, {"mask": True, "mask_act": 1})
+    _conv_case(K, taps, cin, cout, geom, idt, torch.float32, False, {"accumulate": True, "alpha": -1.0, "act": 2})
+
+
+@pytest.mark.parametrize("taps,cin,cout,geom", [(9, 256, 48, (2, 8, 8)), (9, 24, 256, (1, 5, 9)), (1, 96, 256, (2, 6, 6)),
+                                               (9, 152, 32, (1, 7, 5)), (1, 10, 6, (1, 4, 4))])
+@pytest.mark.parametrize("dt", ["fp32", "bf16"])
+def test_wgrad_and_dgrad_pack_simt(K, taps, cin, cout, geom, dt):
+    B, H, W = geom
+    npix = B * H * W
+    idt = torch.float32 if dt == "fp32" else torch.bfloat16
+    k = 3 if taps == 9 else 1
+    x = rnd(npix, cin + 8, seed=30).to(idt)
+    dy = rnd(npix, cout, seed=31).to(idt)
+    dw0 = rnd(cout, cin, k, k, seed=32)
+    ref = dw0.clone()
+    FK.wgrad(x[:, :cin], dy, geom, taps, ref, accumulate=True)
+    got = dw0.clone().to(DEV)
+    K.wgrad(x.to(DEV)[:, :cin], dy.to(DEV), geom, taps, got, accumulate=True)
+    assert (got.cpu() - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item())
+    # wgrad is the adjoint of conv: <dy, conv(x, w)> == <w, wgrad(x, dy)>
+    w = rnd(cout, cin, k, k, seed=33)
+    rp, kp = (cin + 15) // 16 * 16, (cout + 15) // 16 * 16
+    wd = K.pack_weight(w.to(DEV), 1, idt, rp, kp)
+    assert torch.equal(wd.cpu(), FK.pack_weight(w, 1, idt, rp, kp))
+    dx = torch.empty(npix, cin, device=DEV)
+    K.conv(dy.to(DEV), wd, geom, cin, dx)
+    xr = x[:, :cin].float().reshape(B, H, W, cin).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wq = w.to(idt).float()
+    yr = torch.nn.functional.conv2d(xr, wq, padding=k // 2)
+    yr.backward(dy.float().reshape(B, H, W, cout).permute(0, 3, 1, 2))
+    ref_dx = xr.grad.permute(0, 2, 3, 1).reshape(npix, cin)
+    assert (dx.cpu() - ref_dx).abs().max() <= 2e-5 * max(1.0, ref_dx.abs().max().item())
+
+
+def test_bad_arguments_are_reported(K):
+    from sin_inn_b200._lib import SininnError
+    with pytest.raises(SininnError):
+        K.resample_nchw(torch.zeros(1, 3, 5, 8, device=DEV), 0, 0)          # odd height
+    with pytest.raises(SininnError):
+        K.resample_nchw(torch.zeros(1, 3, 4, 8), 0, 0)                      # CPU tensor
+    with pytest.raises(SininnError):
+        K.coupling_apply(torch.zeros(4, 4, device=DEV), torch.zeros(4, 4, device=DEV), torch.zeros(4, 4, device=DEV), 7, 1.0, 0)

@@ -1,0 +1,165 @@
+"""Network-level parity of the CUDA path against the oracle and the committed golden vectors.
+
+Tolerances (BASELINE.json north_star): fp32 path 1e-4 relative on outputs and gradients, bf16 tensor-core
+path 2e-2, round trip inverse(forward(x)) 1e-5 (fp32 path)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_torch as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def build_pair(arch, scale, nc, lrw, H, W, precision, seed=11, tensor_core=True):
+    from sin_inn_b200 import archs
+    opt = R.make_opt(scale=scale, num_coupling=nc, lr_window=lrw, architecture=arch, precision=precision,
+                     tensor_core=tensor_core)
+    torch.manual_seed(seed)
+    ora = R.build(arch, 3, H, W, opt)
+    torch.manual_seed(seed)
+    net = {"SRF": archs.UncondSRFlow, "IRN": archs.InvRescaleNet}[arch](3, H, W, opt)
+    if arch == "IRN":
+        R.randomize_irn_conv5(ora, 1)
+        R.randomize_irn_conv5(net, 1)
+    return opt, ora, net.to(DEV)
+
+
+def run_both(opt, ora, net, B, H, W, seed=3):
+    hr, lr, z = R.synthetic_batch(opt, B, H, W, seed=seed)
+    lrz = torch.cat((lr, z), 1)
+    out = {}
+    for tag, m, dev in (("ora", ora, "cpu"), ("net", net, DEV)):
+        for p in m.parameters():
+            p.grad = None
+        x = hr.to(dev).clone().requires_grad_(True)
+        y = m(x)
+        (R.reconstruction(y[:, :opt.lr_dims], lr.to(dev)) + 0.3 * R.latent_nll(y[:, opt.lr_dims:])).backward()
+        u = lrz.to(dev).clone().requires_grad_(True)
+        xr = m(u, rev=True)
+        R.reconstruction(xr, hr.to(dev)).backward()
+        with torch.no_grad():
+            rt = m(y.detach(), rev=True)
+        assert y.is_contiguous() and xr.is_contiguous()
+        out[tag] = dict(y=y.detach().cpu(), dx=x.grad.cpu(), xr=xr.detach().cpu(), du=u.grad.cpu(), rt=rt.cpu(),
+                        g={n: p.grad.detach().cpu() for n, p in m.named_parameters() if p.requires_grad})
+    return hr, out
+
+
+def check(hr, out, tol, rt_tol):
+    a, b = out["ora"], out["net"]
+    for k in ("y", "dx", "xr", "du"):
+        err = (a[k] - b[k]).abs().max().item()
+        assert err <= tol * max(1.0, a[k].abs().max().item()), (k, err)
+    assert set(a["g"]) == set(b["g"])
+    for n, ref in a["g"].items():
+        err = (ref - b["g"][n]).abs().max().item()
+        assert err <= tol * max(ref.abs().max().item(), 1e-3), (n, err, ref.abs().max().item())
+    assert (b["rt"] - hr).abs().max().item() <= rt_tol
+
+
+FP32_CASES = [("SRF", 2, 4, 1, 2, 32, 32), ("SRF", 4, 2, 10, 2, 40, 72), ("IRN", 2, 2, 1, 2, 32, 32),
+              ("IRN", 4, 1, 10, 1, 40, 72)]
+
+
+@pytest.mark.parametrize("arch,scale,nc,lrw,B,H,W", FP32_CASES)
+def test_fp32_path_matches_oracle(arch, scale, nc, lrw, B, H, W):
+    opt, ora, net = build_pair(arch, scale, nc, lrw, H, W, "fp32")
+    hr, out = run_both(opt, ora, net, B, H, W)
+    check(hr, out, 1e-4, 1e-5)
+
+
+@pytest.mark.parametrize("arch,scale,nc,lrw,B,H,W", [("SRF", 4, 4, 10, 2, 64, 64), ("SRF", 2, 4, 1, 4, 64, 64),
+                                                     ("IRN", 4, 2, 10, 2, 64, 64)])
+@pytest.mark.parametrize("tc", [False, True])
+def test_bf16_path_matches_oracle(arch, scale, nc, lrw, B, H, W, tc):
+    opt, ora, net = build_pair(arch, scale, nc, lrw, H, W, "bf16", tensor_core=tc)
+    hr, out = run_both(opt, ora, net, B, H, W)
+    check(hr, out, 2e-2, 2e-3)
+
+
+@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLD, "*.npz")) if "known" not in p))
+def test_golden_vectors_fp32(path):
+    """CUDA fp32 path against the vectors the UNMODIFIED reference produced (oracle/make_golden.py)."""
+    from sin_inn_b200 import archs
+    f = np.load(path)
+    scale, nc, lrw, B, H, W, wseed, _ = (int(v) for v in f["meta"])
+    arch = str(f["arch"])
+    opt = R.make_opt(scale=scale, num_coupling=nc, lr_window=lrw, architecture=arch, precision="fp32")
+    torch.manual_seed(wseed)
+    net = {"SRF": archs.UncondSRFlow, "IRN": archs.InvRescaleNet}[arch](3, H, W, opt)
+    if arch == "IRN":
+        R.randomize_irn_conv5(net, 1)
+    net = net.to(DEV)
+    hr, lr, z = (torch.from_numpy(f[k]).to(DEV) for k in ("hr", "lr", "z"))
+    x = hr.clone().requires_grad_(True)
+    y = net(x)
+    (R.reconstruction(y[:, :opt.lr_dims], lr) + 0.5 * R.latent_nll(y[:, opt.lr_dims:])).backward()
+    u = torch.cat((lr, z), 1).requires_grad_(True)
+    xr = net(u, rev=True)
+    R.reconstruction(xr, hr).backward()
+    with torch.no_grad():
+        rt = net(y.detach(), rev=True)
+    for k, v in (("y", y), ("dx", x.grad), ("xr", xr), ("du", u.grad), ("rt", rt)):
+        ref = f[k]
+        np.testing.assert_allclose(v.detach().cpu().numpy(), ref, rtol=0, atol=1e-4 * max(1.0, np.abs(ref).max()), err_msg=k)
+    named = dict(net.named_parameters())
+    for i, n in enumerate(f["kept_grad_names"]):
+        g = named[str(n)].grad.cpu()
+        g = g[:8] if g.dim() == 4 else g
+        ref = f[f"kept_grad_{i}"]
+        np.testing.assert_allclose(g.numpy(), ref, rtol=0, atol=1e-4 * max(np.abs(ref).max(), 1e-3))
+    gs = np.array([[float(p.grad.double().sum()), float(p.grad.double().pow(2).sum().sqrt())]
+                   for n, p in net.named_parameters() if p.requires_grad])
+    np.testing.assert_allclose(gs[:, 1], f["gstats"][:, 1], rtol=1e-3, atol=1e-6)
+
+
+def test_full_size_properties_bf16():
+    """BASELINE.json configs[1] shape (256x256 patches): size-independent properties instead of the oracle:
+    round trip, determinism (bit-identical reruns), gradient accumulation linearity."""
+    opt, _, net = build_pair("SRF", 4, 4, 10, 256, 256, "bf16")
+    hr, lr, z = (t.to(DEV) for t in R.synthetic_batch(opt, 8, 256, 256, seed=1))
+    with torch.no_grad():
+        y1 = net(hr)
+        y2 = net(hr)
+        rt = net(y1, rev=True)
+    assert torch.equal(y1, y2)
+    assert (rt - hr).abs().max().item() < 5e-3 and (rt - hr).abs().mean().item() < 1e-5
+    grads = []
+    for _ in range(2):
+        for p in net.parameters():
+            p.grad = None
+        R.reconstruction(net(hr)[:, :opt.lr_dims], lr).backward()
+        grads.append([p.grad.clone() for p in net.parameters()])
+    for a, b in zip(*grads):
+        assert torch.equal(a, b)                       # deterministic wgrad (no float atomics)
+    R.reconstruction(net(hr)[:, :opt.lr_dims], lr).backward()       # second backward accumulates
+    for p, a in zip(net.parameters(), grads[0]):
+        assert torch.allclose(p.grad, 2 * a, rtol=1e-6, atol=1e-12)
+
+
+def test_fp32_roundtrip_1080p_shape():
+    """135x240 level-1 grid (odd extents) as in the 1080p inference config, reduced width for test time."""
+    opt, _, net = build_pair("SRF", 4, 4, 10, 1080, 256, "fp32")
+    g = torch.Generator().manual_seed(0)
+    lrz = torch.randn(1, 192, 135, 32, generator=g).to(DEV)
+    with torch.no_grad():
+        hr = net(lrz, rev=True)
+        back = net(hr, rev=False)
+    assert hr.shape == (1, 3, 1080, 256)
+    assert (back - lrz).abs().max().item() <= 1e-5 * max(1.0, lrz.abs().max().item())
+
+
+def test_state_dict_roundtrip_and_eval():
+    opt, ora, net = build_pair("SRF", 2, 2, 1, 32, 32, "fp32")
+    sd = {k: v.clone() for k, v in ora.state_dict().items()}
+    net.load_state_dict(sd)
+    net.eval()
+    x = torch.rand(1, 3, 32, 32)
+    with torch.no_grad():
+        assert (net(x.to(DEV)).cpu() - ora(x)).abs().max() < 1e-4
