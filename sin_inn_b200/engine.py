@@ -14,6 +14,7 @@ The only tensors that cross the API are NCHW-contiguous fp32 (loss.py:16-17 need
 `.view(b, c*h*w)` to work on the result).
 """
 import os
+import weakref
 from dataclasses import dataclass
 
 import torch
@@ -49,8 +50,16 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
+TRACE = None     # debugging aid: set to a list to collect (label, trunk copy) after every executed op
+
+
+def _trace(label, t):
+    if TRACE is not None:
+        TRACE.append((label, t.detach().float().cpu().clone()))
+
+
 # ----------------------------------------------------------------------------- packed-weight cache
-_pack_cache = {}
+_pack_cache = {}     # id(param) -> (weakref(param), {(mode, dtype): (version, data_ptr, packed)})
 
 
 def invalidate_packs():
@@ -59,15 +68,20 @@ def invalidate_packs():
 
 
 def packed(w, mode, dtype):
-    """Implicit-GEMM layout of an OIHW weight, cached until the parameter changes."""
-    key = (w.data_ptr(), mode, dtype)
-    hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == w._version and hit[2] == tuple(w.shape):
-        return hit[1]
+    """Implicit-GEMM layout of an OIHW weight, cached per parameter OBJECT until it changes (version counter
+    or storage).  Keyed on identity, not on the address: the caching allocator re-uses addresses across nets."""
+    key = id(w)
+    ent = _pack_cache.get(key)
+    if ent is None or ent[0]() is not w:
+        ent = (weakref.ref(w, lambda _r, k=key: _pack_cache.pop(k, None)), {})
+        _pack_cache[key] = ent
+    hit = ent[1].get((mode, dtype))
+    if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
+        return hit[2]
     co, ci = w.shape[0], w.shape[1]
     rows, k = (co, ci) if mode == 0 else (ci, co)
     p = K.pack_weight(w, mode, dtype, _round_up(rows, 16), _round_up(k, 16))
-    _pack_cache[key] = (w._version, p, tuple(w.shape))
+    ent[1][(mode, dtype)] = (w._version, w.data_ptr(), p)
     return p
 
 
@@ -360,6 +374,7 @@ class CouplingOp:
                 bf = None
             if bf is not None:
                 tr.bf[st.dst] = bf
+            _trace(f"half:{st.kind}:{st.src}->{st.dst}", tr.U)
 
     # ---- backward from the output: restores the block input in tr.U and turns tr.dU into dL/d(input)
     def backward(self, ctx, tr, rev):
@@ -499,6 +514,7 @@ class Plan:
         tr = Trunk(U)
         if bf is not None:
             tr.bf[hint] = bf
+        _trace("to_nhwc", tr.U)
         for i, op in enumerate(seq):
             nxt = seq[i + 1] if i + 1 < len(seq) else None
             if op.kind == "coupling":
@@ -509,6 +525,7 @@ class Plan:
                 tr.set(U, None, {hint: bf} if bf is not None else None)
             else:
                 tr.set(op.apply_nhwc(tr.U, rev))
+            _trace(op.kind, tr.U)
         if not rev:
             cmap = self.tail_perm.gather_map(dev, False) if self.tail_perm is not None else None
             return K.nhwc_to_nchw(tr.U, cmap)

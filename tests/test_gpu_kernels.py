@@ -196,6 +196,34 @@ def test_conv_simt(K, taps, cin, cout, geom, dt):
     _conv_case(K, taps, cin, cout, geom, idt, torch.float32, False, {"accumulate": True, "alpha": -1.0, "act": 2})
 
 
+TC_SHAPES = [(9, 24, 256, (2, 16, 16)), (9, 256, 48, (1, 8, 24)), (1, 24, 256, (2, 8, 8)), (1, 256, 192, (1, 5, 9)),
+             (9, 96, 256, (1, 5, 9)), (9, 256, 192, (3, 32, 32)), (9, 48, 256, (1, 17, 33)), (1, 192, 256, (1, 4, 4)),
+             (9, 56, 32, (1, 12, 20)), (9, 152, 24, (1, 9, 7)), (9, 32, 400, (1, 8, 16))]
+
+
+@pytest.mark.parametrize("taps,cin,cout,geom", TC_SHAPES)
+def test_conv_tc(K, taps, cin, cout, geom):
+    """tcgen05 path against the torch restatement: every epilogue variant the engine uses."""
+    bf = torch.bfloat16
+    _conv_case(K, taps, cin, cout, geom, bf, torch.float32, True)
+    _conv_case(K, taps, cin, cout, geom, bf, bf, True, {"act": 1})
+    _conv_case(K, taps, cin, cout, geom, bf, bf, True, {"mask": True, "mask_act": 1})
+    _conv_case(K, taps, cin, cout, geom, bf, torch.float32, True, {"accumulate": True, "alpha": -1.0, "act": 2})
+
+
+def test_conv_tc_matches_simt_bitwise_inputs(K):
+    """Same bf16 operands through the CUDA-core and the tensor-core kernels agree to fp32 accumulation noise."""
+    B, H, W, cin, cout = 4, 64, 64, 256, 48
+    x = rnd(B * H * W, cin, seed=40).to(torch.bfloat16).to(DEV)
+    w = (rnd(cout, cin, 3, 3, seed=41) * 0.05).to(DEV)
+    wp = K.pack_weight(w, 0, torch.bfloat16, 48, 256)
+    o1 = torch.empty(B * H * W, cout, device=DEV)
+    o2 = torch.empty_like(o1)
+    K.conv(x, wp, (B, H, W), cout, o1, tensor_core=False)
+    K.conv(x, wp, (B, H, W), cout, o2, tensor_core=True)
+    assert (o1 - o2).abs().max().item() <= 1e-4 * o1.abs().max().item()
+
+
 @pytest.mark.parametrize("taps,cin,cout,geom", [(9, 256, 48, (2, 8, 8)), (9, 24, 256, (1, 5, 9)), (1, 96, 256, (2, 6, 6)),
                                                (9, 152, 32, (1, 7, 5)), (1, 10, 6, (1, 4, 4))])
 @pytest.mark.parametrize("dt", ["fp32", "bf16"])

