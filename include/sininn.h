@@ -137,6 +137,9 @@ typedef struct {
   const void* mask; int mask_stride; /* NULL, or activation OUTPUT (dtype=out_dtype): result *= act'(mask) */
   int mask_act;
   int accumulate; float alpha;    /* out = (accumulate ? out : 0) + alpha * f(acc + bias) */
+  /* tensor-core path only: 1 bit per element, uint32 [npix][ceil(Cout/32)], bit c%32 of word c/32 */
+  const void* mask_bits;          /* NULL, or sign bits of the ReLU output the gradient flows through: result zeroed where 0 */
+  void* bits_out;                 /* NULL, or receives the sign bits (value > 0) of this call's own output */
 } sininn_conv_desc;
 
 int sininn_conv_simt(const sininn_conv_desc* d, sininn_stream_t stream);   /* fp32-accurate CUDA-core path */

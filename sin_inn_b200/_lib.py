@@ -34,6 +34,7 @@ class ConvDesc(C.Structure):
         ("act", C.c_int), ("slope", C.c_float),
         ("mask", _vp), ("mask_stride", C.c_int), ("mask_act", C.c_int),
         ("accumulate", C.c_int), ("alpha", C.c_float),
+        ("mask_bits", _vp), ("bits_out", _vp),
     ]
 
 

@@ -289,6 +289,7 @@ int sininn_conv_simt(const sininn_conv_desc* d, sininn_stream_t stream) {
   int rc = check_conv_desc(d, "conv_simt");
   if (rc) return rc;
   SININN_CHECK_ARG((d->k_pad % 4) == 0, "conv_simt: k_pad must be a multiple of 4");
+  SININN_CHECK_ARG(d->mask_bits == nullptr && d->bits_out == nullptr, "conv_simt: sign-bit masks are a tensor-core-path feature");
   ConvArgs a;
   a.B = d->B; a.H = d->H; a.W = d->W; a.Cin = d->Cin; a.Cout = d->Cout; a.taps = d->taps;
   a.in = d->in; a.in_stride = d->in_stride; a.w = d->wpack; a.rows_pad = d->rows_pad; a.k_pad = d->k_pad;

@@ -3,36 +3,36 @@
 //   out[p][co] = sum_{tap, ci} in[p + off(tap)][ci] * wpack[tap][co][ci]        (1x1 or 3x3, stride 1, "same")
 //
 // One CTA tile = 128 output pixels (an 8x16 spatial patch of one image) x up to 256 output channels.
-//   warp 0   TMA producer: per K step (tap, 16/32/64-channel slab) one 4-D box load of the shifted
-//            activation patch (out-of-bounds rows/columns are zero-filled by TMA = the conv padding) and
-//            one 3-D box load of the weight slab, both 128B/64B/32B-swizzled, into a 3..8 stage smem ring
-//   warp 1   MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=Cout tile, K=16 per instruction,
-//            fp32 accumulator in TMEM (two 256-column buffers => the epilogue of tile i overlaps the
-//            MMAs of tile i+1); tcgen05.commit releases smem stages / publishes the accumulator
-//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 16 columns), bias / activation / activation-derivative
-//            mask / alpha / accumulate, 128-bit global stores (bf16 or fp32, strided channel slices)
+//   warp 0     TMA producer: per K step (tap, 16/32/64-channel slab) one 4-D box load of the shifted
+//              activation patch (out-of-bounds rows/columns are zero-filled by TMA = the conv padding) and
+//              one 3-D box load of the weight slab, both 128B/64B/32B-swizzled, into a 3..8 stage smem ring
+//   warp 1     MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=Cout tile, K=16 per instruction,
+//              fp32 accumulator in TMEM (two 256-column buffers => the epilogue of tile i overlaps the
+//              MMAs of tile i+1); tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 2-9  epilogue, two warps per TMEM lane quarter taking alternate 128-byte output slabs:
+//              tcgen05.ld -> + bias, activation, ReLU-bit mask, alpha -> 128B-swizzled smem staging box ->
+//              TMA tensor store (or TMA reduce-add for fp32 accumulation) with hardware clipping of partial
+//              tiles; optionally emits the ReLU sign bits of its output (1 bit / element) for the backward pass
 // The grid is persistent (one CTA per SM, static round-robin over tiles).
 //
 // Replaces cuDNN's nn.Conv2d forward / data-gradient inside subnet_conv / subnet_conv_1x1
 // (/root/reference/archs.py:11-17) and DenseBlock (/root/reference/archs.py:77-81,88-95).
-#include <cuda.h>
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace sininn {
-int wgrad_simt_splits(const sininn_wgrad_desc* d);
-
 namespace tc {
 
 constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;   // 128 pixels = UMMA M
-constexpr int MAX_STAGES = 8;
-constexpr int NUM_THREADS = 192;
-constexpr int TMEM_COLS = 512;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int ACC_STRIDE = 256;          // columns between the two accumulator buffers
-constexpr int SMEM_RING_BUDGET = 200 * 1024;
+constexpr int STAGING_BYTES = 32 * 128;  // one epilogue warp: 32 rows x 128 B
+constexpr int EPI_SMEM_BYTES = 256 * 4 + NUM_EPI_WARPS * STAGING_BYTES;
+constexpr int SMEM_RING_BUDGET = 227 * 1024 - EPI_SMEM_BYTES - BARRIER_BYTES - 1024;   // 1024: worst-case alignment pad
 
 struct Params {
   int B, H, W, Cin, Cout;
-  int taps, kc, k_chunks;        // kc = channels per K step (16/32/64), k_chunks = ceil(k_pad / kc)
+  int taps, kc, k_chunks;        // kc = channels per K step (16/32/64), k_chunks = ceil(Cin / kc)
   int n_tile, n_tiles;           // output channels per CTA tile (multiple of 16, <= 256), tiles along N
   int tiles_h, tiles_w;
   long long num_tiles;           // B * tiles_h * tiles_w * n_tiles
@@ -44,92 +44,12 @@ struct Params {
   const float* bias;
   void* out; int out_f32; int out_stride;
   int act; float slope;
-  const void* mask; int mask_stride; int mask_act;
+  const void* mask; int mask_stride; int mask_act;     // element mask (fallback path only)
+  const uint32_t* bits_in;       // ReLU sign bits of the activation this gradient flows through, [npix][bit_words]
+  uint32_t* bits_out;            // sign bits of this kernel's own output, [npix][bit_words]
+  int bit_words;
   int accumulate; float alpha;
-  int vec_out;                   // rows may be written/read 16 B at a time
-};
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, K-major operand with 32/64/128-byte swizzle:
-// start>>4 | LBO>>4 (unused for swizzled K-major, canonical 1) | SBO>>4 | version 1 (bit 46) | layout (bits 61..63)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
-struct __align__(8) Barriers {
-  uint64_t full[MAX_STAGES];
-  uint64_t empty[MAX_STAGES];
-  uint64_t acc_full[2];
-  uint64_t acc_empty[2];
-  uint32_t tmem_base;
-  uint32_t pad;
+  int tma_out;                   // 1: TMA-store epilogue; 0: per-thread fallback (unaligned output slices)
 };
 
 __device__ __forceinline__ void tile_coords(const Params& p, long long t, int& b, int& h0, int& w0, int& n0) {
@@ -140,57 +60,84 @@ __device__ __forceinline__ void tile_coords(const Params& p, long long t, int& b
   h0 = th * TILE_H; w0 = tw * TILE_W; n0 = nt * p.n_tile;
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// per-thread fallback for output slices TMA cannot address (unaligned base / stride)
 template <typename TO>
 __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&v)[16], long long pix, int col0, bool row_ok) {
   if (!row_ok) return;
   TO* __restrict__ out = reinterpret_cast<TO*>(p.out) + pix * p.out_stride + col0;
   const TO* __restrict__ mask = p.mask ? reinterpret_cast<const TO*>(p.mask) + pix * p.mask_stride + col0 : nullptr;
   const int ncol = min(16, p.Cout - col0);
-  float r[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
+  for (int j = 0; j < ncol; ++j) {
     float x = __uint_as_float(v[j]);
-    if (p.bias != nullptr && j < ncol) x += __ldg(p.bias + col0 + j);
-    r[j] = act_fwd(p.act, p.slope, x);
+    if (p.bias != nullptr) x += __ldg(p.bias + col0 + j);
+    x = act_fwd(p.act, p.slope, x);
+    if (mask != nullptr) x *= act_grad(p.mask_act, p.slope, to_f32(mask[j]));
+    if (p.bits_in != nullptr) {
+      const uint32_t w = p.bits_in[pix * p.bit_words + ((col0 + j) >> 5)];
+      if (!((w >> ((col0 + j) & 31)) & 1u)) x = 0.f;
+    }
+    x *= p.alpha;
+    if (p.accumulate) x += to_f32(out[j]);
+    out[j] = from_f32<TO>(x);
   }
-  if (ncol == 16 && p.vec_out) {
-    if (mask != nullptr) {
+}
+
+// One 128-byte output slab (64 bf16 or 32 fp32 columns) of a warp's 32 accumulator rows:
+// registers -> (+bias, activation, sign-bit mask, alpha) -> 128B-swizzled staging rows in shared memory.
+// v holds the slab's accumulator columns; returns the sign bits of the produced values (bit j = value j > 0).
+template <int NCOL>
+__device__ __forceinline__ void slab_math(const Params& p, float (&x)[NCOL], const float* bias_s, const uint32_t* mbits) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 m = load4(mask + 4 * q);
-        r[4 * q + 0] *= act_grad(p.mask_act, p.slope, m.x);
-        r[4 * q + 1] *= act_grad(p.mask_act, p.slope, m.y);
-        r[4 * q + 2] *= act_grad(p.mask_act, p.slope, m.z);
-        r[4 * q + 3] *= act_grad(p.mask_act, p.slope, m.w);
-      }
-    }
+  for (int q = 0; q < NCOL / 4; ++q) {
+    const float4 bq = *reinterpret_cast<const float4*>(bias_s + 4 * q);
+    x[4 * q + 0] = act_fwd(p.act, p.slope, x[4 * q + 0] + bq.x);
+    x[4 * q + 1] = act_fwd(p.act, p.slope, x[4 * q + 1] + bq.y);
+    x[4 * q + 2] = act_fwd(p.act, p.slope, x[4 * q + 2] + bq.z);
+    x[4 * q + 3] = act_fwd(p.act, p.slope, x[4 * q + 3] + bq.w);
+  }
+  if (mbits != nullptr) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 o = make_float4(r[4 * q] * p.alpha, r[4 * q + 1] * p.alpha, r[4 * q + 2] * p.alpha, r[4 * q + 3] * p.alpha);
-      if (p.accumulate) {
-        float4 old = load4(out + 4 * q);
-        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-      }
-      store4(out + 4 * q, o);
-    }
-  } else {
-    for (int j = 0; j < ncol; ++j) {
-      float x = r[j];
-      if (mask != nullptr) x *= act_grad(p.mask_act, p.slope, to_f32(mask[j]));
-      x *= p.alpha;
-      if (p.accumulate) x += to_f32(out[j]);
-      out[j] = from_f32<TO>(x);
-    }
+    for (int j = 0; j < NCOL; ++j)
+      if (!((mbits[j >> 5] >> (j & 31)) & 1u)) x[j] = 0.f;
+  }
+  if (p.alpha != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) x[j] *= p.alpha;
   }
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // ring first (1024-byte aligned for the swizzle atoms), barriers behind it
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;       // both multiples of 1024
-  Barriers* bars = reinterpret_cast<Barriers*>(ring + (size_t)p.stages * stage_bytes);
+  // every pointer is smem_raw + offset so the compiler keeps the shared address space (LDS/STS, not generic)
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* ring = smem_raw + pad;
+  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;                      // both multiples of 1024
+  const uint32_t ring_bytes = (uint32_t)p.stages * stage_bytes;
+  uint8_t* staging = ring + ring_bytes;                                    // [8 warps][32 rows][128 B], 1024-aligned
+  Barriers* bars = reinterpret_cast<Barriers*>(staging + NUM_EPI_WARPS * STAGING_BYTES);
+  float* bias_s = reinterpret_cast<float*>(staging + NUM_EPI_WARPS * STAGING_BYTES + BARRIER_BYTES);   // [256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring_u32 = smem_u32(ring);
@@ -202,11 +149,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bars->acc_full[a]), 1);
-      mbar_init(smem_u32(&bars->acc_empty[a]), 4);           // one arrive per epilogue warp
+      mbar_init(smem_u32(&bars->acc_empty[a]), NUM_EPI_WARPS);     // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_out) tma_prefetch_desc(&tmO);
   }
   if (warp == 1) {   // TMEM allocation (whole warp), address lands in smem
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(TMEM_COLS) : "memory");
@@ -216,7 +164,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-
   const int k_steps = p.taps * p.k_chunks;
 
   if (warp == 0) {
@@ -271,33 +218,118 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ======================= epilogue (warps 2..5) =======================
-    const int quarter = warp & 3;                              // TMEM lanes 32*quarter .. +31
+    // ======================= epilogue (warps 2..9) =======================
+    const int ew = warp - 2;                                   // 0..7
+    const int quarter = warp & 3;                              // TMEM lanes 32*quarter .. +31 (hardware rule: warp id % 4)
+    const int half = ew >> 2;                                  // which of the two warps of this quarter
     const int row = quarter * 32 + lane;                       // pixel row inside the tile
     const int hl = row / TILE_W, wl = row % TILE_W;
+    uint8_t* stg = staging + ew * STAGING_BYTES;
+    const uint32_t stg_u32 = smem_u32(stg);
+    const int etid = threadIdx.x - 64;                         // 0..255 among the epilogue threads
+    const int slab_cols = p.out_f32 ? 32 : 64;                 // 128 bytes of output per row
     int acc = 0; uint32_t acc_phase = 0;
+    int bias_n0 = -1;
     for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       int b, h0, w0, n0;
       tile_coords(p, t, b, h0, w0, n0);
       const int oh = h0 + hl, ow = w0 + wl;
       const bool row_ok = (oh < p.H) && (ow < p.W);
       const long long pix = ((long long)b * p.H + oh) * p.W + ow;
+      if (n0 != bias_n0) {                                     // (re)load the bias slice of this N tile
+        asm volatile("bar.sync 1, 256;" ::: "memory");         // everyone done with the previous slice
+        {
+          const int co = n0 + etid;
+          bias_s[etid] = (p.bias != nullptr && co < p.Cout) ? __ldg(p.bias + co) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        bias_n0 = n0;
+      }
       mbar_wait(smem_u32(&bars->acc_full[acc]), acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE;
       const int n_valid = min(p.n_tile, p.Cout - n0);
-      for (int c = 0; c < n_valid; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_base + c, v);
-        tmem_ld_wait();
-        if (p.out_f32) epilogue_chunk<float>(p, v, pix, n0 + c, row_ok);
-        else epilogue_chunk<__nv_bfloat16>(p, v, pix, n0 + c, row_ok);
+      if (p.tma_out) {
+        const int n_slabs = (n_valid + slab_cols - 1) / slab_cols;
+        for (int s = half; s < n_slabs; s += 2) {
+          const int c = s * slab_cols;                         // first accumulator column of the slab
+          // sign-bit mask words of this row for the slab's columns
+          uint32_t mb[2] = {0xffffffffu, 0xffffffffu};
+          if (p.bits_in != nullptr) {
+            const int w0i = (n0 + c) >> 5;
+            mb[0] = row_ok ? __ldg(p.bits_in + pix * p.bit_words + w0i) : 0u;
+            if (!p.out_f32) mb[1] = (row_ok && w0i + 1 < p.bit_words) ? __ldg(p.bits_in + pix * p.bit_words + w0i + 1) : 0u;
+          }
+          if (lane == 0) bulk_wait_read0();                    // previous TMA store has finished reading the staging rows
+          __syncwarp();
+          uint32_t sign[2] = {0u, 0u};
+          if (p.out_f32) {
+            uint32_t v[32];
+            tmem_ld32(t_base + c, v);
+            tmem_ld_wait();
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+            slab_math<32>(p, x, bias_s + c, p.bits_in ? mb : nullptr);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sign[0] |= (x[j] > 0.f ? 1u : 0u) << j;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)                         // 16-byte piece q of the row, 128B swizzle: q ^ (row & 7)
+              *reinterpret_cast<float4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                  make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+          } else {
+            uint32_t v0[32], v1[32];
+            tmem_ld32(t_base + c, v0);
+            tmem_ld32(t_base + c + 32, v1);                    // (columns past n_valid are clipped by the TMA store)
+            tmem_ld_wait();
+            float x[64];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { x[j] = __uint_as_float(v0[j]); x[32 + j] = __uint_as_float(v1[j]); }
+            slab_math<64>(p, x, bias_s + c, p.bits_in ? mb : nullptr);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              sign[0] |= (x[j] > 0.f ? 1u : 0u) << j;
+              sign[1] |= (x[32 + j] > 0.f ? 1u : 0u) << j;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              uint4 o;
+              o.x = pack_bf16(x[8 * q + 0], x[8 * q + 1]);
+              o.y = pack_bf16(x[8 * q + 2], x[8 * q + 3]);
+              o.z = pack_bf16(x[8 * q + 4], x[8 * q + 5]);
+              o.w = pack_bf16(x[8 * q + 6], x[8 * q + 7]);
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+            }
+          }
+          if (p.bits_out != nullptr && row_ok) {
+            const int w0i = (n0 + c) >> 5;
+            p.bits_out[pix * p.bit_words + w0i] = sign[0];
+            if (!p.out_f32 && w0i + 1 < p.bit_words) p.bits_out[pix * p.bit_words + w0i + 1] = sign[1];
+          }
+          fence_async_smem();                                  // generic-proxy smem writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            // this warp's 32 rows are tile rows h = 2*quarter, 2*quarter+1 (16 pixels each): box {128 B, 16, 2, 1}
+            if (p.accumulate) tma_reduce_add_4d(&tmO, stg_u32, n0 + c, w0, h0 + 2 * quarter, b);
+            else tma_store_4d(&tmO, stg_u32, n0 + c, w0, h0 + 2 * quarter, b);
+            bulk_commit();
+          }
+        }
+      } else if (half == 0) {
+        for (int c = 0; c < n_valid; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_base + c, v);
+          tmem_ld_wait();
+          if (p.out_f32) epilogue_chunk<float>(p, v, pix, n0 + c, row_ok);
+          else epilogue_chunk<__nv_bfloat16>(p, v, pix, n0 + c, row_ok);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_out && lane == 0) bulk_wait_all();               // outstanding tensor stores complete before exit
   }
 
   tc_fence_before();
@@ -308,41 +340,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
-static int pick_kc(int k_pad) {
-  if (k_pad % 64 == 0) return 64;
-  if (k_pad % 32 == 0) return 32;
-  return 16;
-}
-
 }  // namespace tc
 }  // namespace sininn
 
 using namespace sininn;
 
 extern "C" {
-
-size_t sininn_wgrad_workspace_bytes(const sininn_wgrad_desc* d, int tensor_core) {
-  if (!d || d->Cin <= 0 || d->Cout <= 0 || d->taps <= 0) return 0;
-  (void)tensor_core;
-  return (size_t)wgrad_simt_splits(d) * d->taps * d->Cout * d->Cin * sizeof(float);
-}
 
 int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream) {
   using namespace sininn::tc;
@@ -357,6 +360,9 @@ int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream) {
                    "conv_tc: TMA needs a 16-byte aligned input slice and a pixel stride that is a multiple of 8 channels "
                    "(stride %d)", d->in_stride);
   SININN_CHECK_ARG(aligned16(d->wpack), "conv_tc: packed weights misaligned");
+  SININN_CHECK_ARG(!(d->mask && d->mask_bits), "conv_tc: give either an element mask or a bit mask");
+  SININN_CHECK_ARG(!(d->accumulate && d->out_dtype != SININN_F32), "conv_tc: accumulation needs an fp32 output");
+  const int bit_words = (d->Cout + 31) / 32;
   EncodeTiledFn encode = get_encode();
   if (!encode) {
     set_error("conv_tc: cuTensorMapEncodeTiled not available from the driver");
@@ -374,6 +380,7 @@ int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream) {
   const uint32_t row_bytes = (uint32_t)p.kc * 2;
   p.a_bytes = TILE_M * row_bytes;                                  // 4 / 8 / 16 KiB
   p.b_bytes = ((uint32_t)p.n_tile * row_bytes + 1023u) & ~1023u;   // keep every stage 1024-byte aligned
+  p.tx_bytes = p.a_bytes + (uint32_t)p.n_tile * row_bytes;
   p.sbo = 8 * row_bytes;
   p.layout_type = p.kc == 64 ? 2u : (p.kc == 32 ? 4u : 6u);
   int stages = SMEM_RING_BUDGET / (int)(p.a_bytes + p.b_bytes);
@@ -384,15 +391,16 @@ int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream) {
   p.out = d->out; p.out_f32 = d->out_dtype == SININN_F32; p.out_stride = d->out_stride;
   p.act = d->act; p.slope = d->slope;
   p.mask = d->mask; p.mask_stride = d->mask_stride; p.mask_act = d->mask_act;
+  p.bits_in = reinterpret_cast<const uint32_t*>(d->mask_bits);
+  p.bits_out = reinterpret_cast<uint32_t*>(d->bits_out);
+  p.bit_words = bit_words;
   p.accumulate = d->accumulate; p.alpha = d->alpha;
   const int esz = p.out_f32 ? 4 : 2;
-  bool vec = aligned16(d->out) && ((long long)d->out_stride * esz) % 16 == 0;
-  if (d->mask) vec = vec && aligned16(d->mask) && ((long long)d->mask_stride * esz) % 16 == 0;
-  p.vec_out = vec ? 1 : 0;
+  // TMA epilogue needs a 16-byte aligned output slice / pixel stride and no per-element mask tensor
+  p.tma_out = (aligned16(d->out) && ((long long)d->out_stride * esz) % 16 == 0 && d->mask == nullptr) ? 1 : 0;
 
-  p.tx_bytes = p.a_bytes + (uint32_t)p.n_tile * row_bytes;
   const CUtensorMapSwizzle swz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_stride * 2, (cuuint64_t)d->W * d->in_stride * 2,
@@ -422,7 +430,23 @@ int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream) {
       return SININN_ECUDA;
     }
   }
-  const size_t smem = (size_t)p.stages * (p.a_bytes + p.b_bytes) + sizeof(Barriers) + 1024;
+  if (p.tma_out) {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->out_stride * esz, (cuuint64_t)d->W * d->out_stride * esz,
+                             (cuuint64_t)d->H * d->W * d->out_stride * esz};
+    cuuint32_t box[4] = {(cuuint32_t)(128 / esz), TILE_W, 2, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmO, p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out, dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv_tc: cuTensorMapEncodeTiled(output) failed with %d (Cout=%d stride=%d)", (int)r, d->Cout, d->out_stride);
+      return SININN_ECUDA;
+    }
+  } else {
+    tmO = tmA;   // unused
+  }
+  const size_t smem = (size_t)p.stages * (p.a_bytes + p.b_bytes) + EPI_SMEM_BYTES + BARRIER_BYTES + 1024;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -435,15 +459,9 @@ int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream) {
     attr_set[dev] = true;
   }
   long long grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv_tc_kernel<<<(unsigned)grid, NUM_THREADS, smem, as_stream(stream)>>>(tmA, tmB, p);
+  conv_tc_kernel<<<(unsigned)grid, NUM_THREADS, smem, as_stream(stream)>>>(tmA, tmB, tmO, p);
   SININN_CHECK_LAUNCH("conv_tc");
   return SININN_OK;
-}
-
-int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
-  (void)d; (void)stream;
-  set_error("wgrad_tc: not built yet");
-  return SININN_EUNSUPPORTED;
 }
 
 }  // extern "C"

@@ -1,0 +1,318 @@
+// tcgen05 weight-gradient kernel (bf16 operands read MN-major straight from the channels-last activations).
+#include "tc_common.cuh"
+
+namespace sininn {
+int wgrad_simt_splits(const sininn_wgrad_desc* d);
+namespace tc {
+
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_RING_BUDGET = 200 * 1024;
+
+// ================================================================ weight gradient
+//   dW[tap][m][n] = sum_pixels  Wide[p][m] * Narrow[p + off(tap)][n]
+// "Wide" is whichever of (x, dy) has more channels (the 256-wide hidden side of every subnet conv); it is the
+// M operand in 128-channel tiles and is never shifted.  "Narrow" is the N operand; its box is shifted per tap
+// (by +off when it is x, by -off when it is dy), TMA zero-fill provides the padding.  Both operands are read
+// straight from the channels-last activations as MN-major SWIZZLE_128B tiles (64 channels x 64 pixels per box),
+// K = pixels.  One CTA = (M tile, group of taps, pixel split); accumulators for all taps of the group live in
+// TMEM side by side.  fp32 partials go to the workspace, a fixed-order reduction writes OIHW.
+constexpr int WG_KPIX_W = 16, WG_KPIX_H = 4, WG_KPIX = WG_KPIX_W * WG_KPIX_H;    // 64 pixels per K step
+constexpr uint32_t WG_BOX_BYTES = WG_KPIX * 128;                                  // 64 px x 64 ch x 2 B
+
+struct WgradParams {
+  int B, H, W;
+  int taps, narrow_is_x;         // shift sign: +off when the narrow operand is x, -off when it is dy
+  int Cw, Cn;                    // true channel counts of the wide / narrow operands
+  int n_pad, n_groups;           // narrow channels padded to 16; 64-channel boxes per tap
+  int taps_per_cta, tap_groups, m_tiles, splits;
+  int blocks_h, blocks_w;        // pixel blocks per image
+  long long num_blocks, blocks_per_split;
+  int stages;
+  uint32_t stage_bytes, tx_bytes;
+  float* partial;                // [split][tap][Cw][Cn]
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN, const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* ring = smem_raw + pad;
+  Barriers* bars = reinterpret_cast<Barriers*>(ring + (size_t)p.stages * p.stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring_u32 = smem_u32(ring);
+
+  // work item
+  int item = blockIdx.x;
+  const int split = item % p.splits; item /= p.splits;
+  const int tg = item % p.tap_groups;
+  const int mt = item / p.tap_groups;
+  const int tap0 = tg * p.taps_per_cta;
+  const int ntap = min(p.taps_per_cta, p.taps - tap0);
+  const long long blk0 = (long long)split * p.blocks_per_split;
+  long long blk1 = blk0 + p.blocks_per_split;
+  if (blk1 > p.num_blocks) blk1 = p.num_blocks;
+  const long long nblk = blk1 > blk0 ? blk1 - blk0 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bars->full[s]), 1);
+      mbar_init(smem_u32(&bars->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bars->acc_full[0]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmN);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long i = 0; i < nblk; ++i) {
+        long long blk = blk0 + i;
+        const int bw = (int)(blk % p.blocks_w); blk /= p.blocks_w;
+        const int bh = (int)(blk % p.blocks_h);
+        const int b = (int)(blk / p.blocks_h);
+        const int w0 = bw * WG_KPIX_W, h0 = bh * WG_KPIX_H;
+        mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
+        const uint32_t full = smem_u32(&bars->full[stage]);
+        mbar_expect_tx(full, (uint32_t)(2 + ntap * p.n_groups) * WG_BOX_BYTES);
+        uint32_t dst = ring_u32 + stage * p.stage_bytes;
+        tma_load_4d(dst, &tmW, full, mt * 128, w0, h0, b);
+        tma_load_4d(dst + WG_BOX_BYTES, &tmW, full, mt * 128 + 64, w0, h0, b);
+        dst += 2 * WG_BOX_BYTES;
+        for (int t = 0; t < ntap; ++t) {
+          const int tap = tap0 + t;
+          int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+          int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+          if (!p.narrow_is_x) { dy = -dy; dx = -dx; }
+          for (int g = 0; g < p.n_groups; ++g) {
+            tma_load_4d(dst, &tmN, full, g * 64, w0 + dx, h0 + dy, b);
+            dst += WG_BOX_BYTES;
+          }
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D=f32, A=B=bf16, both MN-major (bits 15, 16), N = n_pad, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      for (long long i = 0; i < nblk; ++i) {
+        mbar_wait(smem_u32(&bars->full[stage]), phase);
+        tc_fence_after();
+        const uint32_t a_addr = ring_u32 + stage * p.stage_bytes;
+        for (int t = 0; t < ntap; ++t) {
+          const uint32_t b_addr = a_addr + (2 + t * p.n_groups) * WG_BOX_BYTES;
+#pragma unroll
+          for (int k = 0; k < WG_KPIX / 16; ++k) {
+            // MN-major SW128: LBO = distance between 64-channel boxes, SBO = 8 pixel rows (1024 B);
+            // 16 pixels per MMA = 2048 B further into each box
+            uint64_t ad = make_desc(a_addr + k * 2048, 1024, 2);
+            uint64_t bd = make_desc(b_addr + k * 2048, 1024, 2);
+            ad = (ad & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)(WG_BOX_BYTES >> 4) << 16);
+            bd = (bd & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)(WG_BOX_BYTES >> 4) << 16);
+            umma_bf16(tmem_base + t * p.n_pad, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&bars->empty[stage]));
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(smem_u32(&bars->acc_full[0]));
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int m = mt * 128 + quarter * 32 + lane;            // wide-operand channel of this thread's row
+    const bool m_ok = m < p.Cw;
+    if (nblk > 0) {
+      mbar_wait(smem_u32(&bars->acc_full[0]), 0);
+      tc_fence_after();
+    }
+    for (int t = 0; t < ntap; ++t) {
+      float* dst = p.partial + (((long long)split * p.taps + tap0 + t) * p.Cw + m) * p.Cn;
+      for (int c = 0; c < p.Cn; c += 16) {
+        uint32_t v[16];
+        if (nblk > 0) {
+          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + t * p.n_pad + c, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+        if (m_ok) {
+          const int nc = min(16, p.Cn - c);
+          for (int j = 0; j < nc; ++j) dst[c + j] = __uint_as_float(v[j]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// dw[co][ci][tap] (+)= sum_split partial[split][tap][m][n]; (co,ci) = (m,n) when the wide operand is dy, else (n,m)
+__global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cw, int Cn,
+                                                              int wide_is_dy, int Cout, int Cin, float* __restrict__ dw, int accumulate) {
+  const long long per = (long long)taps * Cw * Cn;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % Cn);
+    long long r = idx / Cn;
+    const int m = (int)(r % Cw);
+    const int tap = (int)(r / Cw);
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[k * per + idx];
+    const int co = wide_is_dy ? m : n, ci = wide_is_dy ? n : m;
+    float* o = dw + ((long long)co * Cin + ci) * taps + tap;
+    *o = accumulate ? *o + s : s;
+  }
+}
+
+struct WgradPlan {
+  int wide_is_dy, Cw, Cn, n_pad, n_groups, taps_per_cta, tap_groups, m_tiles, splits, stages;
+  int blocks_h, blocks_w;
+  long long num_blocks, blocks_per_split;
+  uint32_t stage_bytes;
+};
+
+static bool plan_wgrad(const sininn_wgrad_desc* d, WgradPlan& w) {
+  w.wide_is_dy = d->Cout >= d->Cin ? 1 : 0;
+  w.Cw = w.wide_is_dy ? d->Cout : d->Cin;
+  w.Cn = w.wide_is_dy ? d->Cin : d->Cout;
+  w.n_pad = (w.Cn + 15) / 16 * 16;
+  if (w.n_pad > 256) return false;
+  w.n_groups = (w.n_pad + 63) / 64;
+  int by_tmem = TMEM_COLS / w.n_pad;
+  int by_smem = (int)((56 * 1024 - 2 * WG_BOX_BYTES) / (w.n_groups * WG_BOX_BYTES));
+  int t = by_tmem < by_smem ? by_tmem : by_smem;
+  if (t < 1) t = 1;
+  if (t > d->taps) t = d->taps;
+  w.taps_per_cta = t;
+  w.tap_groups = (d->taps + t - 1) / t;
+  w.m_tiles = (w.Cw + 127) / 128;
+  w.stage_bytes = (2 + t * w.n_groups) * WG_BOX_BYTES;
+  w.stages = SMEM_RING_BUDGET / (int)w.stage_bytes;
+  if (w.stages > MAX_STAGES) w.stages = MAX_STAGES;
+  if (w.stages < 2) return false;
+  w.blocks_h = (d->H + WG_KPIX_H - 1) / WG_KPIX_H;
+  w.blocks_w = (d->W + WG_KPIX_W - 1) / WG_KPIX_W;
+  w.num_blocks = (long long)d->B * w.blocks_h * w.blocks_w;
+  long long items = (long long)w.m_tiles * w.tap_groups;
+  long long s = (sm_count() + items - 1) / items;
+  if (s > w.num_blocks) s = w.num_blocks;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  w.blocks_per_split = (w.num_blocks + s - 1) / s;
+  w.splits = (int)((w.num_blocks + w.blocks_per_split - 1) / w.blocks_per_split);
+  return true;
+}
+
+}  // namespace tc
+}  // namespace sininn
+
+using namespace sininn;
+
+extern "C" {
+
+size_t sininn_wgrad_workspace_bytes(const sininn_wgrad_desc* d, int tensor_core) {
+  if (!d || d->Cin <= 0 || d->Cout <= 0 || d->taps <= 0) return 0;
+  size_t simt = (size_t)wgrad_simt_splits(d) * d->taps * d->Cout * d->Cin * sizeof(float);
+  if (!tensor_core) return simt;
+  sininn::tc::WgradPlan w;
+  if (!sininn::tc::plan_wgrad(d, w)) return simt;
+  size_t tcb = (size_t)w.splits * d->taps * d->Cout * d->Cin * sizeof(float);
+  return tcb > simt ? tcb : simt;
+}
+
+int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
+  using namespace sininn::tc;
+  SININN_CHECK_ARG(d && d->x && d->dy && d->dw, "wgrad_tc: null pointer");
+  SININN_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "wgrad_tc: bad shape");
+  SININN_CHECK_ARG(d->taps == 1 || d->taps == 9, "wgrad_tc: taps must be 1 or 9");
+  SININN_CHECK_ARG(d->x_dtype == SININN_BF16 && d->dy_dtype == SININN_BF16, "wgrad_tc: operands must be bf16");
+  SININN_CHECK_ARG(aligned16(d->x) && aligned16(d->dy) && (d->x_stride % 8) == 0 && (d->dy_stride % 8) == 0,
+                   "wgrad_tc: TMA needs 16-byte aligned operands with pixel strides that are multiples of 8 channels "
+                   "(x stride %d, dy stride %d)", d->x_stride, d->dy_stride);
+  WgradPlan w;
+  if (!plan_wgrad(d, w)) {
+    set_error("wgrad_tc: unsupported shape (Cin=%d Cout=%d)", d->Cin, d->Cout);
+    return SININN_EUNSUPPORTED;
+  }
+  const size_t need = (size_t)w.splits * d->taps * d->Cout * d->Cin * sizeof(float);
+  if (!d->workspace || d->workspace_bytes < need) {
+    set_error("wgrad_tc: workspace too small (%zu < %zu)", d->workspace_bytes, need);
+    return SININN_EWORKSPACE;
+  }
+  EncodeTiledFn encode = get_encode();
+  if (!encode) {
+    set_error("wgrad_tc: cuTensorMapEncodeTiled not available from the driver");
+    return SININN_ECUDA;
+  }
+  const void* wide = w.wide_is_dy ? d->dy : d->x;
+  const void* narrow = w.wide_is_dy ? d->x : d->dy;
+  const int wide_stride = w.wide_is_dy ? d->dy_stride : d->x_stride;
+  const int narrow_stride = w.wide_is_dy ? d->x_stride : d->dy_stride;
+  CUtensorMap tmW, tmN;
+  for (int which = 0; which < 2; ++which) {
+    const void* base = which == 0 ? wide : narrow;
+    const int C = which == 0 ? w.Cw : w.Cn;
+    const int stride = which == 0 ? wide_stride : narrow_stride;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)stride * 2, (cuuint64_t)d->W * stride * 2, (cuuint64_t)d->H * d->W * stride * 2};
+    cuuint32_t box[4] = {64, WG_KPIX_W, WG_KPIX_H, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(which == 0 ? &tmW : &tmN, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("wgrad_tc: cuTensorMapEncodeTiled failed with %d (C=%d stride=%d)", (int)r, C, stride);
+      return SININN_ECUDA;
+    }
+  }
+  WgradParams p;
+  p.B = d->B; p.H = d->H; p.W = d->W; p.taps = d->taps;
+  p.narrow_is_x = w.wide_is_dy;
+  p.Cw = w.Cw; p.Cn = w.Cn; p.n_pad = w.n_pad; p.n_groups = w.n_groups;
+  p.taps_per_cta = w.taps_per_cta; p.tap_groups = w.tap_groups; p.m_tiles = w.m_tiles; p.splits = w.splits;
+  p.blocks_h = w.blocks_h; p.blocks_w = w.blocks_w; p.num_blocks = w.num_blocks; p.blocks_per_split = w.blocks_per_split;
+  p.stages = w.stages; p.stage_bytes = w.stage_bytes; p.tx_bytes = w.stage_bytes;
+  p.partial = reinterpret_cast<float*>(d->workspace);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("wgrad_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return SININN_ECUDA;
+    }
+    attr_set[dev] = true;
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + sizeof(Barriers) + 1024;
+  const unsigned grid = (unsigned)(w.m_tiles * w.tap_groups * w.splits);
+  cudaStream_t st = as_stream(stream);
+  wgrad_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(tmW, tmN, p);
+  const long long per = (long long)d->taps * w.Cw * w.Cn;
+  long long g = (per + 255) / 256;
+  if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
+  wgrad_tc_reduce_kernel<<<(int)g, 256, 0, st>>>(p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
+                                                 d->dw, d->accumulate);
+  SININN_CHECK_LAUNCH("wgrad_tc");
+  return SININN_OK;
+}
+
+}  // extern "C"

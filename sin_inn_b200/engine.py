@@ -171,23 +171,29 @@ class ConvSubnet:
     def parameters(self):
         return [p for p in (self.c1.weight, self.c1.bias, self.c2.weight, self.c2.bias) if p is not None]
 
-    def fwd(self, ctx, tr, src):
+    def fwd(self, ctx, tr, src, keep=False):
         x = tr.operand(src, ctx.adt)
         dev = x.device
         h = torch.empty(tr.npix, self.hidden, dtype=ctx.adt, device=dev)
+        # tensor-core path: the backward pass reads the ReLU mask as 1 bit / element instead of re-reading h
+        bits = (torch.empty(tr.npix, (self.hidden + 31) // 32, dtype=torch.int32, device=dev)
+                if (keep and ctx.tc) else None)
         K.conv(x, packed(self.c1.weight, 0, ctx.adt), tr.geom, self.hidden, h, bias=self.c1.bias, act=ACT_RELU,
-               tensor_core=ctx.tc)
+               tensor_core=ctx.tc, bits_out=bits)
         a = torch.empty(tr.npix, self.cout, dtype=torch.float32, device=dev)
         K.conv(h, packed(self.c2.weight, 0, ctx.adt), tr.geom, self.cout, a, bias=self.c2.bias, tensor_core=ctx.tc)
-        return a, (x, h)
+        return a, (x, h, bits)
 
     def bwd(self, ctx, tr, saved, da, dsrc):
         """da: dL/d(output) [npix, cout] in the activation dtype; accumulates dL/d(input) into dsrc (fp32 view)."""
-        x, h = saved
+        x, h, bits = saved
         dev = x.device
         dh = torch.empty_like(h)
-        K.conv(da, packed(self.c2.weight, 1, ctx.adt), tr.geom, self.hidden, dh, mask=h, mask_act=ACT_RELU,
-               tensor_core=ctx.tc)
+        if bits is not None:
+            K.conv(da, packed(self.c2.weight, 1, ctx.adt), tr.geom, self.hidden, dh, mask_bits=bits, tensor_core=True)
+        else:
+            K.conv(da, packed(self.c2.weight, 1, ctx.adt), tr.geom, self.hidden, dh, mask=h, mask_act=ACT_RELU,
+                   tensor_core=ctx.tc)
         if self.c2.weight.requires_grad:
             ctx.add_grad(self.c2.weight, K.wgrad(h, da, tr.geom, self.taps, torch.empty_like(self.c2.weight),
                                                  tensor_core=ctx.tc))
@@ -224,7 +230,7 @@ class DenseSubnet:
             out += [p for p in (c.weight, c.bias) if p is not None]
         return out
 
-    def fwd(self, ctx, tr, src):
+    def fwd(self, ctx, tr, src, keep=False):
         dev = tr.U.device
         cat = torch.empty(tr.npix, _round_up(self.ctot, 8), dtype=ctx.adt, device=dev)
         K.cast_slice(tr.mat()[:, src[0]:src[1]], cat[:, :self.cin])
@@ -389,14 +395,14 @@ class CouplingOp:
             dsrc = tr.dmat()[:, st.src[0]:st.src[1]]
             dev = u.device
             if st.kind == "glow":
-                a, saved = st.nets[0].fwd(ctx, tr, st.src)
+                a, saved = st.nets[0].fwd(ctx, tr, st.src, keep=True)
                 da = torch.empty(tr.npix, 2 * L, dtype=ctx.adt, device=dev)
                 tr.invalidate(*st.dst)
                 bf = K.coupling_bwd(u, du, a[:, :L], a[:, L:], GLOW, st.clamp, rev, da[:, :L], da[:, L:], want_bf)
                 st.nets[0].bwd(ctx, tr, saved, da, dsrc)
             elif st.kind == "irn_affine":
-                s, saved_s = st.nets[0].fwd(ctx, tr, st.src)
-                t, saved_t = st.nets[1].fwd(ctx, tr, st.src)
+                s, saved_s = st.nets[0].fwd(ctx, tr, st.src, keep=True)
+                t, saved_t = st.nets[1].fwd(ctx, tr, st.src, keep=True)
                 Lp = _round_up(L, 8)
                 ds = torch.empty(tr.npix, Lp, dtype=ctx.adt, device=dev)[:, :L]
                 dt = torch.empty(tr.npix, Lp, dtype=ctx.adt, device=dev)[:, :L]
@@ -406,7 +412,7 @@ class CouplingOp:
                 st.nets[1].bwd(ctx, tr, saved_t, dt, dsrc)
             else:
                 sign = -1.0 if rev else 1.0
-                f, saved = st.nets[0].fwd(ctx, tr, st.src)
+                f, saved = st.nets[0].fwd(ctx, tr, st.src, keep=True)
                 tr.invalidate(*st.dst)
                 K.axpy_slice(u, f, -sign)                       # restore dst
                 df = torch.empty(tr.npix, _round_up(L, 8), dtype=ctx.adt, device=dev)[:, :L]

@@ -221,7 +221,7 @@ def pack_weight(w, mode, dtype, rows_pad, k_pad):
 
 
 def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask_act=0, accumulate=False, alpha=1.0,
-         tensor_core=False):
+         tensor_core=False, mask_bits=None, bits_out=None):
     """Implicit-GEMM 1x1 / 3x3 convolution on channels-last views.
     x: [npix, Cin] view; wpack: [taps, rows_pad, k_pad]; geom = (B, H, W); out: [npix, cout] view."""
     x, out = _view2d(x), _view2d(out)
@@ -244,6 +244,9 @@ def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask
     else:
         d.mask, d.mask_stride, d.mask_act = 0, 0, 0
     d.accumulate, d.alpha = int(accumulate), float(alpha)
+    if (mask_bits is not None or bits_out is not None) and not tensor_core:
+        raise _lib.SininnError("conv: sign-bit masks are a tensor-core-path feature")
+    d.mask_bits, d.bits_out = _p(mask_bits), _p(bits_out)
     lib = load()
     fn = lib.sininn_conv_tc if tensor_core else lib.sininn_conv_simt
     flops = 2.0 * B * H * W * d.Cin * d.Cout * d.taps

@@ -134,8 +134,24 @@ def _shift(x4, dy, dx):
     return xp[:, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W]
 
 
+def _unpack_bits(bits, cout):
+    w = bits.to(torch.int64) & 0xffffffff
+    sh = torch.arange(32)
+    return ((w.unsqueeze(-1) >> sh) & 1).reshape(bits.shape[0], -1)[:, :cout].float()
+
+
+def _pack_bits(vals):
+    npix, c = vals.shape
+    words = (c + 31) // 32
+    b = torch.zeros(npix, words * 32, dtype=torch.int64)
+    b[:, :c] = (vals > 0).to(torch.int64)
+    w = (b.reshape(npix, words, 32) << torch.arange(32)).sum(-1)
+    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)
+    return w.to(torch.int32)
+
+
 def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask_act=0, accumulate=False, alpha=1.0,
-         tensor_core=False):
+         tensor_core=False, mask_bits=None, bits_out=None):
     B, H, W = geom
     cin = x.shape[1]
     taps = wpack.shape[0]
@@ -154,7 +170,11 @@ def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask
     if mask is not None:
         m = mask.float()
         acc = acc * torch.where(m > 0, torch.ones_like(m), torch.full_like(m, slope if mask_act == 2 else 0.0))
+    if mask_bits is not None:
+        acc = acc * _unpack_bits(mask_bits, cout)
     acc = acc * alpha
+    if bits_out is not None:
+        bits_out.copy_(_pack_bits(acc))
     if accumulate:
         acc = acc + out.float()
     out.copy_(acc.to(out.dtype))

@@ -83,7 +83,13 @@ def test_coupling_apply_and_bwd(K, kind, clamp, npix, C, L):
         u = U.clone().to(DEV)
         a = A.to(DEV)
         bf = K.coupling_apply(u[:, :L], a[:, :L], a[:, L:], kind, clamp, inverse, want_bf16=True)
-        assert (u.cpu() - u_ref).abs().max() <= 2e-6 * u_ref.abs().max()
+        # fp64 ground truth: the GPU must be as close to it as fp32 arithmetic allows (the division by a small
+        # exp(g) amplifies rounding, so the bound is relative to the fp32 CPU result's own error, with slack)
+        u64 = U.clone().double()
+        FK.coupling_apply(u64[:, :L], A[:, :L].double(), A[:, L:].double(), kind, clamp, inverse)
+        err_gpu = (u.cpu().double() - u64).abs().max().item()
+        err_cpu = (u_ref.double() - u64).abs().max().item()
+        assert err_gpu <= max(4 * err_cpu, 4e-6 * u64.abs().max().item()), (err_gpu, err_cpu)
         assert torch.equal(u.cpu()[:, L:], U[:, L:])                    # untouched half
         assert (bf.float().cpu() - u_ref[:, :L]).abs().max() <= 8e-3 * u_ref[:, :L].abs().max()
         # backward from the output restores the input and matches autograd
@@ -197,7 +203,7 @@ def test_conv_simt(K, taps, cin, cout, geom, dt):
 
 
 TC_SHAPES = [(9, 24, 256, (2, 16, 16)), (9, 256, 48, (1, 8, 24)), (1, 24, 256, (2, 8, 8)), (1, 256, 192, (1, 5, 9)),
-             (9, 96, 256, (1, 5, 9)), (9, 256, 192, (3, 32, 32)), (9, 48, 256, (1, 17, 33)), (1, 192, 256, (1, 4, 4)),
+             (9, 96, 256, (1, 5, 9)), (9, 256, 192, (2, 8, 32)), (9, 48, 256, (1, 17, 33)), (1, 192, 256, (1, 4, 4)),
              (9, 56, 32, (1, 12, 20)), (9, 152, 24, (1, 9, 7)), (9, 32, 400, (1, 8, 16))]
 
 
@@ -209,6 +215,43 @@ def test_conv_tc(K, taps, cin, cout, geom):
     _conv_case(K, taps, cin, cout, geom, bf, bf, True, {"act": 1})
     _conv_case(K, taps, cin, cout, geom, bf, bf, True, {"mask": True, "mask_act": 1})
     _conv_case(K, taps, cin, cout, geom, bf, torch.float32, True, {"accumulate": True, "alpha": -1.0, "act": 2})
+
+
+@pytest.mark.parametrize("taps,cin,cout,geom", [(9, 24, 256, (2, 16, 16)), (1, 96, 256, (1, 5, 9)), (9, 48, 256, (1, 17, 33)),
+                                               (9, 192, 256, (2, 8, 20)), (9, 32, 72, (1, 7, 7))])
+def test_conv_tc_sign_bits(K, taps, cin, cout, geom):
+    """fprop emits the ReLU sign bits of its output; the masked data-gradient consumes them (1 bit / element)."""
+    B, H, W = geom
+    npix = B * H * W
+    k = 3 if taps == 9 else 1
+    bf = torch.bfloat16
+    x = rnd(npix, cin, seed=60).to(bf)
+    w = (rnd(cout, cin, k, k, seed=61) * 0.1)
+    bias = rnd(cout, seed=62)
+    rp, kp = (cout + 15) // 16 * 16, (cin + 15) // 16 * 16
+    wp = K.pack_weight(w.to(DEV), 0, bf, rp, kp)
+    words = (cout + 31) // 32
+    h = torch.empty(npix, cout, dtype=bf, device=DEV)
+    bits = torch.zeros(npix, words, dtype=torch.int32, device=DEV)
+    K.conv(x.to(DEV), wp, geom, cout, h, bias=bias.to(DEV), act=1, tensor_core=True, bits_out=bits)
+    href = torch.empty(npix, cout, dtype=bf)
+    FK.conv(x, FK.pack_weight(w, 0, bf, rp, kp), geom, cout, href, bias=bias, act=1)
+    got_bits = FK._unpack_bits(bits.cpu(), cout)
+    # bits must agree with the kernel's own output (ties at exactly 0 cannot disagree: bit = value > 0)
+    assert torch.equal(got_bits, (h.cpu().float() > 0).float())
+    assert (h.cpu().float() - href.float()).abs().max() <= 1e-2 * max(1.0, href.float().abs().max().item())
+    # masked dgrad: dy [npix, cin2] -> [npix, cout] zeroed where h == 0
+    cin2 = 48
+    dy = rnd(npix, cin2, seed=63).to(bf)
+    w2 = rnd(cin2, cout, k, k, seed=64) * 0.1
+    wd = K.pack_weight(w2.to(DEV), 1, bf, rp, (cin2 + 15) // 16 * 16)
+    dh = torch.empty(npix, cout, dtype=bf, device=DEV)
+    K.conv(dy.to(DEV), wd, geom, cout, dh, mask_bits=bits, tensor_core=True)
+    ref = torch.empty(npix, cout, dtype=bf)
+    FK.conv(dy, FK.pack_weight(w2, 1, bf, rp, (cin2 + 15) // 16 * 16), geom, cout, ref, mask=h.cpu(), mask_act=1)
+    assert (dh.cpu().float() - ref.float()).abs().max() <= 1e-2 * max(1.0, ref.float().abs().max().item())
+    assert torch.equal(dh.cpu().float() == 0, (ref.float() == 0) | (dh.cpu().float() == 0))
+    assert bool(((h.cpu().float() == 0) <= (dh.cpu().float() == 0)).all())
 
 
 def test_conv_tc_matches_simt_bitwise_inputs(K):
@@ -263,3 +306,30 @@ def test_bad_arguments_are_reported(K):
         K.resample_nchw(torch.zeros(1, 3, 4, 8), 0, 0)                      # CPU tensor
     with pytest.raises(SininnError):
         K.coupling_apply(torch.zeros(4, 4, device=DEV), torch.zeros(4, 4, device=DEV), torch.zeros(4, 4, device=DEV), 7, 1.0, 0)
+
+
+WG_SHAPES = [(9, 24, 256, (2, 16, 16)), (9, 256, 48, (2, 16, 16)), (1, 24, 256, (2, 8, 8)), (1, 256, 192, (1, 5, 9)),
+             (9, 96, 256, (1, 12, 20)), (9, 256, 192, (1, 16, 32)), (9, 152, 32, (1, 9, 7)), (9, 236, 108, (1, 6, 10)),
+             (9, 56, 32, (3, 7, 33)), (1, 96, 256, (2, 6, 6)), (9, 512, 192, (1, 8, 8)), (9, 96, 512, (1, 8, 8))]
+
+
+@pytest.mark.parametrize("taps,cin,cout,geom", WG_SHAPES)
+def test_wgrad_tc(K, taps, cin, cout, geom):
+    B, H, W = geom
+    npix = B * H * W
+    k = 3 if taps == 9 else 1
+    bf = torch.bfloat16
+    x = rnd(npix, (cin + 15) // 8 * 8, seed=50).to(bf)        # TMA: pixel stride must be a multiple of 8 channels
+    dy = rnd(npix, (cout + 15) // 8 * 8, seed=51).to(bf)
+    dw0 = rnd(cout, cin, k, k, seed=52)
+    ref = dw0.clone()
+    FK.wgrad(x[:, :cin], dy[:, :cout], geom, taps, ref, accumulate=True)
+    got = dw0.clone().to(DEV)
+    K.wgrad(x.to(DEV)[:, :cin], dy.to(DEV)[:, :cout], geom, taps, got, accumulate=True, tensor_core=True)
+    err = (got.cpu() - ref).abs().max().item()
+    assert err <= 2e-5 * max(1.0, ref.abs().max().item()) * max(1.0, (npix / 256) ** 0.5), err
+    got2 = torch.empty_like(got)
+    K.wgrad(x.to(DEV)[:, :cin], dy.to(DEV)[:, :cout], geom, taps, got2, accumulate=False, tensor_core=True)
+    got3 = torch.empty_like(got)
+    K.wgrad(x.to(DEV)[:, :cin], dy.to(DEV)[:, :cout], geom, taps, got3, accumulate=False, tensor_core=True)
+    assert torch.equal(got2, got3)                       # deterministic
