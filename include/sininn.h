@@ -151,6 +151,10 @@ int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream);     /* tc
 int sininn_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, int mode,
                             void* out, int out_dtype, int rows_pad, int k_pad, sininn_stream_t stream);
 
+/* The same re-layout for MANY weights in one launch.  jobs: device array of njobs x 8 int64
+ * {src fp32 OIHW ptr, dst ptr, Cout, Cin, taps, mode, rows_pad, k_pad}; all outputs share out_dtype. */
+int sininn_pack_conv_weights_batched(const void* jobs, int njobs, int out_dtype, sininn_stream_t stream);
+
 /* Weight gradient  dw[co][ci][tap] (+)= sum_p dy[p][co] * x[p+off(tap)][ci]  (OIHW fp32),
  * deterministic split over pixels + fixed-order reduction (no float atomics). */
 typedef struct {

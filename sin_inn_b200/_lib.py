@@ -72,6 +72,7 @@ SIGNATURES = {
     "sininn_conv_simt": (C.c_int, [C.POINTER(ConvDesc), _vp]),
     "sininn_conv_tc": (C.c_int, [C.POINTER(ConvDesc), _vp]),
     "sininn_pack_conv_weight": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "sininn_pack_conv_weights_batched": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "sininn_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(WgradDesc), C.c_int]),
     "sininn_wgrad_simt": (C.c_int, [C.POINTER(WgradDesc), _vp]),
     "sininn_wgrad_tc": (C.c_int, [C.POINTER(WgradDesc), _vp]),

@@ -146,6 +146,30 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
   }
 }
 
+// all conv weights of a network in ONE launch: jobs[j] = {src, dst, Cout, Cin, taps, mode, rows_pad, k_pad}
+template <typename TO>
+__global__ void __launch_bounds__(256) pack_weight_batched_kernel(const long long* __restrict__ jobs) {
+  const long long* j = jobs + (long long)blockIdx.y * 8;
+  const float* w = reinterpret_cast<const float*>(j[0]);
+  TO* out = reinterpret_cast<TO*>(j[1]);
+  const int Cout = (int)j[2], Cin = (int)j[3], taps = (int)j[4], mode = (int)j[5], rows_pad = (int)j[6], k_pad = (int)j[7];
+  const long long total = (long long)taps * rows_pad * k_pad;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(idx % k_pad);
+    long long r = idx / k_pad;
+    int row = (int)(r % rows_pad);
+    int tap = (int)(r / rows_pad);
+    float v = 0.f;
+    if (mode == 0) {
+      if (row < Cout && k < Cin) v = w[((long long)row * Cin + k) * taps + tap];
+    } else {
+      if (row < Cin && k < Cout) v = w[((long long)k * Cin + row) * taps + (taps - 1 - tap)];
+    }
+    out[idx] = from_f32<TO>(v);
+  }
+}
+
 // ---------------------------------------------------------------- weight gradient
 // partial[split][tap][co][ci] = sum over the split's pixels of dy[p][co] * x[p+off(tap)][ci]
 struct WgradArgs {
@@ -328,6 +352,16 @@ int sininn_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, in
   else if (out_dtype == SININN_BF16) pack_weight_kernel<__nv_bfloat16><<<(int)g, 256, 0, st>>>(w_oihw, Cout, Cin, taps, mode, (__nv_bfloat16*)out, rows_pad, k_pad);
   else SININN_CHECK_ARG(false, "pack_conv_weight: bad out_dtype");
   SININN_CHECK_LAUNCH("pack_conv_weight");
+  return SININN_OK;
+}
+
+int sininn_pack_conv_weights_batched(const void* jobs, int njobs, int out_dtype, sininn_stream_t stream) {
+  SININN_CHECK_ARG(jobs && njobs > 0, "pack_conv_weights_batched: bad arguments");
+  dim3 grid(64, njobs);
+  if (out_dtype == SININN_F32) pack_weight_batched_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const long long*)jobs);
+  else if (out_dtype == SININN_BF16) pack_weight_batched_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const long long*)jobs);
+  else SININN_CHECK_ARG(false, "pack_conv_weights_batched: bad out_dtype");
+  SININN_CHECK_LAUNCH("pack_conv_weights_batched");
   return SININN_OK;
 }
 

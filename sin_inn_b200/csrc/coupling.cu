@@ -171,6 +171,42 @@ __global__ void __launch_bounds__(CS_COLS* CS_ROWS) colsum_partial_kernel(const 
     partial[(long long)blockIdx.x * N + col] = sum;
   }
 }
+// Vectorised variant: every thread owns one 16-byte column group (8 bf16 / 4 fp32) and walks the rows of its
+// block's chunk with stride RPI (rows per iteration = 256 / groups); rows are read as full coalesced lines.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const T* __restrict__ in, int in_stride, long long npix, int N,
+                                                                 long long rows_per_chunk, float* __restrict__ partial) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  extern __shared__ float red[];                        // [RPI][G*VEC]
+  const int G = N / VEC;
+  const int RPI = 256 / G;
+  const int g = threadIdx.x % G, rl = threadIdx.x / G;
+  const long long r0 = blockIdx.x * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > npix) r1 = npix;
+  float acc[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+  if (rl < RPI) {
+    for (long long r = r0 + rl; r < r1; r += RPI) {
+      const T* src = in + r * in_stride + g * VEC;
+#pragma unroll
+      for (int q = 0; q < VEC / 4; ++q) {
+        const float4 t = load4(src + 4 * q);
+        acc[4 * q] += t.x; acc[4 * q + 1] += t.y; acc[4 * q + 2] += t.z; acc[4 * q + 3] += t.w;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) red[rl * N + g * VEC + e] = acc[e];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < N; c += 256) {
+    float sum = 0.f;
+    for (int k = 0; k < RPI; ++k) sum += red[k * N + c];
+    partial[(long long)blockIdx.x * N + c] = sum;
+  }
+}
+
 __global__ void colsum_finish_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out, int accumulate) {
   int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= N) return;
@@ -352,7 +388,14 @@ int sininn_colsum(const void* in, int dtype, int in_stride, long long npix, int 
   dim3 grid((unsigned)chunks, (N + CS_COLS - 1) / CS_COLS), block(CS_COLS, CS_ROWS);
   cudaStream_t st = as_stream(stream);
   float* partial = reinterpret_cast<float*>(workspace);
-  if (dtype == SININN_F32) colsum_partial_kernel<float><<<grid, block, 0, st>>>((const float*)in, in_stride, npix, N, rows_per_chunk, partial);
+  const int vec = dtype == SININN_F32 ? 4 : 8;
+  const bool vec_ok = (N % vec) == 0 && (N / vec) <= 256 && (in_stride % vec) == 0 && aligned16(in);
+  if (vec_ok) {
+    const int rpi = 256 / (N / vec);
+    const size_t sm = (size_t)rpi * N * sizeof(float);
+    if (dtype == SININN_F32) colsum_partial_vec_kernel<float><<<(unsigned)chunks, 256, sm, st>>>((const float*)in, in_stride, npix, N, rows_per_chunk, partial);
+    else colsum_partial_vec_kernel<__nv_bfloat16><<<(unsigned)chunks, 256, sm, st>>>((const __nv_bfloat16*)in, in_stride, npix, N, rows_per_chunk, partial);
+  } else if (dtype == SININN_F32) colsum_partial_kernel<float><<<grid, block, 0, st>>>((const float*)in, in_stride, npix, N, rows_per_chunk, partial);
   else colsum_partial_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, in_stride, npix, N, rows_per_chunk, partial);
   colsum_finish_kernel<<<(N + 127) / 128, 128, 0, st>>>(partial, (int)chunks, N, out, accumulate);
   SININN_CHECK_LAUNCH("colsum");

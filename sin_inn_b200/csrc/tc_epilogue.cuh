@@ -1,0 +1,233 @@
+// Shared pieces of the tcgen05 convolution kernels (conv_tc.cu, conv_tc_halo.cu): parameter block and the
+// TMA-store epilogue (TMEM -> registers -> 128B-swizzled smem staging -> tensor store / reduce-add).
+#pragma once
+#include "tc_common.cuh"
+
+namespace sininn {
+namespace tc {
+
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int ACC_STRIDE = 256;          // columns between the two accumulator buffers
+constexpr int STAGING_BYTES = 32 * 128;  // one epilogue warp: 32 rows x 128 B
+constexpr int EPI_SMEM_BYTES = 256 * 4 + NUM_EPI_WARPS * STAGING_BYTES;
+constexpr int SMEM_RING_BUDGET = 227 * 1024 - EPI_SMEM_BYTES - BARRIER_BYTES - 1024;   // 1024: worst-case alignment pad
+
+struct Params {
+  int B, H, W, Cin, Cout;
+  int taps, kc, k_chunks;        // kc = channels per K step (16/32/64), k_chunks = ceil(Cin / kc)
+  int n_tile, n_tiles;           // output channels per CTA tile (multiple of 16, <= 256), tiles along N
+  int tiles_h, tiles_w;
+  long long num_tiles;           // B * tiles_h * tiles_w * n_tiles
+  int stages;
+  uint32_t a_bytes, b_bytes;     // smem bytes per stage (each a multiple of 1024)
+  uint32_t tx_bytes;             // bytes TMA delivers per stage (A box + B box)
+  uint32_t sbo;                  // 8 rows * row bytes
+  uint32_t layout_type;          // UMMA smem-descriptor swizzle code
+  const float* bias;
+  void* out; int out_f32; int out_stride;
+  int act; float slope;
+  const void* mask; int mask_stride; int mask_act;     // element mask (fallback path only)
+  const uint32_t* bits_in;       // ReLU sign bits of the activation this gradient flows through, [npix][bit_words]
+  uint32_t* bits_out;            // sign bits of this kernel's own output, [npix][bit_words]
+  int bit_words;
+  int accumulate; float alpha;
+  int tma_out;                   // 1: TMA-store epilogue; 0: per-thread fallback (unaligned output slices)
+};
+
+template <int TW>
+__device__ __forceinline__ void tile_coords(const Params& p, long long t, int& b, int& h0, int& w0, int& n0) {
+  constexpr int TH = 128 / TW;
+  int nt = (int)(t % p.n_tiles); t /= p.n_tiles;
+  int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
+  int th = (int)(t % p.tiles_h);
+  b = (int)(t / p.tiles_h);
+  h0 = th * TH; w0 = tw * TW; n0 = nt * p.n_tile;
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// per-thread fallback for output slices TMA cannot address (unaligned base / stride)
+template <typename TO>
+__device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&v)[16], long long pix, int col0, bool row_ok) {
+  if (!row_ok) return;
+  TO* __restrict__ out = reinterpret_cast<TO*>(p.out) + pix * p.out_stride + col0;
+  const TO* __restrict__ mask = p.mask ? reinterpret_cast<const TO*>(p.mask) + pix * p.mask_stride + col0 : nullptr;
+  const int ncol = min(16, p.Cout - col0);
+  for (int j = 0; j < ncol; ++j) {
+    float x = __uint_as_float(v[j]);
+    if (p.bias != nullptr) x += __ldg(p.bias + col0 + j);
+    x = act_fwd(p.act, p.slope, x);
+    if (mask != nullptr) x *= act_grad(p.mask_act, p.slope, to_f32(mask[j]));
+    if (p.bits_in != nullptr) {
+      const uint32_t w = p.bits_in[pix * p.bit_words + ((col0 + j) >> 5)];
+      if (!((w >> ((col0 + j) & 31)) & 1u)) x = 0.f;
+    }
+    x *= p.alpha;
+    if (p.accumulate) x += to_f32(out[j]);
+    out[j] = from_f32<TO>(x);
+  }
+}
+
+// One 128-byte output slab (64 bf16 or 32 fp32 columns) of a warp's 32 accumulator rows:
+// registers -> (+bias, activation, sign-bit mask, alpha) -> 128B-swizzled staging rows in shared memory.
+// v holds the slab's accumulator columns; returns the sign bits of the produced values (bit j = value j > 0).
+template <int NCOL>
+__device__ __forceinline__ void slab_math(const Params& p, float (&x)[NCOL], const float* bias_s, const uint32_t* mbits) {
+#pragma unroll
+  for (int q = 0; q < NCOL / 4; ++q) {
+    const float4 bq = *reinterpret_cast<const float4*>(bias_s + 4 * q);
+    x[4 * q + 0] = act_fwd(p.act, p.slope, x[4 * q + 0] + bq.x);
+    x[4 * q + 1] = act_fwd(p.act, p.slope, x[4 * q + 1] + bq.y);
+    x[4 * q + 2] = act_fwd(p.act, p.slope, x[4 * q + 2] + bq.z);
+    x[4 * q + 3] = act_fwd(p.act, p.slope, x[4 * q + 3] + bq.w);
+  }
+  if (mbits != nullptr) {
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j)
+      if (!((mbits[j >> 5] >> (j & 31)) & 1u)) x[j] = 0.f;
+  }
+  if (p.alpha != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) x[j] *= p.alpha;
+  }
+}
+
+// Epilogue role of one warp (warps 2..9 of the CTA).  TW = tile width in pixels (tile = TW x 128/TW); the
+// warp's 32 accumulator rows are 32/TW consecutive tile rows, stored as one TMA box {128 B, TW, 32/TW, 1}.
+template <int TW>
+__device__ __forceinline__ void run_epilogue(const Params& p, const CUtensorMap* tmO, Barriers* bars, uint8_t* staging,
+                                             float* bias_s, uint32_t tmem_base, int warp, int lane) {
+    const int ew = warp - 2;                                   // 0..7
+    const int quarter = warp & 3;                              // TMEM lanes 32*quarter .. +31 (hardware rule: warp id % 4)
+    const int half = ew >> 2;                                  // which of the two warps of this quarter
+    const int row = quarter * 32 + lane;                       // pixel row inside the tile
+    const int hl = row / TW, wl = row % TW;
+    uint8_t* stg = staging + ew * STAGING_BYTES;
+    const uint32_t stg_u32 = smem_u32(stg);
+    const int etid = threadIdx.x - 64;                         // 0..255 among the epilogue threads
+    const int slab_cols = p.out_f32 ? 32 : 64;                 // 128 bytes of output per row
+    int acc = 0; uint32_t acc_phase = 0;
+    int bias_n0 = -1;
+    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      int b, h0, w0, n0;
+      tile_coords<TW>(p, t, b, h0, w0, n0);
+      const int oh = h0 + hl, ow = w0 + wl;
+      const bool row_ok = (oh < p.H) && (ow < p.W);
+      const long long pix = ((long long)b * p.H + oh) * p.W + ow;
+      if (n0 != bias_n0) {                                     // (re)load the bias slice of this N tile
+        asm volatile("bar.sync 1, 256;" ::: "memory");         // everyone done with the previous slice
+        {
+          const int co = n0 + etid;
+          bias_s[etid] = (p.bias != nullptr && co < p.Cout) ? __ldg(p.bias + co) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        bias_n0 = n0;
+      }
+      mbar_wait(smem_u32(&bars->acc_full[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE;
+      const int n_valid = min(p.n_tile, p.Cout - n0);
+      if (p.tma_out) {
+        const int n_slabs = (n_valid + slab_cols - 1) / slab_cols;
+        for (int s = half; s < n_slabs; s += 2) {
+          const int c = s * slab_cols;                         // first accumulator column of the slab
+          // sign-bit mask words of this row for the slab's columns
+          uint32_t mb[2] = {0xffffffffu, 0xffffffffu};
+          if (p.bits_in != nullptr) {
+            const int w0i = (n0 + c) >> 5;
+            mb[0] = row_ok ? __ldg(p.bits_in + pix * p.bit_words + w0i) : 0u;
+            if (!p.out_f32) mb[1] = (row_ok && w0i + 1 < p.bit_words) ? __ldg(p.bits_in + pix * p.bit_words + w0i + 1) : 0u;
+          }
+          if (lane == 0) bulk_wait_read0();                    // previous TMA store has finished reading the staging rows
+          __syncwarp();
+          uint32_t sign[2] = {0u, 0u};
+          if (p.out_f32) {
+            uint32_t v[32];
+            tmem_ld32(t_base + c, v);
+            tmem_ld_wait();
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+            slab_math<32>(p, x, bias_s + c, p.bits_in ? mb : nullptr);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sign[0] |= (x[j] > 0.f ? 1u : 0u) << j;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)                         // 16-byte piece q of the row, 128B swizzle: q ^ (row & 7)
+              *reinterpret_cast<float4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                  make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+          } else {
+            uint32_t v0[32], v1[32];
+            tmem_ld32(t_base + c, v0);
+            tmem_ld32(t_base + c + 32, v1);                    // (columns past n_valid are clipped by the TMA store)
+            tmem_ld_wait();
+            float x[64];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { x[j] = __uint_as_float(v0[j]); x[32 + j] = __uint_as_float(v1[j]); }
+            slab_math<64>(p, x, bias_s + c, p.bits_in ? mb : nullptr);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              sign[0] |= (x[j] > 0.f ? 1u : 0u) << j;
+              sign[1] |= (x[32 + j] > 0.f ? 1u : 0u) << j;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              uint4 o;
+              o.x = pack_bf16(x[8 * q + 0], x[8 * q + 1]);
+              o.y = pack_bf16(x[8 * q + 2], x[8 * q + 3]);
+              o.z = pack_bf16(x[8 * q + 4], x[8 * q + 5]);
+              o.w = pack_bf16(x[8 * q + 6], x[8 * q + 7]);
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+            }
+          }
+          if (p.bits_out != nullptr && row_ok) {
+            const int w0i = (n0 + c) >> 5;
+            p.bits_out[pix * p.bit_words + w0i] = sign[0];
+            if (!p.out_f32 && w0i + 1 < p.bit_words) p.bits_out[pix * p.bit_words + w0i + 1] = sign[1];
+          }
+          fence_async_smem();                                  // generic-proxy smem writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            // this warp's 32 rows are tile rows h = 2*quarter, 2*quarter+1 (16 pixels each): box {128 B, 16, 2, 1}
+            if (p.accumulate) tma_reduce_add_4d(tmO, stg_u32, n0 + c, w0, h0 + (32 / TW) * quarter, b);
+            else tma_store_4d(tmO, stg_u32, n0 + c, w0, h0 + (32 / TW) * quarter, b);
+            bulk_commit();
+          }
+        }
+      } else if (half == 0) {
+        for (int c = 0; c < n_valid; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_base + c, v);
+          tmem_ld_wait();
+          if (p.out_f32) epilogue_chunk<float>(p, v, pix, n0 + c, row_ok);
+          else epilogue_chunk<__nv_bfloat16>(p, v, pix, n0 + c, row_ok);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.tma_out && lane == 0) bulk_wait_all();               // outstanding tensor stores complete before exit
+}
+
+}  // namespace tc
+}  // namespace sininn

@@ -11,13 +11,18 @@ constexpr int SMEM_RING_BUDGET = 200 * 1024;
 // ================================================================ weight gradient
 //   dW[tap][m][n] = sum_pixels  Wide[p][m] * Narrow[p + off(tap)][n]
 // "Wide" is whichever of (x, dy) has more channels (the 256-wide hidden side of every subnet conv); it is the
-// M operand in 128-channel tiles and is never shifted.  "Narrow" is the N operand; its box is shifted per tap
-// (by +off when it is x, by -off when it is dy), TMA zero-fill provides the padding.  Both operands are read
-// straight from the channels-last activations as MN-major SWIZZLE_128B tiles (64 channels x 64 pixels per box),
-// K = pixels.  One CTA = (M tile, group of taps, pixel split); accumulators for all taps of the group live in
-// TMEM side by side.  fp32 partials go to the workspace, a fixed-order reduction writes OIHW.
-constexpr int WG_KPIX_W = 16, WG_KPIX_H = 4, WG_KPIX = WG_KPIX_W * WG_KPIX_H;    // 64 pixels per K step
-constexpr uint32_t WG_BOX_BYTES = WG_KPIX * 128;                                  // 64 px x 64 ch x 2 B
+// M operand in 128-channel tiles and is never shifted.  "Narrow" is the N operand, shifted per tap (by +off when
+// it is x, by -off when it is dy).  Both operands are read straight from the channels-last activations as
+// MN-major SWIZZLE_128B tiles (K = pixels, 64 channels x 128 B rows): no transposed copies exist anywhere.
+// One K step = an 8x8 pixel block.  For 3x3 filters the narrow operand is loaded ONCE per step with its halo
+// (box 16 w x 10 h, origin (w0-1, h0-1)) and every tap is a descriptor into that buffer:
+//     start = base + ((1+sy)*16 + (1+sx)) * 128 B, K-group (8 pixels of one image row) stride SBO = 2048 B.
+// One CTA = (M tile, group of taps, pixel split); the accumulators of all its taps live in TMEM side by side.
+// fp32 partials go to the workspace, a fixed-order reduction writes OIHW (deterministic, no float atomics).
+constexpr int WG_BLK = 8;                                        // pixel block edge: 64 pixels per K step
+constexpr uint32_t WG_BOX_BYTES = WG_BLK * WG_BLK * 128;          // plain 8x8 box: 64 px x 64 ch x 2 B
+constexpr int WG_HALO_W = 16, WG_HALO_H = WG_BLK + 2;
+constexpr uint32_t WG_HALO_BYTES = WG_HALO_W * WG_HALO_H * 128;   // 20480
 
 struct WgradParams {
   int B, H, W;
@@ -29,6 +34,7 @@ struct WgradParams {
   long long num_blocks, blocks_per_split;
   int stages;
   uint32_t stage_bytes, tx_bytes;
+  uint32_t narrow_bytes;         // bytes of one 64-channel narrow box (halo'd for 3x3)
   float* partial;                // [split][tap][Cw][Cn]
 };
 
@@ -73,61 +79,83 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp loops (uniform control flow), one elected lane issues the TMA loads
       int stage = 0; uint32_t phase = 0;
       for (long long i = 0; i < nblk; ++i) {
         long long blk = blk0 + i;
         const int bw = (int)(blk % p.blocks_w); blk /= p.blocks_w;
         const int bh = (int)(blk % p.blocks_h);
         const int b = (int)(blk / p.blocks_h);
-        const int w0 = bw * WG_KPIX_W, h0 = bh * WG_KPIX_H;
+        const int w0 = bw * WG_BLK, h0 = bh * WG_BLK;
         mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
-        const uint32_t full = smem_u32(&bars->full[stage]);
-        mbar_expect_tx(full, (uint32_t)(2 + ntap * p.n_groups) * WG_BOX_BYTES);
-        uint32_t dst = ring_u32 + stage * p.stage_bytes;
-        tma_load_4d(dst, &tmW, full, mt * 128, w0, h0, b);
-        tma_load_4d(dst + WG_BOX_BYTES, &tmW, full, mt * 128 + 64, w0, h0, b);
-        dst += 2 * WG_BOX_BYTES;
-        for (int t = 0; t < ntap; ++t) {
-          const int tap = tap0 + t;
-          int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
-          int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
-          if (!p.narrow_is_x) { dy = -dy; dx = -dx; }
+        if (elect_one()) {
+          const uint32_t full = smem_u32(&bars->full[stage]);
+          mbar_expect_tx(full, p.tx_bytes);
+          uint32_t dst = ring_u32 + stage * p.stage_bytes;
+          tma_load_4d(dst, &tmW, full, mt * 128, w0, h0, b);
+          tma_load_4d(dst + WG_BOX_BYTES, &tmW, full, mt * 128 + 64, w0, h0, b);
+          dst += 2 * WG_BOX_BYTES;
+          const int ho = (p.taps == 9) ? 1 : 0;                  // halo origin offset
           for (int g = 0; g < p.n_groups; ++g) {
-            tma_load_4d(dst, &tmN, full, g * 64, w0 + dx, h0 + dy, b);
-            dst += WG_BOX_BYTES;
+            tma_load_4d(dst, &tmN, full, g * 64, w0 - ho, h0 - ho, b);
+            dst += p.narrow_bytes;
           }
         }
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp loops, one elected lane issues the MMAs
       // D=f32, A=B=bf16, both MN-major (bits 15, 16), N = n_pad, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
+      // descriptors built once (MN-major SW128: LBO = distance between 64-channel boxes, SBO = distance between
+      // 8-pixel K groups); per MMA only the start-address field (units of 16 B) is advanced
+      const bool halo = p.taps == 9;
+      uint64_t a_desc0 = make_desc(ring_u32, 1024, 2);
+      a_desc0 = (a_desc0 & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)(WG_BOX_BYTES >> 4) << 16);
+      uint64_t b_desc0 = make_desc(ring_u32 + 2 * WG_BOX_BYTES, halo ? WG_HALO_W * 128u : 1024u, 2);
+      b_desc0 = (b_desc0 & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)(p.narrow_bytes >> 4) << 16);
+      const uint32_t b_kstep = (halo ? 2 * WG_HALO_W * 128u : 2048u) >> 4;      // 16 pixels further along K
+      uint32_t tap_off[9];                                                       // start row of each tap, in 16 B units
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        int sy = 0, sx = 0;
+        if (halo) {
+          const int tap = tap0 + t;
+          sy = tap / 3 - 1; sx = tap % 3 - 1;
+          if (!p.narrow_is_x) { sy = -sy; sx = -sx; }
+          sy += 1; sx += 1;
+        }
+        tap_off[t] = (uint32_t)(sy * WG_HALO_W + sx) * 8u;
+      }
+      const uint32_t stage_step = p.stage_bytes >> 4;
       for (long long i = 0; i < nblk; ++i) {
         mbar_wait(smem_u32(&bars->full[stage]), phase);
         tc_fence_after();
-        const uint32_t a_addr = ring_u32 + stage * p.stage_bytes;
-        for (int t = 0; t < ntap; ++t) {
-          const uint32_t b_addr = a_addr + (2 + t * p.n_groups) * WG_BOX_BYTES;
+        const uint64_t ad = a_desc0 + (uint64_t)(stage * stage_step);
+        const uint64_t bs = b_desc0 + (uint64_t)(stage * stage_step);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < WG_KPIX / 16; ++k) {
-            // MN-major SW128: LBO = distance between 64-channel boxes, SBO = 8 pixel rows (1024 B);
-            // 16 pixels per MMA = 2048 B further into each box
-            uint64_t ad = make_desc(a_addr + k * 2048, 1024, 2);
-            uint64_t bd = make_desc(b_addr + k * 2048, 1024, 2);
-            ad = (ad & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)(WG_BOX_BYTES >> 4) << 16);
-            bd = (bd & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)(WG_BOX_BYTES >> 4) << 16);
-            umma_bf16(tmem_base + t * p.n_pad, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+          for (int t = 0; t < 9; ++t) {
+            if (t < ntap) {
+              const uint64_t bd = bs + tap_off[t];
+              const uint32_t d_tmem = tmem_base + t * p.n_pad;
+              umma_bf16(d_tmem, ad, bd, idesc, i != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, ad + 128, bd + b_kstep, idesc, 1u);
+              umma_bf16(d_tmem, ad + 256, bd + 2 * b_kstep, idesc, 1u);
+              umma_bf16(d_tmem, ad + 384, bd + 3 * b_kstep, idesc, 1u);
+            }
           }
+          umma_commit(smem_u32(&bars->empty[stage]));
         }
-        umma_commit(smem_u32(&bars->empty[stage]));
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(smem_u32(&bars->acc_full[0]));
+      if (elect_one()) umma_commit(smem_u32(&bars->acc_full[0]));
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;
@@ -186,7 +214,7 @@ struct WgradPlan {
   int wide_is_dy, Cw, Cn, n_pad, n_groups, taps_per_cta, tap_groups, m_tiles, splits, stages;
   int blocks_h, blocks_w;
   long long num_blocks, blocks_per_split;
-  uint32_t stage_bytes;
+  uint32_t stage_bytes, narrow_bytes;
 };
 
 static bool plan_wgrad(const sininn_wgrad_desc* d, WgradPlan& w) {
@@ -196,24 +224,22 @@ static bool plan_wgrad(const sininn_wgrad_desc* d, WgradPlan& w) {
   w.n_pad = (w.Cn + 15) / 16 * 16;
   if (w.n_pad > 256) return false;
   w.n_groups = (w.n_pad + 63) / 64;
-  int by_tmem = TMEM_COLS / w.n_pad;
-  int by_smem = (int)((56 * 1024 - 2 * WG_BOX_BYTES) / (w.n_groups * WG_BOX_BYTES));
-  int t = by_tmem < by_smem ? by_tmem : by_smem;
-  if (t < 1) t = 1;
+  w.narrow_bytes = d->taps == 9 ? WG_HALO_BYTES : WG_BOX_BYTES;
+  int t = TMEM_COLS / w.n_pad;                       // accumulators of all taps of a CTA sit side by side in TMEM
   if (t > d->taps) t = d->taps;
   w.taps_per_cta = t;
   w.tap_groups = (d->taps + t - 1) / t;
   w.m_tiles = (w.Cw + 127) / 128;
-  w.stage_bytes = (2 + t * w.n_groups) * WG_BOX_BYTES;
+  w.stage_bytes = 2 * WG_BOX_BYTES + w.n_groups * w.narrow_bytes;
   w.stages = SMEM_RING_BUDGET / (int)w.stage_bytes;
   if (w.stages > MAX_STAGES) w.stages = MAX_STAGES;
   if (w.stages < 2) return false;
-  w.blocks_h = (d->H + WG_KPIX_H - 1) / WG_KPIX_H;
-  w.blocks_w = (d->W + WG_KPIX_W - 1) / WG_KPIX_W;
+  w.blocks_h = (d->H + WG_BLK - 1) / WG_BLK;
+  w.blocks_w = (d->W + WG_BLK - 1) / WG_BLK;
   w.num_blocks = (long long)d->B * w.blocks_h * w.blocks_w;
   long long items = (long long)w.m_tiles * w.tap_groups;
-  long long s = (sm_count() + items - 1) / items;
-  if (s > w.num_blocks) s = w.num_blocks;
+  long long s = (sm_count() + items - 1) / items;      // about one CTA per SM ...
+  if (s > w.num_blocks / 16) s = w.num_blocks / 16;    // ... but at least 16 K steps each (partials cost bandwidth)
   if (s > 64) s = 64;
   if (s < 1) s = 1;
   w.blocks_per_split = (w.num_blocks + s - 1) / s;
@@ -273,7 +299,8 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
     const int stride = which == 0 ? wide_stride : narrow_stride;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)stride * 2, (cuuint64_t)d->W * stride * 2, (cuuint64_t)d->H * d->W * stride * 2};
-    cuuint32_t box[4] = {64, WG_KPIX_W, WG_KPIX_H, 1};
+    const bool halo = which == 1 && d->taps == 9;
+    cuuint32_t box[4] = {64, (cuuint32_t)(halo ? WG_HALO_W : WG_BLK), (cuuint32_t)(halo ? WG_HALO_H : WG_BLK), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(which == 0 ? &tmW : &tmN, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -289,7 +316,7 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
   p.Cw = w.Cw; p.Cn = w.Cn; p.n_pad = w.n_pad; p.n_groups = w.n_groups;
   p.taps_per_cta = w.taps_per_cta; p.tap_groups = w.tap_groups; p.m_tiles = w.m_tiles; p.splits = w.splits;
   p.blocks_h = w.blocks_h; p.blocks_w = w.blocks_w; p.num_blocks = w.num_blocks; p.blocks_per_split = w.blocks_per_split;
-  p.stages = w.stages; p.stage_bytes = w.stage_bytes; p.tx_bytes = w.stage_bytes;
+  p.stages = w.stages; p.stage_bytes = w.stage_bytes; p.tx_bytes = w.stage_bytes; p.narrow_bytes = w.narrow_bytes;
   p.partial = reinterpret_cast<float*>(d->workspace);
   static bool attr_set[64] = {false};
   int dev = 0;

@@ -65,6 +65,7 @@ _pack_cache = {}     # id(param) -> (weakref(param), {(mode, dtype): (version, d
 def invalidate_packs():
     """Forget packed weights (call after parameters were modified outside torch's version tracking)."""
     _pack_cache.clear()
+    _pack_epoch[0] += 1
 
 
 def packed(w, mode, dtype):
@@ -83,6 +84,47 @@ def packed(w, mode, dtype):
     p = K.pack_weight(w, mode, dtype, _round_up(rows, 16), _round_up(k, 16))
     ent[1][(mode, dtype)] = (w._version, w.data_ptr(), p)
     return p
+
+
+_pack_epoch = [0]
+
+
+class PackSet:
+    """All conv weights of one plan, re-laid-out for the implicit GEMMs by ONE batched kernel launch whenever any
+    of them changed (fprop and dgrad layouts).  Outputs and the device-side job table are allocated once."""
+
+    def __init__(self, weights, dtype):
+        self.weights, self.dtype = list(weights), dtype
+        self.out, self.jobs, self.sig, self.ptrs = {}, None, None, None
+
+    def _build(self, dev):
+        rows = []
+        self.out = {}
+        for w in self.weights:
+            co, ci, kh, kw = w.shape
+            for mode in (0, 1):
+                r, k = (co, ci) if mode == 0 else (ci, co)
+                rp, kp = _round_up(r, 16), _round_up(k, 16)
+                t = torch.empty(kh * kw, rp, kp, dtype=self.dtype, device=dev)
+                self.out[(id(w), mode)] = t
+                rows.append([w.data_ptr(), t.data_ptr(), co, ci, kh * kw, mode, rp, kp])
+        self.jobs = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self.ptrs = tuple(w.data_ptr() for w in self.weights)
+
+    def ensure(self):
+        if not self.weights:
+            return
+        ptrs = tuple(w.data_ptr() for w in self.weights)
+        if ptrs != self.ptrs:
+            self._build(self.weights[0].device)
+            self.sig = None
+        sig = (tuple(w._version for w in self.weights), _pack_epoch[0])
+        if sig != self.sig:
+            K.pack_weights_batched(self.jobs, self.jobs.shape[0], self.dtype)
+            self.sig = sig
+
+    def get(self, w, mode):
+        return self.out[(id(w), mode)]
 
 
 # ----------------------------------------------------------------------------- trunk state
@@ -135,11 +177,18 @@ class Trunk:
 
 
 class RunCtx:
-    def __init__(self, cfg, want_grads=False):
+    def __init__(self, cfg, want_grads=False, packs=None):
         self.cfg = cfg
         self.adt = cfg.act_dtype
         self.tc = cfg.tc
         self.grads = {} if want_grads else None
+        self.packs = packs
+
+    def pack(self, w, mode):
+        """Implicit-GEMM layout of conv weight w (mode 0 fprop, 1 dgrad) in the activation dtype."""
+        if self.packs is not None:
+            return self.packs.get(w, mode)
+        return packed(w, mode, self.adt)
 
     def add_grad(self, param, g):
         if param is None or not param.requires_grad:
@@ -178,10 +227,10 @@ class ConvSubnet:
         # tensor-core path: the backward pass reads the ReLU mask as 1 bit / element instead of re-reading h
         bits = (torch.empty(tr.npix, (self.hidden + 31) // 32, dtype=torch.int32, device=dev)
                 if (keep and ctx.tc) else None)
-        K.conv(x, packed(self.c1.weight, 0, ctx.adt), tr.geom, self.hidden, h, bias=self.c1.bias, act=ACT_RELU,
+        K.conv(x, ctx.pack(self.c1.weight, 0), tr.geom, self.hidden, h, bias=self.c1.bias, act=ACT_RELU,
                tensor_core=ctx.tc, bits_out=bits)
         a = torch.empty(tr.npix, self.cout, dtype=torch.float32, device=dev)
-        K.conv(h, packed(self.c2.weight, 0, ctx.adt), tr.geom, self.cout, a, bias=self.c2.bias, tensor_core=ctx.tc)
+        K.conv(h, ctx.pack(self.c2.weight, 0), tr.geom, self.cout, a, bias=self.c2.bias, tensor_core=ctx.tc)
         return a, (x, h, bits)
 
     def bwd(self, ctx, tr, saved, da, dsrc):
@@ -190,16 +239,16 @@ class ConvSubnet:
         dev = x.device
         dh = torch.empty_like(h)
         if bits is not None:
-            K.conv(da, packed(self.c2.weight, 1, ctx.adt), tr.geom, self.hidden, dh, mask_bits=bits, tensor_core=True)
+            K.conv(da, ctx.pack(self.c2.weight, 1), tr.geom, self.hidden, dh, mask_bits=bits, tensor_core=True)
         else:
-            K.conv(da, packed(self.c2.weight, 1, ctx.adt), tr.geom, self.hidden, dh, mask=h, mask_act=ACT_RELU,
+            K.conv(da, ctx.pack(self.c2.weight, 1), tr.geom, self.hidden, dh, mask=h, mask_act=ACT_RELU,
                    tensor_core=ctx.tc)
         if self.c2.weight.requires_grad:
             ctx.add_grad(self.c2.weight, K.wgrad(h, da, tr.geom, self.taps, torch.empty_like(self.c2.weight),
                                                  tensor_core=ctx.tc))
         if self.c2.bias is not None and self.c2.bias.requires_grad:
             ctx.add_grad(self.c2.bias, K.colsum(da, torch.empty(self.cout, dtype=torch.float32, device=dev)))
-        K.conv(dh, packed(self.c1.weight, 1, ctx.adt), tr.geom, self.cin, dsrc, accumulate=True, tensor_core=ctx.tc)
+        K.conv(dh, ctx.pack(self.c1.weight, 1), tr.geom, self.cin, dsrc, accumulate=True, tensor_core=ctx.tc)
         if self.c1.weight.requires_grad:
             ctx.add_grad(self.c1.weight, K.wgrad(x, dh, tr.geom, self.taps, torch.empty_like(self.c1.weight),
                                                  tensor_core=ctx.tc))
@@ -236,10 +285,10 @@ class DenseSubnet:
         K.cast_slice(tr.mat()[:, src[0]:src[1]], cat[:, :self.cin])
         for j in range(4):
             lo = self.cin + self.gc * j
-            K.conv(cat[:, :lo], packed(self.convs[j].weight, 0, ctx.adt), tr.geom, self.gc, cat[:, lo:lo + self.gc],
+            K.conv(cat[:, :lo], ctx.pack(self.convs[j].weight, 0), tr.geom, self.gc, cat[:, lo:lo + self.gc],
                    bias=self.convs[j].bias, act=ACT_LRELU, slope=self.SLOPE, tensor_core=ctx.tc)
         out = torch.empty(tr.npix, self.cout, dtype=torch.float32, device=dev)
-        K.conv(cat[:, :self.ctot], packed(self.convs[4].weight, 0, ctx.adt), tr.geom, self.cout, out,
+        K.conv(cat[:, :self.ctot], ctx.pack(self.convs[4].weight, 0), tr.geom, self.cout, out,
                bias=self.convs[4].bias, tensor_core=ctx.tc)
         return out, (cat,)
 
@@ -250,7 +299,7 @@ class DenseSubnet:
         # cast to the operand dtype (compact, aligned) after the LeakyReLU derivative is applied
         dcat = torch.empty(tr.npix, self.ctot, dtype=torch.float32, device=dev)
         c5 = self.convs[4]
-        K.conv(dout, packed(c5.weight, 1, ctx.adt), tr.geom, self.ctot, dcat, tensor_core=ctx.tc)
+        K.conv(dout, ctx.pack(c5.weight, 1), tr.geom, self.ctot, dcat, tensor_core=ctx.tc)
         if c5.weight.requires_grad:
             ctx.add_grad(c5.weight, K.wgrad(cat[:, :self.ctot], dout, tr.geom, 9, torch.empty_like(c5.weight),
                                             tensor_core=ctx.tc))
@@ -261,7 +310,7 @@ class DenseSubnet:
             g = torch.empty(tr.npix, self.gc, dtype=ctx.adt, device=dev)
             K.act_bwd(dcat[:, lo:lo + self.gc], cat[:, lo:lo + self.gc], g, ACT_LRELU, self.SLOPE)
             cj = self.convs[j]
-            K.conv(g, packed(cj.weight, 1, ctx.adt), tr.geom, lo, dcat[:, :lo], accumulate=True, tensor_core=ctx.tc)
+            K.conv(g, ctx.pack(cj.weight, 1), tr.geom, lo, dcat[:, :lo], accumulate=True, tensor_core=ctx.tc)
             if cj.weight.requires_grad:
                 ctx.add_grad(cj.weight, K.wgrad(cat[:, :lo], g, tr.geom, 9, torch.empty_like(cj.weight),
                                                 tensor_core=ctx.tc))
@@ -464,6 +513,7 @@ class Plan:
             if o.kind == "resample":
                 c, h, w = c * 4, h // 2, w // 2
         self.out_dims = (c, h, w)
+        self._packsets = {}
 
     def parameters(self):
         out, seen = [], set()
@@ -473,6 +523,14 @@ class Plan:
                     seen.add(id(p))
                     out.append(p)
         return out
+
+    def packs(self, dtype):
+        """The plan's conv weights packed for `dtype`, refreshed (one launch) if any weight changed."""
+        ps = self._packsets.get(dtype)
+        if ps is None:
+            ps = self._packsets[dtype] = PackSet([p for p in self.parameters() if p.dim() == 4], dtype)
+        ps.ensure()
+        return ps
 
     def _check_input(self, x, rev):
         require_cuda(x, "network input")
@@ -499,7 +557,7 @@ class Plan:
     # ---- value pass ---------------------------------------------------------------------------
     def execute(self, x, rev, cfg):
         self._check_input(x, rev)
-        ctx = RunCtx(cfg)
+        ctx = RunCtx(cfg, packs=self.packs(cfg.act_dtype) if (self.body and K.__name__ == "sin_inn_b200.kernels" and x.is_cuda) else None)
         if not self.body:
             seq = self.prefix[::-1] if rev else self.prefix
             for op in seq:
@@ -544,7 +602,8 @@ class Plan:
     def backward(self, y, dy, rev, cfg, need_dx=True):
         """y: the output execute(x, rev) produced; dy: dL/dy.  Returns (dL/dx or None, {id(param): grad})."""
         require_cuda(dy, "grad_output")
-        ctx = RunCtx(cfg, want_grads=True)
+        ctx = RunCtx(cfg, want_grads=True,
+                     packs=self.packs(cfg.act_dtype) if (self.body and K.__name__ == "sin_inn_b200.kernels" and dy.is_cuda) else None)
         dy = dy.contiguous()
         if dy.dtype != torch.float32:
             raise SininnError("grad_output must be fp32")

@@ -220,6 +220,13 @@ def pack_weight(w, mode, dtype, rows_pad, k_pad):
     return out
 
 
+def pack_weights_batched(jobs, njobs, dtype):
+    """jobs: device int64 tensor [njobs, 8] = {src, dst, Cout, Cin, taps, mode, rows_pad, k_pad}."""
+    code = F32 if dtype == torch.float32 else BF16
+    check(_run("pack", lambda: load().sininn_pack_conv_weights_batched(jobs.data_ptr(), njobs, code, stream_ptr()), 1),
+          "pack_conv_weights_batched")
+
+
 def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask_act=0, accumulate=False, alpha=1.0,
          tensor_core=False, mask_bits=None, bits_out=None):
     """Implicit-GEMM 1x1 / 3x3 convolution on channels-last views.

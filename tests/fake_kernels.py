@@ -127,6 +127,10 @@ def pack_weight(w, mode, dtype, rows_pad, k_pad):
     return out.to(dtype)
 
 
+def pack_weights_batched(jobs, njobs, dtype):
+    raise NotImplementedError("the CPU stand-in packs weights one by one")
+
+
 def _shift(x4, dy, dx):
     """x4: [B,H,W,C]; result[b,h,w] = x4[b,h+dy,w+dx] with zero fill."""
     B, H, W, C = x4.shape

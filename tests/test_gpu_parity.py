@@ -88,9 +88,7 @@ def check(hr, out, tol, rt_tol, norm_wise=False):
         print("bf16 rel_l2:", {k: f"{rels[k]:.2e}" for k in ("y", "xr", "dx", "du")}, "wgrad median", f"{gr[len(gr)//2]:.2e}",
               "worst", f"{gr[-1]:.2e}")
     assert (b["rt"] - hr).abs().max().item() <= rt_tol
-    if worst:
-        k = max(worst, key=lambda n: worst[n][0])
-        print(f"bf16 worst tensor {k}: rel_l2 {worst[k][0]:.3e}, max/|max| {worst[k][1]:.3e}")
+
 
 
 FP32_CASES = [("SRF", 2, 4, 1, 2, 32, 32), ("SRF", 4, 2, 10, 2, 40, 72), ("IRN", 2, 2, 1, 2, 32, 32),
