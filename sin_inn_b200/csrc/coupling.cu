@@ -188,7 +188,24 @@ __global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const T* __rest
 #pragma unroll
   for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
   if (rl < RPI) {
-    for (long long r = r0 + rl; r < r1; r += RPI) {
+    long long r = r0 + rl;
+    // four rows in flight per thread: the kernel is pure streaming, memory-level parallelism is what matters
+    for (; r + 3 * RPI < r1; r += 4 * RPI) {
+      float4 t[4][VEC / 4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const T* src = in + (r + (long long)u * RPI) * in_stride + g * VEC;
+#pragma unroll
+        for (int q = 0; q < VEC / 4; ++q) t[u][q] = load4(src + 4 * q);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < VEC / 4; ++q) {
+          acc[4 * q] += t[u][q].x; acc[4 * q + 1] += t[u][q].y; acc[4 * q + 2] += t[u][q].z; acc[4 * q + 3] += t[u][q].w;
+        }
+    }
+    for (; r < r1; r += RPI) {
       const T* src = in + r * in_stride + g * VEC;
 #pragma unroll
       for (int q = 0; q < VEC / 4; ++q) {
@@ -207,17 +224,28 @@ __global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const T* __rest
   }
 }
 
-__global__ void colsum_finish_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out, int accumulate) {
-  int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= N) return;
+// block = 32 columns x 8 chunk-lanes; fixed-order tree over the lanes => deterministic
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partial, int chunks, int N,
+                                                            float* __restrict__ out, int accumulate) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
   float sum = 0.f;
-  for (int k = 0; k < chunks; ++k) sum += partial[(long long)k * N + col];
-  out[col] = accumulate ? out[col] + sum : sum;
+  if (col < N)
+    for (int k = ky; k < chunks; k += 8) sum += partial[(long long)k * N + col];
+  red[ky][cx] = sum;
+  __syncthreads();
+  if (ky == 0 && col < N) {
+    float t = red[0][cx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][cx];
+    out[col] = accumulate ? out[col] + t : t;
+  }
 }
 
 static inline long long colsum_chunks(long long npix) {
   long long chunks = (npix + 255) / 256;          // >= 256 rows per chunk
-  long long cap = (long long)sm_count() * 8;
+  long long cap = (long long)sm_count() * 4;
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   return chunks;
@@ -397,7 +425,7 @@ int sininn_colsum(const void* in, int dtype, int in_stride, long long npix, int 
     else colsum_partial_vec_kernel<__nv_bfloat16><<<(unsigned)chunks, 256, sm, st>>>((const __nv_bfloat16*)in, in_stride, npix, N, rows_per_chunk, partial);
   } else if (dtype == SININN_F32) colsum_partial_kernel<float><<<grid, block, 0, st>>>((const float*)in, in_stride, npix, N, rows_per_chunk, partial);
   else colsum_partial_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, in_stride, npix, N, rows_per_chunk, partial);
-  colsum_finish_kernel<<<(N + 127) / 128, 128, 0, st>>>(partial, (int)chunks, N, out, accumulate);
+  colsum_finish_kernel<<<(N + 31) / 32, 256, 0, st>>>(partial, (int)chunks, N, out, accumulate);
   SININN_CHECK_LAUNCH("colsum");
   return SININN_OK;
 }

@@ -165,20 +165,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       mbar_wait(smem_u32(&bars->acc_full[0]), 0);
       tc_fence_after();
     }
+    const bool vec4 = (p.Cn % 4) == 0;                        // rows of the partial buffer are then 16-byte aligned
     for (int t = 0; t < ntap; ++t) {
       float* dst = p.partial + (((long long)split * p.taps + tap0 + t) * p.Cw + m) * p.Cn;
-      for (int c = 0; c < p.Cn; c += 16) {
-        uint32_t v[16];
+      for (int c = 0; c < p.Cn; c += 32) {
+        uint32_t v[32];
         if (nblk > 0) {
-          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + t * p.n_pad + c, v);
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + t * p.n_pad + c, v);   // columns past n_pad are never stored
           tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0u;
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
         if (m_ok) {
-          const int nc = min(16, p.Cn - c);
-          for (int j = 0; j < nc; ++j) dst[c + j] = __uint_as_float(v[j]);
+          const int nc = min(32, p.Cn - c);
+          if (vec4) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (4 * q < nc)
+                *reinterpret_cast<float4*>(dst + c + 4 * q) = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                          __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          } else {
+            for (int j = 0; j < nc; ++j) dst[c + j] = __uint_as_float(v[j]);
+          }
         }
       }
     }
@@ -192,21 +201,37 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   }
 }
 
-// dw[co][ci][tap] (+)= sum_split partial[split][tap][m][n]; (co,ci) = (m,n) when the wide operand is dy, else (n,m)
+// dw[co][ci][tap] (+)= sum_split partial[split][tap][m][n]; (co,ci) = (m,n) when the wide operand is dy, else (n,m).
+// Fixed summation order over the splits => bit-reproducible gradients.
+template <int VEC>
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cw, int Cn,
                                                               int wide_is_dy, int Cout, int Cin, float* __restrict__ dw, int accumulate) {
   const long long per = (long long)taps * Cw * Cn;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(idx % Cn);
+  const long long perv = per / VEC;
+  for (long long iv = blockIdx.x * (long long)blockDim.x + threadIdx.x; iv < perv; iv += (long long)gridDim.x * blockDim.x) {
+    const long long idx = iv * VEC;
+    float s[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) s[e] = 0.f;
+    for (int k = 0; k < splits; ++k) {
+      if (VEC == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(partial + k * per + idx);
+        s[0] += t.x; s[VEC > 1 ? 1 : 0] += t.y; s[VEC > 2 ? 2 : 0] += t.z; s[VEC > 3 ? 3 : 0] += t.w;
+      } else {
+        s[0] += partial[k * per + idx];
+      }
+    }
+    const int n0 = (int)(idx % Cn);
     long long r = idx / Cn;
     const int m = (int)(r % Cw);
     const int tap = (int)(r / Cw);
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += partial[k * per + idx];
-    const int co = wide_is_dy ? m : n, ci = wide_is_dy ? n : m;
-    float* o = dw + ((long long)co * Cin + ci) * taps + tap;
-    *o = accumulate ? *o + s : s;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int n = n0 + e;
+      const int co = wide_is_dy ? m : n, ci = wide_is_dy ? n : m;
+      float* o = dw + ((long long)co * Cin + ci) * taps + tap;
+      *o = accumulate ? *o + s[e] : s[e];
+    }
   }
 }
 
@@ -334,10 +359,17 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
   cudaStream_t st = as_stream(stream);
   wgrad_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(tmW, tmN, p);
   const long long per = (long long)d->taps * w.Cw * w.Cn;
-  long long g = (per + 255) / 256;
-  if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
-  wgrad_tc_reduce_kernel<<<(int)g, 256, 0, st>>>(p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
-                                                 d->dw, d->accumulate);
+  if ((w.Cn % 4) == 0) {
+    long long g = (per / 4 + 255) / 256;
+    if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
+    wgrad_tc_reduce_kernel<4><<<(int)g, 256, 0, st>>>(p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
+                                                      d->dw, d->accumulate);
+  } else {
+    long long g = (per + 255) / 256;
+    if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
+    wgrad_tc_reduce_kernel<1><<<(int)g, 256, 0, st>>>(p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
+                                                      d->dw, d->accumulate);
+  }
   SININN_CHECK_LAUNCH("wgrad_tc");
   return SININN_OK;
 }

@@ -127,3 +127,39 @@ def test_bf16_operand_path_bookkeeping(fake_kernels, arch, scale, nc, lrw):
     for n, g in out["ora"][2].items():
         rel = (g - out["net"][2][n]).norm() / (g.norm() + 1e-12)
         assert rel < 1e-1, (n, float(rel))   # tiny 2x4-pixel grids: little averaging of bf16 rounding
+
+
+def test_unmodified_reference_archs_runs_on_the_freia_dropin(fake_kernels):
+    """INTEGRATION.md level 2: alias sin_inn_b200.freia as FrEIA and import the reference's own archs.py."""
+    import importlib
+    import sys
+    ref = "/root/reference"
+    import os
+    if not os.path.exists(os.path.join(ref, "archs.py")):
+        pytest.skip("reference checkout not present (GPU box)")
+    import sin_inn_b200.freia as f
+    saved = {k: sys.modules.get(k) for k in ("FrEIA", "FrEIA.framework", "FrEIA.modules", "archs")}
+    sys.modules.update({"FrEIA": f, "FrEIA.framework": f.framework, "FrEIA.modules": f.modules})
+    sys.modules.pop("archs", None)
+    sys.path.insert(0, ref)
+    try:
+        ref_archs = importlib.import_module("archs")
+        assert ref_archs.__file__.startswith(ref)
+        opt = R.make_opt(scale=4, num_coupling=2, lr_window=10)
+        torch.manual_seed(3)
+        net = ref_archs.UncondSRFlow(3, 16, 32, opt)
+        net.engine_config = E.EngineConfig(precision="fp32", tensor_core=False)
+        torch.manual_seed(3)
+        ora = R.build_srf(3, 16, 32, opt)
+        x = torch.rand(2, 3, 16, 32)
+        y = net(x)
+        assert (y - ora(x)).abs().max() < 1e-4
+        assert (net(y, rev=True) - x).abs().max() < 1e-4
+    finally:
+        sys.path.remove(ref)
+        sys.modules.pop("archs", None)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
