@@ -177,12 +177,28 @@ class Trunk:
 
 
 class RunCtx:
-    def __init__(self, cfg, want_grads=False, packs=None):
+    def __init__(self, cfg, want_grads=False, packs=None, direct_grad=False):
         self.cfg = cfg
         self.adt = cfg.act_dtype
         self.tc = cfg.tc
         self.grads = {} if want_grads else None
         self.packs = packs
+        self.direct_grad = direct_grad      # accumulate weight gradients straight into param.grad (no autograd add)
+        self.direct = set()
+
+    def grad_out(self, param):
+        """(tensor, accumulate) the weight-gradient kernels should write to for `param`."""
+        g = param.grad
+        if (self.direct_grad and g is not None and g.dtype == torch.float32 and g.is_contiguous()
+                and g.shape == param.shape and g.device == param.device):
+            self.direct.add(id(param))
+            return g, True
+        cur = self.grads.get(id(param))
+        if cur is not None:
+            return cur, True
+        t = torch.empty_like(param, dtype=torch.float32)
+        self.grads[id(param)] = t
+        return t, False
 
     def pack(self, w, mode):
         """Implicit-GEMM layout of conv weight w (mode 0 fprop, 1 dgrad) in the activation dtype."""
@@ -244,16 +260,18 @@ class ConvSubnet:
             K.conv(da, ctx.pack(self.c2.weight, 1), tr.geom, self.hidden, dh, mask=h, mask_act=ACT_RELU,
                    tensor_core=ctx.tc)
         if self.c2.weight.requires_grad:
-            ctx.add_grad(self.c2.weight, K.wgrad(h, da, tr.geom, self.taps, torch.empty_like(self.c2.weight),
-                                                 tensor_core=ctx.tc))
+            g, acc = ctx.grad_out(self.c2.weight)
+            K.wgrad(h, da, tr.geom, self.taps, g, accumulate=acc, tensor_core=ctx.tc)
         if self.c2.bias is not None and self.c2.bias.requires_grad:
-            ctx.add_grad(self.c2.bias, K.colsum(da, torch.empty(self.cout, dtype=torch.float32, device=dev)))
+            g, acc = ctx.grad_out(self.c2.bias)
+            K.colsum(da, g, accumulate=acc)
         K.conv(dh, ctx.pack(self.c1.weight, 1), tr.geom, self.cin, dsrc, accumulate=True, tensor_core=ctx.tc)
         if self.c1.weight.requires_grad:
-            ctx.add_grad(self.c1.weight, K.wgrad(x, dh, tr.geom, self.taps, torch.empty_like(self.c1.weight),
-                                                 tensor_core=ctx.tc))
+            g, acc = ctx.grad_out(self.c1.weight)
+            K.wgrad(x, dh, tr.geom, self.taps, g, accumulate=acc, tensor_core=ctx.tc)
         if self.c1.bias is not None and self.c1.bias.requires_grad:
-            ctx.add_grad(self.c1.bias, K.colsum(dh, torch.empty(self.hidden, dtype=torch.float32, device=dev)))
+            g, acc = ctx.grad_out(self.c1.bias)
+            K.colsum(dh, g, accumulate=acc)
 
 
 class DenseSubnet:
@@ -301,10 +319,11 @@ class DenseSubnet:
         c5 = self.convs[4]
         K.conv(dout, ctx.pack(c5.weight, 1), tr.geom, self.ctot, dcat, tensor_core=ctx.tc)
         if c5.weight.requires_grad:
-            ctx.add_grad(c5.weight, K.wgrad(cat[:, :self.ctot], dout, tr.geom, 9, torch.empty_like(c5.weight),
-                                            tensor_core=ctx.tc))
+            gw, acc = ctx.grad_out(c5.weight)
+            K.wgrad(cat[:, :self.ctot], dout, tr.geom, 9, gw, accumulate=acc, tensor_core=ctx.tc)
         if c5.bias is not None and c5.bias.requires_grad:
-            ctx.add_grad(c5.bias, K.colsum(dout, torch.empty(self.cout, dtype=torch.float32, device=dev)))
+            gb, acc = ctx.grad_out(c5.bias)
+            K.colsum(dout, gb, accumulate=acc)
         for j in (3, 2, 1, 0):
             lo = self.cin + self.gc * j
             g = torch.empty(tr.npix, self.gc, dtype=ctx.adt, device=dev)
@@ -312,10 +331,11 @@ class DenseSubnet:
             cj = self.convs[j]
             K.conv(g, ctx.pack(cj.weight, 1), tr.geom, lo, dcat[:, :lo], accumulate=True, tensor_core=ctx.tc)
             if cj.weight.requires_grad:
-                ctx.add_grad(cj.weight, K.wgrad(cat[:, :lo], g, tr.geom, 9, torch.empty_like(cj.weight),
-                                                tensor_core=ctx.tc))
+                gw, acc = ctx.grad_out(cj.weight)
+                K.wgrad(cat[:, :lo], g, tr.geom, 9, gw, accumulate=acc, tensor_core=ctx.tc)
             if cj.bias is not None and cj.bias.requires_grad:
-                ctx.add_grad(cj.bias, K.colsum(g, torch.empty(self.gc, dtype=torch.float32, device=dev)))
+                gb, acc = ctx.grad_out(cj.bias)
+                K.colsum(g, gb, accumulate=acc)
         K.axpy_slice(dsrc, dcat[:, :self.cin], 1.0)
 
 
@@ -514,6 +534,9 @@ class Plan:
                 c, h, w = c * 4, h // 2, w // 2
         self.out_dims = (c, h, w)
         self._packsets = {}
+        # opt-in (train.SingleVideoTrainer): weight-gradient kernels accumulate straight into param.grad and autograd
+        # receives None for those parameters -- saves one elementwise add per parameter per backward pass
+        self.direct_grad = False
 
     def parameters(self):
         out, seen = [], set()
@@ -602,7 +625,7 @@ class Plan:
     def backward(self, y, dy, rev, cfg, need_dx=True):
         """y: the output execute(x, rev) produced; dy: dL/dy.  Returns (dL/dx or None, {id(param): grad})."""
         require_cuda(dy, "grad_output")
-        ctx = RunCtx(cfg, want_grads=True,
+        ctx = RunCtx(cfg, want_grads=True, direct_grad=self.direct_grad,
                      packs=self.packs(cfg.act_dtype) if (self.body and K.__name__ == "sin_inn_b200.kernels" and dy.is_cuda) else None)
         dy = dy.contiguous()
         if dy.dtype != torch.float32:

@@ -88,6 +88,8 @@ class SingleVideoTrainer:
         self.flat = FlatParams(inn)
         self.optim = FusedAdam(self.flat, lr=opt.learning_rate, betas=opt.adam_betas, weight_decay=opt.weight_decay)
         self.world_size = world_size
+        if hasattr(inn, "plan"):
+            inn.plan().direct_grad = True      # gradients accumulate straight into the flat arena
 
     def broadcast_params(self):
         if self.world_size > 1:

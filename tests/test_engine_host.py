@@ -163,3 +163,20 @@ def test_unmodified_reference_archs_runs_on_the_freia_dropin(fake_kernels):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_direct_gradient_accumulation_matches_autograd_accumulation(fake_kernels):
+    """train.SingleVideoTrainer mode: weight-gradient kernels add straight into pre-allocated param.grad."""
+    opt, ora, net = _pair("SRF", 4, 2, 10, 16, 32)
+    hr, lr, z = R.synthetic_batch(opt, 2, 16, 32, seed=9)
+    lrz = torch.cat((lr, z), 1)
+    net.plan().direct_grad = True
+    for p in net.parameters():
+        p.grad = torch.zeros_like(p)
+    ptrs = [p.grad.data_ptr() for p in net.parameters()]
+    for m in (ora, net):
+        R.reconstruction(m(hr)[:, :opt.lr_dims], lr).backward()
+        R.reconstruction(m(lrz, rev=True), hr).backward()
+    assert ptrs == [p.grad.data_ptr() for p in net.parameters()]          # accumulated in place
+    for (n, a), (_, b) in zip(ora.named_parameters(), net.named_parameters()):
+        assert (a.grad - b.grad).abs().max() <= 2e-4 * max(a.grad.abs().max().item(), 1e-3), n
