@@ -145,6 +145,27 @@ typedef struct {
 int sininn_conv_simt(const sininn_conv_desc* d, sininn_stream_t stream);   /* fp32-accurate CUDA-core path */
 int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream);     /* tcgen05/TMEM/TMA bf16 path */
 
+/* Fused 1x1 coupling subnet, forward (tcgen05/TMEM/TMA, bf16 operands):
+ *   out[p][:] = W2 * relu(W1 * x[p][:] + b1) + b2        per pixel p
+ * Replaces subnet_conv_1x1 (archs.py:15-17: Conv2d(c_in,256,1) -> ReLU -> Conv2d(256,c_out,1)) as called by
+ * the GLOW coupling halves (archs.py:56-64).  The hidden activation stays in shared memory; h_out / bits_out
+ * (both optional) additionally store it (bf16 [npix][hidden]) and its ReLU sign bits (uint32 [npix][hidden/32])
+ * for the backward kernels.  w1pack / w2pack are fprop packs (sininn_pack_conv_weight mode 0, taps = 1). */
+typedef struct {
+  long long npix;
+  int Cin, hidden, Cout;
+  const void* x;  int x_stride;          /* bf16 [npix][Cin] */
+  const void* w1pack; int k1_pad;        /* bf16 [hidden][k1_pad] */
+  const float* b1;                       /* [hidden] or NULL */
+  const void* w2pack; int n2_pad;        /* bf16 [n2_pad][hidden] */
+  const float* b2;                       /* [Cout] or NULL */
+  float* out;     int out_stride;        /* fp32 [npix][Cout] */
+  void* h_out;    int h_stride;          /* NULL or bf16 [npix][hidden] */
+  void* bits_out;                        /* NULL or uint32 [npix][hidden/32] */
+} sininn_subnet1x1_desc;
+
+int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stream);
+
 /* Re-layout nn.Conv2d OIHW fp32 weights for the implicit GEMMs above.
  *   mode 0 (fprop): out[tap][co][ci] = w[co][ci][tap]           rows = Cout, k = Cin
  *   mode 1 (dgrad): out[tap][ci][co] = w[co][ci][taps-1-tap]    rows = Cin,  k = Cout */

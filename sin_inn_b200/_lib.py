@@ -49,6 +49,21 @@ class WgradDesc(C.Structure):
     ]
 
 
+class Subnet1x1Desc(C.Structure):
+    _fields_ = [
+        ("npix", _c_ll),
+        ("Cin", C.c_int), ("hidden", C.c_int), ("Cout", C.c_int),
+        ("x", _vp), ("x_stride", C.c_int),
+        ("w1pack", _vp), ("k1_pad", C.c_int),
+        ("b1", _vp),
+        ("w2pack", _vp), ("n2_pad", C.c_int),
+        ("b2", _vp),
+        ("out", _vp), ("out_stride", C.c_int),
+        ("h_out", _vp), ("h_stride", C.c_int),
+        ("bits_out", _vp),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/sininn.h declares
 SIGNATURES = {
     "sininn_version": (C.c_int, []),
@@ -71,6 +86,7 @@ SIGNATURES = {
     "sininn_axpy_slice": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _c_ll, C.c_int, C.c_float, _vp]),
     "sininn_conv_simt": (C.c_int, [C.POINTER(ConvDesc), _vp]),
     "sininn_conv_tc": (C.c_int, [C.POINTER(ConvDesc), _vp]),
+    "sininn_subnet1x1_fwd_tc": (C.c_int, [C.POINTER(Subnet1x1Desc), _vp]),
     "sininn_pack_conv_weight": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "sininn_pack_conv_weights_batched": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "sininn_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(WgradDesc), C.c_int]),

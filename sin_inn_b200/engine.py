@@ -50,6 +50,8 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
+FUSE_1X1 = os.environ.get("SININN_FUSE_1X1", "1") != "0"     # fused 1x1 subnet kernel (subnet1x1_tc.cu)
+
 TRACE = None     # debugging aid: set to a list to collect (label, trunk copy) after every executed op
 
 
@@ -239,6 +241,16 @@ class ConvSubnet:
     def fwd(self, ctx, tr, src, keep=False):
         x = tr.operand(src, ctx.adt)
         dev = x.device
+        if (ctx.tc and self.taps == 1 and FUSE_1X1 and K.subnet1x1_supported(self.cin, self.hidden, self.cout)
+                and x.stride(0) % 8 == 0):
+            # one launch for the whole subnet: the hidden activation stays in shared memory (it is only written
+            # out, with its ReLU sign bits, when the backward kernels need it)
+            a = torch.empty(tr.npix, self.cout, dtype=torch.float32, device=dev)
+            h = torch.empty(tr.npix, self.hidden, dtype=ctx.adt, device=dev) if keep else None
+            bits = torch.empty(tr.npix, self.hidden // 32, dtype=torch.int32, device=dev) if keep else None
+            K.subnet1x1_fwd(x, ctx.pack(self.c1.weight, 0), self.c1.bias, ctx.pack(self.c2.weight, 0), self.c2.bias, a,
+                            h_out=h, bits_out=bits)
+            return a, (x, h, bits)
         h = torch.empty(tr.npix, self.hidden, dtype=ctx.adt, device=dev)
         # tensor-core path: the backward pass reads the ReLU mask as 1 bit / element instead of re-reading h
         bits = (torch.empty(tr.npix, (self.hidden + 31) // 32, dtype=torch.int32, device=dev)

@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import F32, BF16, ConvDesc, WgradDesc, check, dtype_code, load, stream_ptr
+from ._lib import F32, BF16, ConvDesc, Subnet1x1Desc, WgradDesc, check, dtype_code, load, stream_ptr
 
 _workspaces = {}
 
@@ -258,6 +258,40 @@ def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask
     fn = lib.sininn_conv_tc if tensor_core else lib.sininn_conv_simt
     flops = 2.0 * B * H * W * d.Cin * d.Cout * d.taps
     check(_run("conv", lambda: fn(C.byref(d), stream_ptr()), 1, flops), "conv_tc" if tensor_core else "conv_simt")
+    return out
+
+
+def subnet1x1_supported(cin, hidden, cout):
+    """Shapes the fused 1x1 subnet kernel takes (everything else runs as two conv launches)."""
+    return hidden % 64 == 0 and 64 <= hidden <= 256 and cout <= 256 and cout % 4 == 0 and cin % 8 == 0
+
+
+def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None):
+    """out = W2 relu(W1 x + b1) + b2 per pixel, one launch (tcgen05; hidden activation stays on chip).
+    x: bf16 [npix, Cin] view; w1pack [1, hidden, k1_pad]; w2pack [1, n2_pad, hidden]; out: fp32 [npix, Cout] view;
+    h_out (bf16 [npix, hidden]) / bits_out (int32 [npix, hidden/32]) optionally receive the hidden activation."""
+    x, out = _view2d(x), _view2d(out)
+    d = Subnet1x1Desc()
+    d.npix = x.shape[0]
+    d.Cin, d.hidden, d.Cout = x.shape[1], w1pack.shape[1], out.shape[1]
+    d.x, d.x_stride = x.data_ptr(), x.stride(0)
+    d.w1pack, d.k1_pad = w1pack.data_ptr(), w1pack.shape[2]
+    d.b1 = _p(b1)
+    d.w2pack, d.n2_pad = w2pack.data_ptr(), w2pack.shape[1]
+    d.b2 = _p(b2)
+    d.out, d.out_stride = out.data_ptr(), out.stride(0)
+    if x.dtype != torch.bfloat16 or out.dtype != torch.float32 or w1pack.dtype != torch.bfloat16 or w2pack.dtype != torch.bfloat16:
+        raise _lib.SininnError("subnet1x1_fwd: bf16 operands and an fp32 output are required")
+    if w2pack.shape[2] != d.hidden or w1pack.shape[0] != 1 or w2pack.shape[0] != 1:
+        raise _lib.SininnError("subnet1x1_fwd: packed weights do not describe a 1x1 Cin->hidden->Cout subnet")
+    if h_out is not None:
+        h_out = _view2d(h_out)
+        d.h_out, d.h_stride = h_out.data_ptr(), h_out.stride(0)
+    else:
+        d.h_out, d.h_stride = 0, 0
+    d.bits_out = _p(bits_out)
+    flops = 2.0 * d.npix * d.hidden * (d.Cin + d.Cout)
+    check(_run("conv", lambda: load().sininn_subnet1x1_fwd_tc(C.byref(d), stream_ptr()), 1, flops), "subnet1x1_fwd_tc")
     return out
 
 

@@ -333,3 +333,42 @@ def test_wgrad_tc(K, taps, cin, cout, geom):
     got3 = torch.empty_like(got)
     K.wgrad(x.to(DEV)[:, :cin], dy.to(DEV)[:, :cout], geom, taps, got3, accumulate=False, tensor_core=True)
     assert torch.equal(got2, got3)                       # deterministic
+
+
+@pytest.mark.parametrize("cin,hidden,cout,npix", [(24, 256, 48, 128), (24, 256, 48, 20000), (96, 256, 192, 45), (96, 256, 192, 33 * 40),
+                                                   (8, 64, 16, 300), (64, 128, 256, 700), (40, 192, 100, 129)])
+@pytest.mark.parametrize("keep", [False, True])
+def test_subnet1x1_fused_forward(K, cin, hidden, cout, npix, keep):
+    """Fused conv1x1 -> ReLU -> conv1x1 (hidden tile in shared memory) against the torch restatement, with and
+    without the hidden activation / ReLU sign bits stored for the backward pass; input and output are channel
+    slices of wider matrices."""
+    bf = torch.bfloat16
+    assert K.subnet1x1_supported(cin, hidden, cout)
+    w1 = rnd(hidden, cin, 1, 1, seed=70) * 0.2
+    w2 = rnd(cout, hidden, 1, 1, seed=71) * 0.1
+    b1, b2 = rnd(hidden, seed=72) * 0.3, rnd(cout, seed=73)
+    xw = rnd(npix, cin + 8, seed=74).to(bf)
+    k1p, n2p, hp = (cin + 15) // 16 * 16, (cout + 15) // 16 * 16, (hidden + 15) // 16 * 16
+    w1r, w2r = FK.pack_weight(w1, 0, bf, hp, k1p), FK.pack_weight(w2, 0, bf, n2p, hp)
+    w1d, w2d = K.pack_weight(w1.to(DEV), 0, bf, hp, k1p), K.pack_weight(w2.to(DEV), 0, bf, n2p, hp)
+    base = rnd(npix, cout + 4, seed=75)
+    ref = base.clone()
+    href = torch.empty(npix, hidden, dtype=bf)
+    bref = torch.zeros(npix, hidden // 32, dtype=torch.int32)
+    FK.subnet1x1_fwd(xw[:, :cin], w1r, b1, w2r, b2, ref[:, :cout], h_out=href, bits_out=bref)
+    got = base.clone().to(DEV)
+    h = torch.zeros(npix, hidden, dtype=bf, device=DEV) if keep else None
+    bits = torch.zeros(npix, hidden // 32, dtype=torch.int32, device=DEV) if keep else None
+    K.subnet1x1_fwd(xw.to(DEV)[:, :cin], w1d, b1.to(DEV), w2d, b2.to(DEV), got[:, :cout], h_out=h, bits_out=bits)
+    got = got.cpu()
+    assert torch.equal(got[:, cout:], base[:, cout:]), "fused subnet wrote outside its channel slice"
+    tol = 1e-2 * max(1.0, ref[:, :cout].abs().max().item())
+    assert (got[:, :cout] - ref[:, :cout]).abs().max().item() <= tol
+    if keep:
+        hc = h.cpu().float()
+        assert (hc - href.float()).abs().max().item() <= 1e-2 * max(1.0, href.float().abs().max().item())
+        assert torch.equal(FK._unpack_bits(bits.cpu(), hidden), (hc > 0).float())
+    # determinism: the inverse pass re-evaluates the subnet on the same bits and must get the same bits back
+    again = base.clone().to(DEV)
+    K.subnet1x1_fwd(xw.to(DEV)[:, :cin], w1d, b1.to(DEV), w2d, b2.to(DEV), again[:, :cout])
+    assert torch.equal(again.cpu(), got)

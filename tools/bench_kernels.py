@@ -48,7 +48,29 @@ def wgrad_case(name, hw, cin, cout, taps):
     print(f"{name:34s} M={npix:7d} K={cin*taps:5d} N={cout:4d}  {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TFLOP/s")
     return ms
 
+def fused1x1_case(name, hw, cin, cout, keep):
+    npix = B * hw * hw
+    x = torch.randn(npix, cin, device=DEV).to(torch.bfloat16)
+    w1 = torch.randn(256, cin, 1, 1, device=DEV) * 0.05
+    w2 = torch.randn(cout, 256, 1, 1, device=DEV) * 0.05
+    w1p = K.pack_weight(w1, 0, torch.bfloat16, 256, (cin + 15) // 16 * 16)
+    w2p = K.pack_weight(w2, 0, torch.bfloat16, (cout + 15) // 16 * 16, 256)
+    b1, b2 = torch.randn(256, device=DEV), torch.randn(cout, device=DEV)
+    out = torch.zeros(npix, cout, device=DEV)
+    h = torch.empty(npix, 256, dtype=torch.bfloat16, device=DEV) if keep else None
+    bits = torch.empty(npix, 8, dtype=torch.int32, device=DEV) if keep else None
+    ms = timeit(lambda: K.subnet1x1_fwd(x, w1p, b1, w2p, b2, out, h_out=h, bits_out=bits))
+    fl = 2.0 * npix * 256 * (cin + cout)
+    print(f"{name:34s} M={npix:7d} {cin:3d}->256->{cout:3d} keep={int(keep)}  {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TFLOP/s")
+    return ms
+
+
 if __name__ == "__main__":
+    if os.environ.get("ONLY") == "fused1x1":
+        for lvl, hw, c in (("L0", 64, 48), ("L1", 32, 192)):
+            for keep in (False, True):
+                fused1x1_case(f"{lvl} fused 1x1 subnet fwd", hw, c // 2, c, keep)
+        sys.exit(0)
     bf, f32 = torch.bfloat16, torch.float32
     tot = 0.0
     for lvl, hw, c in (("L0", 64, 48), ("L1", 32, 192)):
