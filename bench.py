@@ -151,17 +151,28 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The step is captured once into a CUDA graph (train.SingleVideoTrainer.capture): ~560 kernel launches, the
+    # NCCL all-reduce and Adam replay as ONE graph launch.  --no-graph runs the same step eagerly.
+    kernels.LAUNCHES = 0
+    trainer.training_step(*dev_batches[0])
+    launches_per_step = kernels.LAUNCHES
+    graphed = None if args.no_graph else trainer.capture(*dev_batches[0], warmup=2)
+
     def step_resident(i):
+        if graphed is not None:
+            return graphed(*dev_batches[i % 2])       # device-to-device copy into the graph's static inputs + replay
         return trainer.training_step(*dev_batches[i % 2])
 
     def step_e2e(i):
-        hr, lr, z = (t.to(dev, non_blocking=True) for t in pool[i % 2])
-        lf, lb = trainer.training_step(hr, lr, z)
+        if graphed is not None:
+            lf, lb = graphed(*pool[i % 2])            # pinned host -> static device inputs (async H2D) + replay
+        else:
+            hr, lr, z = (t.to(dev, non_blocking=True) for t in pool[i % 2])
+            lf, lb = trainer.training_step(hr, lr, z)
         return float(lf.item() + lb.item())          # D2H read of the step's result
 
     for i in range(args.warmup):
         step_resident(i)
-    kernels.LAUNCHES = 0
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -172,12 +183,12 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = kernels.LAUNCHES
+    launches = launches_per_step * args.steps      # kernels executed in the timed region (graph replays included)
     # same K steps again with a CUDA-event pair around every kernel launch (per-family durations for the roofline);
     # kept out of the headline region because ~1300 extra event records per step perturb a launch-dense step
     kernels.profile_begin()
     for i in range(args.steps):
-        step_resident(i)
+        trainer.training_step(*dev_batches[i % 2])     # eager: events cannot be recorded inside a graph replay
     prof = kernels.profile_end()
     sampler.stop_flag = True
     # end-to-end: pinned host inputs -> device, step, loss back to host, every step
@@ -215,7 +226,7 @@ def run_ours(args):
             "config": {"workload": f"SRF scale4 c4 lr_window10 {P}x{P} train step, batch {B}/GPU", **WORKLOAD,
                        "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision, "tensor_core": not args.no_tensor_core,
                        "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2",
-                       "backward": "recompute-from-inverse"},
+                       "backward": "recompute-from-inverse", "cuda_graph": graphed is not None},
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
@@ -245,6 +256,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=WORKLOAD["batch_per_gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-tensor-core", action="store_true", help="route the subnet GEMMs to the CUDA-core kernels")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

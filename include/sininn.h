@@ -142,6 +142,10 @@ typedef struct {
   void* bits_out;                 /* NULL, or receives the sign bits (value > 0) of this call's own output */
 } sininn_conv_desc;
 
+/* Debugging aid: when set to a device buffer of 3 x 512 int64, the CTA-pair 3x3 kernel records clock64() stamps of
+ * CTA 0's producer / MMA / epilogue roles into it (NULL switches tracing off, the default). */
+int sininn_debug_set_trace(void* device_buf_3x512_int64);
+
 int sininn_conv_simt(const sininn_conv_desc* d, sininn_stream_t stream);   /* fp32-accurate CUDA-core path */
 int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream);     /* tcgen05/TMEM/TMA bf16 path */
 
@@ -202,6 +206,12 @@ int sininn_sqdiff_nchw(const float* a, const float* b, long long n, float scale,
 int sininn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                      float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                      float grad_scale, sininn_stream_t stream);
+/* The same update with the step count kept on the DEVICE so that the launch can be replayed from a CUDA graph:
+ * step_state is 3 x 4 bytes {int32 steps done so far, float scratch, float scratch}, zero-initialised by the
+ * caller; every call increments it and derives the bias corrections from it (two launches). */
+int sininn_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                         float lr, float beta1, float beta2, float eps, float weight_decay, int* step_state,
+                         float grad_scale, sininn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -84,6 +84,7 @@ SIGNATURES = {
     "sininn_colsum_workspace_bytes": (C.c_size_t, [_c_ll, C.c_int]),
     "sininn_colsum": (C.c_int, [_vp, C.c_int, C.c_int, _c_ll, C.c_int, _vp, C.c_int, _vp, C.c_size_t, _vp]),
     "sininn_axpy_slice": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _c_ll, C.c_int, C.c_float, _vp]),
+    "sininn_debug_set_trace": (C.c_int, [_vp]),
     "sininn_conv_simt": (C.c_int, [C.POINTER(ConvDesc), _vp]),
     "sininn_conv_tc": (C.c_int, [C.POINTER(ConvDesc), _vp]),
     "sininn_subnet1x1_fwd_tc": (C.c_int, [C.POINTER(Subnet1x1Desc), _vp]),
@@ -96,6 +97,8 @@ SIGNATURES = {
     "sininn_sqdiff_nchw": (C.c_int, [_vp, _vp, _c_ll, C.c_float, _vp, _vp, _vp, C.c_size_t, _vp]),
     "sininn_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _c_ll, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                    C.c_int, C.c_float, _vp]),
+    "sininn_adam_step_dev": (C.c_int, [_vp, _vp, _vp, _vp, _c_ll, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                       _vp, C.c_float, _vp]),
 }
 
 _lib = None

@@ -24,6 +24,7 @@ namespace sininn {
 namespace tc {
 
 int launch_conv_halo(const sininn_conv_desc* d, Params p, int base_offset_mode, cudaStream_t st);   // conv_tc_halo.cu
+int launch_conv_pair(const sininn_conv_desc* d, Params p, cudaStream_t st);                          // conv_tc_pair.cu
 
 constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;   // 128 pixels = UMMA M
 
@@ -40,7 +41,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   Barriers* bars = reinterpret_cast<Barriers*>(staging + NUM_EPI_WARPS * STAGING_BYTES);
   float* bias_s = reinterpret_cast<float*>(staging + NUM_EPI_WARPS * STAGING_BYTES + BARRIER_BYTES);   // [256]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells ptxas the role branches below are warp-uniform, which lets it keep the
+  // MMA/TMA issue loops on the uniform datapath (without it every tcgen05.mma operand costs an R2UR move)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const uint32_t ring_u32 = smem_u32(ring);
 
   if (threadIdx.x == 0) {
@@ -201,6 +204,16 @@ int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream) {
   // 3x3 with 64-channel slabs: halo-reuse kernel (activation patch loaded once per slab instead of nine times)
   // (SININN_HALO=0 disables it; measured on B200: the UMMA swizzle XOR is taken from the absolute shared-memory
   //  address bits, so a descriptor may start at any 128-byte row of the TMA-written halo box with base_offset 0)
+  // 3x3: CTA-pair kernel (cta_group::2, weight rows split over the pair, resident when they fit); SININN_PAIR=0 disables
+  static int pair_mode = -1;
+  if (pair_mode < 0) {
+    const char* e = getenv("SININN_PAIR");
+    pair_mode = e ? atoi(e) : 1;
+  }
+  if (pair_mode > 0 && d->taps == 9) {
+    const int rc = launch_conv_pair(d, p, as_stream(stream));
+    if (rc != SININN_EUNSUPPORTED) return rc;
+  }
   static int halo_mode = -1;
   if (halo_mode < 0) {
     const char* e = getenv("SININN_HALO");

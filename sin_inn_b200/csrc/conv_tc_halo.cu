@@ -43,7 +43,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   float* bias_s = reinterpret_cast<float*>(staging + NUM_EPI_WARPS * STAGING_BYTES + BARRIER_BYTES);
   HaloBarriers* hb = reinterpret_cast<HaloBarriers*>(staging + NUM_EPI_WARPS * STAGING_BYTES + BARRIER_BYTES + 1024);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells ptxas the role branches below are warp-uniform, which lets it keep the
+  // MMA/TMA issue loops on the uniform datapath (without it every tcgen05.mma operand costs an R2UR move)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const uint32_t a_u32 = smem_u32(a_ring), b_u32 = smem_u32(b_ring);
 
   if (threadIdx.x == 0) {

@@ -294,6 +294,31 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+// Graph-replayable Adam: the step count lives on the device.  state = {int step, float bc1, float sqrt(bc2)}.
+__global__ void adam_tick_kernel(int* __restrict__ state, float b1, float b2) {
+  const int step = state[0] + 1;
+  state[0] = step;
+  float* f = reinterpret_cast<float*>(state);
+  f[1] = 1.f - powf(b1, (float)step);
+  f[2] = sqrtf(1.f - powf(b2, (float)step));
+}
+
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                       float wd, const int* __restrict__ state, float gscale) {
+  const float bc1 = reinterpret_cast<const float*>(state)[1], bc2_sqrt = reinterpret_cast<const float*>(state)[2];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float w = p[i];
+    float gr = g[i] * gscale + wd * w;
+    float mi = b1 * m[i] + (1.f - b1) * gr;
+    float vi = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = w - (lr / bc1) * (mi / denom);
+  }
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   long long cap = (long long)sm_count() * 32;
@@ -462,6 +487,18 @@ int sininn_adam_step(float* param, const float* grad, float* exp_avg, float* exp
   adam_kernel<<<grid, block, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                      weight_decay, bc1, sqrtf(bc2), grad_scale);
   SININN_CHECK_LAUNCH("adam_step");
+  return SININN_OK;
+}
+
+int sininn_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, int* step_state, float grad_scale,
+                         sininn_stream_t stream) {
+  SININN_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step_state && n > 0, "adam_step_dev: bad arguments");
+  const int block = 256, grid = grid_for(n, block);
+  adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(step_state, beta1, beta2);
+  adam_dev_kernel<<<grid, block, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                         weight_decay, step_state, grad_scale);
+  SININN_CHECK_LAUNCH("adam_step_dev");
   return SININN_OK;
 }
 

@@ -78,7 +78,9 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   float* b1_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [256]
   float* b2_s = b1_s + 256;                                                             // [256]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells ptxas the role branches below are warp-uniform, which lets it keep the
+  // MMA/TMA issue loops on the uniform datapath (without it every tcgen05.mma operand costs an R2UR move)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const bool w2_resident = p.w2_stages == p.hs;
 
   if (threadIdx.x == 0) {

@@ -92,13 +92,18 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
 // v holds the slab's accumulator columns; returns the sign bits of the produced values (bit j = value j > 0).
 template <int NCOL>
 __device__ __forceinline__ void slab_math(const Params& p, float (&x)[NCOL], const float* bias_s, const uint32_t* mbits) {
+  // branch-free activation: f(v) = v > 0 ? v : ns * v with ns = 1 (none), 0 (ReLU), slope (LeakyReLU).  A per-element
+  // switch on p.act costs three uniform branches per value -- measured at ~5000 cycles per 64-column slab.
+  const float ns = p.act == SININN_ACT_RELU ? 0.f : (p.act == SININN_ACT_LRELU ? p.slope : 1.f);
 #pragma unroll
   for (int q = 0; q < NCOL / 4; ++q) {
     const float4 bq = *reinterpret_cast<const float4*>(bias_s + 4 * q);
-    x[4 * q + 0] = act_fwd(p.act, p.slope, x[4 * q + 0] + bq.x);
-    x[4 * q + 1] = act_fwd(p.act, p.slope, x[4 * q + 1] + bq.y);
-    x[4 * q + 2] = act_fwd(p.act, p.slope, x[4 * q + 2] + bq.z);
-    x[4 * q + 3] = act_fwd(p.act, p.slope, x[4 * q + 3] + bq.w);
+    const float b4[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v = x[4 * q + e] + b4[e];
+      x[4 * q + e] = v > 0.f ? v : ns * v;
+    }
   }
   if (mbits != nullptr) {
 #pragma unroll
@@ -111,116 +116,145 @@ __device__ __forceinline__ void slab_math(const Params& p, float (&x)[NCOL], con
   }
 }
 
-// Epilogue role of one warp (warps 2..9 of the CTA).  TW = tile width in pixels (tile = TW x 128/TW); the
-// warp's 32 accumulator rows are 32/TW consecutive tile rows, stored as one TMA box {128 B, TW, 32/TW, 1}.
+// (Re)load the bias slice of N tile n0 into bias_s (all 256 epilogue threads take part; named barrier 1).
+__device__ __forceinline__ void epilogue_load_bias(const Params& p, float* bias_s, int n0, int etid, int& bias_n0) {
+  if (n0 == bias_n0) return;
+  asm volatile("bar.sync 1, 256;" ::: "memory");           // everyone done with the previous slice
+  {
+    const int co = n0 + etid;
+    bias_s[etid] = (p.bias != nullptr && co < p.Cout) ? __ldg(p.bias + co) : 0.f;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  bias_n0 = n0;
+}
+
+// One output tile of one epilogue warp: the warp's 32 accumulator rows (TMEM lanes 32*quarter..+31, columns from
+// t_base) are 32/TW consecutive tile rows, stored as one TMA box {128 B, TW, 32/TW, 1} per 128-byte output slab.
+// The two warps of a lane quarter (half = 0/1) take alternate slabs.  Tile origin (b, h0, w0), first channel n0;
+// a tile with b >= p.B is a phantom (nothing is stored).
+#ifdef SININN_PAIR_TRACE
+#define EPI_STAMP() do { if (etrace != nullptr && lane == 0) { *etrace++ = clock64(); } } while (0)
+#else
+#define EPI_STAMP() do { } while (0)
+#endif
+template <int TW>
+__device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap* tmO, uint8_t* stg, const float* bias_s,
+                                              uint32_t t_base, int b, int h0, int w0, int n0, int quarter, int half, int lane,
+                                              long long* etrace = nullptr) {
+  const uint32_t stg_u32 = smem_u32(stg);
+  const int row = quarter * 32 + lane;                       // pixel row inside the tile
+  const int hl = row / TW, wl = row % TW;
+  const int slab_cols = p.out_f32 ? 32 : 64;                 // 128 bytes of output per row
+  const int oh = h0 + hl, ow = w0 + wl;
+  const bool row_ok = (oh < p.H) && (ow < p.W) && (b < p.B);
+  const long long pix = ((long long)b * p.H + oh) * p.W + ow;
+  const int n_valid = min(p.n_tile, p.Cout - n0);
+  if (p.tma_out) {
+    const int n_slabs = (n_valid + slab_cols - 1) / slab_cols;
+    for (int s = half; s < n_slabs; s += 2) {
+      const int c = s * slab_cols;                         // first accumulator column of the slab
+      // sign-bit mask words of this row for the slab's columns
+      uint32_t mb[2] = {0xffffffffu, 0xffffffffu};
+      if (p.bits_in != nullptr) {
+        const int w0i = (n0 + c) >> 5;
+        mb[0] = row_ok ? __ldg(p.bits_in + pix * p.bit_words + w0i) : 0u;
+        if (!p.out_f32) mb[1] = (row_ok && w0i + 1 < p.bit_words) ? __ldg(p.bits_in + pix * p.bit_words + w0i + 1) : 0u;
+      }
+      EPI_STAMP();
+      if (lane == 0) bulk_wait_read0();                    // previous TMA store has finished reading the staging rows
+      __syncwarp();
+      EPI_STAMP();
+      uint32_t sign[2] = {0u, 0u};
+      if (p.out_f32) {
+        uint32_t v[32];
+        tmem_ld32(t_base + c, v);
+        tmem_ld_wait();
+        EPI_STAMP();
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        slab_math<32>(p, x, bias_s + c, p.bits_in ? mb : nullptr);
+        if (p.bits_out != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sign[0] |= (x[j] > 0.f ? 1u : 0u) << j;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)                         // 16-byte piece q of the row, 128B swizzle: q ^ (row & 7)
+          *reinterpret_cast<float4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+              make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+      } else {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(t_base + c, v0);
+        tmem_ld32(t_base + c + 32, v1);                    // (columns past n_valid are clipped by the TMA store)
+        tmem_ld_wait();
+        EPI_STAMP();
+        float x[64];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { x[j] = __uint_as_float(v0[j]); x[32 + j] = __uint_as_float(v1[j]); }
+        slab_math<64>(p, x, bias_s + c, p.bits_in ? mb : nullptr);
+        if (p.bits_out != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            sign[0] |= (x[j] > 0.f ? 1u : 0u) << j;
+            sign[1] |= (x[32 + j] > 0.f ? 1u : 0u) << j;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint4 o;
+          o.x = pack_bf16(x[8 * q + 0], x[8 * q + 1]);
+          o.y = pack_bf16(x[8 * q + 2], x[8 * q + 3]);
+          o.z = pack_bf16(x[8 * q + 4], x[8 * q + 5]);
+          o.w = pack_bf16(x[8 * q + 6], x[8 * q + 7]);
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+        }
+      }
+      EPI_STAMP();
+      if (p.bits_out != nullptr && row_ok) {
+        const int w0i = (n0 + c) >> 5;
+        p.bits_out[pix * p.bit_words + w0i] = sign[0];
+        if (!p.out_f32 && w0i + 1 < p.bit_words) p.bits_out[pix * p.bit_words + w0i + 1] = sign[1];
+      }
+      fence_async_smem();                                  // generic-proxy smem writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        // this warp's 32 rows are 32/TW consecutive tile rows: box {128 B, TW, 32/TW, 1}
+        if (p.accumulate) tma_reduce_add_4d(tmO, stg_u32, n0 + c, w0, h0 + (32 / TW) * quarter, b);
+        else tma_store_4d(tmO, stg_u32, n0 + c, w0, h0 + (32 / TW) * quarter, b);
+        bulk_commit();
+      }
+      EPI_STAMP();
+    }
+  } else if (half == 0) {
+    for (int c = 0; c < n_valid; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(t_base + c, v);
+      tmem_ld_wait();
+      if (p.out_f32) epilogue_chunk<float>(p, v, pix, n0 + c, row_ok);
+      else epilogue_chunk<__nv_bfloat16>(p, v, pix, n0 + c, row_ok);
+    }
+  }
+}
+
+// Epilogue role of one warp (warps 2..9 of the CTA) of the single-CTA kernels.  TW = tile width in pixels.
 template <int TW>
 __device__ __forceinline__ void run_epilogue(const Params& p, const CUtensorMap* tmO, Barriers* bars, uint8_t* staging,
                                              float* bias_s, uint32_t tmem_base, int warp, int lane) {
     const int ew = warp - 2;                                   // 0..7
     const int quarter = warp & 3;                              // TMEM lanes 32*quarter .. +31 (hardware rule: warp id % 4)
     const int half = ew >> 2;                                  // which of the two warps of this quarter
-    const int row = quarter * 32 + lane;                       // pixel row inside the tile
-    const int hl = row / TW, wl = row % TW;
     uint8_t* stg = staging + ew * STAGING_BYTES;
-    const uint32_t stg_u32 = smem_u32(stg);
     const int etid = threadIdx.x - 64;                         // 0..255 among the epilogue threads
-    const int slab_cols = p.out_f32 ? 32 : 64;                 // 128 bytes of output per row
     int acc = 0; uint32_t acc_phase = 0;
     int bias_n0 = -1;
     for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       int b, h0, w0, n0;
       tile_coords<TW>(p, t, b, h0, w0, n0);
-      const int oh = h0 + hl, ow = w0 + wl;
-      const bool row_ok = (oh < p.H) && (ow < p.W);
-      const long long pix = ((long long)b * p.H + oh) * p.W + ow;
-      if (n0 != bias_n0) {                                     // (re)load the bias slice of this N tile
-        asm volatile("bar.sync 1, 256;" ::: "memory");         // everyone done with the previous slice
-        {
-          const int co = n0 + etid;
-          bias_s[etid] = (p.bias != nullptr && co < p.Cout) ? __ldg(p.bias + co) : 0.f;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        bias_n0 = n0;
-      }
+      epilogue_load_bias(p, bias_s, n0, etid, bias_n0);
       mbar_wait(smem_u32(&bars->acc_full[acc]), acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE;
-      const int n_valid = min(p.n_tile, p.Cout - n0);
-      if (p.tma_out) {
-        const int n_slabs = (n_valid + slab_cols - 1) / slab_cols;
-        for (int s = half; s < n_slabs; s += 2) {
-          const int c = s * slab_cols;                         // first accumulator column of the slab
-          // sign-bit mask words of this row for the slab's columns
-          uint32_t mb[2] = {0xffffffffu, 0xffffffffu};
-          if (p.bits_in != nullptr) {
-            const int w0i = (n0 + c) >> 5;
-            mb[0] = row_ok ? __ldg(p.bits_in + pix * p.bit_words + w0i) : 0u;
-            if (!p.out_f32) mb[1] = (row_ok && w0i + 1 < p.bit_words) ? __ldg(p.bits_in + pix * p.bit_words + w0i + 1) : 0u;
-          }
-          if (lane == 0) bulk_wait_read0();                    // previous TMA store has finished reading the staging rows
-          __syncwarp();
-          uint32_t sign[2] = {0u, 0u};
-          if (p.out_f32) {
-            uint32_t v[32];
-            tmem_ld32(t_base + c, v);
-            tmem_ld_wait();
-            float x[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-            slab_math<32>(p, x, bias_s + c, p.bits_in ? mb : nullptr);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sign[0] |= (x[j] > 0.f ? 1u : 0u) << j;
-#pragma unroll
-            for (int q = 0; q < 8; ++q)                         // 16-byte piece q of the row, 128B swizzle: q ^ (row & 7)
-              *reinterpret_cast<float4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                  make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-          } else {
-            uint32_t v0[32], v1[32];
-            tmem_ld32(t_base + c, v0);
-            tmem_ld32(t_base + c + 32, v1);                    // (columns past n_valid are clipped by the TMA store)
-            tmem_ld_wait();
-            float x[64];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { x[j] = __uint_as_float(v0[j]); x[32 + j] = __uint_as_float(v1[j]); }
-            slab_math<64>(p, x, bias_s + c, p.bits_in ? mb : nullptr);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              sign[0] |= (x[j] > 0.f ? 1u : 0u) << j;
-              sign[1] |= (x[32 + j] > 0.f ? 1u : 0u) << j;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              uint4 o;
-              o.x = pack_bf16(x[8 * q + 0], x[8 * q + 1]);
-              o.y = pack_bf16(x[8 * q + 2], x[8 * q + 3]);
-              o.z = pack_bf16(x[8 * q + 4], x[8 * q + 5]);
-              o.w = pack_bf16(x[8 * q + 6], x[8 * q + 7]);
-              *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
-            }
-          }
-          if (p.bits_out != nullptr && row_ok) {
-            const int w0i = (n0 + c) >> 5;
-            p.bits_out[pix * p.bit_words + w0i] = sign[0];
-            if (!p.out_f32 && w0i + 1 < p.bit_words) p.bits_out[pix * p.bit_words + w0i + 1] = sign[1];
-          }
-          fence_async_smem();                                  // generic-proxy smem writes -> visible to the TMA engine
-          __syncwarp();
-          if (lane == 0) {
-            // this warp's 32 rows are tile rows h = 2*quarter, 2*quarter+1 (16 pixels each): box {128 B, 16, 2, 1}
-            if (p.accumulate) tma_reduce_add_4d(tmO, stg_u32, n0 + c, w0, h0 + (32 / TW) * quarter, b);
-            else tma_store_4d(tmO, stg_u32, n0 + c, w0, h0 + (32 / TW) * quarter, b);
-            bulk_commit();
-          }
-        }
-      } else if (half == 0) {
-        for (int c = 0; c < n_valid; c += 16) {
-          uint32_t v[16];
-          tmem_ld16(t_base + c, v);
-          tmem_ld_wait();
-          if (p.out_f32) epilogue_chunk<float>(p, v, pix, n0 + c, row_ok);
-          else epilogue_chunk<__nv_bfloat16>(p, v, pix, n0 + c, row_ok);
-        }
-      }
+      epilogue_tile<TW>(p, tmO, stg, bias_s, t_base, b, h0, w0, n0, quarter, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));

@@ -44,7 +44,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* ring = smem_raw + pad;
   Barriers* bars = reinterpret_cast<Barriers*>(ring + (size_t)p.stages * p.stage_bytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells ptxas the role branches below are warp-uniform, which lets it keep the
+  // MMA/TMA issue loops on the uniform datapath (without it every tcgen05.mma operand costs an R2UR move)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const uint32_t ring_u32 = smem_u32(ring);
 
   // work item

@@ -337,3 +337,11 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, st
     check(_run("adam", lambda: load().sininn_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n,
                                   float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
                                   int(step), float(grad_scale), stream_ptr()), 1, 0.0, 28.0 * n), "adam_step")
+
+
+def adam_step_dev(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step_state, grad_scale=1.0):
+    """Adam with the step count on the device (int32[3] state tensor): replayable from a CUDA graph."""
+    n = param.numel()
+    check(_run("adam", lambda: load().sininn_adam_step_dev(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                      n, float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                      step_state.data_ptr(), float(grad_scale), stream_ptr()), 2, 0.0, 28.0 * n), "adam_step_dev")

@@ -67,14 +67,16 @@ class FusedAdam:
         self.exp_avg = torch.zeros_like(flat.flat)
         self.exp_avg_sq = torch.zeros_like(flat.flat)
         self.steps = 0
+        # step count on the device ({int32 steps, 2 floats of scratch}) so that a captured step replays correctly
+        self.state = torch.zeros(3, dtype=torch.int32, device=flat.flat.device)
 
     def zero_grad(self):
         self.fp.zero_grad()
 
     def step(self, grad_scale=1.0):
         self.steps += 1
-        K.adam_step(self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas, self.eps, self.wd,
-                    self.steps, grad_scale)
+        K.adam_step_dev(self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas, self.eps, self.wd,
+                        self.state, grad_scale)
         # the kernel wrote the parameters through raw pointers (no tensor version bump): drop the packed copies
         engine.invalidate_packs()
 
@@ -114,6 +116,40 @@ class SingleVideoTrainer:
             dist.all_reduce(self.flat.grad)                            # one NCCL all-reduce per step
         self.optim.step(grad_scale=1.0 / self.world_size)              # lit_wrapper.py:76
         return fwd_loss.detach(), bwd_loss.detach()
+
+    def capture(self, hr, lr, z, warmup=3):
+        """Capture the whole training step (both passes, both backward passes, all-reduce, Adam) into ONE CUDA graph
+        over static input buffers shaped like (hr, lr, z).  Returns step(hr, lr, z) -> (fwd_loss, bwd_loss) that copies
+        the batch into the static buffers and replays the graph: ~560 kernel launches become one graph launch, so the
+        step is no longer bounded by the Python/ctypes launch path.  `warmup` eager steps run first (allocator and
+        workspaces reach steady state, function attributes are set, weight packs are built); they DO update the
+        weights, exactly like `warmup` ordinary training steps."""
+        s_hr, s_lr, s_z = (torch.empty_like(t) for t in (hr, lr, z))
+        for t, src in ((s_hr, hr), (s_lr, lr), (s_z, z)):
+            t.copy_(src)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.training_step(s_hr, s_lr, s_z)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            losses = self.training_step(s_hr, s_lr, s_z)
+        self._graph = (graph, (s_hr, s_lr, s_z), losses)
+
+        def step(hr, lr, z):
+            if hr.data_ptr() != s_hr.data_ptr():
+                s_hr.copy_(hr, non_blocking=True)
+                s_lr.copy_(lr, non_blocking=True)
+                s_z.copy_(z, non_blocking=True)
+            graph.replay()
+            self.optim.steps += 1
+            return losses
+
+        step.static_inputs = (s_hr, s_lr, s_z)
+        return step
 
     @torch.no_grad()
     def validation_step(self, hr, lr, z):

@@ -229,3 +229,8 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, st
     exp_avg_sq.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
     bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
     param.sub_((lr / bc1) * exp_avg / (exp_avg_sq.sqrt() / bc2 ** 0.5 + eps))
+
+
+def adam_step_dev(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step_state, grad_scale=1.0):
+    step_state[0] += 1
+    adam_step(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, int(step_state[0]), grad_scale)
