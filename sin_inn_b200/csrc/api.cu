@@ -1,5 +1,6 @@
 // libsininn: error reporting, device info.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -12,6 +13,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("SININN_PDL");
+    mode = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return mode == 1;
 }
 
 int sm_count() {

@@ -34,6 +34,33 @@ static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>
 
 int sm_count();
 
+// ---- programmatic dependent launch (PDL).  Every kernel of this library is launched with the
+// programmaticStreamSerialization attribute and starts with pdl_wait(): a kernel's CTAs may be scheduled (and run
+// their prologue: barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel in the stream is
+// still draining, but touch no global memory before the previous kernel has completed and flushed.  That hides the
+// launch latency and prologue of ~560 back-to-back launches per training step.  SININN_PDL=0 switches it off.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// first statement (before any global-memory access) of every kernel launched through launch_k
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the next kernel's CTAs be scheduled as SMs free up (they still block in their own pdl_wait)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);

@@ -29,6 +29,8 @@ struct ConvArgs {
 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const TI* __restrict__ in = reinterpret_cast<const TI*>(a.in);
@@ -129,6 +131,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
 template <typename TO>
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int mode,
                                                           TO* __restrict__ out, int rows_pad, int k_pad) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)taps * rows_pad * k_pad;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -149,6 +153,8 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
 // all conv weights of a network in ONE launch: jobs[j] = {src, dst, Cout, Cin, taps, mode, rows_pad, k_pad}
 template <typename TO>
 __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const long long* __restrict__ jobs) {
+  pdl_wait();
+  pdl_trigger();
   const long long* j = jobs + (long long)blockIdx.y * 8;
   const float* w = reinterpret_cast<const float*>(j[0]);
   TO* out = reinterpret_cast<TO*>(j[1]);
@@ -184,6 +190,8 @@ struct WgradArgs {
 
 template <typename TX, typename TD>
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradArgs a) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float As[BK][BM + 4];   // dy  [k = pixel][co]
   __shared__ float Bs[BK][BN + 4];   // x   [k = pixel][ci]
   const TX* __restrict__ x = reinterpret_cast<const TX*>(a.x);
@@ -267,6 +275,8 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradArgs a) {
 // dw[co][ci][tap] (+)= sum_split partial[split][tap][co][ci]   (fixed order => deterministic)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cout, int Cin,
                                                            float* __restrict__ dw, int accumulate) {
+  pdl_wait();
+  pdl_trigger();
   const long long per = (long long)taps * Cout * Cin;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -329,10 +339,10 @@ int sininn_conv_simt(const sininn_conv_desc* d, sininn_stream_t stream) {
   dim3 grid((unsigned)tiles, (d->Cout + BN - 1) / BN), block(256);
   cudaStream_t st = as_stream(stream);
   const bool f32out = d->out_dtype == SININN_F32;
-  if (f32in && f32out) conv_simt_kernel<float, float><<<grid, block, 0, st>>>(a);
-  else if (f32in && !f32out) conv_simt_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>(a);
-  else if (!f32in && f32out) conv_simt_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>(a);
-  else conv_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>(a);
+  if (f32in && f32out) launch_k(conv_simt_kernel<float, float>, dim3(grid), dim3(block), 0, st, a);
+  else if (f32in && !f32out) launch_k(conv_simt_kernel<float, __nv_bfloat16>, dim3(grid), dim3(block), 0, st, a);
+  else if (!f32in && f32out) launch_k(conv_simt_kernel<__nv_bfloat16, float>, dim3(grid), dim3(block), 0, st, a);
+  else launch_k(conv_simt_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid), dim3(block), 0, st, a);
   SININN_CHECK_LAUNCH("conv_simt");
   return SININN_OK;
 }
@@ -348,8 +358,8 @@ int sininn_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, in
   long long g = (total + 255) / 256;
   if (g > (long long)sm_count() * 16) g = (long long)sm_count() * 16;
   cudaStream_t st = as_stream(stream);
-  if (out_dtype == SININN_F32) pack_weight_kernel<float><<<(int)g, 256, 0, st>>>(w_oihw, Cout, Cin, taps, mode, (float*)out, rows_pad, k_pad);
-  else if (out_dtype == SININN_BF16) pack_weight_kernel<__nv_bfloat16><<<(int)g, 256, 0, st>>>(w_oihw, Cout, Cin, taps, mode, (__nv_bfloat16*)out, rows_pad, k_pad);
+  if (out_dtype == SININN_F32) launch_k(pack_weight_kernel<float>, dim3((int)g), dim3(256), 0, st, w_oihw, Cout, Cin, taps, mode, (float*)out, rows_pad, k_pad);
+  else if (out_dtype == SININN_BF16) launch_k(pack_weight_kernel<__nv_bfloat16>, dim3((int)g), dim3(256), 0, st, w_oihw, Cout, Cin, taps, mode, (__nv_bfloat16*)out, rows_pad, k_pad);
   else SININN_CHECK_ARG(false, "pack_conv_weight: bad out_dtype");
   SININN_CHECK_LAUNCH("pack_conv_weight");
   return SININN_OK;
@@ -358,8 +368,8 @@ int sininn_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, in
 int sininn_pack_conv_weights_batched(const void* jobs, int njobs, int out_dtype, sininn_stream_t stream) {
   SININN_CHECK_ARG(jobs && njobs > 0, "pack_conv_weights_batched: bad arguments");
   dim3 grid(64, njobs);
-  if (out_dtype == SININN_F32) pack_weight_batched_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const long long*)jobs);
-  else if (out_dtype == SININN_BF16) pack_weight_batched_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const long long*)jobs);
+  if (out_dtype == SININN_F32) launch_k(pack_weight_batched_kernel<float>, dim3(grid), dim3(256), 0, as_stream(stream), (const long long*)jobs);
+  else if (out_dtype == SININN_BF16) launch_k(pack_weight_batched_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(stream), (const long long*)jobs);
   else SININN_CHECK_ARG(false, "pack_conv_weights_batched: bad out_dtype");
   SININN_CHECK_LAUNCH("pack_conv_weights_batched");
   return SININN_OK;
@@ -387,14 +397,14 @@ int sininn_wgrad_simt(const sininn_wgrad_desc* d, sininn_stream_t stream) {
   a.vec_dy = ((d->dy_stride % 4) == 0 && (df ? aligned16(d->dy) : aligned8(d->dy))) ? 1 : 0;
   dim3 grid((d->Cout + BM - 1) / BM, a.ci_tiles * d->taps, splits), block(256);
   cudaStream_t st = as_stream(stream);
-  if (xf && df) wgrad_simt_kernel<float, float><<<grid, block, 0, st>>>(a);
-  else if (xf && !df) wgrad_simt_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>(a);
-  else if (!xf && df) wgrad_simt_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>(a);
-  else wgrad_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>(a);
+  if (xf && df) launch_k(wgrad_simt_kernel<float, float>, dim3(grid), dim3(block), 0, st, a);
+  else if (xf && !df) launch_k(wgrad_simt_kernel<float, __nv_bfloat16>, dim3(grid), dim3(block), 0, st, a);
+  else if (!xf && df) launch_k(wgrad_simt_kernel<__nv_bfloat16, float>, dim3(grid), dim3(block), 0, st, a);
+  else launch_k(wgrad_simt_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid), dim3(block), 0, st, a);
   const long long per = (long long)d->taps * d->Cout * d->Cin;
   long long g = (per + 255) / 256;
   if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
-  wgrad_reduce_kernel<<<(int)g, 256, 0, st>>>(a.partial, splits, d->taps, d->Cout, d->Cin, d->dw, d->accumulate);
+  launch_k(wgrad_reduce_kernel, dim3((int)g), dim3(256), 0, st, a.partial, splits, d->taps, d->Cout, d->Cin, d->dw, d->accumulate);
   SININN_CHECK_LAUNCH("wgrad_simt");
   return SININN_OK;
 }

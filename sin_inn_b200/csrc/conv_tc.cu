@@ -68,6 +68,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();       // prologue above overlaps the previous kernel's tail; no global memory is touched before this
+  pdl_trigger();
   const int k_steps = p.taps * p.k_chunks;
 
   if (warp == 0) {
@@ -282,7 +284,7 @@ int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream) {
     attr_set[dev] = true;
   }
   long long grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv_tc_kernel<<<(unsigned)grid, NUM_THREADS, smem, as_stream(stream)>>>(tmA, tmB, tmO, p);
+  launch_k(conv_tc_kernel, dim3((unsigned)grid), dim3(NUM_THREADS), smem, as_stream(stream), tmA, tmB, tmO, p);
   SININN_CHECK_LAUNCH("conv_tc");
   return SININN_OK;
 }

@@ -74,6 +74,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();       // prologue above overlaps the previous kernel's tail; no global memory is touched before this
+  pdl_trigger();
 
   if (warp == 0) {
     // ======================= TMA producer (whole warp loops, one elected lane issues) =======================
@@ -234,7 +236,7 @@ int launch_conv_halo(const sininn_conv_desc* d, Params p, int base_offset_mode, 
     attr_set[dev] = true;
   }
   long long grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv_tc_halo_kernel<<<(unsigned)grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmO, hp);
+  launch_k(conv_tc_halo_kernel, dim3((unsigned)grid), dim3(NUM_THREADS), smem, st, tmA, tmB, tmO, hp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv_tc(halo): launch failed: %s", cudaGetErrorString(e)); return SININN_ECUDA; }
   return SININN_OK;

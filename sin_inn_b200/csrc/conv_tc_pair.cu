@@ -118,6 +118,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   cluster_sync_all();          // barrier inits of both CTAs visible before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();       // prologue above overlaps the previous kernel's tail; no global memory is touched before this
+  pdl_trigger();
 
   if (warp == 0) {
     // ======================= TMA producer (both CTAs) =======================
@@ -388,7 +390,7 @@ int launch_conv_pair(const sininn_conv_desc* d, Params p, cudaStream_t st) {
   }
   long long pairs = hp.num_items < npairs ? hp.num_items : npairs;
   if (b_stages == 0 && p.n_tiles > 1) pairs = npairs;            // resident N tile must be invariant per pair
-  conv_tc_pair_kernel<<<(unsigned)(2 * pairs), PAIR_THREADS, smem, st>>>(tmA, tmB, tmO, hp);
+  launch_k(conv_tc_pair_kernel, dim3((unsigned)(2 * pairs)), dim3(PAIR_THREADS), smem, st, tmA, tmB, tmO, hp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv_tc(pair): launch failed: %s", cudaGetErrorString(e)); return SININN_ECUDA; }
   return SININN_OK;

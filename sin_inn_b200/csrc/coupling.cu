@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(256) coupling_apply_kernel(float* __restrict__
                                                              int s_stride, const float* __restrict__ t, int t_stride,
                                                              long long npix, int L, int kind, float clamp, int inverse,
                                                              __nv_bfloat16* __restrict__ ubf) {
+  pdl_wait();
+  pdl_trigger();
   const int Lv = L / VEC;
   const long long total = npix * Lv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -71,6 +73,8 @@ __global__ void __launch_bounds__(256) coupling_bwd_kernel(float* __restrict__ u
                                                            int t_stride, long long npix, int L, int kind, float clamp, int inverse,
                                                            TO* __restrict__ ds, int ds_stride, TO* __restrict__ dt, int dt_stride,
                                                            __nv_bfloat16* __restrict__ xbf) {
+  pdl_wait();
+  pdl_trigger();
   const int Lv = L / VEC;
   const long long total = npix * Lv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -111,6 +115,8 @@ __global__ void __launch_bounds__(256) coupling_bwd_kernel(float* __restrict__ u
 template <int VEC, typename TO>
 __global__ void __launch_bounds__(256) cast_slice_kernel(const float* __restrict__ in, int in_stride, long long npix, int L,
                                                          float scale, TO* __restrict__ out, int out_stride) {
+  pdl_wait();
+  pdl_trigger();
   const int Lv = L / VEC;
   const long long total = npix * Lv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -127,6 +133,8 @@ __global__ void __launch_bounds__(256) cast_slice_kernel(const float* __restrict
 template <typename TY, typename TO>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* d, int d_stride, const TY* __restrict__ y, int y_stride,
                                                       TO* out, int out_stride, long long npix, int L, int act, float slope) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = npix * L;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -140,6 +148,8 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* d, int d_stri
 template <typename TA>
 __global__ void __launch_bounds__(256) axpy_slice_kernel(float* __restrict__ out, int out_stride, const TA* __restrict__ a,
                                                          int a_stride, long long npix, int L, float alpha) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = npix * L;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -154,6 +164,8 @@ constexpr int CS_COLS = 64, CS_ROWS = 4;
 template <typename T>
 __global__ void __launch_bounds__(CS_COLS* CS_ROWS) colsum_partial_kernel(const T* __restrict__ in, int in_stride, long long npix,
                                                                           int N, long long rows_per_chunk, float* __restrict__ partial) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[CS_ROWS][CS_COLS];
   const int col = blockIdx.y * CS_COLS + threadIdx.x;
   const long long r0 = blockIdx.x * rows_per_chunk;
@@ -176,6 +188,8 @@ __global__ void __launch_bounds__(CS_COLS* CS_ROWS) colsum_partial_kernel(const 
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const T* __restrict__ in, int in_stride, long long npix, int N,
                                                                  long long rows_per_chunk, float* __restrict__ partial) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int VEC = 16 / (int)sizeof(T);
   extern __shared__ float red[];                        // [RPI][G*VEC]
   const int G = N / VEC;
@@ -227,6 +241,8 @@ __global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const T* __rest
 // block = 32 columns x 8 chunk-lanes; fixed-order tree over the lanes => deterministic
 __global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partial, int chunks, int N,
                                                             float* __restrict__ out, int accumulate) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
@@ -254,6 +270,8 @@ static inline long long colsum_chunks(long long npix) {
 // ---- sum of squared differences with optional gradient (loss.reconstruction / latent_nll)
 __global__ void __launch_bounds__(256) sqdiff_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
                                                              float gscale, float* __restrict__ grad, float* __restrict__ partial) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[8];
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -272,6 +290,8 @@ __global__ void __launch_bounds__(256) sqdiff_partial_kernel(const float* __rest
   }
 }
 __global__ void sqdiff_finish_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double s = 0.0;
     for (int k = 0; k < n; ++k) s += (double)partial[k];
@@ -282,6 +302,8 @@ __global__ void sqdiff_finish_kernel(const float* __restrict__ partial, int n, f
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                                                    float wd, float bc1, float bc2_sqrt, float gscale) {
+  pdl_wait();
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float w = p[i];
     float gr = g[i] * gscale + wd * w;             // torch.optim.Adam: L2 weight decay folded into the gradient
@@ -296,6 +318,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 // Graph-replayable Adam: the step count lives on the device.  state = {int step, float bc1, float sqrt(bc2)}.
 __global__ void adam_tick_kernel(int* __restrict__ state, float b1, float b2) {
+  pdl_wait();
+  pdl_trigger();
   const int step = state[0] + 1;
   state[0] = step;
   float* f = reinterpret_cast<float*>(state);
@@ -306,6 +330,8 @@ __global__ void adam_tick_kernel(int* __restrict__ state, float b1, float b2) {
 __global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                        float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                                                        float wd, const int* __restrict__ state, float gscale) {
+  pdl_wait();
+  pdl_trigger();
   const float bc1 = reinterpret_cast<const float*>(state)[1], bc2_sqrt = reinterpret_cast<const float*>(state)[2];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float w = p[i];
@@ -344,8 +370,8 @@ int sininn_coupling_apply(float* u, int u_stride, const float* s, int s_stride, 
             aligned16(s) && aligned16(t) && (!bf || aligned8(bf));
   const long long total = npix * (v4 ? L / 4 : L);
   const int block = 256, grid = grid_for(total, block);
-  if (v4) coupling_apply_kernel<4><<<grid, block, 0, as_stream(stream)>>>(u, u_stride, s, s_stride, t, t_stride, npix, L, kind, clamp, inverse, bf);
-  else coupling_apply_kernel<1><<<grid, block, 0, as_stream(stream)>>>(u, u_stride, s, s_stride, t, t_stride, npix, L, kind, clamp, inverse, bf);
+  if (v4) launch_k(coupling_apply_kernel<4>, dim3(grid), dim3(block), 0, as_stream(stream), u, u_stride, s, s_stride, t, t_stride, npix, L, kind, clamp, inverse, bf);
+  else launch_k(coupling_apply_kernel<1>, dim3(grid), dim3(block), 0, as_stream(stream), u, u_stride, s, s_stride, t, t_stride, npix, L, kind, clamp, inverse, bf);
   SININN_CHECK_LAUNCH("coupling_apply");
   return SININN_OK;
 }
@@ -365,7 +391,7 @@ int sininn_coupling_bwd(float* u, int u_stride, float* du, int du_stride, const 
   const int block = 256, grid = grid_for(total, block);
   cudaStream_t st = as_stream(stream);
 #define LAUNCH(V, T)                                                                                                    \
-  coupling_bwd_kernel<V, T><<<grid, block, 0, st>>>(u, u_stride, du, du_stride, s, s_stride, t, t_stride, npix, L, kind, \
+  launch_k(coupling_bwd_kernel<V, T>, dim3(grid), dim3(block), 0, st, u, u_stride, du, du_stride, s, s_stride, t, t_stride, npix, L, kind, \
                                                     clamp, inverse, reinterpret_cast<T*>(ds_out), ds_stride,            \
                                                     reinterpret_cast<T*>(dt_out), dt_stride, bf)
   if (f32) { if (v4) LAUNCH(4, float); else LAUNCH(1, float); }
@@ -385,11 +411,11 @@ int sininn_cast_slice(const float* in, int in_stride, long long npix, int L, flo
   const int block = 256, grid = grid_for(total, block);
   cudaStream_t st = as_stream(stream);
   if (f32) {
-    if (v4) cast_slice_kernel<4, float><<<grid, block, 0, st>>>(in, in_stride, npix, L, scale, (float*)out, out_stride);
-    else cast_slice_kernel<1, float><<<grid, block, 0, st>>>(in, in_stride, npix, L, scale, (float*)out, out_stride);
+    if (v4) launch_k(cast_slice_kernel<4, float>, dim3(grid), dim3(block), 0, st, in, in_stride, npix, L, scale, (float*)out, out_stride);
+    else launch_k(cast_slice_kernel<1, float>, dim3(grid), dim3(block), 0, st, in, in_stride, npix, L, scale, (float*)out, out_stride);
   } else {
-    if (v4) cast_slice_kernel<4, __nv_bfloat16><<<grid, block, 0, st>>>(in, in_stride, npix, L, scale, (__nv_bfloat16*)out, out_stride);
-    else cast_slice_kernel<1, __nv_bfloat16><<<grid, block, 0, st>>>(in, in_stride, npix, L, scale, (__nv_bfloat16*)out, out_stride);
+    if (v4) launch_k(cast_slice_kernel<4, __nv_bfloat16>, dim3(grid), dim3(block), 0, st, in, in_stride, npix, L, scale, (__nv_bfloat16*)out, out_stride);
+    else launch_k(cast_slice_kernel<1, __nv_bfloat16>, dim3(grid), dim3(block), 0, st, in, in_stride, npix, L, scale, (__nv_bfloat16*)out, out_stride);
   }
   SININN_CHECK_LAUNCH("cast_slice");
   return SININN_OK;
@@ -403,7 +429,7 @@ int sininn_act_bwd(const float* d, int d_stride, const void* y, int y_dtype, int
   const long long total = npix * L;
   const int block = 256, grid = grid_for(total, block);
   cudaStream_t st = as_stream(stream);
-#define LAUNCH(TY, TO) act_bwd_kernel<TY, TO><<<grid, block, 0, st>>>(d, d_stride, (const TY*)y, y_stride, (TO*)out, out_stride, npix, L, act, slope)
+#define LAUNCH(TY, TO) launch_k(act_bwd_kernel<TY, TO>, dim3(grid), dim3(block), 0, st, d, d_stride, (const TY*)y, y_stride, (TO*)out, out_stride, npix, L, act, slope)
   if (y_dtype == SININN_F32) { if (out_dtype == SININN_F32) LAUNCH(float, float); else LAUNCH(float, __nv_bfloat16); }
   else                       { if (out_dtype == SININN_F32) LAUNCH(__nv_bfloat16, float); else LAUNCH(__nv_bfloat16, __nv_bfloat16); }
 #undef LAUNCH
@@ -417,8 +443,8 @@ int sininn_axpy_slice(float* out, int out_stride, const void* a, int a_dtype, in
   SININN_CHECK_ARG(a_dtype == SININN_F32 || a_dtype == SININN_BF16, "axpy_slice: bad dtype");
   const long long total = npix * L;
   const int block = 256, grid = grid_for(total, block);
-  if (a_dtype == SININN_F32) axpy_slice_kernel<float><<<grid, block, 0, as_stream(stream)>>>(out, out_stride, (const float*)a, a_stride, npix, L, alpha);
-  else axpy_slice_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>(out, out_stride, (const __nv_bfloat16*)a, a_stride, npix, L, alpha);
+  if (a_dtype == SININN_F32) launch_k(axpy_slice_kernel<float>, dim3(grid), dim3(block), 0, as_stream(stream), out, out_stride, (const float*)a, a_stride, npix, L, alpha);
+  else launch_k(axpy_slice_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, as_stream(stream), out, out_stride, (const __nv_bfloat16*)a, a_stride, npix, L, alpha);
   SININN_CHECK_LAUNCH("axpy_slice");
   return SININN_OK;
 }
@@ -446,11 +472,11 @@ int sininn_colsum(const void* in, int dtype, int in_stride, long long npix, int 
   if (vec_ok) {
     const int rpi = 256 / (N / vec);
     const size_t sm = (size_t)rpi * N * sizeof(float);
-    if (dtype == SININN_F32) colsum_partial_vec_kernel<float><<<(unsigned)chunks, 256, sm, st>>>((const float*)in, in_stride, npix, N, rows_per_chunk, partial);
-    else colsum_partial_vec_kernel<__nv_bfloat16><<<(unsigned)chunks, 256, sm, st>>>((const __nv_bfloat16*)in, in_stride, npix, N, rows_per_chunk, partial);
-  } else if (dtype == SININN_F32) colsum_partial_kernel<float><<<grid, block, 0, st>>>((const float*)in, in_stride, npix, N, rows_per_chunk, partial);
-  else colsum_partial_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, in_stride, npix, N, rows_per_chunk, partial);
-  colsum_finish_kernel<<<(N + 31) / 32, 256, 0, st>>>(partial, (int)chunks, N, out, accumulate);
+    if (dtype == SININN_F32) launch_k(colsum_partial_vec_kernel<float>, dim3((unsigned)chunks), dim3(256), sm, st, (const float*)in, in_stride, npix, N, rows_per_chunk, partial);
+    else launch_k(colsum_partial_vec_kernel<__nv_bfloat16>, dim3((unsigned)chunks), dim3(256), sm, st, (const __nv_bfloat16*)in, in_stride, npix, N, rows_per_chunk, partial);
+  } else if (dtype == SININN_F32) launch_k(colsum_partial_kernel<float>, dim3(grid), dim3(block), 0, st, (const float*)in, in_stride, npix, N, rows_per_chunk, partial);
+  else launch_k(colsum_partial_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, st, (const __nv_bfloat16*)in, in_stride, npix, N, rows_per_chunk, partial);
+  launch_k(colsum_finish_kernel, dim3((N + 31) / 32), dim3(256), 0, st, partial, (int)chunks, N, out, accumulate);
   SININN_CHECK_LAUNCH("colsum");
   return SININN_OK;
 }
@@ -471,8 +497,8 @@ int sininn_sqdiff_nchw(const float* a, const float* b, long long n, float scale,
     return SININN_EWORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
-  sqdiff_partial_kernel<<<grid, 256, 0, st>>>(a, b, n, 2.f * scale, grad_out, (float*)workspace);
-  sqdiff_finish_kernel<<<1, 32, 0, st>>>((const float*)workspace, grid, scale, loss_out);
+  launch_k(sqdiff_partial_kernel, dim3(grid), dim3(256), 0, st, a, b, n, 2.f * scale, grad_out, (float*)workspace);
+  launch_k(sqdiff_finish_kernel, dim3(1), dim3(32), 0, st, (const float*)workspace, grid, scale, loss_out);
   SININN_CHECK_LAUNCH("sqdiff");
   return SININN_OK;
 }
@@ -484,7 +510,7 @@ int sininn_adam_step(float* param, const float* grad, float* exp_avg, float* exp
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   const int block = 256, grid = grid_for(n, block);
-  adam_kernel<<<grid, block, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+  launch_k(adam_kernel, dim3(grid), dim3(block), 0, as_stream(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                      weight_decay, bc1, sqrtf(bc2), grad_scale);
   SININN_CHECK_LAUNCH("adam_step");
   return SININN_OK;
@@ -495,8 +521,8 @@ int sininn_adam_step_dev(float* param, const float* grad, float* exp_avg, float*
                          sininn_stream_t stream) {
   SININN_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step_state && n > 0, "adam_step_dev: bad arguments");
   const int block = 256, grid = grid_for(n, block);
-  adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(step_state, beta1, beta2);
-  adam_dev_kernel<<<grid, block, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+  launch_k(adam_tick_kernel, dim3(1), dim3(1), 0, as_stream(stream), step_state, beta1, beta2);
+  launch_k(adam_dev_kernel, dim3(grid), dim3(block), 0, as_stream(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                          weight_decay, step_state, grad_scale);
   SININN_CHECK_LAUNCH("adam_step_dev");
   return SININN_OK;

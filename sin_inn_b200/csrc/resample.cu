@@ -46,6 +46,8 @@ template <> struct VecT<4> { typedef float4 type; };
 template <int VEC, bool HAAR>
 __global__ void __launch_bounds__(256) resample_nchw_fwd_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                 int C, int H, int W, float scale, long long total) {
+  pdl_wait();
+  pdl_trigger();
   const int Ho = H >> 1, Wo = W >> 1, Wv = Wo / VEC;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -84,6 +86,8 @@ __global__ void __launch_bounds__(256) resample_nchw_fwd_kernel(const float* __r
 template <int VEC, bool HAAR>
 __global__ void __launch_bounds__(256) resample_nchw_inv_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                 int C, int H, int W, float scale, long long total) {
+  pdl_wait();
+  pdl_trigger();
   const int Ho = H >> 1, Wo = W >> 1, Wv = Wo / VEC;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -123,6 +127,8 @@ __global__ void __launch_bounds__(256) resample_nchw_inv_kernel(const float* __r
 template <int VEC, bool HAAR, bool REV>
 __global__ void __launch_bounds__(256) resample_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                             int C, int H, int W, float scale, long long total) {
+  pdl_wait();
+  pdl_trigger();
   const int Ho = H >> 1, Wo = W >> 1, Cv = C / VEC;
   typedef typename VecT<VEC>::type VT;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -175,6 +181,8 @@ template <bool TO_NHWC>
 __global__ void __launch_bounds__(256) layout_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW,
                                                      const int32_t* __restrict__ map, __nv_bfloat16* __restrict__ bf,
                                                      int bc0, int bc1) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[32][33];
   const long long b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -221,6 +229,8 @@ template <int VEC>
 __global__ void __launch_bounds__(256) permute_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, long long npix,
                                                            int C, const int32_t* __restrict__ map,
                                                            __nv_bfloat16* __restrict__ bf, int bc0, int bc1) {
+  pdl_wait();
+  pdl_trigger();
   const int Cv = C / VEC;
   const long long total = npix * Cv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -276,8 +286,8 @@ int sininn_resample_nchw(const float* in, float* out, int B, int C, int H, int W
   const int block = 256, grid = grid_for(total, block);
 #define LAUNCH(V, HA)                                                                                   \
   do {                                                                                                  \
-    if (!rev) resample_nchw_fwd_kernel<V, HA><<<grid, block, 0, st>>>(in, out, C, H, W, scale, total);  \
-    else resample_nchw_inv_kernel<V, HA><<<grid, block, 0, st>>>(in, out, C, H, W, scale, total);       \
+    if (!rev) launch_k(resample_nchw_fwd_kernel<V, HA>, dim3(grid), dim3(block), 0, st, in, out, C, H, W, scale, total);  \
+    else launch_k(resample_nchw_inv_kernel<V, HA>, dim3(grid), dim3(block), 0, st, in, out, C, H, W, scale, total);       \
   } while (0)
   if (mode == 1) {
     if (vec == 4) LAUNCH(4, true); else if (vec == 2) LAUNCH(2, true); else LAUNCH(1, true);
@@ -299,7 +309,7 @@ int sininn_resample_nhwc(const float* in, float* out, int B, int C, int H, int W
   const int vec = ((C % 4) == 0 && aligned16(in) && aligned16(out)) ? 4 : 1;
   const long long total = (long long)B * (H / 2) * (W / 2) * (C / vec);
   const int block = 256, grid = grid_for(total, block);
-#define LAUNCH(V, HA, RV) resample_nhwc_kernel<V, HA, RV><<<grid, block, 0, st>>>(in, out, C, H, W, scale, total)
+#define LAUNCH(V, HA, RV) launch_k(resample_nhwc_kernel<V, HA, RV>, dim3(grid), dim3(block), 0, st, in, out, C, H, W, scale, total)
   if (vec == 4) {
     if (mode == 1) { if (rev) LAUNCH(4, true, true); else LAUNCH(4, true, false); }
     else           { if (rev) LAUNCH(4, false, true); else LAUNCH(4, false, false); }
@@ -318,7 +328,7 @@ int sininn_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, const
   SININN_CHECK_ARG(B <= 65535, "nchw_to_nhwc: batch too large for grid.z");
   if (bf16_out) SININN_CHECK_ARG(0 <= c0 && c0 < c1 && c1 <= C, "nchw_to_nhwc: bad bf16 channel range");
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  layout_kernel<true><<<grid, block, 0, as_stream(stream)>>>(in, out, C, HW, chan_map,
+  launch_k(layout_kernel<true>, dim3(grid), dim3(block), 0, as_stream(stream), in, out, C, HW, chan_map,
                                                              reinterpret_cast<__nv_bfloat16*>(bf16_out), c0, c1);
   SININN_CHECK_LAUNCH("nchw_to_nhwc");
   return SININN_OK;
@@ -329,7 +339,7 @@ int sininn_nhwc_to_nchw(const float* in, float* out, int B, int C, int HW, const
   SININN_CHECK_ARG(in && out && B > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad arguments");
   SININN_CHECK_ARG(B <= 65535, "nhwc_to_nchw: batch too large for grid.z");
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  layout_kernel<false><<<grid, block, 0, as_stream(stream)>>>(in, out, C, HW, chan_map, nullptr, 0, 0);
+  launch_k(layout_kernel<false>, dim3(grid), dim3(block), 0, as_stream(stream), in, out, C, HW, chan_map, nullptr, 0, 0);
   SININN_CHECK_LAUNCH("nhwc_to_nchw");
   return SININN_OK;
 }
@@ -343,8 +353,8 @@ int sininn_permute_nhwc(const float* in, float* out, long long npix, int C, cons
   bool v4 = (C % 4) == 0 && aligned16(out) && (!bf || ((c0 % 4) == 0 && (c1 % 4) == 0 && aligned8(bf)));
   const long long total = npix * (v4 ? C / 4 : C);
   const int block = 256, grid = grid_for(total, block);
-  if (v4) permute_nhwc_kernel<4><<<grid, block, 0, as_stream(stream)>>>(in, out, npix, C, chan_map, bf, c0, c1);
-  else permute_nhwc_kernel<1><<<grid, block, 0, as_stream(stream)>>>(in, out, npix, C, chan_map, bf, c0, c1);
+  if (v4) launch_k(permute_nhwc_kernel<4>, dim3(grid), dim3(block), 0, as_stream(stream), in, out, npix, C, chan_map, bf, c0, c1);
+  else launch_k(permute_nhwc_kernel<1>, dim3(grid), dim3(block), 0, as_stream(stream), in, out, npix, C, chan_map, bf, c0, c1);
   SININN_CHECK_LAUNCH("permute_nhwc");
   return SININN_OK;
 }

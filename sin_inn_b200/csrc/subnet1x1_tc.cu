@@ -105,6 +105,8 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();       // barrier init / TMEM allocation above overlap the previous kernel's tail; global memory from here on
+  pdl_trigger();
   if (warp >= 2) {      // biases -> shared memory (zero beyond the real channel counts)
     const int e = threadIdx.x - 64;
     b1_s[e] = (p.b1 != nullptr && e < p.hidden) ? __ldg(p.b1 + e) : 0.f;
@@ -418,7 +420,7 @@ int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stre
     attr_set[dev] = true;
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  subnet1x1_fwd_kernel<<<(unsigned)grid, NUM_THREADS, smem, as_stream(stream)>>>(tmX, tmW1, tmW2, tmO, tmH, p);
+  launch_k(subnet1x1_fwd_kernel, dim3((unsigned)grid), dim3(NUM_THREADS), smem, as_stream(stream), tmX, tmW1, tmW2, tmO, tmH, p);
   SININN_CHECK_LAUNCH("subnet1x1_fwd");
   return SININN_OK;
 }

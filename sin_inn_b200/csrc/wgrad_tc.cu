@@ -79,6 +79,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();       // prologue above overlaps the previous kernel's tail; no global memory is touched before this
+  pdl_trigger();
 
   if (warp == 0) {
     {   // whole warp loops (uniform control flow), one elected lane issues the TMA loads
@@ -208,6 +210,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 template <int VEC>
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cw, int Cn,
                                                               int wide_is_dy, int Cout, int Cin, float* __restrict__ dw, int accumulate) {
+  pdl_wait();
+  pdl_trigger();
   const long long per = (long long)taps * Cw * Cn;
   const long long perv = per / VEC;
   for (long long iv = blockIdx.x * (long long)blockDim.x + threadIdx.x; iv < perv; iv += (long long)gridDim.x * blockDim.x) {
@@ -359,17 +363,17 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
   const size_t smem = (size_t)p.stages * p.stage_bytes + sizeof(Barriers) + 1024;
   const unsigned grid = (unsigned)(w.m_tiles * w.tap_groups * w.splits);
   cudaStream_t st = as_stream(stream);
-  wgrad_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(tmW, tmN, p);
+  launch_k(wgrad_tc_kernel, dim3(grid), dim3(NUM_THREADS), smem, st, tmW, tmN, p);
   const long long per = (long long)d->taps * w.Cw * w.Cn;
   if ((w.Cn % 4) == 0) {
     long long g = (per / 4 + 255) / 256;
     if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
-    wgrad_tc_reduce_kernel<4><<<(int)g, 256, 0, st>>>(p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
+    launch_k(wgrad_tc_reduce_kernel<4>, dim3((int)g), dim3(256), 0, st, p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
                                                       d->dw, d->accumulate);
   } else {
     long long g = (per + 255) / 256;
     if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
-    wgrad_tc_reduce_kernel<1><<<(int)g, 256, 0, st>>>(p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
+    launch_k(wgrad_tc_reduce_kernel<1>, dim3((int)g), dim3(256), 0, st, p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
                                                       d->dw, d->accumulate);
   }
   SININN_CHECK_LAUNCH("wgrad_tc");
