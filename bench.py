@@ -163,12 +163,15 @@ def run_ours(args):
             return graphed(*dev_batches[i % 2])       # device-to-device copy into the graph's static inputs + replay
         return trainer.training_step(*dev_batches[i % 2])
 
+    # end-to-end: every step's inputs come from pinned host memory; the copy of batch i+1 is issued on a side
+    # stream before step i runs (train.HostBatchFeeder), so H2D overlaps compute; the losses are read back every step
+    feeder = train.HostBatchFeeder(pool[0], dev)
+
     def step_e2e(i):
-        if graphed is not None:
-            lf, lb = graphed(*pool[i % 2])            # pinned host -> static device inputs (async H2D) + replay
-        else:
-            hr, lr, z = (t.to(dev, non_blocking=True) for t in pool[i % 2])
-            lf, lb = trainer.training_step(hr, lr, z)
+        feeder.submit(pool[(i + 1) % 2], (i + 1) % 2)             # prefetch the next step's batch
+        batch = feeder.take(i % 2)
+        lf, lb = (graphed or trainer.training_step)(*batch)
+        feeder.release(i % 2)
         return float(lf.item() + lb.item())          # D2H read of the step's result
 
     for i in range(args.warmup):
@@ -192,21 +195,34 @@ def run_ours(args):
     prof = kernels.profile_end()
     sampler.stop_flag = True
     # end-to-end: pinned host inputs -> device, step, loss back to host, every step
+    feeder.submit(pool[0], 0)
     for i in range(2):
         step_e2e(i)
     barrier()
     flush.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(args.steps):                      # K steps, K host->device batch copies, K loss read-backs
         step_e2e(i)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    # second half of BASELINE.json's metric: full-video inference, 1080p frames through forward (HR -> LR,z) and
+    # inverse (LR,z -> HR = the reference's infer, lit_wrapper.py:105-115), frames sharded over the ranks, no
+    # communication (configs[3]).  Each rank times its own micro-batches; frames/s = all ranks' frames / max time.
+    inf = None
+    used_graph = graphed is not None
+    if not args.no_inference:
+        used_graph = graphed is not None
+        graphed = feeder = None
+        trainer._graph = None
+        trainer.optim.zero_grad()
+        torch.cuda.empty_cache()
+        inf = inference_1080p(net, opt, dev, args.infer_batch, iters=args.infer_iters)
+    t = torch.tensor([ms, ms_e2e] + ([inf["fwd_ms"], inf["inv_ms"]] if inf else [0.0, 0.0]), dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, inf_fwd_ms, inf_inv_ms = t.tolist()
     if rank == 0:
         pk = peaks()
         value = world * B * args.steps / (ms / 1e3)
@@ -226,7 +242,7 @@ def run_ours(args):
             "config": {"workload": f"SRF scale4 c4 lr_window10 {P}x{P} train step, batch {B}/GPU", **WORKLOAD,
                        "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision, "tensor_core": not args.no_tensor_core,
                        "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2",
-                       "backward": "recompute-from-inverse", "cuda_graph": graphed is not None},
+                       "backward": "recompute-from-inverse", "cuda_graph": used_graph},
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
@@ -238,6 +254,14 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "profile_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
         }
+        if inf:
+            fr = world * inf["frames"]
+            line["inference_1080p"] = {
+                "workload": "SRF scale4 c4 1920x1080 frames, forward + inverse, no_grad, micro-batch %d/GPU, frame-sharded" % args.infer_batch,
+                "fwd_inv_frames_per_s": fr / ((inf_fwd_ms + inf_inv_ms) / 1e3),
+                "fwd_frames_per_s": fr / (inf_fwd_ms / 1e3), "inv_frames_per_s": fr / (inf_inv_ms / 1e3),
+                "frames_timed_per_gpu": inf["frames"], "roundtrip_max_abs_err": inf["roundtrip"],
+                "algorithmic_tflops": 2 * 382.2e9 * fr / ((inf_fwd_ms + inf_inv_ms) / 1e3) / 1e12}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(steps=3, warmup=1, batch=2)
             line["cpu_baseline"] = {"value": r["value"], "unit": "patches/s", "cores": r["cores"], "kind": "port",
@@ -245,6 +269,32 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def inference_1080p(net, opt, dev, micro_batch, iters):
+    """Times `iters` micro-batches of 1920x1080 frames through net(x) and net(lr_z, rev=True) (CUDA events)."""
+    H, W = 1080, 1920
+    g = torch.Generator(device="cpu").manual_seed(7)
+    hr = torch.rand(micro_batch, 3, H, W, generator=g).to(dev)
+    out = {}
+    with torch.no_grad():
+        lrz = net(hr)
+        back = net(lrz, rev=True)
+        out["roundtrip"] = float((back - hr).abs().max())
+        del back
+        for tag, fn in (("fwd_ms", lambda: net(hr)), ("inv_ms", lambda: net(lrz, rev=True))):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            out[tag] = e0.elapsed_time(e1)
+    out["frames"] = micro_batch * iters
+    return out
 
 
 def main():
@@ -256,6 +306,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=WORKLOAD["batch_per_gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true", help="skip the 1080p forward+inverse measurement")
+    ap.add_argument("--infer-batch", type=int, default=2, help="1080p frames per micro-batch and GPU")
+    ap.add_argument("--infer-iters", type=int, default=8)
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-tensor-core", action="store_true", help="route the subnet GEMMs to the CUDA-core kernels")
     args = ap.parse_args()

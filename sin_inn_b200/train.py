@@ -169,6 +169,40 @@ class SingleVideoTrainer:
         return self.inn(torch.cat((lr, z), dim=1), rev=True)
 
 
+class HostBatchFeeder:
+    """Overlaps the host->device copy of the NEXT batch with the current training step.
+
+    Two pre-allocated device staging slots are filled from pinned host memory on a side stream;
+    ``take(slot)`` makes the compute stream wait for that copy and returns the device tensors, and a slot is
+    only overwritten after the step that consumed it was enqueued (events both ways, no host synchronisation).
+    The reference does the same job with Lightning's DataLoader workers + pin_memory (main.py:100-111)."""
+
+    def __init__(self, example, device):
+        self.dev = device
+        self.side = torch.cuda.Stream(device=device)
+        self.slots = [tuple(torch.empty_like(t, device=device) for t in example) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        for e in self.consumed:
+            e.record()
+
+    def submit(self, host_batch, slot):
+        """Start copying host_batch (pinned tensors) into staging slot `slot`."""
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.consumed[slot])
+            for dst, src in zip(self.slots[slot], host_batch):
+                dst.copy_(src, non_blocking=True)
+            self.ready[slot].record(self.side)
+
+    def take(self, slot):
+        torch.cuda.current_stream().wait_event(self.ready[slot])
+        return self.slots[slot]
+
+    def release(self, slot):
+        """Call after the step that reads `slot` has been enqueued on the compute stream."""
+        self.consumed[slot].record()
+
+
 def shard_frames(n_frames, rank, world_size):
     """Frame-sharded inference (no communication): contiguous block of frames per rank."""
     per = (n_frames + world_size - 1) // world_size
