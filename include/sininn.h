@@ -189,6 +189,9 @@ typedef struct {
   const void* dy; int dy_dtype; int dy_stride;
   float* dw;      int accumulate;
   void* workspace; size_t workspace_bytes;
+  /* tensor-core path only: NULL, or the bias gradient  dbias[co] (+)= sum_p dy[p][co]  computed in the same two
+   * launches (column sums of the dy tiles the weight-gradient kernel streams through shared memory anyway) */
+  float* dbias;   int dbias_accumulate;
 } sininn_wgrad_desc;
 
 size_t sininn_wgrad_workspace_bytes(const sininn_wgrad_desc* d, int tensor_core);

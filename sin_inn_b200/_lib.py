@@ -46,6 +46,7 @@ class WgradDesc(C.Structure):
         ("dy", _vp), ("dy_dtype", C.c_int), ("dy_stride", C.c_int),
         ("dw", _vp), ("accumulate", C.c_int),
         ("workspace", _vp), ("workspace_bytes", C.c_size_t),
+        ("dbias", _vp), ("dbias_accumulate", C.c_int),
     ]
 
 

@@ -36,6 +36,10 @@ struct WgradParams {
   uint32_t stage_bytes, tx_bytes;
   uint32_t narrow_bytes;         // bytes of one 64-channel narrow box (halo'd for 3x3)
   float* partial;                // [split][tap][Cw][Cn]
+  // bias gradient = column sums of dy, computed from the operand tiles the MMA loop streams through shared memory
+  // anyway (the four epilogue warps are idle during that loop): 0 off, 1 dy is the wide operand, 2 dy is the narrow one
+  int bias_mode;
+  float* bias_partial;           // mode 1: [2 * split + row half][Cw]; mode 2: [split][Cn]
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -61,10 +65,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   if (blk1 > p.num_blocks) blk1 = p.num_blocks;
   const long long nblk = blk1 > blk0 ? blk1 - blk0 : 0;
 
+  const bool do_bias = p.bias_mode != 0 && tg == 0 && (p.bias_mode == 1 || mt == 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&bars->full[s]), 1);
-      mbar_init(smem_u32(&bars->empty[s]), 1);
+      mbar_init(smem_u32(&bars->empty[s]), do_bias ? 5 : 1);     // MMA commit (+ the four column-sum warps)
     }
     mbar_init(smem_u32(&bars->acc_full[0]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -165,6 +170,58 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int quarter = warp & 3;
     const int m = mt * 128 + quarter * 32 + lane;            // wide-operand channel of this thread's row
     const bool m_ok = m < p.Cw;
+    if (do_bias) {
+      // Column sums of dy over this CTA's pixel blocks, read from the MN-major SWIZZLE_128B tiles in the ring
+      // (pixel row r = 128 B of 64 channels, 16-byte chunk c stored at c ^ (r & 7)).  Each thread owns a channel
+      // pair; within a warp the 32 lanes read 32 different 4-byte words of one row: conflict-free.
+      const int et = threadIdx.x - 64;                       // 0..127
+      float s0 = 0.f, s1 = 0.f;
+      int box, q, r_lo, r_hi;
+      uint32_t tile_off;
+      if (p.bias_mode == 1) {                                // wide tile: 2 boxes x 64 channels, plain 8x8 pixel boxes
+        const int pair = et & 63;
+        box = pair >> 5; q = pair & 31;
+        r_lo = (et >> 6) * 32; r_hi = r_lo + 32;             // the two thread halves split the 64 pixels
+        tile_off = (uint32_t)box * WG_BOX_BYTES;
+      } else {                                               // narrow tile: n_groups boxes (halo'd for 3x3)
+        box = et >> 5; q = et & 31;
+        r_lo = 0; r_hi = 64;
+        tile_off = 2 * WG_BOX_BYTES + (uint32_t)box * p.narrow_bytes;
+      }
+      const bool active = p.bias_mode == 1 || box < p.n_groups;
+      const bool halo_rows = p.bias_mode == 2 && p.taps == 9;
+      const uint32_t chunk = (uint32_t)(q >> 2), word = (uint32_t)(q & 3) * 4u;
+      int stage = 0; uint32_t phase = 0;
+      for (long long i = 0; i < nblk; ++i) {
+        mbar_wait(smem_u32(&bars->full[stage]), phase);
+        if (active) {
+          const uint8_t* tile = ring + (size_t)stage * p.stage_bytes + tile_off;
+#pragma unroll 8
+          for (int r = r_lo; r < r_hi; ++r) {
+            const int row = halo_rows ? ((r >> 3) + 1) * WG_HALO_W + (r & 7) + 1 : r;      // interior pixel of the halo box
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(tile + row * 128 + ((chunk ^ (uint32_t)(row & 7)) << 4) + word);
+            s0 += __uint_as_float(v << 16);
+            s1 += __uint_as_float(v & 0xffff0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->empty[stage]));
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (active) {
+        if (p.bias_mode == 1) {
+          const int ch = mt * 128 + (et & 63) * 2;
+          float* dst = p.bias_partial + ((long long)(2 * split + (et >> 6))) * p.Cw + ch;
+          if (ch < p.Cw) dst[0] = s0;
+          if (ch + 1 < p.Cw) dst[1] = s1;
+        } else {
+          const int ch = et * 2;
+          float* dst = p.bias_partial + (long long)split * p.Cn + ch;
+          if (ch < p.Cn) dst[0] = s0;
+          if (ch + 1 < p.Cn) dst[1] = s1;
+        }
+      }
+    }
     if (nblk > 0) {
       mbar_wait(smem_u32(&bars->acc_full[0]), 0);
       tc_fence_after();
@@ -209,9 +266,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 // Fixed summation order over the splits => bit-reproducible gradients.
 template <int VEC>
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cw, int Cn,
-                                                              int wide_is_dy, int Cout, int Cin, float* __restrict__ dw, int accumulate) {
+                                                              int wide_is_dy, int Cout, int Cin, float* __restrict__ dw, int accumulate,
+                                                              const float* __restrict__ bias_partial, int bias_rows, int bias_n,
+                                                              float* __restrict__ dbias, int dbias_accumulate) {
   pdl_wait();
   pdl_trigger();
+  if (bias_partial != nullptr && blockIdx.x == gridDim.x - 1) {     // fixed-order sum of the per-split column sums of dy
+    for (int c = threadIdx.x; c < bias_n; c += blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < bias_rows; ++k) s += bias_partial[(long long)k * bias_n + c];
+      dbias[c] = dbias_accumulate ? dbias[c] + s : s;
+    }
+  }
   const long long per = (long long)taps * Cw * Cn;
   const long long perv = per / VEC;
   for (long long iv = blockIdx.x * (long long)blockDim.x + threadIdx.x; iv < perv; iv += (long long)gridDim.x * blockDim.x) {
@@ -291,7 +357,7 @@ size_t sininn_wgrad_workspace_bytes(const sininn_wgrad_desc* d, int tensor_core)
   if (!tensor_core) return simt;
   sininn::tc::WgradPlan w;
   if (!sininn::tc::plan_wgrad(d, w)) return simt;
-  size_t tcb = (size_t)w.splits * d->taps * d->Cout * d->Cin * sizeof(float);
+  size_t tcb = (size_t)w.splits * d->taps * d->Cout * d->Cin * sizeof(float) + (size_t)2 * w.splits * d->Cout * sizeof(float);
   return tcb > simt ? tcb : simt;
 }
 
@@ -309,7 +375,8 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
     set_error("wgrad_tc: unsupported shape (Cin=%d Cout=%d)", d->Cin, d->Cout);
     return SININN_EUNSUPPORTED;
   }
-  const size_t need = (size_t)w.splits * d->taps * d->Cout * d->Cin * sizeof(float);
+  const size_t need_w = (size_t)w.splits * d->taps * d->Cout * d->Cin * sizeof(float);
+  const size_t need = need_w + (d->dbias ? (size_t)2 * w.splits * d->Cout * sizeof(float) : 0);
   if (!d->workspace || d->workspace_bytes < need) {
     set_error("wgrad_tc: workspace too small (%zu < %zu)", d->workspace_bytes, need);
     return SININN_EWORKSPACE;
@@ -349,6 +416,9 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
   p.blocks_h = w.blocks_h; p.blocks_w = w.blocks_w; p.num_blocks = w.num_blocks; p.blocks_per_split = w.blocks_per_split;
   p.stages = w.stages; p.stage_bytes = w.stage_bytes; p.tx_bytes = w.stage_bytes; p.narrow_bytes = w.narrow_bytes;
   p.partial = reinterpret_cast<float*>(d->workspace);
+  p.bias_mode = d->dbias ? (w.wide_is_dy ? 1 : 2) : 0;
+  p.bias_partial = d->dbias ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d->workspace) + need_w) : nullptr;
+  const int bias_rows = d->dbias ? (w.wide_is_dy ? 2 * w.splits : w.splits) : 0;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -369,12 +439,12 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
     long long g = (per / 4 + 255) / 256;
     if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
     launch_k(wgrad_tc_reduce_kernel<4>, dim3((int)g), dim3(256), 0, st, p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
-                                                      d->dw, d->accumulate);
+                                                      d->dw, d->accumulate, p.bias_partial, bias_rows, d->Cout, d->dbias, d->dbias_accumulate);
   } else {
     long long g = (per + 255) / 256;
     if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
     launch_k(wgrad_tc_reduce_kernel<1>, dim3((int)g), dim3(256), 0, st, p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
-                                                      d->dw, d->accumulate);
+                                                      d->dw, d->accumulate, p.bias_partial, bias_rows, d->Cout, d->dbias, d->dbias_accumulate);
   }
   SININN_CHECK_LAUNCH("wgrad_tc");
   return SININN_OK;

@@ -216,6 +216,23 @@ class RunCtx:
 
 
 # ----------------------------------------------------------------------------- subnets
+def _param_grads(ctx, conv, x, dy, geom, taps):
+    """Weight and bias gradients of one conv from its input x and output gradient dy.  On the tensor-core path the
+    bias gradient (column sums of dy) is produced by the weight-gradient launches themselves; otherwise by colsum."""
+    wants_w = conv.weight.requires_grad
+    wants_b = conv.bias is not None and conv.bias.requires_grad
+    if wants_w:
+        g, acc = ctx.grad_out(conv.weight)
+        if wants_b and ctx.tc:
+            gb, accb = ctx.grad_out(conv.bias)
+            K.wgrad(x, dy, geom, taps, g, accumulate=acc, tensor_core=True, dbias=gb, dbias_accumulate=accb)
+            return
+        K.wgrad(x, dy, geom, taps, g, accumulate=acc, tensor_core=ctx.tc)
+    if wants_b:
+        gb, accb = ctx.grad_out(conv.bias)
+        K.colsum(dy, gb, accumulate=accb)
+
+
 def _is_conv(m, k=None):
     return (isinstance(m, nn.Conv2d) and m.kernel_size[0] == m.kernel_size[1] and m.kernel_size[0] in (1, 3)
             and m.stride == (1, 1) and m.dilation == (1, 1) and m.groups == 1
@@ -271,19 +288,9 @@ class ConvSubnet:
         else:
             K.conv(da, ctx.pack(self.c2.weight, 1), tr.geom, self.hidden, dh, mask=h, mask_act=ACT_RELU,
                    tensor_core=ctx.tc)
-        if self.c2.weight.requires_grad:
-            g, acc = ctx.grad_out(self.c2.weight)
-            K.wgrad(h, da, tr.geom, self.taps, g, accumulate=acc, tensor_core=ctx.tc)
-        if self.c2.bias is not None and self.c2.bias.requires_grad:
-            g, acc = ctx.grad_out(self.c2.bias)
-            K.colsum(da, g, accumulate=acc)
+        _param_grads(ctx, self.c2, h, da, tr.geom, self.taps)
         K.conv(dh, ctx.pack(self.c1.weight, 1), tr.geom, self.cin, dsrc, accumulate=True, tensor_core=ctx.tc)
-        if self.c1.weight.requires_grad:
-            g, acc = ctx.grad_out(self.c1.weight)
-            K.wgrad(x, dh, tr.geom, self.taps, g, accumulate=acc, tensor_core=ctx.tc)
-        if self.c1.bias is not None and self.c1.bias.requires_grad:
-            g, acc = ctx.grad_out(self.c1.bias)
-            K.colsum(dh, g, accumulate=acc)
+        _param_grads(ctx, self.c1, x, dh, tr.geom, self.taps)
 
 
 class DenseSubnet:
@@ -330,24 +337,14 @@ class DenseSubnet:
         dcat = torch.empty(tr.npix, self.ctot, dtype=torch.float32, device=dev)
         c5 = self.convs[4]
         K.conv(dout, ctx.pack(c5.weight, 1), tr.geom, self.ctot, dcat, tensor_core=ctx.tc)
-        if c5.weight.requires_grad:
-            gw, acc = ctx.grad_out(c5.weight)
-            K.wgrad(cat[:, :self.ctot], dout, tr.geom, 9, gw, accumulate=acc, tensor_core=ctx.tc)
-        if c5.bias is not None and c5.bias.requires_grad:
-            gb, acc = ctx.grad_out(c5.bias)
-            K.colsum(dout, gb, accumulate=acc)
+        _param_grads(ctx, c5, cat[:, :self.ctot], dout, tr.geom, 9)
         for j in (3, 2, 1, 0):
             lo = self.cin + self.gc * j
             g = torch.empty(tr.npix, self.gc, dtype=ctx.adt, device=dev)
             K.act_bwd(dcat[:, lo:lo + self.gc], cat[:, lo:lo + self.gc], g, ACT_LRELU, self.SLOPE)
             cj = self.convs[j]
             K.conv(g, ctx.pack(cj.weight, 1), tr.geom, lo, dcat[:, :lo], accumulate=True, tensor_core=ctx.tc)
-            if cj.weight.requires_grad:
-                gw, acc = ctx.grad_out(cj.weight)
-                K.wgrad(cat[:, :lo], g, tr.geom, 9, gw, accumulate=acc, tensor_core=ctx.tc)
-            if cj.bias is not None and cj.bias.requires_grad:
-                gb, acc = ctx.grad_out(cj.bias)
-                K.colsum(g, gb, accumulate=acc)
+            _param_grads(ctx, cj, cat[:, :lo], g, tr.geom, 9)
         K.axpy_slice(dsrc, dcat[:, :self.cin], 1.0)
 
 

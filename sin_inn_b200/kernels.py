@@ -295,8 +295,9 @@ def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None):
     return out
 
 
-def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False):
-    """dw[co][ci][tap] (+)= sum_p dy[p][co] * x[p+off(tap)][ci];  dw: OIHW fp32 contiguous."""
+def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False, dbias=None, dbias_accumulate=False):
+    """dw[co][ci][tap] (+)= sum_p dy[p][co] * x[p+off(tap)][ci];  dw: OIHW fp32 contiguous.
+    dbias (tensor-core path only): additionally dbias[co] (+)= sum_p dy[p][co] in the same launches."""
     x, dy = _view2d(x), _view2d(dy)
     B, H, W = geom
     d = WgradDesc()
@@ -305,6 +306,9 @@ def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False):
     d.x, d.x_dtype, d.x_stride = x.data_ptr(), dtype_code(x), x.stride(0)
     d.dy, d.dy_dtype, d.dy_stride = dy.data_ptr(), dtype_code(dy), dy.stride(0)
     d.dw, d.accumulate = dw.data_ptr(), int(accumulate)
+    if dbias is not None and not tensor_core:
+        raise _lib.SininnError("wgrad: the fused bias gradient is a tensor-core-path feature (use colsum)")
+    d.dbias, d.dbias_accumulate = _p(dbias), int(dbias_accumulate)
     lib = load()
     nbytes = lib.sininn_wgrad_workspace_bytes(C.byref(d), int(tensor_core))
     ws = _workspace(x.device, "wgrad", nbytes)

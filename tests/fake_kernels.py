@@ -203,8 +203,11 @@ def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None):
     return out
 
 
-def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False):
+def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False, dbias=None, dbias_accumulate=False):
     B, H, W = geom
+    if dbias is not None:
+        bsum = dy.float().sum(0)
+        dbias.copy_(dbias + bsum if dbias_accumulate else bsum)
     cin, cout = x.shape[1], dy.shape[1]
     x4 = x.float().reshape(B, H, W, cin)
     dyf = dy.float()

@@ -333,6 +333,18 @@ def test_wgrad_tc(K, taps, cin, cout, geom):
     got3 = torch.empty_like(got)
     K.wgrad(x.to(DEV)[:, :cin], dy.to(DEV)[:, :cout], geom, taps, got3, accumulate=False, tensor_core=True)
     assert torch.equal(got2, got3)                       # deterministic
+    # fused bias gradient: column sums of dy from the same two launches, with and without accumulation
+    bsum = dy[:, :cout].float().sum(0)
+    db0 = rnd(cout, seed=53)
+    db = db0.clone().to(DEV)
+    got4 = torch.empty_like(got)
+    K.wgrad(x.to(DEV)[:, :cin], dy.to(DEV)[:, :cout], geom, taps, got4, tensor_core=True, dbias=db, dbias_accumulate=True)
+    assert torch.equal(got4, got2)
+    tolb = 1e-5 * max(1.0, bsum.abs().max().item()) * max(1.0, (npix / 256) ** 0.5)
+    assert (db.cpu() - (db0 + bsum)).abs().max().item() <= tolb
+    db2 = torch.full((cout,), 7.0, device=DEV)
+    K.wgrad(x.to(DEV)[:, :cin], dy.to(DEV)[:, :cout], geom, taps, got4, tensor_core=True, dbias=db2)
+    assert (db2.cpu() - bsum).abs().max().item() <= tolb
 
 
 @pytest.mark.parametrize("cin,hidden,cout,npix", [(24, 256, 48, 128), (24, 256, 48, 20000), (96, 256, 192, 45), (96, 256, 192, 33 * 40),

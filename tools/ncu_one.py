@@ -13,7 +13,26 @@ shapes = {  # hw, cin, cout, taps, out dtype, relu
     "c3x3_conv2": (64, 256, 48, 9, torch.float32, False),
     "l1_conv2": (32, 256, 192, 9, torch.float32, False),
 }
-if case.startswith("wg_"):
+if case in ("coupling_bwd", "coupling_apply", "permute", "resample", "colsum"):
+    # HBM-bound kernels at the bench workload's level-0 shapes (B=32: 131072 pixels x 48 channels fp32 trunk)
+    npix, C, L = B * 64 * 64, 48, 24
+    U = torch.randn(npix, C, device=DEV); dU = torch.randn(npix, C, device=DEV)
+    a = torch.randn(npix, 2 * L, device=DEV)
+    da = torch.empty(npix, 2 * L, dtype=torch.bfloat16, device=DEV)
+    cmap = torch.randperm(C, device=DEV).to(torch.int32)
+    x4 = torch.randn(B, 12, 128, 128, device=DEV)
+    for _ in range(3):
+        if case == "coupling_bwd":
+            K.coupling_bwd(U[:, :L], dU[:, :L], a[:, :L], a[:, L:], 0, 1.2, 0, da[:, :L], da[:, L:], True)
+        elif case == "coupling_apply":
+            K.coupling_apply(U[:, :L], a[:, :L], a[:, L:], 0, 1.2, 0, True)
+        elif case == "permute":
+            K.permute_nhwc(U.view(B, 64, 64, C), cmap, (0, 24))
+        elif case == "resample":
+            K.resample_nchw(x4, 0, 0)
+        else:
+            K.colsum(da, torch.zeros(2 * L, device=DEV))
+elif case.startswith("wg_"):
     hw, cin, cout, taps = {"wg_l0c2": (64, 256, 48, 9), "wg_l1c2": (32, 256, 192, 9), "wg_l0c1": (64, 24, 256, 9)}[case]
     npix = B * hw * hw
     x = torch.randn(npix, cin, device=DEV).to(torch.bfloat16); dy = torch.randn(npix, cout, device=DEV).to(torch.bfloat16)
