@@ -166,9 +166,17 @@ typedef struct {
   float* out;     int out_stride;        /* fp32 [npix][Cout] */
   void* h_out;    int h_stride;          /* NULL or bf16 [npix][hidden] */
   void* bits_out;                        /* NULL or uint32 [npix][hidden/32] */
+  /* The same pipeline is the subnet's DATA GRADIENT: with x = dL/d(out) [npix][Cout'], w1pack / w2pack the dgrad
+   * packs (sininn_pack_conv_weight mode 1) of conv2 / conv1, b1 = b2 = NULL, mask_bits = the sign bits stored by
+   * the forward call, the hidden tile is dL/dh = mask * (W2^T x) (h_out receives it for the weight gradient) and
+   * out (+)= W1^T dL/dh is the gradient w.r.t. the subnet input. */
+  const void* mask_bits;                 /* NULL, or uint32 [npix][hidden/32]: first stage = zero where the bit is 0 */
+  int accumulate;                        /* 1: out += result */
 } sininn_subnet1x1_desc;
 
 int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stream);
+/* 1 when the fused kernel takes a Cin -> hidden -> Cout subnet (channel multiples and shared-memory budget), else 0 */
+int sininn_subnet1x1_supported(int Cin, int hidden, int Cout);
 
 /* Re-layout nn.Conv2d OIHW fp32 weights for the implicit GEMMs above.
  *   mode 0 (fprop): out[tap][co][ci] = w[co][ci][tap]           rows = Cout, k = Cin

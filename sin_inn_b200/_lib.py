@@ -62,6 +62,7 @@ class Subnet1x1Desc(C.Structure):
         ("out", _vp), ("out_stride", C.c_int),
         ("h_out", _vp), ("h_stride", C.c_int),
         ("bits_out", _vp),
+        ("mask_bits", _vp), ("accumulate", C.c_int),
     ]
 
 
@@ -89,6 +90,7 @@ SIGNATURES = {
     "sininn_conv_simt": (C.c_int, [C.POINTER(ConvDesc), _vp]),
     "sininn_conv_tc": (C.c_int, [C.POINTER(ConvDesc), _vp]),
     "sininn_subnet1x1_fwd_tc": (C.c_int, [C.POINTER(Subnet1x1Desc), _vp]),
+    "sininn_subnet1x1_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "sininn_pack_conv_weight": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "sininn_pack_conv_weights_batched": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "sininn_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(WgradDesc), C.c_int]),

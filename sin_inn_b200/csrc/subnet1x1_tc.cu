@@ -48,6 +48,9 @@ struct S1Params {
   const float* b2;
   uint32_t* bits_out;           // optional ReLU sign bits [npix][hidden/32]
   int store_h;                  // 1: also store the hidden tile (bf16) through tmH
+  // data-gradient use of the same pipeline (x := dL/d(out), W1 := conv2 dgrad pack, W2 := conv1 dgrad pack):
+  const uint32_t* bits_in;      // non-NULL: first epilogue = zero where the stored ReLU sign bit is 0 (no bias, no ReLU)
+  int accumulate;               // 1: out += result (TMA reduce-add) instead of out = result
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -58,6 +61,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
@@ -237,14 +245,24 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         float x[64];
 #pragma unroll
         for (int j = 0; j < 32; ++j) { x[j] = __uint_as_float(v0[j]); x[32 + j] = __uint_as_float(v1[j]); }
-        const float* bs = b1_s + s * 64;
+        if (p.bits_in != nullptr) {                  // gradient through the ReLU: keep where the forward output was > 0
+          uint2 mb = make_uint2(0u, 0u);
+          if (row_ok) mb = __ldg(reinterpret_cast<const uint2*>(p.bits_in + pix * bit_words + 2 * s));
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float4 bq = *reinterpret_cast<const float4*>(bs + 4 * q);
-          x[4 * q + 0] = fmaxf(x[4 * q + 0] + bq.x, 0.f);
-          x[4 * q + 1] = fmaxf(x[4 * q + 1] + bq.y, 0.f);
-          x[4 * q + 2] = fmaxf(x[4 * q + 2] + bq.z, 0.f);
-          x[4 * q + 3] = fmaxf(x[4 * q + 3] + bq.w, 0.f);
+          for (int j = 0; j < 32; ++j) {
+            if (!((mb.x >> j) & 1u)) x[j] = 0.f;
+            if (!((mb.y >> j) & 1u)) x[32 + j] = 0.f;
+          }
+        } else {
+          const float* bs = b1_s + s * 64;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float4 bq = *reinterpret_cast<const float4*>(bs + 4 * q);
+            x[4 * q + 0] = fmaxf(x[4 * q + 0] + bq.x, 0.f);
+            x[4 * q + 1] = fmaxf(x[4 * q + 1] + bq.y, 0.f);
+            x[4 * q + 2] = fmaxf(x[4 * q + 2] + bq.z, 0.f);
+            x[4 * q + 3] = fmaxf(x[4 * q + 3] + bq.w, 0.f);
+          }
         }
         if (p.bits_out != nullptr) {
           uint32_t s0 = 0u, s1 = 0u;
@@ -308,7 +326,8 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmO, smem_u32(stg), o * 32, t * 128 + quarter * 32);
+          if (p.accumulate) tma_reduce_add_2d(&tmO, smem_u32(stg), o * 32, t * 128 + quarter * 32);
+          else tma_store_2d(&tmO, smem_u32(stg), o * 32, t * 128 + quarter * 32);
           bulk_commit();
         }
       }
@@ -340,7 +359,23 @@ static bool encode_2d(EncodeTiledFn encode, CUtensorMap* tm, CUtensorMapDataType
 
 using namespace sininn;
 
+// shared-memory plan of the fused kernel: W1 resident, hidden tile, >= 2 W2 slabs, >= 2 x stages
+static bool s1_fits(int Cin, int hidden, int n2pad, int k1_pad) {
+  const int kc1 = sininn::tc::pick_kc(k1_pad);
+  const int k1_slabs = (Cin + kc1 - 1) / kc1;
+  const int row1 = kc1 * 2;
+  const int budget = 227 * 1024 - 1024 - 256 - 2048;
+  const int fixed = k1_slabs * hidden * row1 + (hidden / 64) * 16384;
+  const int x_stage = k1_slabs * 128 * row1;
+  return fixed + 2 * n2pad * 128 + 2 * x_stage <= budget;
+}
+
 extern "C" {
+
+int sininn_subnet1x1_supported(int Cin, int hidden, int Cout) {
+  if (hidden % 64 != 0 || hidden < 64 || hidden > 256 || Cout <= 0 || Cout > 256 || Cout % 4 != 0 || Cin <= 0 || Cin % 8 != 0) return 0;
+  return s1_fits(Cin, hidden, (Cout + 15) / 16 * 16, (Cin + 15) / 16 * 16) ? 1 : 0;
+}
 
 int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stream) {
   using namespace sininn::tc;
@@ -354,6 +389,7 @@ int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stre
   SININN_CHECK_ARG(aligned16(d->w1pack) && aligned16(d->w2pack), "subnet1x1: packed weights misaligned");
   SININN_CHECK_ARG(d->h_out == nullptr || (aligned16(d->h_out) && (d->h_stride * 2) % 16 == 0), "subnet1x1: h_out misaligned");
   SININN_CHECK_ARG(d->npix < (1ll << 31) - 256, "subnet1x1: too many pixels");
+  SININN_CHECK_ARG(!(d->mask_bits && (d->b1 || d->bits_out)), "subnet1x1: mask_bits (gradient mode) excludes b1 and bits_out");
   EncodeTiledFn encode = get_encode();
   if (!encode) { set_error("subnet1x1: cuTensorMapEncodeTiled not available from the driver"); return SININN_ECUDA; }
 
@@ -374,6 +410,8 @@ int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stre
   p.b1 = d->b1; p.b2 = d->b2;
   p.bits_out = reinterpret_cast<uint32_t*>(d->bits_out);
   p.store_h = d->h_out != nullptr ? 1 : 0;
+  p.bits_in = reinterpret_cast<const uint32_t*>(d->mask_bits);
+  p.accumulate = d->accumulate;
   // shared-memory plan: W1 resident, hidden tile, then as much of W2 as fits (all of it => resident), x ring
   const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 2048 /*biases*/;
   const int fixed = p.k1_slabs * (int)p.w1_slab_bytes + p.hs * 16384;

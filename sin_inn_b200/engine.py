@@ -283,6 +283,16 @@ class ConvSubnet:
         x, h, bits = saved
         dev = x.device
         dh = torch.empty_like(h)
+        if (ctx.tc and self.taps == 1 and FUSE_1X1 and bits is not None and da.stride(0) % 8 == 0
+                and K.subnet1x1_supported(self.cout, self.hidden, self.cin) and dsrc.stride(0) % 4 == 0
+                and dsrc.data_ptr() % 16 == 0):
+            # both data gradients in ONE launch of the fused pipeline: dh = mask * (W2^T da) stays in shared memory
+            # for dsrc += W1^T dh and is stored once for the weight gradient of conv1
+            K.subnet1x1_fwd(da, ctx.pack(self.c2.weight, 1), None, ctx.pack(self.c1.weight, 1), None, dsrc,
+                            h_out=dh, mask_bits=bits, accumulate=True)
+            _param_grads(ctx, self.c2, h, da, tr.geom, self.taps)
+            _param_grads(ctx, self.c1, x, dh, tr.geom, self.taps)
+            return
         if bits is not None:
             K.conv(da, ctx.pack(self.c2.weight, 1), tr.geom, self.hidden, dh, mask_bits=bits, tensor_core=True)
         else:

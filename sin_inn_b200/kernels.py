@@ -263,10 +263,10 @@ def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask
 
 def subnet1x1_supported(cin, hidden, cout):
     """Shapes the fused 1x1 subnet kernel takes (everything else runs as two conv launches)."""
-    return hidden % 64 == 0 and 64 <= hidden <= 256 and cout <= 256 and cout % 4 == 0 and cin % 8 == 0
+    return bool(load().sininn_subnet1x1_supported(int(cin), int(hidden), int(cout)))
 
 
-def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None):
+def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None, mask_bits=None, accumulate=False):
     """out = W2 relu(W1 x + b1) + b2 per pixel, one launch (tcgen05; hidden activation stays on chip).
     x: bf16 [npix, Cin] view; w1pack [1, hidden, k1_pad]; w2pack [1, n2_pad, hidden]; out: fp32 [npix, Cout] view;
     h_out (bf16 [npix, hidden]) / bits_out (int32 [npix, hidden/32]) optionally receive the hidden activation."""
@@ -290,6 +290,8 @@ def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None):
     else:
         d.h_out, d.h_stride = 0, 0
     d.bits_out = _p(bits_out)
+    # gradient use (see sininn.h): hidden stage masked by the forward's ReLU sign bits, output accumulated
+    d.mask_bits, d.accumulate = _p(mask_bits), int(accumulate)
     flops = 2.0 * d.npix * d.hidden * (d.Cin + d.Cout)
     check(_run("conv", lambda: load().sininn_subnet1x1_fwd_tc(C.byref(d), stream_ptr()), 1, flops), "subnet1x1_fwd_tc")
     return out

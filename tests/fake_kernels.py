@@ -189,17 +189,21 @@ def subnet1x1_supported(cin, hidden, cout):
     return hidden % 64 == 0 and 64 <= hidden <= 256 and cout <= 256 and cout % 4 == 0 and cin % 8 == 0
 
 
-def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None):
+def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None, mask_bits=None, accumulate=False):
     npix, cin = x.shape
     hidden, cout = w1pack.shape[1], out.shape[1]
-    h = torch.relu(x.float() @ w1pack[0, :hidden, :cin].float().t() + (0 if b1 is None else b1.detach().float()))
+    h = x.float() @ w1pack[0, :hidden, :cin].float().t()
+    if mask_bits is not None:                 # gradient mode: masked by the forward's ReLU sign bits
+        h = h * _unpack_bits(mask_bits, hidden)
+    else:
+        h = torch.relu(h + (0 if b1 is None else b1.detach().float()))
     hb = h.to(torch.bfloat16)                 # the kernel feeds the second GEMM with the bf16-rounded hidden tile
     if bits_out is not None:
         bits_out.copy_(_pack_bits(hb.float()))
     if h_out is not None:
         h_out.copy_(hb)
     o = hb.float() @ w2pack[0, :cout, :hidden].float().t() + (0 if b2 is None else b2.detach().float())
-    out.copy_(o)
+    out.copy_(out + o if accumulate else o)
     return out
 
 

@@ -384,3 +384,39 @@ def test_subnet1x1_fused_forward(K, cin, hidden, cout, npix, keep):
     again = base.clone().to(DEV)
     K.subnet1x1_fwd(xw.to(DEV)[:, :cin], w1d, b1.to(DEV), w2d, b2.to(DEV), again[:, :cout])
     assert torch.equal(again.cpu(), got)
+
+
+def test_subnet1x1_support_query(K):
+    assert K.subnet1x1_supported(24, 256, 48) and K.subnet1x1_supported(96, 256, 192) and K.subnet1x1_supported(48, 256, 24)
+    assert not K.subnet1x1_supported(192, 256, 96)       # W1 (192 x 256) + hidden tile + rings exceed 227 KB
+    assert not K.subnet1x1_supported(24, 512, 48) and not K.subnet1x1_supported(20, 256, 48)
+
+
+@pytest.mark.parametrize("cin,hidden,cout,npix", [(24, 256, 48, 128), (24, 256, 48, 5000), (24, 128, 48, 777)])
+def test_subnet1x1_fused_data_gradient(K, cin, hidden, cout, npix):
+    """The fused 1x1 pipeline in gradient mode: dh = relu_mask * (W2^T da) (stored for the weight gradient) and
+    dsrc += W1^T dh accumulated into a channel slice of a wider fp32 matrix, against the torch restatement."""
+    bf = torch.bfloat16
+    assert K.subnet1x1_supported(cout, hidden, cin)
+    w1 = rnd(hidden, cin, 1, 1, seed=80) * 0.2           # conv1: cin -> hidden
+    w2 = rnd(cout, hidden, 1, 1, seed=81) * 0.1          # conv2: hidden -> cout
+    da = rnd(npix, cout + 8, seed=82).to(bf)
+    hfwd = rnd(npix, hidden, seed=83)
+    bits_ref = FK._pack_bits((hfwd > 0).float())
+    hp, cop, cip = (hidden + 15) // 16 * 16, (cout + 15) // 16 * 16, (cin + 15) // 16 * 16
+    # dgrad packs: conv2 -> [hidden][cout], conv1 -> [cin][hidden]
+    w2r, w1r = FK.pack_weight(w2, 1, bf, hp, cop), FK.pack_weight(w1, 1, bf, cip, hp)
+    w2d, w1d = K.pack_weight(w2.to(DEV), 1, bf, hp, cop), K.pack_weight(w1.to(DEV), 1, bf, cip, hp)
+    base = rnd(npix, cin + 4, seed=84)
+    ref = base.clone()
+    dh_ref = torch.empty(npix, hidden, dtype=bf)
+    FK.subnet1x1_fwd(da[:, :cout], w2r, None, w1r, None, ref[:, :cin], h_out=dh_ref, mask_bits=bits_ref, accumulate=True)
+    got = base.clone().to(DEV)
+    dh = torch.zeros(npix, hidden, dtype=bf, device=DEV)
+    K.subnet1x1_fwd(da.to(DEV)[:, :cout], w2d, None, w1d, None, got[:, :cin], h_out=dh, mask_bits=bits_ref.to(DEV), accumulate=True)
+    got = got.cpu()
+    assert torch.equal(got[:, cin:], base[:, cin:]), "fused data gradient wrote outside its channel slice"
+    assert (got[:, :cin] - ref[:, :cin]).abs().max().item() <= 1e-2 * max(1.0, ref[:, :cin].abs().max().item())
+    dhc = dh.cpu().float()
+    assert (dhc - dh_ref.float()).abs().max().item() <= 1e-2 * max(1.0, dh_ref.float().abs().max().item())
+    assert bool(((hfwd <= 0) <= (dhc == 0)).all())       # exactly zero wherever the forward ReLU was off
