@@ -92,17 +92,32 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
 // v holds the slab's accumulator columns; returns the sign bits of the produced values (bit j = value j > 0).
 template <int NCOL>
 __device__ __forceinline__ void slab_math(const Params& p, float (&x)[NCOL], const float* bias_s, const uint32_t* mbits) {
-  // branch-free activation: f(v) = v > 0 ? v : ns * v with ns = 1 (none), 0 (ReLU), slope (LeakyReLU).  A per-element
-  // switch on p.act costs three uniform branches per value -- measured at ~5000 cycles per 64-column slab.
-  const float ns = p.act == SININN_ACT_RELU ? 0.f : (p.act == SININN_ACT_LRELU ? p.slope : 1.f);
+  // The epilogue warps are instruction-bound on the 256-wide outputs (measured: ~1600 cycles per 64-column slab and
+  // warp), so every variant is branch-free per element and does only what its launch needs; the branches below are
+  // warp-uniform and outside the element loops.
+  if (p.bias != nullptr || p.act != SININN_ACT_NONE) {
+    if (p.act == SININN_ACT_RELU) {                      // FADD + FMNMX per element
 #pragma unroll
-  for (int q = 0; q < NCOL / 4; ++q) {
-    const float4 bq = *reinterpret_cast<const float4*>(bias_s + 4 * q);
-    const float b4[4] = {bq.x, bq.y, bq.z, bq.w};
+      for (int q = 0; q < NCOL / 4; ++q) {
+        const float4 bq = *reinterpret_cast<const float4*>(bias_s + 4 * q);
+        x[4 * q + 0] = fmaxf(x[4 * q + 0] + bq.x, 0.f);
+        x[4 * q + 1] = fmaxf(x[4 * q + 1] + bq.y, 0.f);
+        x[4 * q + 2] = fmaxf(x[4 * q + 2] + bq.z, 0.f);
+        x[4 * q + 3] = fmaxf(x[4 * q + 3] + bq.w, 0.f);
+      }
+    } else {
+      // f(v) = max(v, ns * v): identity for ns = 1 (no activation), LeakyReLU for 0 <= ns = slope <= 1
+      const float ns = p.act == SININN_ACT_LRELU ? p.slope : 1.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float v = x[4 * q + e] + b4[e];
-      x[4 * q + e] = v > 0.f ? v : ns * v;
+      for (int q = 0; q < NCOL / 4; ++q) {
+        const float4 bq = *reinterpret_cast<const float4*>(bias_s + 4 * q);
+        const float b4[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v = x[4 * q + e] + b4[e];
+          x[4 * q + e] = ns == 1.f ? v : (v > 0.f ? v : ns * v);
+        }
+      }
     }
   }
   if (mbits != nullptr) {

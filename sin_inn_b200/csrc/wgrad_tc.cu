@@ -263,7 +263,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 }
 
 // dw[co][ci][tap] (+)= sum_split partial[split][tap][m][n]; (co,ci) = (m,n) when the wide operand is dy, else (n,m).
-// Fixed summation order over the splits => bit-reproducible gradients.
+// Fixed summation order => bit-reproducible gradients.  RG threads share one output vector: thread g sums splits
+// g, g+RG, g+2RG, ... (independent loads in flight instead of one dependent chain of `splits` L2 round trips), the
+// RG partial sums are combined in a fixed order through shared memory.
+constexpr int RG = 8;
 template <int VEC>
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cw, int Cn,
                                                               int wide_is_dy, int Cout, int Cin, float* __restrict__ dw, int accumulate,
@@ -271,6 +274,7 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
                                                               float* __restrict__ dbias, int dbias_accumulate) {
   pdl_wait();
   pdl_trigger();
+  __shared__ float red[RG][32][VEC + 1];
   if (bias_partial != nullptr && blockIdx.x == gridDim.x - 1) {     // fixed-order sum of the per-split column sums of dy
     for (int c = threadIdx.x; c < bias_n; c += blockDim.x) {
       float s = 0.f;
@@ -280,30 +284,48 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
   }
   const long long per = (long long)taps * Cw * Cn;
   const long long perv = per / VEC;
-  for (long long iv = blockIdx.x * (long long)blockDim.x + threadIdx.x; iv < perv; iv += (long long)gridDim.x * blockDim.x) {
+  const int o = threadIdx.x & 31, g = threadIdx.x >> 5;            // output slot within the block, split group
+  for (long long base = (long long)blockIdx.x * 32; base < perv; base += (long long)gridDim.x * 32) {
+    const long long iv = base + o;
     const long long idx = iv * VEC;
     float s[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) s[e] = 0.f;
-    for (int k = 0; k < splits; ++k) {
-      if (VEC == 4) {
-        const float4 t = *reinterpret_cast<const float4*>(partial + k * per + idx);
-        s[0] += t.x; s[VEC > 1 ? 1 : 0] += t.y; s[VEC > 2 ? 2 : 0] += t.z; s[VEC > 3 ? 3 : 0] += t.w;
-      } else {
-        s[0] += partial[k * per + idx];
+    if (iv < perv) {
+#pragma unroll 4
+      for (int k = g; k < splits; k += RG) {
+        if (VEC == 4) {
+          const float4 t = __ldcs(reinterpret_cast<const float4*>(partial + k * per + idx));
+          s[0] += t.x; s[VEC > 1 ? 1 : 0] += t.y; s[VEC > 2 ? 2 : 0] += t.z; s[VEC > 3 ? 3 : 0] += t.w;
+        } else {
+          s[0] += partial[k * per + idx];
+        }
       }
     }
-    const int n0 = (int)(idx % Cn);
-    long long r = idx / Cn;
-    const int m = (int)(r % Cw);
-    const int tap = (int)(r / Cw);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const int n = n0 + e;
-      const int co = wide_is_dy ? m : n, ci = wide_is_dy ? n : m;
-      float* o = dw + ((long long)co * Cin + ci) * taps + tap;
-      *o = accumulate ? *o + s[e] : s[e];
+    for (int e = 0; e < VEC; ++e) red[g][o][e] = s[e];
+    __syncthreads();
+    if (g == 0 && iv < perv) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        float t = red[0][o][e];
+#pragma unroll
+        for (int q = 1; q < RG; ++q) t += red[q][o][e];
+        s[e] = t;
+      }
+      const int n0 = (int)(idx % Cn);
+      long long r = idx / Cn;
+      const int m = (int)(r % Cw);
+      const int tap = (int)(r / Cw);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const int n = n0 + e;
+        const int co = wide_is_dy ? m : n, ci = wide_is_dy ? n : m;
+        float* out = dw + ((long long)co * Cin + ci) * taps + tap;
+        *out = accumulate ? *out + s[e] : s[e];
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -436,12 +458,12 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
   launch_k(wgrad_tc_kernel, dim3(grid), dim3(NUM_THREADS), smem, st, tmW, tmN, p);
   const long long per = (long long)d->taps * w.Cw * w.Cn;
   if ((w.Cn % 4) == 0) {
-    long long g = (per / 4 + 255) / 256;
+    long long g = (per / 4 + 31) / 32;
     if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
     launch_k(wgrad_tc_reduce_kernel<4>, dim3((int)g), dim3(256), 0, st, p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
                                                       d->dw, d->accumulate, p.bias_partial, bias_rows, d->Cout, d->dbias, d->dbias_accumulate);
   } else {
-    long long g = (per + 255) / 256;
+    long long g = (per + 31) / 32;
     if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
     launch_k(wgrad_tc_reduce_kernel<1>, dim3((int)g), dim3(256), 0, st, p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
                                                       d->dw, d->accumulate, p.bias_partial, bias_rows, d->Cout, d->dbias, d->dbias_accumulate);

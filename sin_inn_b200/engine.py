@@ -416,6 +416,47 @@ class PermOp:
         return []
 
 
+class LinearOp:
+    """Fixed invertible 1x1 convolution (FrEIA Fixed1x1Conv, offered at archs.py:40-50): y[:, o] = sum_i M[i][o] x[:, i]
+    per pixel, reverse with M^-1 (inverted in fp64 on the host).  Always evaluated by the fp32 CUDA-core GEMM kernel,
+    whatever the subnet precision: the exactness of the round trip (1e-5) rests on it and C <= 192 makes it cheap.
+    PermuteRandom is the special case of a permutation matrix."""
+    kind = "linear"
+
+    def __init__(self, M):
+        M = torch.as_tensor(M, dtype=torch.float64)
+        if M.dim() != 2 or M.shape[0] != M.shape[1]:
+            raise SininnError(f"Fixed1x1Conv needs a square matrix, got {tuple(M.shape)}")
+        sign, logabs = torch.linalg.slogdet(M)
+        if sign == 0:
+            raise SininnError("Fixed1x1Conv: the matrix is singular")
+        self.C = M.shape[0]
+        self.logdet = float(logabs)                       # log |det M|, per pixel
+        W = M.t().contiguous()                            # y = W x
+        Wi = torch.linalg.inv(W)
+        # matrices applied to a pixel's channel vector, by (reverse direction?, gradient pass?)
+        self.mats = {(False, False): W, (True, False): Wi, (False, True): W.t().contiguous(), (True, True): Wi.t().contiguous()}
+        self._packs = {}
+
+    def pack(self, device, rev, grad=False):
+        key = (device.type, device.index, bool(rev), bool(grad))
+        if key not in self._packs:
+            w = self.mats[(bool(rev), bool(grad))].to(torch.float32).reshape(self.C, self.C, 1, 1).to(device)
+            self._packs[key] = K.pack_weight(w, 0, torch.float32, _round_up(self.C, 16), _round_up(self.C, 16))
+        return self._packs[key]
+
+    def apply(self, U, rev, grad=False):
+        """U: channels-last [B,h,w,C] fp32 -> new tensor of the same shape."""
+        out = torch.empty_like(U)
+        npix = U.numel() // self.C
+        K.conv(U.view(npix, self.C), self.pack(U.device, rev, grad), tuple(U.shape[:3]), self.C, out.view(npix, self.C),
+               tensor_core=False)
+        return out
+
+    def parameters(self):
+        return []
+
+
 class HalfStep:
     """dst <- affine(dst; nets(src)).  kind: 'glow' (one net, output = [s | t]), 'irn_affine' (s from
     nets[0], t from nets[1]), 'irn_add' (dst <- dst + sign * nets[0](src))."""
@@ -629,6 +670,8 @@ class Plan:
                 hint = self._hint(nxt, rev, ctx)
                 U, bf = K.permute_nhwc(tr.U, op.gather_map(dev, rev), hint)
                 tr.set(U, None, {hint: bf} if bf is not None else None)
+            elif op.kind == "linear":
+                tr.set(op.apply(tr.U, rev))
             else:
                 tr.set(op.apply_nhwc(tr.U, rev))
             _trace(op.kind, tr.U)
@@ -679,6 +722,9 @@ class Plan:
                 U, _ = K.permute_nhwc(tr.U, m_val, None)
                 dU, _ = K.permute_nhwc(tr.dU, m_grad, None)
                 tr.set(U, dU)
+            elif op.kind == "linear":
+                # executed y = A x (A = W or W^-1): the input is A^-1 y, its gradient A^T dy
+                tr.set(op.apply(tr.U, not rev), op.apply(tr.dU, rev, grad=True))
             else:
                 U = op.apply_nhwc(tr.U, not rev)
                 dU = op.apply_nhwc(tr.dU, rev, grad=True)

@@ -102,3 +102,30 @@ class PermuteRandom(_PlanModule):
 
     def jacobian(self, x, rev=False):
         return 0.0
+
+
+class Fixed1x1Conv(_PlanModule):
+    """Fixed invertible 1x1 convolution: forward conv2d(x, M^T as a [C,C,1,1] kernel), i.e. y[:, o] = sum_i M[i, o]
+    x[:, i]; reverse with M^-1; log|det J| = +-(H*W) * log|det M|.  The reference leaves this node commented out
+    (archs.py:40-50, "How do we compute M"); M is supplied by the caller, e.g. a random rotation."""
+
+    def __init__(self, dims_in, M):
+        super().__init__()
+        self.dims_in = tuple(dims_in[0])
+        M = torch.as_tensor(M)
+        if tuple(M.shape) != (self.dims_in[0], self.dims_in[0]):
+            raise E.SininnError(f"Fixed1x1Conv: M must be {self.dims_in[0]}x{self.dims_in[0]}, got {tuple(M.shape)}")
+        self._lin = E.LinearOp(M)
+        # frozen parameters with the upstream names, so checkpoints carry the matrix
+        self.M = nn.Parameter(M.t().to(torch.float32).contiguous().view(*M.shape, 1, 1), requires_grad=False)
+        self.M_inv = nn.Parameter(self._lin.mats[(True, False)].to(torch.float32).contiguous().view(*M.shape, 1, 1), requires_grad=False)
+        self.logDetM = nn.Parameter(torch.tensor(self._lin.logdet, dtype=torch.float32), requires_grad=False)
+
+    def _op(self):
+        return self._lin
+
+    def jacobian(self, x, rev=False):
+        x0 = x[0] if isinstance(x, (list, tuple)) else x
+        n_pixels = x0.shape[2] * x0.shape[3]
+        j = self._lin.logdet * n_pixels
+        return torch.full((x0.shape[0],), -j if rev else j, dtype=torch.float32, device=x0.device)

@@ -180,3 +180,10 @@ def test_direct_gradient_accumulation_matches_autograd_accumulation(fake_kernels
     assert ptrs == [p.grad.data_ptr() for p in net.parameters()]          # accumulated in place
     for (n, a), (_, b) in zip(ora.named_parameters(), net.named_parameters()):
         assert (a.grad - b.grad).abs().max() <= 2e-4 * max(a.grad.abs().max().item(), 1e-3), n
+
+
+def test_fixed1x1conv_host(fake_kernels):
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shared_checks import fixed1x1_checks
+    fixed1x1_checks("cpu")

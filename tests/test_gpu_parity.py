@@ -274,3 +274,12 @@ def test_host_batch_feeder_delivers_batches_in_order():
         seen.append([float(t.mean()) for t in batch])
         feeder.release(i % 2)
     assert seen == [[float(10 * i + j) for j in range(3)] for i in range(5)]
+
+
+def test_fixed1x1conv_gpu():
+    """North-star item (3), the invertible 1x1 convolution and its log-determinant (FrEIA Fixed1x1Conv, left
+    commented out at archs.py:40-50): same checks as the host test, on the real kernels."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shared_checks import fixed1x1_checks
+    fixed1x1_checks(DEV)
