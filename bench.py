@@ -227,12 +227,20 @@ def run_ours(args):
         pk = peaks()
         value = world * B * args.steps / (ms / 1e3)
         e2e = world * B * args.steps / (ms_e2e / 1e3)
-        # roofline of the dominant kernel family (subnet convolutions): algorithmic FLOPs of the launches
-        # timed with CUDA events inside the timed region / their summed duration
-        conv = prof.get("conv", {"ms": 0.0, "flops": 0.0, "n": 0})
-        wg = prof.get("wgrad", {"ms": 0.0, "flops": 0.0, "n": 0})
-        tc_ms, tc_fl = conv["ms"] + wg["ms"], conv["flops"] + wg["flops"]
-        achieved = tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
+        # roofline of the dominant kernel (conv_tc_pair_kernel = every 3x3 subnet convolution, ~30 % of the step's
+        # device time): algorithmic FLOPs of its launches / their summed CUDA-event duration in the eager pass
+        zero = {"ms": 0.0, "flops": 0.0, "n": 0}
+        c3 = prof.get("conv3x3", zero)
+        fams = [prof.get(k, zero) for k in ("conv3x3", "conv1x1", "subnet1x1", "wgrad")]
+        tc_ms, tc_fl, tc_n = sum(f["ms"] for f in fams), sum(f["flops"] for f in fams), sum(f["n"] for f in fams)
+        achieved = c3["flops"] / (c3["ms"] / 1e3) / 1e12 if c3["ms"] > 0 else 0.0
+        achieved_all = tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
+        traffic, traffic_detail = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            per = [v["dram_read"] + v["dram_write"] for v in tj["shapes"].values()]
+            traffic, traffic_detail = sum(per) / len(per), tj
         alg_flops_step = 6 * 2 * conv_macs_per_patch(P) * B
         line = {
             "metric": "INN train-step patches/sec", "value": value, "unit": "patches/s", "n_gpus": world,
@@ -247,10 +255,19 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
-                         "kernel": "subnet conv implicit GEMMs (fprop+dgrad+wgrad launches)",
-                         "kernel_ms_per_step": tc_ms / args.steps, "kernel_launches": conv["n"] + wg["n"],
+                         "frac": achieved / pk["tf_sustained"], "traffic": traffic, "peak_source": pk["source"] + " (sustained)",
+                         "kernel": "conv_tc_pair_kernel (3x3 subnet convolutions: fprop, recompute, dgrad)",
+                         "kernel_ms_per_step": c3["ms"] / args.steps, "kernel_launches": c3["n"],
+                         "traffic_note": "mean DRAM bytes per launch over the three ncu --set full captures in profiles/traffic_r1.json",
+                         "all_subnet_gemms": {"achieved": achieved_all, "frac": achieved_all / pk["tf_sustained"],
+                                              "ms_per_step": tc_ms / args.steps, "launches": tc_n},
                          "whole_step_algorithmic_tflops": alg_flops_step / (ms / args.steps / 1e3) / 1e12},
+            # bandwidth-bound kernel families: algorithmic bytes of their launches / CUDA-event time, vs measured HBM peak
+            "roofline_hbm": {fam: {"achieved": prof[fam]["bytes"] / (prof[fam]["ms"] / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                   "frac": prof[fam]["bytes"] / (prof[fam]["ms"] / 1e3) / 1e9 / pk["hbm"],
+                                   "launches": prof[fam]["n"], "ms_per_step": prof[fam]["ms"] / args.steps}
+                             for fam in ("coupling_bwd", "coupling", "permute", "resample", "layout")
+                             if fam in prof and prof[fam]["ms"] > 0 and prof[fam]["bytes"] > 0},
             "clocks": sampler.summary(),
             "profile_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
         }

@@ -257,7 +257,8 @@ def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask
     lib = load()
     fn = lib.sininn_conv_tc if tensor_core else lib.sininn_conv_simt
     flops = 2.0 * B * H * W * d.Cin * d.Cout * d.taps
-    check(_run("conv", lambda: fn(C.byref(d), stream_ptr()), 1, flops), "conv_tc" if tensor_core else "conv_simt")
+    fam = "conv3x3" if d.taps == 9 else "conv1x1"
+    check(_run(fam, lambda: fn(C.byref(d), stream_ptr()), 1, flops), "conv_tc" if tensor_core else "conv_simt")
     return out
 
 
@@ -293,7 +294,7 @@ def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None, mas
     # gradient use (see sininn.h): hidden stage masked by the forward's ReLU sign bits, output accumulated
     d.mask_bits, d.accumulate = _p(mask_bits), int(accumulate)
     flops = 2.0 * d.npix * d.hidden * (d.Cin + d.Cout)
-    check(_run("conv", lambda: load().sininn_subnet1x1_fwd_tc(C.byref(d), stream_ptr()), 1, flops), "subnet1x1_fwd_tc")
+    check(_run("subnet1x1", lambda: load().sininn_subnet1x1_fwd_tc(C.byref(d), stream_ptr()), 1, flops), "subnet1x1_fwd_tc")
     return out
 
 
