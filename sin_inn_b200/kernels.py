@@ -53,7 +53,8 @@ def _run(family, fn, nk=1, flops=0.0, nbytes=0.0):
 
 
 def _workspace(dev, name, nbytes):
-    key = (dev.index, name)
+    # one buffer per (device, purpose, STREAM): the two halves of a training step run on two streams
+    key = (dev.index, name, torch.cuda.current_stream(dev).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)

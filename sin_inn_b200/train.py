@@ -9,6 +9,8 @@ Differences from the reference, all outside the INN kernels:
     all-reduce inside each of its two manual_backward calls);
   * the TCR branch (lit_wrapper.py:58-72) is off by default and not reproduced.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -92,6 +94,21 @@ class SingleVideoTrainer:
         self.world_size = world_size
         if hasattr(inn, "plan"):
             inn.plan().direct_grad = True      # gradients accumulate straight into the flat arena
+        # The two halves of a step (forward pass + its backward, inverse pass + its backward) only meet in the
+        # gradient sum, so they are enqueued on two streams: kernels of one half fill the tails, prologues and
+        # partial waves of the other.  The second half accumulates into its own gradient arena (no read-modify-write
+        # race on the shared .grad) and the two arenas are added before the all-reduce.  SININN_OVERLAP=0: one stream.
+        self.overlap = (os.environ.get("SININN_OVERLAP", "1") != "0" and self.flat.flat.is_cuda and hasattr(inn, "plan"))
+        if self.overlap:
+            self.grad_b = torch.zeros_like(self.flat.grad)
+            self.side = torch.cuda.Stream(device=self.flat.flat.device)
+
+    def _point_grads(self, arena):
+        off = 0
+        for p in self.flat.params:
+            m = p.numel()
+            p.grad = arena[off:off + m].view(p.shape)
+            off += m
 
     def broadcast_params(self):
         if self.world_size > 1:
@@ -101,6 +118,8 @@ class SingleVideoTrainer:
         """hr (b,3,H,W), lr (b,lr_dims,h,w), z (b,z_dims,h,w) on the GPU.  Returns the two loss tensors."""
         o = self.opt
         self.optim.zero_grad()
+        if self.overlap:
+            return self._training_step_two_streams(hr, lr, z)
         lr_z = torch.cat((lr, z), dim=1)
         # forward pass HR -> (LR, z)                                   lit_wrapper.py:45-49
         lr_z_hat = self.inn(hr)
@@ -115,6 +134,36 @@ class SingleVideoTrainer:
         if self.world_size > 1:
             dist.all_reduce(self.flat.grad)                            # one NCCL all-reduce per step
         self.optim.step(grad_scale=1.0 / self.world_size)              # lit_wrapper.py:76
+        return fwd_loss.detach(), bwd_loss.detach()
+
+    def _training_step_two_streams(self, hr, lr, z):
+        o = self.opt
+        main = torch.cuda.current_stream()
+        cfg = self.inn.engine_config or engine.default_config()
+        self.inn.plan().packs(cfg.act_dtype)           # packed weights refreshed BEFORE the fork: both halves read them
+        self.grad_b.zero_()
+        self.side.wait_stream(main)
+        # forward pass HR -> (LR, z) and its backward on the current stream      lit_wrapper.py:45-49
+        lr_z_hat = self.inn(hr)
+        fwd_loss = o.lambda_fwd_rec * reconstruction(lr_z_hat[:, :o.lr_dims], lr)
+        if o.lambda_latent_nll:
+            fwd_loss = fwd_loss + o.lambda_latent_nll * latent_nll(lr_z_hat[:, o.lr_dims:])
+        fwd_loss.backward()
+        # reverse pass (LR, z) -> HR and its backward on the side stream         lit_wrapper.py:53-56
+        self._point_grads(self.grad_b)
+        try:
+            with torch.cuda.stream(self.side):
+                lr_z = torch.cat((lr, z), dim=1)
+                hr_hat = self.inn(lr_z, rev=True)
+                bwd_loss = o.lambda_bwd_rec * reconstruction(hr_hat, hr)
+                bwd_loss.backward()
+        finally:
+            self._point_grads(self.flat.grad)
+        main.wait_stream(self.side)
+        self.flat.grad.add_(self.grad_b)
+        if self.world_size > 1:
+            dist.all_reduce(self.flat.grad)
+        self.optim.step(grad_scale=1.0 / self.world_size)
         return fwd_loss.detach(), bwd_loss.detach()
 
     def capture(self, hr, lr, z, warmup=3):
