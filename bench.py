@@ -189,10 +189,16 @@ def run_ours(args):
     launches = launches_per_step * args.steps      # kernels executed in the timed region (graph replays included)
     # same K steps again with a CUDA-event pair around every kernel launch (per-family durations for the roofline);
     # kept out of the headline region because ~1300 extra event records per step perturb a launch-dense step
+    # (single stream for this pass: with the step's halves overlapped on several streams an event pair would also
+    #  time whatever the other streams ran in between)
+    saved = (trainer.overlap, net.plan().side_wgrad)
+    trainer.overlap, net.plan().side_wgrad = False, False
+    trainer.training_step(*dev_batches[0])
     kernels.profile_begin()
     for i in range(args.steps):
         trainer.training_step(*dev_batches[i % 2])     # eager: events cannot be recorded inside a graph replay
     prof = kernels.profile_end()
+    trainer.overlap, net.plan().side_wgrad = saved
     sampler.stop_flag = True
     # end-to-end: pinned host inputs -> device, step, loss back to host, every step
     feeder.submit(pool[0], 0)
@@ -218,7 +224,7 @@ def run_ours(args):
         trainer._graph = None
         trainer.optim.zero_grad()
         torch.cuda.empty_cache()
-        inf = inference_1080p(net, opt, dev, args.infer_batch, iters=args.infer_iters)
+        inf = inference_1080p(net, opt, dev, args.infer_batch, iters=args.infer_iters, use_graph=not args.no_graph)
     t = torch.tensor([ms, ms_e2e] + ([inf["fwd_ms"], inf["inv_ms"]] if inf else [0.0, 0.0]), dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -288,8 +294,10 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def inference_1080p(net, opt, dev, micro_batch, iters):
-    """Times `iters` micro-batches of 1920x1080 frames through net(x) and net(lr_z, rev=True) (CUDA events)."""
+def inference_1080p(net, opt, dev, micro_batch, iters, use_graph=True):
+    """Times `iters` micro-batches of 1920x1080 frames through net(x) and net(lr_z, rev=True) (CUDA events); each
+    direction is one replayed CUDA graph (train.GraphedInference) unless use_graph is False."""
+    from sin_inn_b200 import train
     H, W = 1080, 1920
     g = torch.Generator(device="cpu").manual_seed(7)
     hr = torch.rand(micro_batch, 3, H, W, generator=g).to(dev)
@@ -299,7 +307,12 @@ def inference_1080p(net, opt, dev, micro_batch, iters):
         back = net(lrz, rev=True)
         out["roundtrip"] = float((back - hr).abs().max())
         del back
-        for tag, fn in (("fwd_ms", lambda: net(hr)), ("inv_ms", lambda: net(lrz, rev=True))):
+        if use_graph:
+            gf, gi = train.GraphedInference(net, hr, False), train.GraphedInference(net, lrz, True)
+            runs = (("fwd_ms", lambda: gf(hr)), ("inv_ms", lambda: gi(lrz)))
+        else:
+            runs = (("fwd_ms", lambda: net(hr)), ("inv_ms", lambda: net(lrz, rev=True)))
+        for tag, fn in runs:
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()

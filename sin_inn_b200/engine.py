@@ -187,6 +187,7 @@ class RunCtx:
         self.packs = packs
         self.direct_grad = direct_grad      # accumulate weight gradients straight into param.grad (no autograd add)
         self.direct = set()
+        self.wstream = None                 # side stream for the parameter-gradient launches (Plan.backward sets it)
 
     def grad_out(self, param):
         """(tensor, accumulate) the weight-gradient kernels should write to for `param`."""
@@ -221,6 +222,20 @@ def _param_grads(ctx, conv, x, dy, geom, taps):
     bias gradient (column sums of dy) is produced by the weight-gradient launches themselves; otherwise by colsum."""
     wants_w = conv.weight.requires_grad
     wants_b = conv.bias is not None and conv.bias.requires_grad
+    if ctx.wstream is not None and (wants_w or wants_b):
+        # parameter gradients are leaves of the backward pass: nothing downstream reads them before the pass ends,
+        # so they go to a side stream and fill the gaps of the data-gradient chain (joined in Plan.backward)
+        cur = torch.cuda.current_stream()
+        ctx.wstream.wait_stream(cur)
+        with torch.cuda.stream(ctx.wstream):
+            _param_grads_here(ctx, conv, x, dy, geom, taps, wants_w, wants_b)
+        for t in (x, dy):
+            t.record_stream(ctx.wstream)          # keep the operands alive until the side stream has consumed them
+        return
+    _param_grads_here(ctx, conv, x, dy, geom, taps, wants_w, wants_b)
+
+
+def _param_grads_here(ctx, conv, x, dy, geom, taps, wants_w, wants_b):
     if wants_w:
         g, acc = ctx.grad_out(conv.weight)
         if wants_b and ctx.tc:
@@ -597,6 +612,16 @@ class Plan:
         # opt-in (train.SingleVideoTrainer): weight-gradient kernels accumulate straight into param.grad and autograd
         # receives None for those parameters -- saves one elementwise add per parameter per backward pass
         self.direct_grad = False
+        # opt-in with direct_grad: weight/bias gradient launches run on a side stream next to the data-gradient chain
+        self.side_wgrad = False
+        self._wstreams = {}
+
+    def _wgrad_stream(self):
+        cur = torch.cuda.current_stream()
+        key = cur.cuda_stream
+        if key not in self._wstreams:
+            self._wstreams[key] = torch.cuda.Stream(device=cur.device)
+        return self._wstreams[key]
 
     def parameters(self):
         out, seen = [], set()
@@ -712,6 +737,8 @@ class Plan:
             dU, _ = K.nchw_to_nhwc(dy, None, None)
             undo = self.core                       # executed order was reversed(core)
         tr = Trunk(U, dU)
+        if self.side_wgrad and self.direct_grad and dy.is_cuda and K.__name__ == "sin_inn_b200.kernels":
+            ctx.wstream = self._wgrad_stream()
         # 2. walk the executed ops backwards
         for op in undo:
             if op.kind == "coupling":
@@ -729,6 +756,8 @@ class Plan:
                 U = op.apply_nhwc(tr.U, not rev)
                 dU = op.apply_nhwc(tr.dU, rev, grad=True)
                 tr.set(U, dU)
+        if ctx.wstream is not None:
+            torch.cuda.current_stream().wait_stream(ctx.wstream)       # parameter gradients complete with the pass
         if not need_dx:
             return None, ctx.grads
         # 3. gradient back out through the API-side layout change and the NCHW resamples

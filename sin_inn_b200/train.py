@@ -100,6 +100,7 @@ class SingleVideoTrainer:
         # race on the shared .grad) and the two arenas are added before the all-reduce.  SININN_OVERLAP=0: one stream.
         self.overlap = (os.environ.get("SININN_OVERLAP", "1") != "0" and self.flat.flat.is_cuda and hasattr(inn, "plan"))
         if self.overlap:
+            inn.plan().side_wgrad = os.environ.get("SININN_SIDE_WGRAD", "1") != "0"
             self.grad_b = torch.zeros_like(self.flat.grad)
             self.side = torch.cuda.Stream(device=self.flat.flat.device)
 
@@ -250,6 +251,31 @@ class HostBatchFeeder:
     def release(self, slot):
         """Call after the step that reads `slot` has been enqueued on the compute stream."""
         self.consumed[slot].record()
+
+
+class GraphedInference:
+    """net(x) / net(x, rev=True) under no_grad as ONE replayed CUDA graph over a static input buffer (full-video
+    inference runs the same ~60 launches for every micro-batch of frames; eager launching is host-bound)."""
+
+    def __init__(self, net, example, rev, warmup=2):
+        self.static_in = example.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                net(self.static_in, rev=rev)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = net(self.static_in, rev=rev)
+
+    def __call__(self, x):
+        """Returns the static output buffer (overwritten by the next call: copy it if you keep it)."""
+        if x.data_ptr() != self.static_in.data_ptr():
+            self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
 
 
 def shard_frames(n_frames, rank, world_size):

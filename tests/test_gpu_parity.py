@@ -283,3 +283,17 @@ def test_fixed1x1conv_gpu():
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from shared_checks import fixed1x1_checks
     fixed1x1_checks(DEV)
+
+
+def test_graphed_inference_matches_eager():
+    from sin_inn_b200 import train
+    opt, _, net = build_pair("SRF", 4, 2, 10, 64, 96, "bf16")
+    x = torch.rand(2, 3, 64, 96, device=DEV)
+    with torch.no_grad():
+        y = net(x)
+        xr = net(y, rev=True)
+    gf, gi = train.GraphedInference(net, x, False), train.GraphedInference(net, y, True)
+    assert torch.equal(gf(x), y) and torch.equal(gi(y), xr)
+    x2 = torch.rand(2, 3, 64, 96, device=DEV)
+    with torch.no_grad():
+        assert torch.equal(gf(x2), net(x2))
