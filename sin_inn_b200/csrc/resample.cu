@@ -256,6 +256,26 @@ __global__ void __launch_bounds__(256) permute_nhwc_kernel(const float* __restri
   }
 }
 
+// the backward pass undoes a permutation on the trunk AND its gradient with the same map: one launch for both
+__global__ void __launch_bounds__(256) permute_nhwc_pair_kernel(const float* __restrict__ in_a, float* __restrict__ out_a,
+                                                                const float* __restrict__ in_b, float* __restrict__ out_b,
+                                                                long long npix, int C, const int32_t* __restrict__ map) {
+  pdl_wait();
+  pdl_trigger();
+  const int Cv = C / 4;
+  const long long total = npix * Cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cv) * 4;
+    const long long p = idx / Cv;
+    const int m0 = __ldg(map + c), m1 = __ldg(map + c + 1), m2 = __ldg(map + c + 2), m3 = __ldg(map + c + 3);
+    const float* ra = in_a + p * C;
+    const float* rb = in_b + p * C;
+    store4(out_a + p * C + c, make_float4(ra[m0], ra[m1], ra[m2], ra[m3]));
+    store4(out_b + p * C + c, make_float4(rb[m0], rb[m1], rb[m2], rb[m3]));
+  }
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   long long cap = (long long)sm_count() * 32;   // grid-stride beyond ~32 CTAs per SM
@@ -356,6 +376,18 @@ int sininn_permute_nhwc(const float* in, float* out, long long npix, int C, cons
   if (v4) launch_k(permute_nhwc_kernel<4>, dim3(grid), dim3(block), 0, as_stream(stream), in, out, npix, C, chan_map, bf, c0, c1);
   else launch_k(permute_nhwc_kernel<1>, dim3(grid), dim3(block), 0, as_stream(stream), in, out, npix, C, chan_map, bf, c0, c1);
   SININN_CHECK_LAUNCH("permute_nhwc");
+  return SININN_OK;
+}
+
+int sininn_permute_nhwc_pair(const float* in_a, float* out_a, const float* in_b, float* out_b, long long npix, int C,
+                             const int32_t* chan_map, sininn_stream_t stream) {
+  SININN_CHECK_ARG(in_a && out_a && in_b && out_b && chan_map && npix > 0 && C > 0, "permute_nhwc_pair: bad arguments");
+  SININN_CHECK_ARG(in_a != out_a && in_b != out_b, "permute_nhwc_pair: cannot run in place");
+  SININN_CHECK_ARG((C % 4) == 0 && aligned16(out_a) && aligned16(out_b), "permute_nhwc_pair: needs C %% 4 == 0 and 16-byte aligned outputs");
+  const long long total = npix * (C / 4);
+  const int block = 256, grid = grid_for(total, block);
+  launch_k(permute_nhwc_pair_kernel, dim3(grid), dim3(block), 0, as_stream(stream), in_a, out_a, in_b, out_b, npix, C, chan_map);
+  SININN_CHECK_LAUNCH("permute_nhwc_pair");
   return SININN_OK;
 }
 

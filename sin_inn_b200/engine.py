@@ -746,8 +746,11 @@ class Plan:
             elif op.kind == "perm":
                 m_val = op.gather_map(dev, not rev)            # inverse of the executed value map
                 m_grad = op.gather_map(dev, rev, grad=True)
-                U, _ = K.permute_nhwc(tr.U, m_val, None)
-                dU, _ = K.permute_nhwc(tr.dU, m_grad, None)
+                if m_val is m_grad:                            # always: both undo the same gather
+                    U, dU = K.permute_nhwc_pair(tr.U, tr.dU, m_val)
+                else:
+                    U, _ = K.permute_nhwc(tr.U, m_val, None)
+                    dU, _ = K.permute_nhwc(tr.dU, m_grad, None)
                 tr.set(U, dU)
             elif op.kind == "linear":
                 # executed y = A x (A = W or W^-1): the input is A^-1 y, its gradient A^T dy

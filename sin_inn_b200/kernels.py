@@ -147,6 +147,19 @@ def permute_nhwc(x, chan_map, bf16_range=None):
     return out, bf
 
 
+def permute_nhwc_pair(xa, xb, chan_map):
+    """Both gathers of the backward pass (activations and their gradient, same map) in one launch."""
+    _lib.require_cuda(xa)
+    c = xa.shape[-1]
+    if c % 4 or xa.shape != xb.shape:
+        return permute_nhwc(xa, chan_map)[0], permute_nhwc(xb, chan_map)[0]
+    npix = xa.numel() // c
+    oa, ob = torch.empty_like(xa), torch.empty_like(xb)
+    check(_run("permute", lambda: load().sininn_permute_nhwc_pair(xa.data_ptr(), oa.data_ptr(), xb.data_ptr(), ob.data_ptr(), npix, c,
+                                          chan_map.data_ptr(), stream_ptr()), 1, 0.0, 16.0 * xa.numel()), "permute_nhwc_pair")
+    return oa, ob
+
+
 # ----------------------------------------------------------------------------- coupling
 def coupling_apply(u, s, t, kind, clamp, inverse, want_bf16=False):
     u, s, t = _view2d(u), _view2d(s), _view2d(t)

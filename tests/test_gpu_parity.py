@@ -297,3 +297,27 @@ def test_graphed_inference_matches_eager():
     x2 = torch.rand(2, 3, 64, 96, device=DEV)
     with torch.no_grad():
         assert torch.equal(gf(x2), net(x2))
+
+
+def test_overlapped_step_matches_single_stream_step():
+    """The two-stream / side-stream schedule of train.SingleVideoTrainer changes WHEN kernels run, never what they
+    compute: losses and parameters are bit-identical to the single-stream step."""
+    from sin_inn_b200 import archs, train
+    opt = R.make_opt(scale=4, num_coupling=2, lr_window=10, architecture="SRF", precision="bf16")
+
+    def make(overlap):
+        torch.manual_seed(0)
+        t = train.SingleVideoTrainer(archs.UncondSRFlow(3, 64, 64, opt).to(DEV), opt)
+        if not overlap:
+            t.overlap = False
+            t.inn.plan().side_wgrad = False
+        return t
+
+    batches = [tuple(t.to(DEV) for t in R.synthetic_batch(opt, 2, 64, 64, seed=s)) for s in range(2)]
+    a, b = make(True), make(False)
+    assert a.overlap and a.inn.plan().side_wgrad
+    for i in range(4):
+        la, lb = a.training_step(*batches[i % 2]), b.training_step(*batches[i % 2])
+        assert torch.equal(la[0], lb[0]) and torch.equal(la[1], lb[1])
+    torch.cuda.synchronize()
+    assert torch.equal(a.flat.flat, b.flat.flat)
