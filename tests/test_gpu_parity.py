@@ -103,7 +103,9 @@ def test_fp32_path_matches_oracle(arch, scale, nc, lrw, B, H, W):
 
 
 @pytest.mark.parametrize("arch,scale,nc,lrw,B,H,W", [("SRF", 4, 4, 10, 2, 64, 64), ("SRF", 2, 4, 1, 4, 64, 64),
-                                                     ("IRN", 4, 2, 10, 2, 64, 64)])
+                                                     ("IRN", 4, 2, 10, 2, 64, 64),
+                                                     # odd level-1 grids (9 x 13, 27 x 5): partial tiles, phantom pair tiles
+                                                     ("SRF", 4, 2, 10, 1, 72, 104), ("SRF", 4, 2, 10, 3, 216, 40)])
 @pytest.mark.parametrize("tc", [False, True])
 def test_bf16_path_matches_oracle(arch, scale, nc, lrw, B, H, W, tc):
     opt, ora, net = build_pair(arch, scale, nc, lrw, H, W, "bf16", tensor_core=tc)
