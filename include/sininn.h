@@ -81,9 +81,10 @@ int sininn_permute_nhwc(const float* in, float* out, long long npix, int C, cons
                         void* bf16_out, int c0, int c1, sininn_stream_t stream);
 
 /* the same gather on two tensors of one shape in ONE launch (the backward pass undoes a permutation on the
- * activations and on their gradient with the same map); needs C % 4 == 0 */
+ * activations and on their gradient with the same map); needs C % 4 == 0.  bf16_out_a (may be NULL): compact bf16
+ * copy of out_a[:, c0:c1] (c0, c1 multiples of 4), the operand of the subnet evaluated next. */
 int sininn_permute_nhwc_pair(const float* in_a, float* out_a, const float* in_b, float* out_b, long long npix, int C,
-                             const int32_t* chan_map, sininn_stream_t stream);
+                             const int32_t* chan_map, void* bf16_out_a, int c0, int c1, sininn_stream_t stream);
 
 /* ---------------------------------------------------------------- coupling
  * One half of an affine coupling, in place on a channel slice u[npix][L]

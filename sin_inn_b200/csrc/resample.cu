@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(256) permute_nhwc_kernel(const float* __restri
 // the backward pass undoes a permutation on the trunk AND its gradient with the same map: one launch for both
 __global__ void __launch_bounds__(256) permute_nhwc_pair_kernel(const float* __restrict__ in_a, float* __restrict__ out_a,
                                                                 const float* __restrict__ in_b, float* __restrict__ out_b,
-                                                                long long npix, int C, const int32_t* __restrict__ map) {
+                                                                long long npix, int C, const int32_t* __restrict__ map,
+                                                                __nv_bfloat16* __restrict__ bf, int bc0, int bc1) {
   pdl_wait();
   pdl_trigger();
   const int Cv = C / 4;
@@ -271,8 +272,11 @@ __global__ void __launch_bounds__(256) permute_nhwc_pair_kernel(const float* __r
     const int m0 = __ldg(map + c), m1 = __ldg(map + c + 1), m2 = __ldg(map + c + 2), m3 = __ldg(map + c + 3);
     const float* ra = in_a + p * C;
     const float* rb = in_b + p * C;
-    store4(out_a + p * C + c, make_float4(ra[m0], ra[m1], ra[m2], ra[m3]));
+    const float4 va = make_float4(ra[m0], ra[m1], ra[m2], ra[m3]);
+    store4(out_a + p * C + c, va);
     store4(out_b + p * C + c, make_float4(rb[m0], rb[m1], rb[m2], rb[m3]));
+    if (bf != nullptr && c >= bc0 && c < bc1)      // compact bf16 copy of out_a[:, bc0:bc1] (bc0, bc1 multiples of 4)
+      store4(bf + p * (long long)(bc1 - bc0) + (c - bc0), va);
   }
 }
 
@@ -380,13 +384,15 @@ int sininn_permute_nhwc(const float* in, float* out, long long npix, int C, cons
 }
 
 int sininn_permute_nhwc_pair(const float* in_a, float* out_a, const float* in_b, float* out_b, long long npix, int C,
-                             const int32_t* chan_map, sininn_stream_t stream) {
+                             const int32_t* chan_map, void* bf16_out_a, int c0, int c1, sininn_stream_t stream) {
   SININN_CHECK_ARG(in_a && out_a && in_b && out_b && chan_map && npix > 0 && C > 0, "permute_nhwc_pair: bad arguments");
   SININN_CHECK_ARG(in_a != out_a && in_b != out_b, "permute_nhwc_pair: cannot run in place");
   SININN_CHECK_ARG((C % 4) == 0 && aligned16(out_a) && aligned16(out_b), "permute_nhwc_pair: needs C %% 4 == 0 and 16-byte aligned outputs");
+  __nv_bfloat16* bf = reinterpret_cast<__nv_bfloat16*>(bf16_out_a);
+  if (bf) SININN_CHECK_ARG(0 <= c0 && c0 < c1 && c1 <= C && (c0 % 4) == 0 && (c1 % 4) == 0 && aligned8(bf), "permute_nhwc_pair: bad bf16 channel range");
   const long long total = npix * (C / 4);
   const int block = 256, grid = grid_for(total, block);
-  launch_k(permute_nhwc_pair_kernel, dim3(grid), dim3(block), 0, as_stream(stream), in_a, out_a, in_b, out_b, npix, C, chan_map);
+  launch_k(permute_nhwc_pair_kernel, dim3(grid), dim3(block), 0, as_stream(stream), in_a, out_a, in_b, out_b, npix, C, chan_map, bf, c0, c1);
   SININN_CHECK_LAUNCH("permute_nhwc_pair");
   return SININN_OK;
 }

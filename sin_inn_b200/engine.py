@@ -500,6 +500,10 @@ class CouplingOp:
     def first_src(self, rev):
         return (self.steps[-1] if rev else self.steps[0]).src
 
+    def first_step_backward(self, rev):
+        """The half-step whose subnet the backward pass of a value pass `rev` evaluates first."""
+        return self.steps[0] if rev else self.steps[-1]
+
     # ---- value pass
     def run(self, ctx, tr, rev):
         steps = self.steps[::-1] if rev else self.steps
@@ -740,18 +744,25 @@ class Plan:
         if self.side_wgrad and self.direct_grad and dy.is_cuda and K.__name__ == "sin_inn_b200.kernels":
             ctx.wstream = self._wgrad_stream()
         # 2. walk the executed ops backwards
-        for op in undo:
+        for i, op in enumerate(undo):
             if op.kind == "coupling":
                 op.backward(ctx, tr, rev)
             elif op.kind == "perm":
                 m_val = op.gather_map(dev, not rev)            # inverse of the executed value map
                 m_grad = op.gather_map(dev, rev, grad=True)
+                # the gather also emits the bf16 operand of the subnet the next block's backward evaluates first
+                hint = None
+                nxt = undo[i + 1] if i + 1 < len(undo) else None
+                if nxt is not None and nxt.kind == "coupling" and ctx.adt == torch.bfloat16:
+                    st = nxt.first_step_backward(rev)
+                    if (st.src[1] - st.src[0]) % 8 == 0 and st.src[0] % 4 == 0 and not isinstance(st.nets[0], DenseSubnet):
+                        hint = st.src
                 if m_val is m_grad:                            # always: both undo the same gather
-                    U, dU = K.permute_nhwc_pair(tr.U, tr.dU, m_val)
+                    U, dU, bf = K.permute_nhwc_pair(tr.U, tr.dU, m_val, hint)
                 else:
-                    U, _ = K.permute_nhwc(tr.U, m_val, None)
+                    U, bf = K.permute_nhwc(tr.U, m_val, hint)
                     dU, _ = K.permute_nhwc(tr.dU, m_grad, None)
-                tr.set(U, dU)
+                tr.set(U, dU, {hint: bf} if bf is not None else None)
             elif op.kind == "linear":
                 # executed y = A x (A = W or W^-1): the input is A^-1 y, its gradient A^T dy
                 tr.set(op.apply(tr.U, not rev), op.apply(tr.dU, rev, grad=True))

@@ -147,17 +147,23 @@ def permute_nhwc(x, chan_map, bf16_range=None):
     return out, bf
 
 
-def permute_nhwc_pair(xa, xb, chan_map):
-    """Both gathers of the backward pass (activations and their gradient, same map) in one launch."""
+def permute_nhwc_pair(xa, xb, chan_map, bf16_range=None):
+    """Both gathers of the backward pass (activations and their gradient, same map) in one launch; optionally also
+    the compact bf16 copy of the gathered activations' channels bf16_range.  Returns (out_a, out_b, bf16 or None)."""
     _lib.require_cuda(xa)
     c = xa.shape[-1]
-    if c % 4 or xa.shape != xb.shape:
-        return permute_nhwc(xa, chan_map)[0], permute_nhwc(xb, chan_map)[0]
+    if c % 4 or xa.shape != xb.shape or (bf16_range is not None and (bf16_range[0] % 4 or bf16_range[1] % 4)):
+        oa, bf = permute_nhwc(xa, chan_map, bf16_range)
+        return oa, permute_nhwc(xb, chan_map)[0], bf
     npix = xa.numel() // c
     oa, ob = torch.empty_like(xa), torch.empty_like(xb)
+    bf, c0, c1 = None, 0, 0
+    if bf16_range is not None:
+        c0, c1 = bf16_range
+        bf = torch.empty(npix, c1 - c0, dtype=torch.bfloat16, device=xa.device)
     check(_run("permute", lambda: load().sininn_permute_nhwc_pair(xa.data_ptr(), oa.data_ptr(), xb.data_ptr(), ob.data_ptr(), npix, c,
-                                          chan_map.data_ptr(), stream_ptr()), 1, 0.0, 16.0 * xa.numel()), "permute_nhwc_pair")
-    return oa, ob
+                                          chan_map.data_ptr(), _p(bf), c0, c1, stream_ptr()), 1, 0.0, 16.0 * xa.numel()), "permute_nhwc_pair")
+    return oa, ob, bf
 
 
 # ----------------------------------------------------------------------------- coupling

@@ -60,8 +60,9 @@ def permute_nhwc(x, chan_map, bf16_range=None):
     return out, _bf(out.view(-1, out.shape[-1]), bf16_range)
 
 
-def permute_nhwc_pair(xa, xb, chan_map):
-    return permute_nhwc(xa, chan_map)[0], permute_nhwc(xb, chan_map)[0]
+def permute_nhwc_pair(xa, xb, chan_map, bf16_range=None):
+    oa, bf = permute_nhwc(xa, chan_map, bf16_range)
+    return oa, permute_nhwc(xb, chan_map)[0], bf
 
 
 def _log_scale(kind, clamp, raw):

@@ -72,8 +72,10 @@ def test_layout_and_permute(K, C, hw):
         assert torch.equal(zbf.cpu(), rzbf)
     # two tensors, one map, one launch (falls back to two launches when C % 4 != 0)
     y2 = (y * 2 + 1).contiguous()
-    pa, pb = K.permute_nhwc_pair(y, y2, perm.to(DEV))
+    pa, pb, pbf = K.permute_nhwc_pair(y, y2, perm.to(DEV), rng)
     assert torch.equal(pa.cpu(), rz) and torch.equal(pb.cpu(), FK.permute_nhwc(y2.cpu(), perm)[0])
+    if rng:
+        assert torch.equal(pbf.cpu(), rzbf)
 
 
 @pytest.mark.parametrize("kind,clamp", [(0, 1.2), (1, 1.0)])
