@@ -180,12 +180,18 @@ def run_ours(args):
     sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]     # per-step spread (p10/p50/p90)
     ev0.record()
+    marks[0].record()
     for i in range(args.steps):
         step_resident(i)
+        marks[i + 1].record()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
+    spread = {"p10": per_step[int(0.1 * (len(per_step) - 1))], "p50": per_step[len(per_step) // 2],
+              "p90": per_step[int(0.9 * (len(per_step) - 1) + 0.5)]}
     launches = launches_per_step * args.steps      # kernels executed in the timed region (graph replays included)
     # same K steps again with a CUDA-event pair around every kernel launch (per-family durations for the roofline);
     # kept out of the headline region because ~1300 extra event records per step perturb a launch-dense step
@@ -250,7 +256,7 @@ def run_ours(args):
         alg_flops_step = 6 * 2 * conv_macs_per_patch(P) * B
         line = {
             "metric": "INN train-step patches/sec", "value": value, "unit": "patches/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_per_step_spread": spread, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic",
             "config": {"workload": f"SRF scale4 c4 lr_window10 {P}x{P} train step, batch {B}/GPU", **WORKLOAD,
