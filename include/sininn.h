@@ -218,6 +218,11 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream);
 size_t sininn_sqdiff_workspace_bytes(long long n);
 int sininn_sqdiff_nchw(const float* a, const float* b, long long n, float scale, float* loss_out,
                        float* grad_out, void* workspace, size_t workspace_bytes, sininn_stream_t stream);
+/* The forward half's loss in one pass (lit_wrapper.py:45-48 with loss.py:3-5,38-39): y [B][C][HW] is the network output,
+ * lr [B][L][HW] the low-resolution target;  loss = w_rec * mean((y[:, :L] - lr)^2) + w_nll * mean(y[:, L:]^2)  and
+ * grad_out [B][C][HW] = dloss/dy.  workspace >= 2 * sininn_sqdiff_workspace_bytes(B*C*HW). */
+int sininn_inn_fwd_loss(const float* y, const float* lr, int B, int C, int L, long long HW, float w_rec, float w_nll,
+                        float* loss_out, float* grad_out, void* workspace, size_t workspace_bytes, sininn_stream_t stream);
 /* torch.optim.Adam semantics (lit_wrapper.py:134-137: L2 weight decay folded into the gradient) over a
  * flat fp32 arena; step is the 1-based step count. */
 int sininn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,

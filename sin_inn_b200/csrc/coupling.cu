@@ -289,6 +289,54 @@ __global__ void __launch_bounds__(256) sqdiff_partial_kernel(const float* __rest
     partial[blockIdx.x] = s;
   }
 }
+// ---- the forward half's whole loss in one pass over the network output y [B][C][HW] (lit_wrapper.py:45-48):
+//   w_rec * mean((y[:, :L] - lr)^2)  +  w_nll * mean(y[:, L:]^2)      and its gradient w.r.t. y (full tensor)
+__global__ void __launch_bounds__(256) inn_fwd_loss_partial_kernel(const float* __restrict__ y, const float* __restrict__ lr, int C, int L,
+                                                                   long long HW, long long total, float g_rec, float g_nll,
+                                                                   float* __restrict__ grad, float* __restrict__ partial, int nblk) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[2][8];
+  float a_rec = 0.f, a_nll = 0.f;
+  const long long chw = (long long)C * HW, lhw = (long long)L * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / chw, r = i - b * chw;
+    const float v = y[i];
+    float g;
+    if (r < lhw) {
+      const float d = v - lr[b * lhw + r];
+      a_rec += d * d;
+      g = g_rec * d;
+    } else {
+      a_nll += v * v;
+      g = g_nll * v;
+    }
+    grad[i] = g;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a_rec += __shfl_xor_sync(0xffffffffu, a_rec, o);
+    a_nll += __shfl_xor_sync(0xffffffffu, a_nll, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a_rec; red[1][threadIdx.x >> 5] = a_nll; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int k = 0; k < 8; ++k) { s0 += red[0][k]; s1 += red[1][k]; }
+    partial[blockIdx.x] = s0;
+    partial[nblk + blockIdx.x] = s1;
+  }
+}
+__global__ void inn_fwd_loss_finish_kernel(const float* __restrict__ partial, int n, float s_rec, float s_nll, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < n; ++k) { a += (double)partial[k]; b += (double)partial[n + k]; }
+    out[0] = (float)(a * (double)s_rec + b * (double)s_nll);
+  }
+}
+
 __global__ void sqdiff_finish_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
   pdl_wait();
   pdl_trigger();
@@ -500,6 +548,27 @@ int sininn_sqdiff_nchw(const float* a, const float* b, long long n, float scale,
   launch_k(sqdiff_partial_kernel, dim3(grid), dim3(256), 0, st, a, b, n, 2.f * scale, grad_out, (float*)workspace);
   launch_k(sqdiff_finish_kernel, dim3(1), dim3(32), 0, st, (const float*)workspace, grid, scale, loss_out);
   SININN_CHECK_LAUNCH("sqdiff");
+  return SININN_OK;
+}
+
+int sininn_inn_fwd_loss(const float* y, const float* lr, int B, int C, int L, long long HW, float w_rec, float w_nll,
+                        float* loss_out, float* grad_out, void* workspace, size_t workspace_bytes, sininn_stream_t stream) {
+  SININN_CHECK_ARG(y && lr && loss_out && grad_out && B > 0 && C > 0 && L > 0 && L <= C && HW > 0, "inn_fwd_loss: bad arguments");
+  const long long total = (long long)B * C * HW;
+  int grid = grid_for(total, 256);
+  int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  if (!workspace || workspace_bytes < (size_t)2 * grid * sizeof(float)) {
+    set_error("inn_fwd_loss: workspace too small");
+    return SININN_EWORKSPACE;
+  }
+  const float s_rec = w_rec / (float)((double)B * L * HW);
+  const float s_nll = (C > L) ? w_nll / (float)((double)B * (C - L) * HW) : 0.f;
+  cudaStream_t st = as_stream(stream);
+  launch_k(inn_fwd_loss_partial_kernel, dim3(grid), dim3(256), 0, st, y, lr, C, L, HW, total, 2.f * s_rec, 2.f * s_nll, grad_out,
+           (float*)workspace, grid);
+  launch_k(inn_fwd_loss_finish_kernel, dim3(1), dim3(32), 0, st, (const float*)workspace, grid, s_rec, s_nll, loss_out);
+  SININN_CHECK_LAUNCH("inn_fwd_loss");
   return SININN_OK;
 }
 

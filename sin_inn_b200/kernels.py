@@ -359,6 +359,22 @@ def sqdiff(a, b, scale, want_grad=False):
     return out, grad
 
 
+def inn_fwd_loss(y, lr, w_rec, w_nll):
+    """w_rec*mean((y[:, :L]-lr)^2) + w_nll*mean(y[:, L:]^2) -> (0-dim loss, d loss / d y), one pass over y."""
+    _lib.require_cuda(y)
+    y, lr = y.contiguous(), lr.contiguous()
+    B, Cc, H, W = y.shape
+    L = lr.shape[1]
+    lib = load()
+    ws = _workspace(y.device, "fwd_loss", 2 * lib.sininn_sqdiff_workspace_bytes(y.numel()))
+    out = torch.empty((), dtype=torch.float32, device=y.device)
+    grad = torch.empty_like(y)
+    check(_run("loss", lambda: lib.sininn_inn_fwd_loss(y.data_ptr(), lr.data_ptr(), B, Cc, L, H * W, float(w_rec), float(w_nll),
+                                                       out.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()), 2),
+          "inn_fwd_loss")
+    return out, grad
+
+
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step, grad_scale=1.0):
     n = param.numel()
     check(_run("adam", lambda: load().sininn_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n,

@@ -28,6 +28,38 @@ def latent_nll(z):
     return torch.mean(z ** 2)
 
 
+class _FusedLoss(torch.autograd.Function):
+    """A loss whose value and gradient w.r.t. its first input come out of one fused pass (kernels.inn_fwd_loss /
+    kernels.sqdiff): forward returns the scalar, backward scales the stored gradient."""
+
+    @staticmethod
+    def forward(ctx, x, loss, grad):
+        ctx.save_for_backward(grad)
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None
+
+
+def forward_half_loss(lr_z_hat, lr, w_rec, w_nll):
+    """lit_wrapper.py:45-48: w_rec * reconstruction(lr_z_hat[:, :lr_dims], lr) + w_nll * latent_nll(lr_z_hat[:, lr_dims:])."""
+    if not lr_z_hat.is_cuda:
+        loss = w_rec * reconstruction(lr_z_hat[:, :lr.shape[1]], lr)
+        return loss + w_nll * latent_nll(lr_z_hat[:, lr.shape[1]:]) if w_nll else loss
+    loss, grad = K.inn_fwd_loss(lr_z_hat.detach(), lr, w_rec, w_nll)
+    return _FusedLoss.apply(lr_z_hat, loss, grad)
+
+
+def inverse_half_loss(hr_hat, hr, w_rec):
+    """lit_wrapper.py:53-55: w_rec * reconstruction(hr_hat, hr)."""
+    if not hr_hat.is_cuda:
+        return w_rec * reconstruction(hr_hat, hr)
+    loss, grad = K.sqdiff(hr_hat.detach(), hr, w_rec / hr_hat.numel(), want_grad=True)
+    return _FusedLoss.apply(hr_hat, loss, grad)
+
+
 class FlatParams:
     """Re-homes a module's trainable parameters (and their .grad) into two contiguous fp32 arenas.
     Parameter objects, names and shapes are untouched, so state_dict()/load_state_dict() keep working."""
@@ -124,13 +156,11 @@ class SingleVideoTrainer:
         lr_z = torch.cat((lr, z), dim=1)
         # forward pass HR -> (LR, z)                                   lit_wrapper.py:45-49
         lr_z_hat = self.inn(hr)
-        fwd_loss = o.lambda_fwd_rec * reconstruction(lr_z_hat[:, :o.lr_dims], lr)
-        if o.lambda_latent_nll:
-            fwd_loss = fwd_loss + o.lambda_latent_nll * latent_nll(lr_z_hat[:, o.lr_dims:])
+        fwd_loss = forward_half_loss(lr_z_hat, lr, o.lambda_fwd_rec, o.lambda_latent_nll)
         fwd_loss.backward()
         # reverse pass (LR, z) -> HR                                    lit_wrapper.py:53-56
         hr_hat = self.inn(lr_z, rev=True)
-        bwd_loss = o.lambda_bwd_rec * reconstruction(hr_hat, hr)
+        bwd_loss = inverse_half_loss(hr_hat, hr, o.lambda_bwd_rec)
         bwd_loss.backward()
         if self.world_size > 1:
             dist.all_reduce(self.flat.grad)                            # one NCCL all-reduce per step
@@ -146,9 +176,7 @@ class SingleVideoTrainer:
         self.side.wait_stream(main)
         # forward pass HR -> (LR, z) and its backward on the current stream      lit_wrapper.py:45-49
         lr_z_hat = self.inn(hr)
-        fwd_loss = o.lambda_fwd_rec * reconstruction(lr_z_hat[:, :o.lr_dims], lr)
-        if o.lambda_latent_nll:
-            fwd_loss = fwd_loss + o.lambda_latent_nll * latent_nll(lr_z_hat[:, o.lr_dims:])
+        fwd_loss = forward_half_loss(lr_z_hat, lr, o.lambda_fwd_rec, o.lambda_latent_nll)
         fwd_loss.backward()
         # reverse pass (LR, z) -> HR and its backward on the side stream         lit_wrapper.py:53-56
         self._point_grads(self.grad_b)
@@ -156,7 +184,7 @@ class SingleVideoTrainer:
             with torch.cuda.stream(self.side):
                 lr_z = torch.cat((lr, z), dim=1)
                 hr_hat = self.inn(lr_z, rev=True)
-                bwd_loss = o.lambda_bwd_rec * reconstruction(hr_hat, hr)
+                bwd_loss = inverse_half_loss(hr_hat, hr, o.lambda_bwd_rec)
                 bwd_loss.backward()
         finally:
             self._point_grads(self.flat.grad)

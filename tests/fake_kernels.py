@@ -235,6 +235,16 @@ def sqdiff(a, b, scale, want_grad=False):
     return (d * d).sum() * scale, (2 * scale * d if want_grad else None)
 
 
+def inn_fwd_loss(y, lr, w_rec, w_nll):
+    y = y.detach().clone().requires_grad_(True)
+    L = lr.shape[1]
+    loss = w_rec * torch.mean((y[:, :L] - lr) ** 2)
+    if y.shape[1] > L:
+        loss = loss + w_nll * torch.mean(y[:, L:] ** 2)
+    loss.backward()
+    return loss.detach(), y.grad
+
+
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step, grad_scale=1.0):
     g = grad * grad_scale + weight_decay * param
     exp_avg.mul_(betas[0]).add_(g, alpha=1 - betas[0])

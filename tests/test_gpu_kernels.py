@@ -426,3 +426,19 @@ def test_subnet1x1_fused_data_gradient(K, cin, hidden, cout, npix):
     dhc = dh.cpu().float()
     assert (dhc - dh_ref.float()).abs().max().item() <= 1e-2 * max(1.0, dh_ref.float().abs().max().item())
     assert bool(((hfwd <= 0) <= (dhc == 0)).all())       # exactly zero wherever the forward ReLU was off
+
+
+@pytest.mark.parametrize("B,C,L,hw,w_nll", [(3, 48, 12, (16, 16), 0.0), (2, 192, 84, (5, 9), 0.7), (1, 12, 12, (8, 8), 0.3)])
+def test_fused_forward_half_loss(K, B, C, L, hw, w_nll):
+    """lit_wrapper.py:45-48 (loss.reconstruction on the LR channels + loss.latent_nll on the z channels) and the gradient
+    w.r.t. the network output, one pass."""
+    y = rnd(B, C, *hw, seed=90)
+    lr = rnd(B, L, *hw, seed=91)
+    yr = y.clone().requires_grad_(True)
+    ref = 1.3 * torch.mean((yr[:, :L] - lr) ** 2)
+    if C > L:
+        ref = ref + w_nll * torch.mean(yr[:, L:] ** 2)
+    ref.backward()
+    loss, grad = K.inn_fwd_loss(y.to(DEV), lr.to(DEV), 1.3, w_nll)
+    assert abs(loss.item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item()))
+    assert (grad.cpu() - yr.grad).abs().max().item() <= 1e-6 * max(1e-3, yr.grad.abs().max().item())
