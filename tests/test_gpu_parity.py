@@ -301,15 +301,19 @@ def test_graphed_inference_matches_eager():
         assert torch.equal(gf(x2), net(x2))
 
 
-def test_overlapped_step_matches_single_stream_step():
+@pytest.mark.parametrize("arch", ["SRF", "IRN"])
+def test_overlapped_step_matches_single_stream_step(arch):
     """The two-stream / side-stream schedule of train.SingleVideoTrainer changes WHEN kernels run, never what they
     compute: losses and parameters are bit-identical to the single-stream step."""
     from sin_inn_b200 import archs, train
-    opt = R.make_opt(scale=4, num_coupling=2, lr_window=10, architecture="SRF", precision="bf16")
+    opt = R.make_opt(scale=4, num_coupling=2, lr_window=10, architecture=arch, precision="bf16")
 
     def make(overlap):
         torch.manual_seed(0)
-        t = train.SingleVideoTrainer(archs.UncondSRFlow(3, 64, 64, opt).to(DEV), opt)
+        net = {"SRF": archs.UncondSRFlow, "IRN": archs.InvRescaleNet}[arch](3, 64, 64, opt)
+        if arch == "IRN":
+            R.randomize_irn_conv5(net, 1)
+        t = train.SingleVideoTrainer(net.to(DEV), opt)
         if not overlap:
             t.overlap = False
             t.inn.plan().side_wgrad = False
