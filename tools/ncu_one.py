@@ -13,7 +13,27 @@ shapes = {  # hw, cin, cout, taps, out dtype, relu
     "c3x3_conv2": (64, 256, 48, 9, torch.float32, False),
     "l1_conv2": (32, 256, 192, 9, torch.float32, False),
 }
-if case in ("coupling_bwd", "coupling_apply", "permute", "resample", "colsum"):
+if case.startswith("s1x1"):
+    # fused 1x1 subnet at level 0: forward (s1x1_fwd), forward storing h + sign bits (s1x1_keep), data gradient (s1x1_grad)
+    npix, cin, hid, cout = B * 64 * 64, 24, 256, 48
+    x = torch.randn(npix, cin, device=DEV).to(torch.bfloat16)
+    w1 = torch.randn(hid, cin, 1, 1, device=DEV) * 0.05
+    w2 = torch.randn(cout, hid, 1, 1, device=DEV) * 0.05
+    b1, b2 = torch.randn(hid, device=DEV), torch.randn(cout, device=DEV)
+    out = torch.zeros(npix, cout, device=DEV)
+    h = torch.empty(npix, hid, dtype=torch.bfloat16, device=DEV)
+    bits = torch.zeros(npix, hid // 32, dtype=torch.int32, device=DEV)
+    for _ in range(3):
+        if case == "s1x1_grad":
+            da = torch.randn(npix, cout, device=DEV).to(torch.bfloat16)
+            dsrc = torch.zeros(npix, cin, device=DEV)
+            K.subnet1x1_fwd(da, K.pack_weight(w2, 1, torch.bfloat16, 256, 48), None, K.pack_weight(w1, 1, torch.bfloat16, 32, 256), None,
+                            dsrc, h_out=h, mask_bits=bits, accumulate=True)
+        else:
+            keep = case == "s1x1_keep"
+            K.subnet1x1_fwd(x, K.pack_weight(w1, 0, torch.bfloat16, 256, 32), b1, K.pack_weight(w2, 0, torch.bfloat16, 48, 256), b2, out,
+                            h_out=h if keep else None, bits_out=bits if keep else None)
+elif case in ("coupling_bwd", "coupling_apply", "permute", "resample", "colsum"):
     # HBM-bound kernels at the bench workload's level-0 shapes (B=32: 131072 pixels x 48 channels fp32 trunk)
     npix, C, L = B * 64 * 64, 48, 24
     U = torch.randn(npix, C, device=DEV); dU = torch.randn(npix, C, device=DEV)
