@@ -24,6 +24,12 @@ namespace sininn {
 namespace tc {
 
 constexpr int S1_MAX_STAGES = 4;
+// 16 epilogue warps, four per TMEM lane quarter (ncu: the forward kernel is neither DRAM- (3 %) nor tensor-bound (12 %);
+// its tile period is the serial chain MMA1 -> first epilogue (128 x 256 values) -> MMA2 -> second epilogue, and the
+// first epilogue took ~3200 cycles on eight warps)
+constexpr int S1_EPI_WARPS = 16;
+constexpr int S1_SUBS = S1_EPI_WARPS / 4;
+constexpr int S1_THREADS = 64 + 32 * S1_EPI_WARPS;
 
 struct S1Barriers {
   uint64_t w1_full;
@@ -71,7 +77,7 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
 }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(S1_THREADS, 1)
 subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO,
                      const __grid_constant__ CUtensorMap tmH, const S1Params p) {
@@ -101,7 +107,7 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
     mbar_init(smem_u32(&bars->d1_full), 1);
     mbar_init(smem_u32(&bars->d2_full), 1);
-    mbar_init(smem_u32(&bars->h_full), NUM_EPI_WARPS);
+    mbar_init(smem_u32(&bars->h_full), S1_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW1);
@@ -117,8 +123,8 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   pdl_trigger();
   if (warp >= 2) {      // biases -> shared memory (zero beyond the real channel counts)
     const int e = threadIdx.x - 64;
-    b1_s[e] = (p.b1 != nullptr && e < p.hidden) ? __ldg(p.b1 + e) : 0.f;
-    b2_s[e] = (p.b2 != nullptr && e < p.cout) ? __ldg(p.b2 + e) : 0.f;
+    if (e < 256) b1_s[e] = (p.b1 != nullptr && e < p.hidden) ? __ldg(p.b1 + e) : 0.f;
+    if (e < 256) b2_s[e] = (p.b2 != nullptr && e < p.cout) ? __ldg(p.b2 + e) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -221,13 +227,13 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     // ======================= epilogue warps =======================
     const int ew = warp - 2;
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may read (warp id % 4)
-    const int half = ew >> 2;
+    const int half = ew >> 2;                        // which of the S1_SUBS warps of this quarter (0..3)
     const int row = quarter * 32 + lane;             // pixel row inside the tile
     const uint32_t lane_base = ((uint32_t)(quarter * 32) << 16);
     const int bit_words = p.hidden >> 5;
     const int n_out_slabs = (p.cout + 31) / 32;
     int n_pieces = 0;
-    for (int s = half; s < p.hs; s += 2) ++n_pieces;
+    for (int s = half; s < p.hs; s += S1_SUBS) ++n_pieces;
     uint32_t dph = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const long long pix = (long long)t * 128 + row;
@@ -237,7 +243,7 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tc_fence_after();
       if (lane == 0) bulk_wait_read0();              // this warp's earlier TMA stores have finished reading its rows
       __syncwarp();
-      for (int s = half; s < p.hs; s += 2) {
+      for (int s = half; s < p.hs; s += S1_SUBS) {
         uint32_t v0[32], v1[32];
         tmem_ld32(d1_tmem + lane_base + s * 64, v0);
         tmem_ld32(d1_tmem + lane_base + s * 64 + 32, v1);
@@ -293,7 +299,7 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       if (lane == 0) {
         mbar_arrive(smem_u32(&bars->h_full));
         if (p.store_h) {
-          for (int s = half; s < p.hs; s += 2)
+          for (int s = half; s < p.hs; s += S1_SUBS)
             tma_store_2d(&tmH, smem_u32(h_s) + s * 16384 + quarter * 4096, s * 64, t * 128 + quarter * 32);
           bulk_commit();
         }
@@ -305,8 +311,10 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       if (lane == 0) bulk_wait_read0();
       __syncwarp();
       int idx = 0;
-      for (int o = half; o < n_out_slabs; o += 2, ++idx) {
-        const int piece = half + 2 * (idx % n_pieces);
+      // (only warps that own a piece of the hidden tile have rows to stage in: min(S1_SUBS, hidden / 64) per quarter)
+      const int n_act = p.hs < S1_SUBS ? p.hs : S1_SUBS;
+      for (int o = half; half < n_act && o < n_out_slabs; o += n_act, ++idx) {
+        const int piece = half + S1_SUBS * (idx % n_pieces);
         uint8_t* stg = h_s + piece * 16384 + quarter * 4096;
         if (idx > 0) {
           if (lane == 0) { if (n_pieces > 1) bulk_wait_read1(); else bulk_wait_read0(); }
@@ -458,7 +466,7 @@ int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stre
     attr_set[dev] = true;
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  launch_k(subnet1x1_fwd_kernel, dim3((unsigned)grid), dim3(NUM_THREADS), smem, as_stream(stream), tmX, tmW1, tmW2, tmO, tmH, p);
+  launch_k(subnet1x1_fwd_kernel, dim3((unsigned)grid), dim3(S1_THREADS), smem, as_stream(stream), tmX, tmW1, tmW2, tmO, tmH, p);
   SININN_CHECK_LAUNCH("subnet1x1_fwd");
   return SININN_OK;
 }
