@@ -43,6 +43,8 @@ struct PairParams {
   int a_stages, b_stages;      // b_stages == 0: weights resident in shared memory
   int n_half;                  // weight rows per CTA (n_tile / 2)
   uint32_t chunk_bytes;        // shared-memory bytes of one (slab, tap) weight chunk of one CTA (multiple of 1024)
+  int tps;                     // taps per weight-ring stage (1 or 3): small chunks share a barrier round trip (an
+                               // already-complete mbarrier wait costs ~90 cycles, a small-N tap only ~230 of MMA time)
   uint32_t b_region_bytes;     // resident weights or the weight ring
   int ksteps_last;             // K = 16 steps with real channels in the last slab (1..4)
   long long num_ptiles;        // B * tiles_h * tiles_w
@@ -162,12 +164,13 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (long long it = pair; it < hp.num_items; it += npairs) {
         const int n0 = (int)(it % p.n_tiles) * p.n_tile;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < 9; tap += hp.tps) {
             mbar_wait(smem_u32(&bars->b_empty[sb]), pb ^ 1);
             if (elect_one()) {
-              if (rank == 0) mbar_expect_tx(smem_u32(&bars->b_full[sb]), 2u * (uint32_t)hp.n_half * 128u);
-              tma_load_3d_2sm(b_u32 + sb * hp.chunk_bytes, &tmB, mapa_u32(smem_u32(&bars->b_full[sb]), 0), kc * 64,
-                              n0 + rank * hp.n_half, tap);
+              if (rank == 0) mbar_expect_tx(smem_u32(&bars->b_full[sb]), 2u * (uint32_t)hp.tps * (uint32_t)hp.n_half * 128u);
+              const uint32_t full_l = mapa_u32(smem_u32(&bars->b_full[sb]), 0);
+              for (int j = 0; j < hp.tps; ++j)
+                tma_load_3d_2sm(b_u32 + (sb * hp.tps + j) * hp.chunk_bytes, &tmB, full_l, kc * 64, n0 + rank * hp.n_half, tap + j);
             }
             __syncwarp();
             if (++sb == hp.b_stages) { sb = 0; pb ^= 1; }
@@ -207,15 +210,19 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t a_stage = a_desc0 + (uint64_t)(sa * a_step);
           const uint64_t b_slab = b_desc0 + (uint64_t)(kc * 9 * b_step);
           const int ksteps = (kc == p.k_chunks - 1) ? hp.ksteps_last : 4;
+          const bool three = hp.tps == 3;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             uint64_t bdesc;
             if (resident) {
               bdesc = b_slab + (uint64_t)(tap * b_step);
             } else {
-              mbar_wait(smem_u32(&bars->b_full[sb]), pb);
-              tc_fence_after();
-              bdesc = b_desc0 + (uint64_t)(sb * b_step);
+              // (tap is a compile-time constant of the unrolled loop: no runtime division)
+              if (!three || tap % 3 == 0) {
+                mbar_wait(smem_u32(&bars->b_full[sb]), pb);
+                tc_fence_after();
+              }
+              bdesc = b_desc0 + (uint64_t)((three ? sb * 3 + tap % 3 : sb) * b_step);
             }
             // tap (dy, dx) in 0..2 (halo origin is (h0-1, w0-1)): start row dy*16 + dx of the halo box, 8 x 16 B per row
             const uint64_t adesc = a_stage + (uint64_t)(((tap / 3) * PH_W + (tap % 3)) * 8);
@@ -223,7 +230,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (ksteps > 1) umma_bf16_2sm_p(lead, d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
             if (ksteps > 2) umma_bf16_2sm_p(lead, d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
             if (ksteps > 3) umma_bf16_2sm_p(lead, d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
-            if (!resident) {
+            if (!resident && (!three || tap % 3 == 2)) {
               umma_commit_2sm_p(lead, smem_u32(&bars->b_empty[sb]), 3);
               if (++sb == hp.b_stages) { sb = 0; pb ^= 1; }
             }
@@ -304,7 +311,7 @@ int launch_conv_pair(const sininn_conv_desc* d, Params p, cudaStream_t st) {
   const int total = 227 * 1024;
   auto chunk_of = [](int n_tile) { return (uint32_t)(((n_tile / 2) * 128 + 1023) & ~1023); };
   // 1. weights resident: whole N (<= 256), or N split in 128-channel tiles when the pair count divides evenly
-  int n_tile = 0, a_stages = 2, b_stages = 0;
+  int n_tile = 0, a_stages = 2, b_stages = 0, tps = 1;
   {
     int cands[2] = {d->rows_pad <= 256 ? d->rows_pad : 0, (d->rows_pad > 128 && d->rows_pad % 128 == 0) ? 128 : 0};
     for (int ci = 0; ci < 2 && n_tile == 0; ++ci) {
@@ -326,9 +333,11 @@ int launch_conv_pair(const sininn_conv_desc* d, Params p, cudaStream_t st) {
     if (d->rows_pad % n_tile != 0) return SININN_EUNSUPPORTED;
     // the weight ring comes first (a tap consumes a chunk every few hundred cycles and a chunk takes ~1500 cycles to
     // land: 8 chunks in flight), the halo stages (one per slab) get what is left: 2..4
-    const int chunk = (int)chunk_of(n_tile);
+    tps = chunk_of(n_tile) <= 8192 ? 3 : 1;
+    const int chunk = (int)chunk_of(n_tile) * tps;               // bytes of one ring stage
+    const int want = tps == 3 ? 4 : P_MAX_B;
     a_stages = 4;
-    while (a_stages > 2 && (total - fixed - a_stages * (int)PHALO_BYTES) / chunk < P_MAX_B) --a_stages;
+    while (a_stages > 2 && (total - fixed - a_stages * (int)PHALO_BYTES) / chunk < want) --a_stages;
     b_stages = (total - fixed - a_stages * (int)PHALO_BYTES) / chunk;
     if (b_stages > P_MAX_B) b_stages = P_MAX_B;
     if (b_stages < 3) return SININN_EUNSUPPORTED;
@@ -337,8 +346,8 @@ int launch_conv_pair(const sininn_conv_desc* d, Params p, cudaStream_t st) {
   p.n_tiles = d->rows_pad / n_tile;
   hp.n_half = n_tile / 2;
   hp.chunk_bytes = chunk_of(n_tile);
-  hp.a_stages = a_stages; hp.b_stages = b_stages;
-  hp.b_region_bytes = b_stages == 0 ? (uint32_t)(9 * p.k_chunks) * hp.chunk_bytes : (uint32_t)b_stages * hp.chunk_bytes;
+  hp.a_stages = a_stages; hp.b_stages = b_stages; hp.tps = tps;
+  hp.b_region_bytes = b_stages == 0 ? (uint32_t)(9 * p.k_chunks) * hp.chunk_bytes : (uint32_t)(b_stages * tps) * hp.chunk_bytes;
   hp.num_items = ((hp.num_ptiles + 1) / 2) * p.n_tiles;
   p.num_tiles = hp.num_items;
   hp.p = p;
