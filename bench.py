@@ -156,7 +156,14 @@ def run_ours(args):
     kernels.LAUNCHES = 0
     trainer.training_step(*dev_batches[0])
     launches_per_step = kernels.LAUNCHES
-    graphed = None if args.no_graph else trainer.capture(*dev_batches[0], warmup=2)
+    graphed = None
+    if not args.no_graph:
+        try:
+            graphed = trainer.capture(*dev_batches[0], warmup=2)
+        except Exception as e:                      # keep measuring (eagerly) if stream capture is refused on this box
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running the step eagerly", file=sys.stderr, flush=True)
+            torch.cuda.synchronize()
+            graphed = None
 
     def step_resident(i):
         if graphed is not None:
