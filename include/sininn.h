@@ -86,6 +86,11 @@ int sininn_permute_nhwc(const float* in, float* out, long long npix, int C, cons
 int sininn_permute_nhwc_pair(const float* in_a, float* out_a, const float* in_b, float* out_b, long long npix, int C,
                              const int32_t* chan_map, void* bf16_out_a, int c0, int c1, sininn_stream_t stream);
 
+/* Inference output path (lit_wrapper.py:117-121, transforms.ToPILImage on every frame): fp32 NCHW frames in [0, 1] ->
+ * uint8 HWC, out[b][h][w][c] = (uint8) trunc(255 * clamp(in[b][c][h][w], 0, 1)).  For in-range values this is
+ * pic.mul(255).byte(); out-of-range values are clamped (the reference's cast is undefined there). */
+int sininn_quantize_u8_hwc(const float* in, uint8_t* out, int B, int C, int H, int W, sininn_stream_t stream);
+
 /* ---------------------------------------------------------------- coupling
  * One half of an affine coupling, in place on a channel slice u[npix][L]
  * (pixel stride u_stride) of the fp32 trunk:

@@ -280,6 +280,24 @@ __global__ void __launch_bounds__(256) permute_nhwc_pair_kernel(const float* __r
   }
 }
 
+// fp32 NCHW in [0, 1] -> uint8 HWC: what the reference's inference loop does per image on the host
+// (lit_wrapper.py:117-121: transforms.ToPILImage() = pic.mul(255).byte(), then channels-last for PIL)
+__global__ void __launch_bounds__(256) quantize_u8_hwc_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int C,
+                                                              long long HW, long long total_pix) {
+  pdl_wait();
+  pdl_trigger();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_pix; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, p = i - b * HW;
+    const float* src = in + b * C * HW + p;
+    uint8_t* dst = out + i * C;
+    for (int c = 0; c < C; ++c) {
+      float v = src[c * HW];
+      v = fminf(fmaxf(v, 0.f), 1.f) * 255.f;          // in-range values: identical to mul(255).byte() (truncation)
+      dst[c] = (uint8_t)(int)v;
+    }
+  }
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   long long cap = (long long)sm_count() * 32;   // grid-stride beyond ~32 CTAs per SM
@@ -380,6 +398,14 @@ int sininn_permute_nhwc(const float* in, float* out, long long npix, int C, cons
   if (v4) launch_k(permute_nhwc_kernel<4>, dim3(grid), dim3(block), 0, as_stream(stream), in, out, npix, C, chan_map, bf, c0, c1);
   else launch_k(permute_nhwc_kernel<1>, dim3(grid), dim3(block), 0, as_stream(stream), in, out, npix, C, chan_map, bf, c0, c1);
   SININN_CHECK_LAUNCH("permute_nhwc");
+  return SININN_OK;
+}
+
+int sininn_quantize_u8_hwc(const float* in, uint8_t* out, int B, int C, int H, int W, sininn_stream_t stream) {
+  SININN_CHECK_ARG(in && out && B > 0 && C > 0 && H > 0 && W > 0, "quantize_u8_hwc: bad arguments");
+  const long long HW = (long long)H * W, total = (long long)B * HW;
+  launch_k(quantize_u8_hwc_kernel, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), in, out, C, HW, total);
+  SININN_CHECK_LAUNCH("quantize_u8_hwc");
   return SININN_OK;
 }
 

@@ -147,6 +147,17 @@ def permute_nhwc(x, chan_map, bf16_range=None):
     return out, bf
 
 
+def quantize_u8_hwc(x):
+    """fp32 NCHW frames in [0, 1] -> uint8 [B, H, W, C] (ToPILImage's mul(255).byte(), clamped), on the device."""
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    B, c, h, w = x.shape
+    out = torch.empty(B, h, w, c, dtype=torch.uint8, device=x.device)
+    check(_run("misc", lambda: load().sininn_quantize_u8_hwc(x.data_ptr(), out.data_ptr(), B, c, h, w, stream_ptr()), 1, 0.0,
+               5.0 * x.numel()), "quantize_u8_hwc")
+    return out
+
+
 def permute_nhwc_pair(xa, xb, chan_map, bf16_range=None):
     """Both gathers of the backward pass (activations and their gradient, same map) in one launch; optionally also
     the compact bf16 copy of the gathered activations' channels bf16_range.  Returns (out_a, out_b, bf16 or None)."""

@@ -60,6 +60,10 @@ def permute_nhwc(x, chan_map, bf16_range=None):
     return out, _bf(out.view(-1, out.shape[-1]), bf16_range)
 
 
+def quantize_u8_hwc(x):
+    return (x.clamp(0, 1) * 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+
 def permute_nhwc_pair(xa, xb, chan_map, bf16_range=None):
     oa, bf = permute_nhwc(xa, chan_map, bf16_range)
     return oa, permute_nhwc(xb, chan_map)[0], bf

@@ -442,3 +442,20 @@ def test_fused_forward_half_loss(K, B, C, L, hw, w_nll):
     loss, grad = K.inn_fwd_loss(y.to(DEV), lr.to(DEV), 1.3, w_nll)
     assert abs(loss.item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item()))
     assert (grad.cpu() - yr.grad).abs().max().item() <= 1e-6 * max(1e-3, yr.grad.abs().max().item())
+
+
+def test_quantize_u8_hwc_matches_topilimage_arithmetic(K):
+    """lit_wrapper.py:117-121: ToPILImage on a float frame is pic.mul(255).byte(); same bytes for in-range values,
+    clamping outside [0, 1]."""
+    x = torch.rand(3, 3, 37, 53, generator=torch.Generator().manual_seed(5))
+    x[0, 0, 0, :4] = torch.tensor([0.0, 1.0, 1.0 / 255, 254.999 / 255])
+    got = K.quantize_u8_hwc(x.to(DEV)).cpu()
+    ref = x.mul(255).byte().permute(0, 2, 3, 1)
+    assert got.shape == (3, 37, 53, 3) and torch.equal(got, ref)
+    y = x * 3 - 1                                         # out of range: clamped to 0 / 255
+    g2 = K.quantize_u8_hwc(y.to(DEV)).cpu()
+    assert torch.equal(g2, FK.quantize_u8_hwc(y))
+    from sin_inn_b200 import train
+    host = train.frames_to_uint8(x.to(DEV))
+    torch.cuda.synchronize()
+    assert host.is_pinned() and torch.equal(host, ref)
