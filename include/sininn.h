@@ -86,6 +86,12 @@ int sininn_permute_nhwc(const float* in, float* out, long long npix, int C, cons
 int sininn_permute_nhwc_pair(const float* in_a, float* out_a, const float* in_b, float* out_b, long long npix, int C,
                              const int32_t* chan_map, void* bf16_out_a, int c0, int c1, sininn_stream_t stream);
 
+/* Input pipeline (data.py:31-45 after the PNG decode): video [T][H][W][C] uint8 resident on the device, centers [B]
+ * int32 frame indices; out [B][(2*win+1)*C][ph][pw] fp32 = frames centre-win..centre+win cropped to the patch at
+ * (y0, x0), concatenated along channels, divided by 255.  win = 0, C = 3 gives the HR batch. */
+int sininn_gather_windows_u8(const uint8_t* video, int T, int H, int W, int C, const int32_t* centers, int B, int win,
+                             int y0, int x0, int ph, int pw, float* out, sininn_stream_t stream);
+
 /* Inference output path (lit_wrapper.py:117-121, transforms.ToPILImage on every frame): fp32 NCHW frames in [0, 1] ->
  * uint8 HWC, out[b][h][w][c] = (uint8) trunc(255 * clamp(in[b][c][h][w], 0, 1)).  For in-range values this is
  * pic.mul(255).byte(); out-of-range values are clamped (the reference's cast is undefined there). */

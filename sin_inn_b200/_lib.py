@@ -77,6 +77,8 @@ SIGNATURES = {
     "sininn_nhwc_to_nchw": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "sininn_permute_nhwc": (C.c_int, [_vp, _vp, _c_ll, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
     "sininn_permute_nhwc_pair": (C.c_int, [_vp, _vp, _vp, _vp, _c_ll, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "sininn_gather_windows_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, _vp, _vp]),
     "sininn_quantize_u8_hwc": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "sininn_coupling_apply": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _c_ll, C.c_int, C.c_int, C.c_float,
                                         C.c_int, _vp, _vp]),

@@ -298,6 +298,30 @@ __global__ void __launch_bounds__(256) quantize_u8_hwc_kernel(const float* __res
   }
 }
 
+// uint8 video frames resident on the GPU -> one fp32 NCHW training batch: for every sample the frames
+// centre-win .. centre+win of a [T][H][W][C] uint8 video, cropped to a ph x pw patch, concatenated along channels and
+// divided by 255 (data.py:31-45: imread of 2*lr_window+1 files, concatenate(axis=-1), transpose(-1, 0, 1), / 255.)
+__global__ void __launch_bounds__(256) gather_windows_u8_kernel(const uint8_t* __restrict__ video, int T, int H, int W, int C,
+                                                                const int32_t* __restrict__ centers, int win, int y0, int x0,
+                                                                int ph, int pw, float* __restrict__ out, long long total) {
+  pdl_wait();
+  pdl_trigger();
+  const int F = 2 * win + 1;
+  const long long plane = (long long)ph * pw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % pw);
+    long long r = i / pw;
+    const int y = (int)(r % ph); r /= ph;
+    const int f = (int)(r % F);
+    const int b = (int)(r / F);
+    int t = __ldg(centers + b) - win + f;
+    t = t < 0 ? 0 : (t >= T ? T - 1 : t);                  // (the reference never indexes outside the clip)
+    const uint8_t* src = video + (((long long)t * H + (y0 + y)) * W + (x0 + x)) * C;
+    float* dst = out + ((long long)b * F * C + (long long)f * C) * plane + (long long)y * pw + x;
+    for (int c = 0; c < C; ++c) dst[c * plane] = __fdiv_rn((float)src[c], 255.0f);      // bit-exact with the reference's "/ 255."
+  }
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   long long cap = (long long)sm_count() * 32;   // grid-stride beyond ~32 CTAs per SM
@@ -398,6 +422,17 @@ int sininn_permute_nhwc(const float* in, float* out, long long npix, int C, cons
   if (v4) launch_k(permute_nhwc_kernel<4>, dim3(grid), dim3(block), 0, as_stream(stream), in, out, npix, C, chan_map, bf, c0, c1);
   else launch_k(permute_nhwc_kernel<1>, dim3(grid), dim3(block), 0, as_stream(stream), in, out, npix, C, chan_map, bf, c0, c1);
   SININN_CHECK_LAUNCH("permute_nhwc");
+  return SININN_OK;
+}
+
+int sininn_gather_windows_u8(const uint8_t* video, int T, int H, int W, int C, const int32_t* centers, int B, int win,
+                             int y0, int x0, int ph, int pw, float* out, sininn_stream_t stream) {
+  SININN_CHECK_ARG(video && centers && out && T > 0 && H > 0 && W > 0 && C > 0 && B > 0 && win >= 0, "gather_windows_u8: bad arguments");
+  SININN_CHECK_ARG(y0 >= 0 && x0 >= 0 && ph > 0 && pw > 0 && y0 + ph <= H && x0 + pw <= W, "gather_windows_u8: crop outside the frame");
+  const long long total = (long long)B * (2 * win + 1) * ph * pw;
+  launch_k(gather_windows_u8_kernel, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), video, T, H, W, C, centers, win, y0, x0,
+           ph, pw, out, total);
+  SININN_CHECK_LAUNCH("gather_windows_u8");
   return SININN_OK;
 }
 

@@ -147,6 +147,22 @@ def permute_nhwc(x, chan_map, bf16_range=None):
     return out, bf
 
 
+def gather_windows_u8(video, centers, win, crop=None):
+    """video: uint8 [T, H, W, C] on the device; centers: int32 [B] on the device; crop = (y0, x0, ph, pw) or None.
+    Returns fp32 [B, (2*win+1)*C, ph, pw] = the frame windows / 255 (data.py:31-45 without the PNG decode)."""
+    _lib.require_cuda(video)
+    if video.dtype != torch.uint8 or video.dim() != 4 or not video.is_contiguous():
+        raise _lib.SininnError("gather_windows_u8: video must be a contiguous uint8 [T, H, W, C] tensor")
+    T, H, W, Cc = video.shape
+    y0, x0, ph, pw = crop if crop is not None else (0, 0, H, W)
+    B = centers.numel()
+    out = torch.empty(B, (2 * win + 1) * Cc, ph, pw, dtype=torch.float32, device=video.device)
+    check(_run("misc", lambda: load().sininn_gather_windows_u8(video.data_ptr(), T, H, W, Cc, centers.data_ptr(), B, int(win), int(y0),
+                                          int(x0), int(ph), int(pw), out.data_ptr(), stream_ptr()), 1, 0.0, 5.0 * out.numel()),
+          "gather_windows_u8")
+    return out
+
+
 def quantize_u8_hwc(x):
     """fp32 NCHW frames in [0, 1] -> uint8 [B, H, W, C] (ToPILImage's mul(255).byte(), clamped), on the device."""
     _lib.require_cuda(x)

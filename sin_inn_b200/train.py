@@ -306,6 +306,32 @@ class GraphedInference:
         return self.static_out
 
 
+class VideoBatcher:
+    """The reference's VideoTrainDataset / VideoAllDataset (data.py:48-75) for a clip that is already decoded and
+    resident on the GPU as uint8: `lr_video` [T, h, w, 4-or-3] and `hr_frames` [N, H, W, 3] (one HR frame per training
+    centre).  batch(ids, crop) assembles the (hr, lr) tensors of lit_wrapper.training_step with two kernel launches
+    (window gather, channel concatenation, / 255) instead of (2*lr_window+1) imreads + numpy concatenation per sample."""
+
+    def __init__(self, lr_video, hr_frames, opt, centers=None):
+        self.lr_video, self.hr_frames, self.win = lr_video, hr_frames, opt.lr_window
+        num_lr = lr_video.shape[0] - 1
+        if centers is None:                                   # data.py:56: range(1 + fps, num_lr - fps, 120 // fps)
+            centers = list(range(1 + opt.fps, num_lr - opt.fps, 120 // opt.fps))
+        self.centers = torch.tensor(centers, dtype=torch.int32, device=lr_video.device)
+        self.scale = hr_frames.shape[1] // lr_video.shape[1]
+
+    def __len__(self):
+        return self.centers.numel()
+
+    def batch(self, ids, lr_crop=None):
+        """ids: int64/int32 tensor of sample indices on the device; lr_crop = (y0, x0, ph, pw) on the LR grid."""
+        ids = ids.to(self.lr_video.device)
+        lr = K.gather_windows_u8(self.lr_video, self.centers[ids.long()].contiguous(), self.win, lr_crop)
+        hr_crop = None if lr_crop is None else tuple(v * self.scale for v in lr_crop)
+        hr = K.gather_windows_u8(self.hr_frames, ids.to(torch.int32).contiguous(), 0, hr_crop)
+        return hr, lr
+
+
 @torch.no_grad()
 def frames_to_uint8(hr_hat, pinned_out=None):
     """lit_wrapper.py:117-121 without the per-image host loop: quantise a batch of output frames to uint8 HWC on the

@@ -60,6 +60,16 @@ def permute_nhwc(x, chan_map, bf16_range=None):
     return out, _bf(out.view(-1, out.shape[-1]), bf16_range)
 
 
+def gather_windows_u8(video, centers, win, crop=None):
+    T, H, W, Cc = video.shape
+    y0, x0, ph, pw = crop if crop is not None else (0, 0, H, W)
+    outs = []
+    for c in centers.tolist():
+        fr = [video[min(max(t, 0), T - 1), y0:y0 + ph, x0:x0 + pw] for t in range(c - win, c + win + 1)]
+        outs.append(torch.cat(fr, dim=-1).permute(2, 0, 1).float() / 255.)
+    return torch.stack(outs)
+
+
 def quantize_u8_hwc(x):
     return (x.clamp(0, 1) * 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
 

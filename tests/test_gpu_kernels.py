@@ -459,3 +459,29 @@ def test_quantize_u8_hwc_matches_topilimage_arithmetic(K):
     host = train.frames_to_uint8(x.to(DEV))
     torch.cuda.synchronize()
     assert host.is_pinned() and torch.equal(host, ref)
+
+
+def test_gather_windows_u8_matches_data_py_arithmetic(K):
+    """data.py:31-45: per sample np.concatenate of the (2*lr_window+1) decoded LR frames along channels,
+    transpose(-1, 0, 1), / 255 -- here from a uint8 clip resident on the GPU, with an optional patch crop."""
+    g = torch.Generator().manual_seed(9)
+    T, h, w, C, win = 40, 18, 26, 4, 3
+    video = torch.randint(0, 256, (T, h, w, C), generator=g, dtype=torch.uint8)
+    centers = torch.tensor([5, 17, 30, 36], dtype=torch.int32)
+    ref = torch.stack([torch.from_numpy(__import__("numpy").concatenate([video[t].numpy() for t in range(c - win, c + win + 1)], axis=-1)
+                                        .transpose(2, 0, 1).astype("float32")) / 255. for c in centers.tolist()])
+    got = K.gather_windows_u8(video.to(DEV), centers.to(DEV), win)
+    assert got.shape == (4, (2 * win + 1) * C, h, w) and torch.equal(got.cpu(), ref)
+    crop = (3, 5, 8, 16)
+    got = K.gather_windows_u8(video.to(DEV), centers.to(DEV), win, crop)
+    assert torch.equal(got.cpu(), ref[:, :, 3:11, 5:21])
+    assert torch.equal(FK.gather_windows_u8(video, centers, win, crop), ref[:, :, 3:11, 5:21])
+    # the batcher: HR frames (win 0) + LR windows for a set of sample ids
+    from sin_inn_b200 import train
+    import types
+    opt = types.SimpleNamespace(lr_window=win, fps=30)
+    hr_frames = torch.randint(0, 256, (3, 2 * h, 2 * w, 3), generator=g, dtype=torch.uint8)
+    vb = train.VideoBatcher(video.to(DEV), hr_frames.to(DEV), opt, centers=[5, 17, 30])
+    hr, lr = vb.batch(torch.tensor([2, 0]), lr_crop=(2, 4, 8, 8))
+    assert torch.equal(lr.cpu(), ref[[2, 0]][:, :, 2:10, 4:12])
+    assert torch.equal(hr.cpu(), hr_frames[[2, 0]].permute(0, 3, 1, 2).float()[:, :, 4:20, 8:24] / 255.)
