@@ -215,6 +215,7 @@ class SingleVideoTrainer:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             losses = self.training_step(s_hr, s_lr, s_z)
+            loss_pair = torch.stack(losses)          # both losses in one 8-byte buffer: one read-back per step
         self._graph = (graph, (s_hr, s_lr, s_z), losses)
 
         def step(hr, lr, z):
@@ -227,6 +228,7 @@ class SingleVideoTrainer:
             return losses
 
         step.static_inputs = (s_hr, s_lr, s_z)
+        step.loss_pair = loss_pair
         return step
 
     @torch.no_grad()
