@@ -159,8 +159,10 @@ typedef struct {
   void* bits_out;                 /* NULL, or receives the sign bits (value > 0) of this call's own output */
 } sininn_conv_desc;
 
-/* Debugging aid: when set to a device buffer of 3 x 512 int64, the CTA-pair 3x3 kernel records clock64() stamps of
- * CTA 0's producer / MMA / epilogue roles into it (NULL switches tracing off, the default). */
+/* Debugging aid: when set to a device buffer of 4 x 512 int64, the CTA-pair 3x3 kernel records clock64() stamps of
+ * CTA 0's producer / MMA / epilogue roles into words 0..1535 (only when built with -DSININN_PAIR_TRACE) and the CTA-pair
+ * weight-gradient kernel its phase stamps into words 1536..1543: {entry, prologue done, dependency wait done, producer
+ * done, first stage landed, last MMA issued, accumulators ready, partials stored}.  NULL switches tracing off (default). */
 int sininn_debug_set_trace(void* device_buf_3x512_int64);
 
 int sininn_conv_simt(const sininn_conv_desc* d, sininn_stream_t stream);   /* fp32-accurate CUDA-core path */

@@ -406,11 +406,13 @@ int launch_conv_pair(const sininn_conv_desc* d, Params p, cudaStream_t st) {
 }
 
 void set_pair_trace(long long* buf) { g_trace_buf = buf; }
+void set_wgrad_pair_trace(long long* buf);      // wgrad_pair.cu (its 8 stamps go to words 1536.. of the same buffer)
 
 }  // namespace tc
 }  // namespace sininn
 
 extern "C" int sininn_debug_set_trace(void* device_buf_3x512_int64) {
   sininn::tc::set_pair_trace(reinterpret_cast<long long*>(device_buf_3x512_int64));
+  sininn::tc::set_wgrad_pair_trace(device_buf_3x512_int64 ? reinterpret_cast<long long*>(device_buf_3x512_int64) + 3 * 512 : nullptr);
   return SININN_OK;
 }

@@ -5,6 +5,11 @@ namespace sininn {
 int wgrad_simt_splits(const sininn_wgrad_desc* d);
 namespace tc {
 
+// wgrad_pair.cu: the CTA-pair kernel (taken whenever the wide operand has more than 128 channels)
+size_t wgrad_pair_workspace_bytes(const sininn_wgrad_desc* d);
+int launch_wgrad_pair(const sininn_wgrad_desc* d, cudaStream_t st, int* splits, int* wide_is_dy, float** partial,
+                      float** bias_partial, int* bias_rows);
+
 constexpr int NUM_THREADS = 192;
 constexpr int SMEM_RING_BUDGET = 200 * 1024;
 
@@ -275,11 +280,16 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
   pdl_wait();
   pdl_trigger();
   __shared__ float red[RG][32][VEC + 1];
-  if (bias_partial != nullptr && blockIdx.x == gridDim.x - 1) {     // fixed-order sum of the per-split column sums of dy
-    for (int c = threadIdx.x; c < bias_n; c += blockDim.x) {
+  if (bias_partial != nullptr) {
+    // fixed-order sum of the per-split column sums of dy: one warp per channel (lane l adds rows l, l+32, ... in
+    // order, then a fixed xor tree), spread over the blocks instead of one thread walking all rows of a channel
+    const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    for (int c = blockIdx.x * 8 + wid; c < bias_n; c += gridDim.x * 8) {
       float s = 0.f;
-      for (int k = 0; k < bias_rows; ++k) s += bias_partial[(long long)k * bias_n + c];
-      dbias[c] = dbias_accumulate ? dbias[c] + s : s;
+      for (int k = ln; k < bias_rows; k += 32) s += __ldcs(bias_partial + (long long)k * bias_n + c);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (ln == 0) dbias[c] = dbias_accumulate ? dbias[c] + s : s;
     }
   }
   const long long per = (long long)taps * Cw * Cn;
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
 #pragma unroll
     for (int e = 0; e < VEC; ++e) s[e] = 0.f;
     if (iv < perv) {
-#pragma unroll 4
+#pragma unroll 8
       for (int k = g; k < splits; k += RG) {
         if (VEC == 4) {
           const float4 t = __ldcs(reinterpret_cast<const float4*>(partial + k * per + idx));
@@ -336,6 +346,26 @@ struct WgradPlan {
   uint32_t stage_bytes, narrow_bytes;
 };
 
+// second launch: fixed-order sum of the per-split partials into OIHW (and of the per-split dy column sums)
+static int launch_reduce(const sininn_wgrad_desc* d, cudaStream_t st, const float* partial, int splits, int wide_is_dy,
+                         const float* bias_partial, int bias_rows) {
+  const int Cw = wide_is_dy ? d->Cout : d->Cin, Cn = wide_is_dy ? d->Cin : d->Cout;
+  const long long per = (long long)d->taps * Cw * Cn;
+  if ((Cn % 4) == 0) {
+    long long g = (per / 4 + 31) / 32;
+    if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
+    launch_k(wgrad_tc_reduce_kernel<4>, dim3((int)g), dim3(256), 0, st, partial, splits, d->taps, Cw, Cn, wide_is_dy, d->Cout, d->Cin,
+             d->dw, d->accumulate, bias_partial, bias_rows, d->Cout, d->dbias, d->dbias_accumulate);
+  } else {
+    long long g = (per + 31) / 32;
+    if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
+    launch_k(wgrad_tc_reduce_kernel<1>, dim3((int)g), dim3(256), 0, st, partial, splits, d->taps, Cw, Cn, wide_is_dy, d->Cout, d->Cin,
+             d->dw, d->accumulate, bias_partial, bias_rows, d->Cout, d->dbias, d->dbias_accumulate);
+  }
+  SININN_CHECK_LAUNCH("wgrad_tc(reduce)");
+  return SININN_OK;
+}
+
 static bool plan_wgrad(const sininn_wgrad_desc* d, WgradPlan& w) {
   w.wide_is_dy = d->Cout >= d->Cin ? 1 : 0;
   w.Cw = w.wide_is_dy ? d->Cout : d->Cin;
@@ -377,6 +407,8 @@ size_t sininn_wgrad_workspace_bytes(const sininn_wgrad_desc* d, int tensor_core)
   if (!d || d->Cin <= 0 || d->Cout <= 0 || d->taps <= 0) return 0;
   size_t simt = (size_t)wgrad_simt_splits(d) * d->taps * d->Cout * d->Cin * sizeof(float);
   if (!tensor_core) return simt;
+  const size_t pairb = sininn::tc::wgrad_pair_workspace_bytes(d);
+  if (pairb > simt) simt = pairb;
   sininn::tc::WgradPlan w;
   if (!sininn::tc::plan_wgrad(d, w)) return simt;
   size_t tcb = (size_t)w.splits * d->taps * d->Cout * d->Cin * sizeof(float) + (size_t)2 * w.splits * d->Cout * sizeof(float);
@@ -392,6 +424,13 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
   SININN_CHECK_ARG(aligned16(d->x) && aligned16(d->dy) && (d->x_stride % 8) == 0 && (d->dy_stride % 8) == 0,
                    "wgrad_tc: TMA needs 16-byte aligned operands with pixel strides that are multiples of 8 channels "
                    "(x stride %d, dy stride %d)", d->x_stride, d->dy_stride);
+  {
+    int splits = 0, wide_is_dy = 0, bias_rows = 0;
+    float *partial = nullptr, *bias_partial = nullptr;
+    const int rc = launch_wgrad_pair(d, as_stream(stream), &splits, &wide_is_dy, &partial, &bias_partial, &bias_rows);
+    if (rc == SININN_OK) return launch_reduce(d, as_stream(stream), partial, splits, wide_is_dy, bias_partial, bias_rows);
+    if (rc != SININN_EUNSUPPORTED) return rc;
+  }
   WgradPlan w;
   if (!plan_wgrad(d, w)) {
     set_error("wgrad_tc: unsupported shape (Cin=%d Cout=%d)", d->Cin, d->Cout);
@@ -456,20 +495,8 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
   const unsigned grid = (unsigned)(w.m_tiles * w.tap_groups * w.splits);
   cudaStream_t st = as_stream(stream);
   launch_k(wgrad_tc_kernel, dim3(grid), dim3(NUM_THREADS), smem, st, tmW, tmN, p);
-  const long long per = (long long)d->taps * w.Cw * w.Cn;
-  if ((w.Cn % 4) == 0) {
-    long long g = (per / 4 + 31) / 32;
-    if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
-    launch_k(wgrad_tc_reduce_kernel<4>, dim3((int)g), dim3(256), 0, st, p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
-                                                      d->dw, d->accumulate, p.bias_partial, bias_rows, d->Cout, d->dbias, d->dbias_accumulate);
-  } else {
-    long long g = (per + 31) / 32;
-    if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
-    launch_k(wgrad_tc_reduce_kernel<1>, dim3((int)g), dim3(256), 0, st, p.partial, w.splits, d->taps, w.Cw, w.Cn, w.wide_is_dy, d->Cout, d->Cin,
-                                                      d->dw, d->accumulate, p.bias_partial, bias_rows, d->Cout, d->dbias, d->dbias_accumulate);
-  }
   SININN_CHECK_LAUNCH("wgrad_tc");
-  return SININN_OK;
+  return launch_reduce(d, st, p.partial, w.splits, w.wide_is_dy, p.bias_partial, bias_rows);
 }
 
 }  // extern "C"

@@ -48,6 +48,52 @@ def wgrad_case(name, hw, cin, cout, taps):
     print(f"{name:34s} M={npix:7d} K={cin*taps:5d} N={cout:4d}  {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TFLOP/s")
     return ms
 
+def kernel_times(fn, reps=5):
+    """Device duration of every kernel fn() launches (CUPTI through torch.profiler), L2 flushed before each call:
+    {kernel name: mean us}."""
+    from torch.profiler import profile, ProfilerActivity
+    fn(); torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(reps):
+            flush.zero_()
+            fn()
+        torch.cuda.synchronize()
+    out = {}
+    for ev in prof.key_averages():
+        if "Memset" in ev.key or "fill" in ev.key.lower():
+            continue
+        out[ev.key.split("(")[0][-40:]] = ev.device_time_total / max(ev.count, 1)
+    return out
+
+
+def wgrad_check(name, hw, cin, cout, taps, bias=True):
+    """Same shapes, timed with the fused bias gradient, plus the relative error against torch's fp32 weight gradient
+    of the same bf16-rounded operands (cuDNN, TF32 off) and a bit-equality check of two runs."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    npix = B * hw * hw
+    x = torch.randn(npix, cin, device=DEV).to(torch.bfloat16)
+    dy = torch.randn(npix, cout, device=DEV).to(torch.bfloat16)
+    k = 3 if taps == 9 else 1
+    dw = torch.empty(cout, cin, k, k, device=DEV)
+    db = torch.empty(cout, device=DEV) if bias else None
+    fn = lambda: K.wgrad(x, dy, (B, hw, hw), taps, dw, tensor_core=True, dbias=db)
+    ms = timeit(fn)
+    first = dw.clone()
+    fn(); torch.cuda.synchronize()
+    same = torch.equal(first, dw)
+    xn = x.float().view(B, hw, hw, cin).permute(0, 3, 1, 2).contiguous()
+    dyn = dy.float().view(B, hw, hw, cout).permute(0, 3, 1, 2).contiguous()
+    ref = torch.nn.grad.conv2d_weight(xn, (cout, cin, k, k), dyn, padding=k // 2)
+    err = float((dw - ref).norm() / ref.norm())
+    berr = float((db - dyn.sum((0, 2, 3))).norm() / dyn.sum((0, 2, 3)).norm()) if bias else 0.0
+    fl = 2.0 * npix * cin * cout * taps
+    kt = kernel_times(fn) if os.environ.get("KT", "1") != "0" else {}
+    print(f"{name:24s} {cin:3d}x{cout:3d}x{taps}  {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TFLOP/s  rel_err {err:.2e}  bias_err {berr:.2e}  "
+          f"deterministic {same}  " + "  ".join(f"{k}={v:.1f}us" for k, v in kt.items()), flush=True)
+    return ms
+
+
 def fused1x1_case(name, hw, cin, cout, keep):
     npix = B * hw * hw
     x = torch.randn(npix, cin, device=DEV).to(torch.bfloat16)
@@ -70,6 +116,15 @@ if __name__ == "__main__":
         for lvl, hw, c in (("L0", 64, 48), ("L1", 32, 192)):
             for keep in (False, True):
                 fused1x1_case(f"{lvl} fused 1x1 subnet fwd", hw, c // 2, c, keep)
+        sys.exit(0)
+    if os.environ.get("ONLY") == "wgrad":
+        tot = 0.0
+        for lvl, hw, c in (("L0", 64, 48), ("L1", 32, 192)):
+            for taps in (9, 1):
+                t = f"{lvl} {'3x3' if taps == 9 else '1x1'}"
+                tot += wgrad_check(f"{t} conv1 wgrad+bias", hw, c // 2, 256, taps)
+                tot += wgrad_check(f"{t} conv2 wgrad+bias", hw, 256, c, taps)
+        print(f"sum x8 = {8 * tot:.3f} ms of weight-gradient launches per train step (B={B})")
         sys.exit(0)
     bf, f32 = torch.bfloat16, torch.float32
     tot = 0.0

@@ -19,7 +19,7 @@ def run(name, hw, cin, cout, out_dtype, relu=False):
     out = torch.zeros(npix, cout, dtype=out_dtype, device=DEV)
     fn = lambda: K.conv(x, wp, (B, hw, hw), cout, out, act=1 if relu else 0, tensor_core=True)
     fn(); fn()
-    trace = torch.zeros(3, 512, dtype=torch.int64, device=DEV)
+    trace = torch.zeros(4, 512, dtype=torch.int64, device=DEV)
     flush.zero_()
     load().sininn_debug_set_trace(trace.data_ptr())
     fn()
