@@ -224,6 +224,14 @@ typedef struct {
 size_t sininn_wgrad_workspace_bytes(const sininn_wgrad_desc* d, int tensor_core);
 int sininn_wgrad_simt(const sininn_wgrad_desc* d, sininn_stream_t stream);
 int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream);
+/* Several weight gradients (e.g. the two convolutions of a coupling subnet, archs.py:11-17, whose operands become
+ * available together in the backward pass) in ONE pair of launches: the grid is divided among the problems in
+ * proportion to their work, so each is cut in fewer pixel splits than alone.  `workspace` serves the whole group
+ * (>= sininn_wgrad_group_workspace_bytes); the workspace fields of the descriptors are ignored.  Results are
+ * bit-identical from call to call for the same group, but not to the one-by-one calls (different split counts). */
+size_t sininn_wgrad_group_workspace_bytes(const sininn_wgrad_desc* descs, int n);
+int sininn_wgrad_tc_group(const sininn_wgrad_desc* descs, int n, void* workspace, size_t workspace_bytes,
+                          sininn_stream_t stream);
 
 /* ---------------------------------------------------------------- caller-side fusions
  * sum((a[:, :L]-b)^2) over a strided slice -> out[0] (+ optional gradient 2*scale*(a-b)); used for

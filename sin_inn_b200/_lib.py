@@ -100,6 +100,8 @@ SIGNATURES = {
     "sininn_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(WgradDesc), C.c_int]),
     "sininn_wgrad_simt": (C.c_int, [C.POINTER(WgradDesc), _vp]),
     "sininn_wgrad_tc": (C.c_int, [C.POINTER(WgradDesc), _vp]),
+    "sininn_wgrad_group_workspace_bytes": (C.c_size_t, [C.POINTER(WgradDesc), C.c_int]),
+    "sininn_wgrad_tc_group": (C.c_int, [C.POINTER(WgradDesc), C.c_int, _vp, C.c_size_t, _vp]),
     "sininn_sqdiff_workspace_bytes": (C.c_size_t, [_c_ll]),
     "sininn_sqdiff_nchw": (C.c_int, [_vp, _vp, _c_ll, C.c_float, _vp, _vp, _vp, C.c_size_t, _vp]),
     "sininn_inn_fwd_loss": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _c_ll, C.c_float, C.c_float, _vp, _vp, _vp, C.c_size_t, _vp]),

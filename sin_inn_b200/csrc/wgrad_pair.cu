@@ -61,6 +61,19 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
                : "memory");
 }
 
+// Up to four weight gradients share one launch (the two convolutions of a subnet, or the four of a coupling block):
+// the pairs of the grid are divided among the problems in proportion to their work, so every problem is cut in
+// FEWER pixel splits than it would be alone -- fewer partial tiles to write (the epilogue of a pair is bound by one
+// SM's store bandwidth: up to 256 KB of accumulators, ~8000 cycles) and to reduce, and one prologue per pair amortised
+// over 2-4x as many K steps.
+constexpr int WG_MAX_PROBLEMS = 4;
+struct WgTensorMaps { CUtensorMap m[3 * WG_MAX_PROBLEMS]; };      // per problem: wide, narrow, partial
+struct WgGroupParams {
+  int nprob;
+  int pair_begin[WG_MAX_PROBLEMS + 1];
+  WgPairParams prob[WG_MAX_PROBLEMS];
+};
+
 struct __align__(8) WgPairBarriers {
   uint64_t full[MAX_STAGES], empty[MAX_STAGES];
   uint64_t acc_full;
@@ -68,8 +81,11 @@ struct __align__(8) WgPairBarriers {
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 1)
-wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
-                  const __grid_constant__ CUtensorMap tmP, const WgPairParams p) {
+wgrad_pair_kernel(const __grid_constant__ WgTensorMaps T, const __grid_constant__ WgGroupParams G) {
+  int prob = 0;
+  while (prob + 1 < G.nprob && (int)(blockIdx.x >> 1) >= G.pair_begin[prob + 1]) ++prob;
+  const WgPairParams& p = G.prob[prob];
+  const CUtensorMap& tmW = T.m[3 * prob], & tmN = T.m[3 * prob + 1], & tmP = T.m[3 * prob + 2];
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* ring = smem_raw + pad;
@@ -80,7 +96,7 @@ wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   const int rank = (int)cluster_ctarank();
 
   // work item of this pair
-  int q = blockIdx.x >> 1;
+  int q = (int)(blockIdx.x >> 1) - G.pair_begin[prob];
   const int split = q % p.splits; q /= p.splits;
   const int tg = q % p.tap_groups; q /= p.tap_groups;
   const int ns = q % p.n_slices;
@@ -332,6 +348,145 @@ wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------- fixed-order reduction of the partials
+// dw[co][ci][tap] (+)= sum_split partial[split][tap][m][n]; (co,ci) = (m,n) when the wide operand is dy, else (n,m).
+// Fixed summation order => bit-reproducible gradients.  RG threads share one output vector: thread g sums splits
+// g, g+RG, ... (independent loads in flight), the RG partial sums are combined in a fixed order through shared memory.
+// One launch serves all problems of a group (blocks [block_begin, next block_begin) belong to a job).
+struct WgReduceJob {
+  const float* partial; int splits, taps, Cw, Cn, wide_is_dy, Cout, Cin;
+  float* dw; int accumulate;
+  const float* bias_partial; int bias_rows; float* dbias; int dbias_accumulate;
+  int block_begin, vec;
+};
+struct WgReduceParams { int njobs; WgReduceJob job[WG_MAX_PROBLEMS + 1]; };     // job[njobs].block_begin = grid size
+
+constexpr int RG = 8;          // split groups (one warp each)
+constexpr int RU = 4;          // output vectors per thread and pass: RU x ceil(splits / RG) independent loads in flight
+template <int VEC>
+__device__ __forceinline__ void reduce_job(const WgReduceJob& j, int bid, int nblocks, float (*red)[32 * RU][5]) {
+  if (j.bias_partial != nullptr) {
+    // per-split column sums of dy: one warp per channel (lane l adds rows l, l+32, ... in order, then a fixed xor tree)
+    const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    for (int c = bid * 8 + wid; c < j.Cout; c += nblocks * 8) {
+      float s = 0.f;
+      for (int k = ln; k < j.bias_rows; k += 32) s += __ldcs(j.bias_partial + (long long)k * j.Cout + c);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (ln == 0) j.dbias[c] = j.dbias_accumulate ? j.dbias[c] + s : s;
+    }
+  }
+  const long long per = (long long)j.taps * j.Cw * j.Cn;
+  const long long perv = per / VEC;
+  const int o = threadIdx.x & 31, g = threadIdx.x >> 5;            // output slot within the block, split group
+  for (long long base = (long long)bid * (32 * RU); base < perv; base += (long long)nblocks * (32 * RU)) {
+    float s[RU][VEC];
+#pragma unroll
+    for (int u = 0; u < RU; ++u)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) s[u][e] = 0.f;
+    for (int k = g; k < j.splits; k += RG) {
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const long long iv = base + u * 32 + o;
+        if (iv < perv) {
+          if (VEC == 4) {
+            const float4 t = __ldcs(reinterpret_cast<const float4*>(j.partial + k * per + iv * VEC));
+            s[u][0] += t.x; s[u][VEC > 1 ? 1 : 0] += t.y; s[u][VEC > 2 ? 2 : 0] += t.z; s[u][VEC > 3 ? 3 : 0] += t.w;
+          } else {
+            s[u][0] += j.partial[k * per + iv];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) red[g][u * 32 + o][e] = s[u][e];
+    __syncthreads();
+    // the 128 output vectors of the pass are finished by 128 threads (warps 0..3), fixed order over the split groups
+    if (threadIdx.x < 32 * RU) {
+      const int slot = threadIdx.x;
+      const long long iv = base + slot;
+      if (iv < perv) {
+        const long long idx = iv * VEC;
+        const int n0 = (int)(idx % j.Cn);
+        long long r = idx / j.Cn;
+        const int m = (int)(r % j.Cw);
+        const int tap = (int)(r / j.Cw);
+        float old[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const int n = n0 + e;
+          const int co = j.wide_is_dy ? m : n, ci = j.wide_is_dy ? n : m;
+          old[e] = j.accumulate ? j.dw[((long long)co * j.Cin + ci) * j.taps + tap] : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          float t = red[0][slot][e];
+#pragma unroll
+          for (int qq = 1; qq < RG; ++qq) t += red[qq][slot][e];
+          const int n = n0 + e;
+          const int co = j.wide_is_dy ? m : n, ci = j.wide_is_dy ? n : m;
+          j.dw[((long long)co * j.Cin + ci) * j.taps + tap] = old[e] + t;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgReduceParams R) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[RG][32 * RU][5];
+  int ji = 0;
+  while (ji + 1 < R.njobs && (int)blockIdx.x >= R.job[ji + 1].block_begin) ++ji;
+  const WgReduceJob& j = R.job[ji];
+  const int bid = blockIdx.x - j.block_begin, nblocks = R.job[ji + 1].block_begin - j.block_begin;
+  if (j.vec == 4) reduce_job<4>(j, bid, nblocks, red);
+  else reduce_job<1>(j, bid, nblocks, red);
+}
+
+static void reduce_add_job(WgReduceParams& R, const sininn_wgrad_desc* d, const float* partial, int splits, int wide_is_dy,
+                           const float* bias_partial, int bias_rows, int max_blocks) {
+  WgReduceJob& j = R.job[R.njobs];
+  j.partial = partial; j.splits = splits; j.taps = d->taps;
+  j.wide_is_dy = wide_is_dy;
+  j.Cw = wide_is_dy ? d->Cout : d->Cin; j.Cn = wide_is_dy ? d->Cin : d->Cout;
+  j.Cout = d->Cout; j.Cin = d->Cin;
+  j.dw = d->dw; j.accumulate = d->accumulate;
+  j.bias_partial = bias_partial; j.bias_rows = bias_rows; j.dbias = d->dbias; j.dbias_accumulate = d->dbias_accumulate;
+  j.vec = (j.Cn % 4) == 0 ? 4 : 1;
+  const long long per = (long long)d->taps * j.Cw * j.Cn;
+  long long g = (per / j.vec + 32 * RU - 1) / (32 * RU);
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  const int begin = R.njobs == 0 ? 0 : R.job[R.njobs].block_begin;
+  j.block_begin = begin;
+  R.job[R.njobs + 1].block_begin = begin + (int)g;
+  ++R.njobs;
+}
+
+static int launch_reduce_group(const WgReduceParams& R, cudaStream_t st) {
+  launch_k(wgrad_reduce_kernel, dim3((unsigned)R.job[R.njobs].block_begin), dim3(256), 0, st, R);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("wgrad_tc(reduce): launch failed: %s", cudaGetErrorString(e));
+    return SININN_ECUDA;
+  }
+  return SININN_OK;
+}
+
+// used by the single-CTA kernel of wgrad_tc.cu
+int launch_reduce_single(const sininn_wgrad_desc* d, cudaStream_t st, const float* partial, int splits, int wide_is_dy,
+                         const float* bias_partial, int bias_rows) {
+  WgReduceParams R;
+  R.njobs = 0;
+  reduce_add_job(R, d, partial, splits, wide_is_dy, bias_partial, bias_rows, sm_count() * 8);
+  return launch_reduce_group(R, st);
+}
+
 // ---------------------------------------------------------------- host side
 struct WgPairPlan {
   int wide_is_dy, Cw, Cn, n_pair, n_half, n_slices, tap_groups, m_pairs, splits, stages, halo_w;
@@ -339,6 +494,8 @@ struct WgPairPlan {
   int blocks_h, blocks_w;
   long long num_blocks, blocks_per_split;
   uint32_t stage_bytes, narrow_bytes, tx_bytes;
+  int items;
+  double kstep_cycles;           // rough cost of one K step of one pair (for dividing the grid among problems)
 };
 
 static int wg_halo_w() {
@@ -359,9 +516,19 @@ bool wgrad_pair_enabled() {
   return v == 1;
 }
 
-// with_bias: 0 none, else reserve the bias accumulator columns in tap group 0
-bool plan_wgrad_pair(const sininn_wgrad_desc* d, bool with_bias, WgPairPlan& w) {
+static void set_splits(WgPairPlan& w, long long pairs_budget) {
+  long long s = pairs_budget / w.items;                  // one wave of pairs ...
+  if (s > w.num_blocks / 4) s = w.num_blocks / 4;        // ... of at least 4 K steps each (partials cost bandwidth)
+  if (s > 128) s = 128;
+  if (s < 1) s = 1;
+  w.blocks_per_split = (w.num_blocks + s - 1) / s;
+  w.splits = (int)((w.num_blocks + w.blocks_per_split - 1) / w.blocks_per_split);
+}
+
+// Tiling of one problem (everything but the number of pixel splits, which depends on the pairs it is given).
+static bool plan_wgrad_pair(const sininn_wgrad_desc* d, bool with_bias, WgPairPlan& w) {
   if (!wgrad_pair_enabled()) return false;
+  if (d->x_dtype != SININN_BF16 || d->dy_dtype != SININN_BF16 || (d->taps != 1 && d->taps != 9)) return false;
   w.wide_is_dy = d->Cout >= d->Cin ? 1 : 0;
   w.Cw = w.wide_is_dy ? d->Cout : d->Cin;
   w.Cn = w.wide_is_dy ? d->Cin : d->Cout;
@@ -398,91 +565,145 @@ bool plan_wgrad_pair(const sininn_wgrad_desc* d, bool with_bias, WgPairPlan& w) 
   w.blocks_h = (d->H + WP_BLK - 1) / WP_BLK;
   w.blocks_w = (d->W + WP_BLK - 1) / WP_BLK;
   w.num_blocks = (long long)d->B * w.blocks_h * w.blocks_w;
-  const long long items = (long long)w.m_pairs * w.n_slices * w.tap_groups;
-  const long long pairs = sm_count() / 2;
-  long long s = pairs / items;                           // one wave of pairs ...
-  if (s > w.num_blocks / 8) s = w.num_blocks / 8;        // ... of at least 8 K steps each (partials cost bandwidth)
-  if (s > 128) s = 128;
-  if (s < 1) s = 1;
-  w.blocks_per_split = (w.num_blocks + s - 1) / s;
-  w.splits = (int)((w.num_blocks + w.blocks_per_split - 1) / w.blocks_per_split);
+  w.items = w.m_pairs * w.n_slices * w.tap_groups;
+  // measured (tools/wgrad_trace.py): an M=256 MMA costs ~50 cycles for N <= 96 (shared-memory operand reads) and a
+  // pair's SMs take in ~22 B/clk each from L2
+  const double mma = 4.0 * ((double)d->taps / w.tap_groups + (with_bias ? 1.0 / w.tap_groups : 0.0)) * (w.n_pair > 96 ? w.n_pair / 2.0 : 50.0);
+  const double ingest = (double)w.tx_bytes / 22.0;
+  w.kstep_cycles = mma > ingest ? mma : ingest;
   return true;
 }
 
 size_t wgrad_pair_workspace_bytes(const sininn_wgrad_desc* d) {
   WgPairPlan w;
   if (!plan_wgrad_pair(d, true, w)) return 0;
-  return (size_t)w.splits * d->taps * d->Cout * d->Cin * sizeof(float) + (size_t)w.splits * d->Cout * sizeof(float);
+  set_splits(w, sm_count() / 2);
+  return (size_t)w.splits * d->taps * d->Cout * d->Cin * sizeof(float) + (size_t)w.splits * d->Cout * sizeof(float) + 512;
 }
 
-// Launches the pair kernel; on success fills *splits / *bias_rows / *partial / *bias_partial for the reduction launch.
-int launch_wgrad_pair(const sininn_wgrad_desc* d, cudaStream_t st, int* splits, int* wide_is_dy, float** partial,
-                      float** bias_partial, int* bias_rows) {
-  WgPairPlan w;
-  if (!plan_wgrad_pair(d, d->dbias != nullptr, w)) return SININN_EUNSUPPORTED;
-  const size_t need_w = (size_t)w.splits * d->taps * d->Cout * d->Cin * sizeof(float);
-  const size_t need = need_w + (d->dbias ? (size_t)w.splits * d->Cout * sizeof(float) : 0);
-  if (!d->workspace || d->workspace_bytes < need) {
-    set_error("wgrad_tc(pair): workspace too small (%zu < %zu)", d->workspace_bytes, need);
-    return SININN_EWORKSPACE;
+// One pair-kernel launch + one reduction launch for n <= WG_MAX_PROBLEMS problems that all qualify for the pair kernel
+// (SININN_EUNSUPPORTED otherwise: the caller runs them one by one).  The workspace is carved up here.
+int launch_wgrad_pair_group(const sininn_wgrad_desc* ds, int n, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (n < 1 || n > WG_MAX_PROBLEMS) return SININN_EUNSUPPORTED;
+  WgPairPlan w[WG_MAX_PROBLEMS];
+  const int pairs = sm_count() / 2;
+  double work[WG_MAX_PROBLEMS], total = 0.0;
+  int items = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!plan_wgrad_pair(&ds[i], ds[i].dbias != nullptr, w[i])) return SININN_EUNSUPPORTED;
+    work[i] = (double)w[i].num_blocks * w[i].items * w[i].kstep_cycles;
+    total += work[i];
+    items += w[i].items;
+  }
+  if (items > pairs) return SININN_EUNSUPPORTED;
+  // pairs in proportion to the work, at least one per item; leftovers go to the problem with the most work per pair
+  int given[WG_MAX_PROBLEMS], used = 0;
+  for (int i = 0; i < n; ++i) {
+    int g = (int)(pairs * work[i] / total);
+    g = g / w[i].items * w[i].items;
+    if (g < w[i].items) g = w[i].items;
+    given[i] = g;
+    used += g;
+  }
+  while (used > pairs) {           // (rounding up the small ones can overshoot)
+    int worst = -1;
+    for (int i = 0; i < n; ++i)
+      if (given[i] > w[i].items && (worst < 0 || work[i] / given[i] < work[worst] / given[worst])) worst = i;
+    if (worst < 0) return SININN_EUNSUPPORTED;
+    given[worst] -= w[worst].items;
+    used -= w[worst].items;
+  }
+  for (;;) {
+    int best = -1;
+    for (int i = 0; i < n; ++i)
+      if (used + w[i].items <= pairs && (best < 0 || work[i] / given[i] > work[best] / given[best])) best = i;
+    if (best < 0) break;
+    given[best] += w[best].items;
+    used += w[best].items;
   }
   EncodeTiledFn encode = get_encode();
   if (!encode) {
     set_error("wgrad_tc(pair): cuTensorMapEncodeTiled not available from the driver");
     return SININN_ECUDA;
   }
-  const void* wide = w.wide_is_dy ? d->dy : d->x;
-  const void* narrow = w.wide_is_dy ? d->x : d->dy;
-  const int wide_stride = w.wide_is_dy ? d->dy_stride : d->x_stride;
-  const int narrow_stride = w.wide_is_dy ? d->x_stride : d->dy_stride;
-  CUtensorMap tmW, tmN;
-  for (int which = 0; which < 2; ++which) {
-    const void* base = which == 0 ? wide : narrow;
-    const int C = which == 0 ? w.Cw : w.Cn;
-    const int stride = which == 0 ? wide_stride : narrow_stride;
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
-    cuuint64_t strides[3] = {(cuuint64_t)stride * 2, (cuuint64_t)d->W * stride * 2, (cuuint64_t)d->H * d->W * stride * 2};
-    const bool halo = which == 1 && d->taps == 9;
-    cuuint32_t box[4] = {64, (cuuint32_t)(halo ? w.halo_w : WP_BLK), (cuuint32_t)(halo ? WP_BLK + 2 : WP_BLK), 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(which == 0 ? &tmW : &tmN, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
-                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("wgrad_tc(pair): cuTensorMapEncodeTiled failed with %d (C=%d stride=%d)", (int)r, C, stride);
-      return SININN_ECUDA;
+  WgTensorMaps T;
+  WgGroupParams G;
+  WgReduceParams R;
+  R.njobs = 0;
+  G.nprob = n;
+  G.pair_begin[0] = 0;
+  size_t off = 0;
+  size_t max_smem = 0;
+  for (int i = 0; i < n; ++i) {
+    const sininn_wgrad_desc* d = &ds[i];
+    WgPairPlan& wi = w[i];
+    set_splits(wi, given[i]);
+    const size_t need_w = (size_t)wi.splits * d->taps * d->Cout * d->Cin * sizeof(float);
+    const size_t need_b = d->dbias ? (size_t)wi.splits * d->Cout * sizeof(float) : 0;
+    uint8_t* base = reinterpret_cast<uint8_t*>(workspace) + off;
+    off += (need_w + need_b + 255) & ~(size_t)255;
+    if (!workspace || off > workspace_bytes) {
+      set_error("wgrad_tc(pair): workspace too small (%zu < %zu)", workspace_bytes, off);
+      return SININN_EWORKSPACE;
     }
-  }
-  const int tma_out = (w.Cn % 4) == 0 ? 1 : 0;
-  CUtensorMap tmP = tmW;
-  if (tma_out) {
-    cuuint64_t dims[3] = {(cuuint64_t)w.Cn, (cuuint64_t)w.Cw, (cuuint64_t)w.splits * d->taps};
-    cuuint64_t strides[2] = {(cuuint64_t)w.Cn * 4, (cuuint64_t)w.Cw * w.Cn * 4};
-    cuuint32_t box[3] = {32, 32, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&tmP, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d->workspace, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("wgrad_tc(pair): tensor map (partials) failed with %d (Cn=%d Cw=%d)", (int)r, w.Cn, w.Cw);
-      return SININN_ECUDA;
+    const void* wide = wi.wide_is_dy ? d->dy : d->x;
+    const void* narrow = wi.wide_is_dy ? d->x : d->dy;
+    const int wide_stride = wi.wide_is_dy ? d->dy_stride : d->x_stride;
+    const int narrow_stride = wi.wide_is_dy ? d->x_stride : d->dy_stride;
+    for (int which = 0; which < 2; ++which) {
+      const void* ptr = which == 0 ? wide : narrow;
+      const int C = which == 0 ? wi.Cw : wi.Cn;
+      const int stride = which == 0 ? wide_stride : narrow_stride;
+      cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+      cuuint64_t strides[3] = {(cuuint64_t)stride * 2, (cuuint64_t)d->W * stride * 2, (cuuint64_t)d->H * d->W * stride * 2};
+      const bool halo = which == 1 && d->taps == 9;
+      cuuint32_t box[4] = {64, (cuuint32_t)(halo ? wi.halo_w : WP_BLK), (cuuint32_t)(halo ? WP_BLK + 2 : WP_BLK), 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = encode(&T.m[3 * i + which], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("wgrad_tc(pair): cuTensorMapEncodeTiled failed with %d (C=%d stride=%d)", (int)r, C, stride);
+        return SININN_ECUDA;
+      }
     }
+    const int tma_out = (wi.Cn % 4) == 0 ? 1 : 0;
+    T.m[3 * i + 2] = T.m[3 * i];
+    if (tma_out) {
+      cuuint64_t dims[3] = {(cuuint64_t)wi.Cn, (cuuint64_t)wi.Cw, (cuuint64_t)wi.splits * d->taps};
+      cuuint64_t strides[2] = {(cuuint64_t)wi.Cn * 4, (cuuint64_t)wi.Cw * wi.Cn * 4};
+      cuuint32_t box[3] = {32, 32, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = encode(&T.m[3 * i + 2], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("wgrad_tc(pair): tensor map (partials) failed with %d (Cn=%d Cw=%d)", (int)r, wi.Cn, wi.Cw);
+        return SININN_ECUDA;
+      }
+    }
+    WgPairParams& p = G.prob[i];
+    p.tma_out = tma_out;
+    p.trace = i == 0 ? g_wg_trace : nullptr;
+    p.B = d->B; p.H = d->H; p.W = d->W; p.taps = d->taps;
+    p.narrow_is_x = wi.wide_is_dy;
+    p.Cw = wi.Cw; p.Cn = wi.Cn;
+    p.n_pair = wi.n_pair; p.n_half = wi.n_half; p.n_slices = wi.n_slices;
+    p.tap_groups = wi.tap_groups; p.m_pairs = wi.m_pairs; p.splits = wi.splits;
+    for (int k = 0; k <= WP_MAX_GROUPS; ++k) p.tap_begin[k] = k <= wi.tap_groups ? wi.tap_begin[k] : d->taps;
+    p.blocks_h = wi.blocks_h; p.blocks_w = wi.blocks_w; p.num_blocks = wi.num_blocks; p.blocks_per_split = wi.blocks_per_split;
+    p.stages = wi.stages; p.halo_w = wi.halo_w;
+    p.stage_bytes = wi.stage_bytes; p.narrow_bytes = wi.narrow_bytes; p.tx_bytes = wi.tx_bytes;
+    p.partial = reinterpret_cast<float*>(base);
+    p.bias_mode = d->dbias ? (wi.wide_is_dy ? 1 : 2) : 0;
+    p.bias_partial = d->dbias ? reinterpret_cast<float*>(base + need_w) : nullptr;
+    G.pair_begin[i + 1] = G.pair_begin[i] + wi.items * wi.splits;
+    const size_t smem = (size_t)p.stages * p.stage_bytes + WP_ONES_BYTES + sizeof(WgPairBarriers) + 1024;
+    if (smem > max_smem) max_smem = smem;
+    reduce_add_job(R, d, p.partial, wi.splits, wi.wide_is_dy, p.bias_partial, d->dbias ? wi.splits : 0, sm_count() * 8 / n);
   }
-  WgPairParams p;
-  p.tma_out = tma_out;
-  p.trace = g_wg_trace;
-  p.B = d->B; p.H = d->H; p.W = d->W; p.taps = d->taps;
-  p.narrow_is_x = w.wide_is_dy;
-  p.Cw = w.Cw; p.Cn = w.Cn;
-  p.n_pair = w.n_pair; p.n_half = w.n_half; p.n_slices = w.n_slices;
-  p.tap_groups = w.tap_groups; p.m_pairs = w.m_pairs; p.splits = w.splits;
-  for (int i = 0; i <= WP_MAX_GROUPS; ++i) p.tap_begin[i] = i <= w.tap_groups ? w.tap_begin[i] : d->taps;
-  p.blocks_h = w.blocks_h; p.blocks_w = w.blocks_w; p.num_blocks = w.num_blocks; p.blocks_per_split = w.blocks_per_split;
-  p.stages = w.stages; p.halo_w = w.halo_w;
-  p.stage_bytes = w.stage_bytes; p.narrow_bytes = w.narrow_bytes; p.tx_bytes = w.tx_bytes;
-  p.partial = reinterpret_cast<float*>(d->workspace);
-  p.bias_mode = d->dbias ? (w.wide_is_dy ? 1 : 2) : 0;
-  p.bias_partial = d->dbias ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d->workspace) + need_w) : nullptr;
+  for (int i = n; i < WG_MAX_PROBLEMS; ++i) { G.prob[i] = G.prob[0]; G.pair_begin[i + 1] = G.pair_begin[n]; }
+  for (int i = 3 * n; i < 3 * WG_MAX_PROBLEMS; ++i) T.m[i] = T.m[0];
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -494,20 +715,25 @@ int launch_wgrad_pair(const sininn_wgrad_desc* d, cudaStream_t st, int* splits, 
     }
     attr_set[dev] = true;
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + WP_ONES_BYTES + sizeof(WgPairBarriers) + 1024;
-  const unsigned grid = 2u * (unsigned)(w.m_pairs * w.n_slices * w.tap_groups * w.splits);
-  launch_k(wgrad_pair_kernel, dim3(grid), dim3(WP_THREADS), smem, st, tmW, tmN, tmP, p);
+  const unsigned grid = 2u * (unsigned)G.pair_begin[n];
+  launch_k(wgrad_pair_kernel, dim3(grid), dim3(WP_THREADS), max_smem, st, T, G);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("wgrad_tc(pair): launch failed: %s", cudaGetErrorString(e));
     return SININN_ECUDA;
   }
-  *splits = w.splits;
-  *wide_is_dy = w.wide_is_dy;
-  *partial = p.partial;
-  *bias_partial = p.bias_partial;
-  *bias_rows = d->dbias ? w.splits : 0;
-  return SININN_OK;
+  return launch_reduce_group(R, st);
+}
+
+size_t wgrad_pair_group_workspace_bytes(const sininn_wgrad_desc* ds, int n) {
+  // every problem may end up with all the pairs of the device (upper bound of its splits)
+  size_t tot = 0;
+  for (int i = 0; i < n; ++i) {
+    const size_t b = wgrad_pair_workspace_bytes(&ds[i]);
+    if (b == 0) return 0;
+    tot += b;
+  }
+  return tot;
 }
 
 }  // namespace tc

@@ -7,8 +7,10 @@ namespace tc {
 
 // wgrad_pair.cu: the CTA-pair kernel (taken whenever the wide operand has more than 128 channels)
 size_t wgrad_pair_workspace_bytes(const sininn_wgrad_desc* d);
-int launch_wgrad_pair(const sininn_wgrad_desc* d, cudaStream_t st, int* splits, int* wide_is_dy, float** partial,
-                      float** bias_partial, int* bias_rows);
+size_t wgrad_pair_group_workspace_bytes(const sininn_wgrad_desc* ds, int n);
+int launch_wgrad_pair_group(const sininn_wgrad_desc* ds, int n, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int launch_reduce_single(const sininn_wgrad_desc* d, cudaStream_t st, const float* partial, int splits, int wide_is_dy,
+                         const float* bias_partial, int bias_rows);
 
 constexpr int NUM_THREADS = 192;
 constexpr int SMEM_RING_BUDGET = 200 * 1024;
@@ -267,104 +269,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   }
 }
 
-// dw[co][ci][tap] (+)= sum_split partial[split][tap][m][n]; (co,ci) = (m,n) when the wide operand is dy, else (n,m).
-// Fixed summation order => bit-reproducible gradients.  RG threads share one output vector: thread g sums splits
-// g, g+RG, g+2RG, ... (independent loads in flight instead of one dependent chain of `splits` L2 round trips), the
-// RG partial sums are combined in a fixed order through shared memory.
-constexpr int RG = 8;
-template <int VEC>
-__global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cw, int Cn,
-                                                              int wide_is_dy, int Cout, int Cin, float* __restrict__ dw, int accumulate,
-                                                              const float* __restrict__ bias_partial, int bias_rows, int bias_n,
-                                                              float* __restrict__ dbias, int dbias_accumulate) {
-  pdl_wait();
-  pdl_trigger();
-  __shared__ float red[RG][32][VEC + 1];
-  if (bias_partial != nullptr) {
-    // fixed-order sum of the per-split column sums of dy: one warp per channel (lane l adds rows l, l+32, ... in
-    // order, then a fixed xor tree), spread over the blocks instead of one thread walking all rows of a channel
-    const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
-    for (int c = blockIdx.x * 8 + wid; c < bias_n; c += gridDim.x * 8) {
-      float s = 0.f;
-      for (int k = ln; k < bias_rows; k += 32) s += __ldcs(bias_partial + (long long)k * bias_n + c);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (ln == 0) dbias[c] = dbias_accumulate ? dbias[c] + s : s;
-    }
-  }
-  const long long per = (long long)taps * Cw * Cn;
-  const long long perv = per / VEC;
-  const int o = threadIdx.x & 31, g = threadIdx.x >> 5;            // output slot within the block, split group
-  for (long long base = (long long)blockIdx.x * 32; base < perv; base += (long long)gridDim.x * 32) {
-    const long long iv = base + o;
-    const long long idx = iv * VEC;
-    float s[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) s[e] = 0.f;
-    if (iv < perv) {
-#pragma unroll 8
-      for (int k = g; k < splits; k += RG) {
-        if (VEC == 4) {
-          const float4 t = __ldcs(reinterpret_cast<const float4*>(partial + k * per + idx));
-          s[0] += t.x; s[VEC > 1 ? 1 : 0] += t.y; s[VEC > 2 ? 2 : 0] += t.z; s[VEC > 3 ? 3 : 0] += t.w;
-        } else {
-          s[0] += partial[k * per + idx];
-        }
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) red[g][o][e] = s[e];
-    __syncthreads();
-    if (g == 0 && iv < perv) {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        float t = red[0][o][e];
-#pragma unroll
-        for (int q = 1; q < RG; ++q) t += red[q][o][e];
-        s[e] = t;
-      }
-      const int n0 = (int)(idx % Cn);
-      long long r = idx / Cn;
-      const int m = (int)(r % Cw);
-      const int tap = (int)(r / Cw);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const int n = n0 + e;
-        const int co = wide_is_dy ? m : n, ci = wide_is_dy ? n : m;
-        float* out = dw + ((long long)co * Cin + ci) * taps + tap;
-        *out = accumulate ? *out + s[e] : s[e];
-      }
-    }
-    __syncthreads();
-  }
-}
-
 struct WgradPlan {
   int wide_is_dy, Cw, Cn, n_pad, n_groups, taps_per_cta, tap_groups, m_tiles, splits, stages;
   int blocks_h, blocks_w;
   long long num_blocks, blocks_per_split;
   uint32_t stage_bytes, narrow_bytes;
 };
-
-// second launch: fixed-order sum of the per-split partials into OIHW (and of the per-split dy column sums)
-static int launch_reduce(const sininn_wgrad_desc* d, cudaStream_t st, const float* partial, int splits, int wide_is_dy,
-                         const float* bias_partial, int bias_rows) {
-  const int Cw = wide_is_dy ? d->Cout : d->Cin, Cn = wide_is_dy ? d->Cin : d->Cout;
-  const long long per = (long long)d->taps * Cw * Cn;
-  if ((Cn % 4) == 0) {
-    long long g = (per / 4 + 31) / 32;
-    if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
-    launch_k(wgrad_tc_reduce_kernel<4>, dim3((int)g), dim3(256), 0, st, partial, splits, d->taps, Cw, Cn, wide_is_dy, d->Cout, d->Cin,
-             d->dw, d->accumulate, bias_partial, bias_rows, d->Cout, d->dbias, d->dbias_accumulate);
-  } else {
-    long long g = (per + 31) / 32;
-    if (g > (long long)sm_count() * 8) g = (long long)sm_count() * 8;
-    launch_k(wgrad_tc_reduce_kernel<1>, dim3((int)g), dim3(256), 0, st, partial, splits, d->taps, Cw, Cn, wide_is_dy, d->Cout, d->Cin,
-             d->dw, d->accumulate, bias_partial, bias_rows, d->Cout, d->dbias, d->dbias_accumulate);
-  }
-  SININN_CHECK_LAUNCH("wgrad_tc(reduce)");
-  return SININN_OK;
-}
 
 static bool plan_wgrad(const sininn_wgrad_desc* d, WgradPlan& w) {
   w.wide_is_dy = d->Cout >= d->Cin ? 1 : 0;
@@ -415,6 +325,43 @@ size_t sininn_wgrad_workspace_bytes(const sininn_wgrad_desc* d, int tensor_core)
   return tcb > simt ? tcb : simt;
 }
 
+size_t sininn_wgrad_group_workspace_bytes(const sininn_wgrad_desc* descs, int n) {
+  if (!descs || n < 1) return 0;
+  const size_t g = sininn::tc::wgrad_pair_group_workspace_bytes(descs, n);
+  size_t single = 0;
+  for (int i = 0; i < n; ++i) {
+    const size_t b = sininn_wgrad_workspace_bytes(&descs[i], 1);
+    if (b > single) single = b;
+  }
+  return g > single ? g : single;
+}
+
+int sininn_wgrad_tc_group(const sininn_wgrad_desc* descs, int n, void* workspace, size_t workspace_bytes, sininn_stream_t stream) {
+  SININN_CHECK_ARG(descs && n >= 1, "wgrad_tc_group: no problems");
+  for (int i = 0; i < n; ++i) {
+    const sininn_wgrad_desc* d = &descs[i];
+    SININN_CHECK_ARG(d->x && d->dy && d->dw, "wgrad_tc_group: null pointer in problem %d", i);
+    SININN_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "wgrad_tc_group: bad shape in problem %d", i);
+    SININN_CHECK_ARG(d->taps == 1 || d->taps == 9, "wgrad_tc_group: taps must be 1 or 9");
+    SININN_CHECK_ARG(d->x_dtype == SININN_BF16 && d->dy_dtype == SININN_BF16, "wgrad_tc_group: operands must be bf16");
+    SININN_CHECK_ARG(aligned16(d->x) && aligned16(d->dy) && (d->x_stride % 8) == 0 && (d->dy_stride % 8) == 0,
+                     "wgrad_tc_group: TMA needs 16-byte aligned operands with pixel strides that are multiples of 8 channels "
+                     "(x stride %d, dy stride %d)", d->x_stride, d->dy_stride);
+  }
+  if (n <= 4) {
+    const int rc = sininn::tc::launch_wgrad_pair_group(descs, n, workspace, workspace_bytes, sininn::as_stream(stream));
+    if (rc != SININN_EUNSUPPORTED) return rc;
+  }
+  for (int i = 0; i < n; ++i) {       // not a group the pair kernel takes: one by one (stream order makes sharing the workspace safe)
+    sininn_wgrad_desc d = descs[i];
+    d.workspace = workspace;
+    d.workspace_bytes = workspace_bytes;
+    const int rc = sininn_wgrad_tc(&d, stream);
+    if (rc != SININN_OK) return rc;
+  }
+  return SININN_OK;
+}
+
 int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
   using namespace sininn::tc;
   SININN_CHECK_ARG(d && d->x && d->dy && d->dw, "wgrad_tc: null pointer");
@@ -425,10 +372,7 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
                    "wgrad_tc: TMA needs 16-byte aligned operands with pixel strides that are multiples of 8 channels "
                    "(x stride %d, dy stride %d)", d->x_stride, d->dy_stride);
   {
-    int splits = 0, wide_is_dy = 0, bias_rows = 0;
-    float *partial = nullptr, *bias_partial = nullptr;
-    const int rc = launch_wgrad_pair(d, as_stream(stream), &splits, &wide_is_dy, &partial, &bias_partial, &bias_rows);
-    if (rc == SININN_OK) return launch_reduce(d, as_stream(stream), partial, splits, wide_is_dy, bias_partial, bias_rows);
+    const int rc = launch_wgrad_pair_group(d, 1, d->workspace, d->workspace_bytes, as_stream(stream));
     if (rc != SININN_EUNSUPPORTED) return rc;
   }
   WgradPlan w;
@@ -496,7 +440,7 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
   cudaStream_t st = as_stream(stream);
   launch_k(wgrad_tc_kernel, dim3(grid), dim3(NUM_THREADS), smem, st, tmW, tmN, p);
   SININN_CHECK_LAUNCH("wgrad_tc");
-  return launch_reduce(d, st, p.partial, w.splits, w.wide_is_dy, p.bias_partial, bias_rows);
+  return launch_reduce_single(d, st, p.partial, w.splits, w.wide_is_dy, p.bias_partial, bias_rows);
 }
 
 }  // extern "C"

@@ -188,6 +188,9 @@ class RunCtx:
         self.direct_grad = direct_grad      # accumulate weight gradients straight into param.grad (no autograd add)
         self.direct = set()
         self.wstream = None                 # side stream for the parameter-gradient launches (Plan.backward sets it)
+        # tensor-core path: weight gradients are collected and launched in groups of up to WGRAD_GROUP problems (the
+        # convolutions of a coupling block): fewer pixel splits per problem, see sininn_wgrad_tc_group
+        self.pending = []
 
     def grad_out(self, param):
         """(tensor, accumulate) the weight-gradient kernels should write to for `param`."""
@@ -217,11 +220,38 @@ class RunCtx:
 
 
 # ----------------------------------------------------------------------------- subnets
+WGRAD_GROUP = max(1, min(4, int(os.environ.get("SININN_WGRAD_GROUP", "4"))))
+
+
+def flush_param_grads(ctx):
+    """Launch the collected weight/bias gradients as one group (on the side stream when there is one)."""
+    jobs, ctx.pending = ctx.pending, []
+    if not jobs:
+        return
+    if ctx.wstream is not None:
+        cur = torch.cuda.current_stream()
+        ctx.wstream.wait_stream(cur)
+        with torch.cuda.stream(ctx.wstream):
+            K.wgrad_group(jobs)
+        for j in jobs:
+            for t in (j[0], j[1]):
+                t.record_stream(ctx.wstream)      # keep the operands alive until the side stream has consumed them
+        return
+    K.wgrad_group(jobs)
+
+
 def _param_grads(ctx, conv, x, dy, geom, taps):
     """Weight and bias gradients of one conv from its input x and output gradient dy.  On the tensor-core path the
     bias gradient (column sums of dy) is produced by the weight-gradient launches themselves; otherwise by colsum."""
     wants_w = conv.weight.requires_grad
     wants_b = conv.bias is not None and conv.bias.requires_grad
+    if ctx.tc and wants_w and WGRAD_GROUP > 1 and x.stride(0) % 8 == 0 and dy.stride(0) % 8 == 0:
+        g, acc = ctx.grad_out(conv.weight)
+        gb, accb = ctx.grad_out(conv.bias) if wants_b else (None, False)
+        ctx.pending.append((x, dy, geom, taps, g, acc, gb, accb))
+        if len(ctx.pending) >= WGRAD_GROUP:
+            flush_param_grads(ctx)
+        return
     if ctx.wstream is not None and (wants_w or wants_b):
         # parameter gradients are leaves of the backward pass: nothing downstream reads them before the pass ends,
         # so they go to a side stream and fill the gaps of the data-gradient chain (joined in Plan.backward)
@@ -569,6 +599,7 @@ class CouplingOp:
                 bf = None
             if bf is not None:
                 tr.bf[st.dst] = bf
+        flush_param_grads(ctx)
 
 
 def glow_op(channels, s1, s2, clamp):
@@ -741,7 +772,9 @@ class Plan:
             dU, _ = K.nchw_to_nhwc(dy, None, None)
             undo = self.core                       # executed order was reversed(core)
         tr = Trunk(U, dU)
-        if self.side_wgrad and self.direct_grad and dy.is_cuda and K.__name__ == "sin_inn_b200.kernels":
+        # side stream only on the tensor-core path: its operands are private bf16 copies, while the fp32 path reads views
+        # of the live trunk that the next half-step overwrites in place (record_stream does not order that write)
+        if self.side_wgrad and self.direct_grad and dy.is_cuda and cfg.tc and K.__name__ == "sin_inn_b200.kernels":
             ctx.wstream = self._wgrad_stream()
         # 2. walk the executed ops backwards
         for i, op in enumerate(undo):
@@ -770,6 +803,7 @@ class Plan:
                 U = op.apply_nhwc(tr.U, not rev)
                 dU = op.apply_nhwc(tr.dU, rev, grad=True)
                 tr.set(U, dU)
+        flush_param_grads(ctx)
         if ctx.wstream is not None:
             torch.cuda.current_stream().wait_stream(ctx.wstream)       # parameter gradients complete with the pass
         if not need_dx:

@@ -369,6 +369,28 @@ def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False, dbias=None
     return dw
 
 
+def wgrad_group(jobs):
+    """Several tensor-core weight (+ bias) gradients in ONE pair of launches (sininn_wgrad_tc_group).
+    jobs: list of (x, dy, geom, taps, dw, accumulate, dbias, dbias_accumulate) as for wgrad()."""
+    n = len(jobs)
+    arr = (WgradDesc * n)()
+    flops = 0.0
+    for d, (x, dy, geom, taps, dw, acc, dbias, dbacc) in zip(arr, jobs):
+        x, dy = _view2d(x), _view2d(dy)
+        d.B, d.H, d.W = geom
+        d.Cin, d.Cout, d.taps = x.shape[1], dy.shape[1], taps
+        d.x, d.x_dtype, d.x_stride = x.data_ptr(), dtype_code(x), x.stride(0)
+        d.dy, d.dy_dtype, d.dy_stride = dy.data_ptr(), dtype_code(dy), dy.stride(0)
+        d.dw, d.accumulate = dw.data_ptr(), int(acc)
+        d.dbias, d.dbias_accumulate = _p(dbias), int(dbacc)
+        d.workspace, d.workspace_bytes = 0, 0
+        flops += 2.0 * geom[0] * geom[1] * geom[2] * d.Cin * d.Cout * taps
+    lib = load()
+    ws = _workspace(jobs[0][0].device, "wgrad", lib.sininn_wgrad_group_workspace_bytes(arr, n))
+    check(_run("wgrad", lambda: lib.sininn_wgrad_tc_group(arr, n, ws.data_ptr(), ws.numel(), stream_ptr()), 2, flops),
+          "wgrad_tc_group")
+
+
 # ----------------------------------------------------------------------------- caller-side fusions
 def sqdiff(a, b, scale, want_grad=False):
     """scale * sum((a-b)^2) -> 0-dim tensor; optional gradient 2*scale*(a-b)."""

@@ -226,6 +226,11 @@ def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None, mas
     return out
 
 
+def wgrad_group(jobs):
+    for x, dy, geom, taps, dw, acc, dbias, dbacc in jobs:
+        wgrad(x, dy, geom, taps, dw, accumulate=acc, tensor_core=True, dbias=dbias, dbias_accumulate=dbacc)
+
+
 def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False, dbias=None, dbias_accumulate=False):
     B, H, W = geom
     if dbias is not None:

@@ -1,0 +1,11 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+{
+echo "== full gpu tests"; python -m pytest tests -q -x -m gpu 2>&1 | tail -8
+echo "== bench group 4"; python bench.py --no-cpu-baseline --no-inference 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['profile_ms_per_step'])"
+echo "== bench group 2"; SININN_WGRAD_GROUP=2 python bench.py --no-cpu-baseline --no-inference 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['profile_ms_per_step'])"
+echo "== bench group 1"; SININN_WGRAD_GROUP=1 python bench.py --no-cpu-baseline --no-inference 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['profile_ms_per_step'])"
+echo "== timeline eager PDL off"; SININN_PDL=0 MODE=eager python tools/step_timeline.py 2>&1 | grep -v -i warn | head -14
+} > gpurun_out/r2e.log 2>&1
+tail -60 gpurun_out/r2e.log
