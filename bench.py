@@ -109,7 +109,8 @@ def run_reference(args):
         "impl": "reference", "metric": "INN train-step patches/sec", "value": r["value"], "unit": "patches/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SRF scale4 c4 lr_window10 256x256 train step, CPU, batch 2 per step", **WORKLOAD},
+        "config": {"workload": "SRF scale4 c4 lr_window10 256x256 train step, CPU (oracle port of archs.py, all host threads), "
+                               "batch 2 per step", **{**WORKLOAD, "batch_per_gpu": None, "batch_per_step_cpu": batch}},
         "cpu_baseline": {"value": r["value"], "unit": "patches/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -92,10 +92,42 @@ int sininn_permute_nhwc_pair(const float* in_a, float* out_a, const float* in_b,
 int sininn_gather_windows_u8(const uint8_t* video, int T, int H, int W, int C, const int32_t* centers, int B, int win,
                              int y0, int x0, int ph, int pw, float* out, sininn_stream_t stream);
 
+/* The same gather with one patch origin PER SAMPLE: crops_yx is a device int32 [B][2] of (y0, x0) on this video's
+ * grid (the caller keeps y0 + ph <= H, x0 + pw <= W).  This is the "trained on patches" sampler the reference's
+ * transform hook (data.py:43-44) leaves unused: every sample of a batch gets its own random crop. */
+int sininn_gather_windows_u8_crops(const uint8_t* video, int T, int H, int W, int C, const int32_t* centers, int B, int win,
+                                   const int32_t* crops_yx, int ph, int pw, float* out, sininn_stream_t stream);
+
 /* Inference output path (lit_wrapper.py:117-121, transforms.ToPILImage on every frame): fp32 NCHW frames in [0, 1] ->
  * uint8 HWC, out[b][h][w][c] = (uint8) trunc(255 * clamp(in[b][c][h][w], 0, 1)).  For in-range values this is
  * pic.mul(255).byte(); out-of-range values are clamped (the reference's cast is undefined there). */
 int sininn_quantize_u8_hwc(const float* in, uint8_t* out, int B, int C, int H, int W, sininn_stream_t stream);
+
+/* Entry of the inverse pass: cat((lr, z), dim=1) of lit_wrapper.py:41-42 / 110-111 folded into the NCHW -> channels-last
+ * change (plus the trailing PermuteRandom through chan_map and the bf16 operand copy, as sininn_nchw_to_nhwc).
+ * lr [B][L][HW], z [B][Z][HW] fp32; out [B][HW][L+Z].  z == NULL: z = temp * N(0,1) is drawn on the device
+ * (Philox4x32-10 keyed by `seed`, element i of the z tensor uses counter offset + i; Box-Muller), which replaces the
+ * torch.randn + cat + copy of the reference; z_out (may be NULL) then receives the drawn z in NCHW.  step_ptr (may be
+ * NULL): device int32 counter; the counter offset becomes offset + *step_ptr * step_stride, so a launch replayed from a
+ * CUDA graph draws a new z whenever the counter (e.g. the optimizer's device-side step count) has advanced. */
+int sininn_latent_to_nhwc(const float* lr, int L, const float* z, int Z, int B, int HW, const int32_t* chan_map, float* out,
+                          void* bf16_out, int c0, int c1, unsigned long long seed, unsigned long long offset, float temp,
+                          float* z_out, const int32_t* step_ptr, unsigned long long step_stride, sininn_stream_t stream);
+
+/* FrEIA ActNorm (offered, commented out, at archs.py:40-44) on a channels-last fp32 matrix [npix][C], in place:
+ *   inverse=0: u <- u * exp(log_scale[c]) + bias[c];   inverse=1: u <- (u - bias[c]) * exp(-log_scale[c]) */
+int sininn_channel_affine(float* u, long long npix, int C, const float* log_scale, const float* bias, int inverse,
+                          sininn_stream_t stream);
+/* Its backward from the OUTPUT: on entry u = y, du = dL/dy of the direction `inverse` that produced y; on exit u = x,
+ * du = dL/dx, and dlog_scale / dbias [C] (+)= the parameter gradients (deterministic two-pass sums; C <= 256). */
+size_t sininn_channel_affine_bwd_workspace_bytes(void);
+int sininn_channel_affine_bwd(float* u, float* du, long long npix, int C, const float* log_scale, const float* bias, int inverse,
+                              float* dlog_scale, float* dbias, int accumulate, void* workspace, size_t workspace_bytes,
+                              sininn_stream_t stream);
+/* Log-determinant of a coupling half (FrEIA GLOWCouplingBlock.jacobian / last_jac): out[b] (+)= sign * sum over sample
+ * b's pixels and L channels of g(s), g as in SININN_GLOW / SININN_IRN.  s [B * pix_per_sample][L], pixel stride s_stride. */
+int sininn_logscale_sum(const float* s, int s_stride, int B, long long pix_per_sample, int L, int kind, float clamp, float sign,
+                        float* out, int accumulate, sininn_stream_t stream);
 
 /* ---------------------------------------------------------------- coupling
  * One half of an affine coupling, in place on a channel slice u[npix][L]
@@ -244,6 +276,14 @@ int sininn_sqdiff_nchw(const float* a, const float* b, long long n, float scale,
  * grad_out [B][C][HW] = dloss/dy.  workspace >= 2 * sininn_sqdiff_workspace_bytes(B*C*HW). */
 int sininn_inn_fwd_loss(const float* y, const float* lr, int B, int C, int L, long long HW, float w_rec, float w_nll,
                         float* loss_out, float* grad_out, void* workspace, size_t workspace_bytes, sininn_stream_t stream);
+/* loss.mmd (loss.py:9-36): multi-kernel inverse-multiquadric MMD between the flattened batches x, y [b][D] (b <= 64),
+ * kernels (0.2,2),(1.5,2),(3.0,2) or, rev != 0, (0.2,0.1),(0.2,0.5),(0.2,2).  loss_out[0] = scale * mmd; grad_x_out
+ * (may be NULL) [b][D] = scale * d mmd / d x.  Device-agnostic restatement (the reference hard-codes .to('cuda')):
+ * Gram matrices by a split over D with a fixed-order second pass, so the value is bit-reproducible. */
+size_t sininn_mmd_workspace_bytes(int b, long long D);
+int sininn_mmd(const float* x, const float* y, int b, long long D, int rev, float scale, float* loss_out, float* grad_x_out,
+               void* workspace, size_t workspace_bytes, sininn_stream_t stream);
+
 /* torch.optim.Adam semantics (lit_wrapper.py:134-137: L2 weight decay folded into the gradient) over a
  * flat fp32 arena; step is the 1-based step count. */
 int sininn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
@@ -255,6 +295,12 @@ int sininn_adam_step(float* param, const float* grad, float* exp_avg, float* exp
 int sininn_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                          float lr, float beta1, float beta2, float eps, float weight_decay, int* step_state,
                          float grad_scale, sininn_stream_t stream);
+
+/* The same with the gradient given as the sum of TWO arenas (grad + grad_b, grad_b may be NULL): the two halves of a
+ * training step accumulate into separate arenas on separate streams; adding them inside Adam saves a pass. */
+int sininn_adam_step_dev2(float* param, const float* grad, const float* grad_b, float* exp_avg, float* exp_avg_sq, long long n,
+                          float lr, float beta1, float beta2, float eps, float weight_decay, int* step_state,
+                          float grad_scale, sininn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -113,3 +113,45 @@ class PermuteRandom(nn.Module):
 
     def output_dims(self, input_dims):
         return input_dims
+
+
+class ActNorm(nn.Module):
+    """Per-channel affine normalisation with data-dependent initialisation (the node the reference leaves commented
+    out at /root/reference/archs.py:40-44), restated from the published pre-v0.2 source: scale/bias are [1,C,1,1]
+    parameters; the first batch sets scale = log(1/std_c), bias = -mean_c(x * exp(scale)); forward x*exp(scale)+bias;
+    jacobian = sum(scale) * H*W per sample."""
+
+    def __init__(self, dims_in, init_data=None):
+        super().__init__()
+        self.dims_in = dims_in[0]
+        param_dims = [1, self.dims_in[0]] + [1 for _ in range(len(self.dims_in) - 1)]
+        self.scale = nn.Parameter(torch.zeros(*param_dims))
+        self.bias = nn.Parameter(torch.zeros(*param_dims))
+        self.init_on_next_batch = True
+        if init_data is not None:
+            self.initialize_with_data(init_data)
+
+        def on_load_state_dict(*args):
+            self.init_on_next_batch = False
+        self._register_load_state_dict_pre_hook(on_load_state_dict)
+
+    def initialize_with_data(self, data):
+        assert all(data.shape[i + 1] == self.dims_in[i] for i in range(len(self.dims_in)))
+        self.scale.data.view(-1)[:] = torch.log(1 / data.transpose(0, 1).contiguous().view(self.dims_in[0], -1).std(dim=-1))
+        data = data * self.scale.exp()
+        self.bias.data.view(-1)[:] = -data.transpose(0, 1).contiguous().view(self.dims_in[0], -1).mean(dim=-1)
+        self.init_on_next_batch = False
+
+    def forward(self, x, rev=False):
+        if self.init_on_next_batch:
+            self.initialize_with_data(x[0])
+        if not rev:
+            return [x[0] * self.scale.exp() + self.bias]
+        return [(x[0] - self.bias) / self.scale.exp()]
+
+    def jacobian(self, x, rev=False):
+        j = self.scale.sum() * np.prod(self.dims_in[1:])
+        return (-j if rev else j).repeat(x[0].shape[0])
+
+    def output_dims(self, input_dims):
+        return input_dims

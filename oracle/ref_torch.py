@@ -250,6 +250,26 @@ def latent_nll(z):
     return torch.mean(z ** 2)
 
 
+def mmd(x, y, rev=False):
+    """loss.py:9-36 restated device-agnostically (the reference hard-codes .to('cuda') at loss.py:27-29): multi-kernel
+    inverse-multiquadric MMD between the flattened batches."""
+    kernels = [(0.2, 0.1), (0.2, 0.5), (0.2, 2)] if rev else [(0.2, 2), (1.5, 2), (3.0, 2)]
+    b = x.shape[0]
+    xf, yf = x.reshape(b, -1), y.reshape(b, -1)
+    xx, yy, xy = xf @ xf.t(), yf @ yf.t(), xf @ yf.t()
+    rx = xx.diag().unsqueeze(0).expand_as(xx)
+    ry = yy.diag().unsqueeze(0).expand_as(yy)
+    dxx = torch.clamp(rx.t() + rx - 2.0 * xx, 0, float("inf"))
+    dyy = torch.clamp(ry.t() + ry - 2.0 * yy, 0, float("inf"))
+    dxy = torch.clamp(rx.t() + ry - 2.0 * xy, 0, float("inf"))
+    XX, YY, XY = torch.zeros_like(xx), torch.zeros_like(xx), torch.zeros_like(xx)
+    for C, a in kernels:
+        XX = XX + C ** a * ((C + dxx) / a) ** -a
+        YY = YY + C ** a * ((C + dyy) / a) ** -a
+        XY = XY + C ** a * ((C + dxy) / a) ** -a
+    return torch.mean(XX + YY - 2.0 * XY)
+
+
 def train_step(inn, optimizer, hr, lr, z, opt):
     """lit_wrapper.py:36-56,76 without Lightning and without loss.mmd (lambda 0 and
     CUDA-hard-coded, loss.py:27-29): zero_grad; forward pass + L2(+nll) loss +

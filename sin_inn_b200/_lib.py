@@ -79,6 +79,16 @@ SIGNATURES = {
     "sininn_permute_nhwc_pair": (C.c_int, [_vp, _vp, _vp, _vp, _c_ll, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
     "sininn_gather_windows_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_int, _vp, _vp]),
+    "sininn_gather_windows_u8_crops": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int,
+                                                 _vp, _vp]),
+    "sininn_latent_to_nhwc": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int,
+                                        C.c_ulonglong, C.c_ulonglong, C.c_float, _vp, _vp, C.c_ulonglong, _vp]),
+    "sininn_channel_affine": (C.c_int, [_vp, _c_ll, C.c_int, _vp, _vp, C.c_int, _vp]),
+    "sininn_channel_affine_bwd_workspace_bytes": (C.c_size_t, []),
+    "sininn_channel_affine_bwd": (C.c_int, [_vp, _vp, _c_ll, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_size_t, _vp]),
+    "sininn_logscale_sum": (C.c_int, [_vp, C.c_int, C.c_int, _c_ll, C.c_int, C.c_int, C.c_float, C.c_float, _vp, C.c_int, _vp]),
+    "sininn_mmd_workspace_bytes": (C.c_size_t, [C.c_int, _c_ll]),
+    "sininn_mmd": (C.c_int, [_vp, _vp, C.c_int, _c_ll, C.c_int, C.c_float, _vp, _vp, _vp, C.c_size_t, _vp]),
     "sininn_quantize_u8_hwc": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "sininn_coupling_apply": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _c_ll, C.c_int, C.c_int, C.c_float,
                                         C.c_int, _vp, _vp]),
@@ -109,6 +119,8 @@ SIGNATURES = {
                                    C.c_int, C.c_float, _vp]),
     "sininn_adam_step_dev": (C.c_int, [_vp, _vp, _vp, _vp, _c_ll, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                        _vp, C.c_float, _vp]),
+    "sininn_adam_step_dev2": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _c_ll, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        _vp, C.c_float, _vp]),
 }
 
 _lib = None

@@ -11,6 +11,7 @@ names / shapes / initialisation (so reference checkpoints load and ``lit_wrapper
 ``hidden`` (subnet width, reference hard-codes 256) and ``precision`` ("bf16" | "fp32").
 Inputs must be CUDA tensors: there is no CPU implementation in this package.
 """
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -168,6 +169,9 @@ class HaarDownsampling(Fm._PlanModule):
         return E.ResampleOp(1)
 
     def forward(self, x, rev=False):
+        # bookkeeping attributes of the reference (archs.py:184-185, 193-194); nothing reads last_jac
+        self.elements = x.shape[1] * x.shape[2] * x.shape[3]
+        self.last_jac = self.elements / 4 * np.log(16.0 if rev else 1 / 16.0)
         return E.run_network(self._plan(), x, rev, E.default_config())
 
 

@@ -377,13 +377,15 @@ __global__ void adam_tick_kernel(int* __restrict__ state, float b1, float b2) {
 
 __global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                        float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
-                                                       float wd, const int* __restrict__ state, float gscale) {
+                                                       float wd, const int* __restrict__ state, float gscale,
+                                                       const float* __restrict__ g2) {
   pdl_wait();
   pdl_trigger();
   const float bc1 = reinterpret_cast<const float*>(state)[1], bc2_sqrt = reinterpret_cast<const float*>(state)[2];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float w = p[i];
-    float gr = g[i] * gscale + wd * w;
+    const float gsum = g2 != nullptr ? g[i] + g2[i] : g[i];        // second gradient arena of the two-stream step
+    float gr = gsum * gscale + wd * w;
     float mi = b1 * m[i] + (1.f - b1) * gr;
     float vi = b2 * v[i] + (1.f - b2) * gr * gr;
     m[i] = mi;
@@ -592,8 +594,20 @@ int sininn_adam_step_dev(float* param, const float* grad, float* exp_avg, float*
   const int block = 256, grid = grid_for(n, block);
   launch_k(adam_tick_kernel, dim3(1), dim3(1), 0, as_stream(stream), step_state, beta1, beta2);
   launch_k(adam_dev_kernel, dim3(grid), dim3(block), 0, as_stream(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                         weight_decay, step_state, grad_scale);
+                                                         weight_decay, step_state, grad_scale, (const float*)nullptr);
   SININN_CHECK_LAUNCH("adam_step_dev");
+  return SININN_OK;
+}
+
+int sininn_adam_step_dev2(float* param, const float* grad, const float* grad_b, float* exp_avg, float* exp_avg_sq, long long n,
+                          float lr, float beta1, float beta2, float eps, float weight_decay, int* step_state,
+                          float grad_scale, sininn_stream_t stream) {
+  SININN_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step_state && n > 0, "adam_step_dev2: bad arguments");
+  const int block = 256, grid = grid_for(n, block);
+  launch_k(adam_tick_kernel, dim3(1), dim3(1), 0, as_stream(stream), step_state, beta1, beta2);
+  launch_k(adam_dev_kernel, dim3(grid), dim3(block), 0, as_stream(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                         weight_decay, step_state, grad_scale, grad_b);
+  SININN_CHECK_LAUNCH("adam_step_dev2");
   return SININN_OK;
 }
 

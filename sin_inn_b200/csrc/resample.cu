@@ -303,7 +303,8 @@ __global__ void __launch_bounds__(256) quantize_u8_hwc_kernel(const float* __res
 // divided by 255 (data.py:31-45: imread of 2*lr_window+1 files, concatenate(axis=-1), transpose(-1, 0, 1), / 255.)
 __global__ void __launch_bounds__(256) gather_windows_u8_kernel(const uint8_t* __restrict__ video, int T, int H, int W, int C,
                                                                 const int32_t* __restrict__ centers, int win, int y0, int x0,
-                                                                int ph, int pw, float* __restrict__ out, long long total) {
+                                                                int ph, int pw, float* __restrict__ out, long long total,
+                                                                const int32_t* __restrict__ crops) {
   pdl_wait();
   pdl_trigger();
   const int F = 2 * win + 1;
@@ -316,7 +317,8 @@ __global__ void __launch_bounds__(256) gather_windows_u8_kernel(const uint8_t* _
     const int b = (int)(r / F);
     int t = __ldg(centers + b) - win + f;
     t = t < 0 ? 0 : (t >= T ? T - 1 : t);                  // (the reference never indexes outside the clip)
-    const uint8_t* src = video + (((long long)t * H + (y0 + y)) * W + (x0 + x)) * C;
+    const int yy = crops ? __ldg(crops + 2 * b) : y0, xx = crops ? __ldg(crops + 2 * b + 1) : x0;   // per-sample patch origin
+    const uint8_t* src = video + (((long long)t * H + (yy + y)) * W + (xx + x)) * C;
     float* dst = out + ((long long)b * F * C + (long long)f * C) * plane + (long long)y * pw + x;
     for (int c = 0; c < C; ++c) dst[c * plane] = __fdiv_rn((float)src[c], 255.0f);      // bit-exact with the reference's "/ 255."
   }
@@ -431,8 +433,20 @@ int sininn_gather_windows_u8(const uint8_t* video, int T, int H, int W, int C, c
   SININN_CHECK_ARG(y0 >= 0 && x0 >= 0 && ph > 0 && pw > 0 && y0 + ph <= H && x0 + pw <= W, "gather_windows_u8: crop outside the frame");
   const long long total = (long long)B * (2 * win + 1) * ph * pw;
   launch_k(gather_windows_u8_kernel, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), video, T, H, W, C, centers, win, y0, x0,
-           ph, pw, out, total);
+           ph, pw, out, total, (const int32_t*)nullptr);
   SININN_CHECK_LAUNCH("gather_windows_u8");
+  return SININN_OK;
+}
+
+int sininn_gather_windows_u8_crops(const uint8_t* video, int T, int H, int W, int C, const int32_t* centers, int B, int win,
+                                   const int32_t* crops_yx, int ph, int pw, float* out, sininn_stream_t stream) {
+  SININN_CHECK_ARG(video && centers && crops_yx && out && T > 0 && H > 0 && W > 0 && C > 0 && B > 0 && win >= 0,
+                   "gather_windows_u8_crops: bad arguments");
+  SININN_CHECK_ARG(ph > 0 && pw > 0 && ph <= H && pw <= W, "gather_windows_u8_crops: patch larger than the frame");
+  const long long total = (long long)B * (2 * win + 1) * ph * pw;
+  launch_k(gather_windows_u8_kernel, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), video, T, H, W, C, centers, win, 0, 0,
+           ph, pw, out, total, crops_yx);
+  SININN_CHECK_LAUNCH("gather_windows_u8_crops");
   return SININN_OK;
 }
 

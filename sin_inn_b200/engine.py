@@ -60,12 +60,55 @@ def _trace(label, t):
         TRACE.append((label, t.detach().float().cpu().clone()))
 
 
+class LatentInput:
+    """Input of the inverse pass given as its two parts, (lr, z) of lit_wrapper.py:41-42 / 110-111, instead of their
+    concatenation: the cat (and, with z=None, the draw z = temp * N(0,1)) happens inside the kernel that brings the
+    input into the channels-last trunk.  step_state: device int32 counter that advances the random stream (a CUDA-graph
+    replay then draws a fresh z each step).  Not differentiable w.r.t. lr / z (the reference never asks for that)."""
+
+    def __init__(self, lr, z=None, z_dims=None, temp=1.0, seed=0, offset=0, step_state=None):
+        if z is None and z_dims is None:
+            raise SininnError("LatentInput: give z or z_dims")
+        self.lr, self.z = lr, z
+        self.z_dims = z.shape[1] if z is not None else int(z_dims)
+        self.temp, self.seed, self.offset, self.step_state = float(temp), int(seed), int(offset), step_state
+
+    @property
+    def device(self):
+        return self.lr.device
+
+    @property
+    def is_cuda(self):
+        return self.lr.is_cuda
+
+    @property
+    def requires_grad(self):
+        return False
+
+    @property
+    def shape(self):
+        b, l, h, w = self.lr.shape
+        return torch.Size((b, l + self.z_dims, h, w))
+
+    @property
+    def dtype(self):
+        return self.lr.dtype
+
+    def dim(self):
+        return 4
+
+    def detach(self):
+        return self
+
+
 # ----------------------------------------------------------------------------- packed-weight cache
 _pack_cache = {}     # id(param) -> (weakref(param), {(mode, dtype): (version, data_ptr, packed)})
 
 
 def invalidate_packs():
-    """Forget packed weights (call after parameters were modified outside torch's version tracking)."""
+    """Forget packed weights.  Call after parameters were modified outside torch's version tracking: an update through
+    ``param.data`` or through a raw pointer (the fused Adam kernel, a replayed CUDA graph) does not bump ``_version``,
+    so the packed bf16 copies the kernels read would silently stay stale."""
     _pack_cache.clear()
     _pack_epoch[0] += 1
 
@@ -502,6 +545,43 @@ class LinearOp:
         return []
 
 
+class ActNormOp:
+    """FrEIA ActNorm (offered, commented out, at archs.py:40-44): y = x * exp(scale_c) + bias_c, reverse
+    (y - bias_c) / exp(scale_c); log|det J| = H*W*sum(scale).  scale / bias are trainable [1, C, 1, 1] parameters; with
+    `module.init_on_next_batch` the first batch sets them so that the output has zero mean / unit std per channel."""
+    kind = "actnorm"
+
+    def __init__(self, module):
+        self.m = module
+
+    def parameters(self):
+        return [self.m.scale, self.m.bias]
+
+    def _maybe_init(self, tr):
+        m = self.m
+        if getattr(m, "init_on_next_batch", False):
+            with torch.no_grad():                       # one-time statistics of the first batch (plain torch reductions)
+                flat = tr.mat()
+                ls = torch.log(1.0 / flat.std(dim=0))
+                m.scale.data.view(-1).copy_(ls)
+                m.bias.data.view(-1).copy_(-(flat * ls.exp()).mean(dim=0))
+            m.init_on_next_batch = False
+
+    def apply(self, tr, rev):
+        self._maybe_init(tr)
+        tr.bf = {}
+        K.channel_affine(tr.U, self.m.scale.detach().view(-1), self.m.bias.detach().view(-1), rev)
+
+    def backward(self, ctx, tr, rev):
+        m = self.m
+        gs, acc_s = ctx.grad_out(m.scale)
+        gb, acc_b = ctx.grad_out(m.bias)
+        if acc_s != acc_b:                              # (both come from the same arena or both are fresh)
+            raise SininnError("ActNorm: scale and bias gradients must be accumulated the same way")
+        tr.bf = {}
+        K.channel_affine_bwd(tr.U, tr.dU, m.scale.detach().view(-1), m.bias.detach().view(-1), rev, gs.view(-1), gb.view(-1), acc_s)
+
+
 class HalfStep:
     """dst <- affine(dst; nets(src)).  kind: 'glow' (one net, output = [s | t]), 'irn_affine' (s from
     nets[0], t from nets[1]), 'irn_add' (dst <- dst + sign * nets[0](src))."""
@@ -535,8 +615,10 @@ class CouplingOp:
         return self.steps[0] if rev else self.steps[-1]
 
     # ---- value pass
-    def run(self, ctx, tr, rev):
+    def run(self, ctx, tr, rev, logdet=None):
+        """logdet (optional fp32 [B] tensor): accumulates the block's log|det J| per sample (FrEIA's last_jac)."""
         steps = self.steps[::-1] if rev else self.steps
+        B = tr.U.shape[0]
         for i, st in enumerate(steps):
             L = st.dst[1] - st.dst[0]
             nxt = steps[i + 1].src if i + 1 < len(steps) else None
@@ -545,11 +627,15 @@ class CouplingOp:
             if st.kind == "glow":
                 a, _ = st.nets[0].fwd(ctx, tr, st.src)
                 tr.invalidate(*st.dst)
+                if logdet is not None:
+                    K.logscale_sum(a[:, :L], B, GLOW, st.clamp, -1.0 if rev else 1.0, logdet, True)
                 bf = K.coupling_apply(u, a[:, :L], a[:, L:], GLOW, st.clamp, rev, want_bf)
             elif st.kind == "irn_affine":
                 s, _ = st.nets[0].fwd(ctx, tr, st.src)
                 t, _ = st.nets[1].fwd(ctx, tr, st.src)
                 tr.invalidate(*st.dst)
+                if logdet is not None:
+                    K.logscale_sum(s, B, IRN, st.clamp, -1.0 if rev else 1.0, logdet, True)
                 bf = K.coupling_apply(u, s, t, IRN, st.clamp, rev, want_bf)
             else:
                 f, _ = st.nets[0].fwd(ctx, tr, st.src)
@@ -676,7 +762,10 @@ class Plan:
         return ps
 
     def _check_input(self, x, rev):
-        require_cuda(x, "network input")
+        if isinstance(x, LatentInput):
+            if not rev or not self.body:
+                raise SininnError("a LatentInput (lr, z) is the input of the inverse pass of a network with coupling blocks")
+        require_cuda(x.lr if isinstance(x, LatentInput) else x, "network input")
         if x.dtype != torch.float32 or x.dim() != 4:
             raise SininnError(f"network input must be a 4-D fp32 NCHW tensor, got {x.dtype} {tuple(x.shape)}")
         want = self.out_dims if rev else self.in_dims
@@ -707,6 +796,8 @@ class Plan:
                 x = op.apply_nchw(x, rev)
             return x
         dev = x.device
+        if x.is_cuda and isinstance(x, LatentInput) and x.z is not None and x.z.device != dev:
+            raise SininnError("LatentInput: lr and z live on different devices")
         if not rev:
             for op in self.prefix:
                 x = op.apply_nchw(x, False)
@@ -717,7 +808,11 @@ class Plan:
             seq = self.core[::-1]
             cmap = self.tail_perm.gather_map(dev, True) if self.tail_perm is not None else None
             hint = self._hint(seq[0] if seq else None, rev, ctx)
-            U, bf = K.nchw_to_nhwc(x, cmap, hint)
+            if isinstance(x, LatentInput):
+                U, bf = K.latent_to_nhwc(x.lr, x.z, x.z_dims, cmap, hint, seed=x.seed, offset=x.offset, temp=x.temp,
+                                         step_state=x.step_state)
+            else:
+                U, bf = K.nchw_to_nhwc(x, cmap, hint)
         tr = Trunk(U)
         if bf is not None:
             tr.bf[hint] = bf
@@ -732,6 +827,8 @@ class Plan:
                 tr.set(U, None, {hint: bf} if bf is not None else None)
             elif op.kind == "linear":
                 tr.set(op.apply(tr.U, rev))
+            elif op.kind == "actnorm":
+                op.apply(tr, rev)
             else:
                 tr.set(op.apply_nhwc(tr.U, rev))
             _trace(op.kind, tr.U)
@@ -799,6 +896,8 @@ class Plan:
             elif op.kind == "linear":
                 # executed y = A x (A = W or W^-1): the input is A^-1 y, its gradient A^T dy
                 tr.set(op.apply(tr.U, not rev), op.apply(tr.dU, rev, grad=True))
+            elif op.kind == "actnorm":
+                op.backward(ctx, tr, rev)
             else:
                 U = op.apply_nhwc(tr.U, not rev)
                 dU = op.apply_nhwc(tr.dU, rev, grad=True)
@@ -823,25 +922,42 @@ class _INNFunction(torch.autograd.Function):
     """Differentiable net(x) / net(x, rev=True) that keeps only its output for backward."""
 
     @staticmethod
-    def forward(ctx, x, plan, rev, cfg, *params):
-        y = plan.execute(x.detach(), rev, cfg)
+    def forward(ctx, x, plan, rev, cfg, latent, *params):
+        y = plan.execute(latent if latent is not None else x.detach(), rev, cfg)
         ctx.plan, ctx.rev, ctx.cfg = plan, rev, cfg
         ctx.params = params
-        ctx.need_dx = x.requires_grad
+        ctx.need_dx = x.requires_grad and latent is None
         ctx.save_for_backward(y)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         (y,) = ctx.saved_tensors
-        dx, grads = ctx.plan.backward(y, dy, ctx.rev, ctx.cfg, need_dx=ctx.need_dx)
+        with _device_ctx(y):
+            dx, grads = ctx.plan.backward(y, dy, ctx.rev, ctx.cfg, need_dx=ctx.need_dx)
         gl = [grads.get(id(p)) if p.requires_grad else None for p in ctx.params]
-        return (dx, None, None, None, *gl)
+        return (dx, None, None, None, None, *gl)
+
+
+def _device_ctx(t):
+    return torch.cuda.device(t.device)
 
 
 def run_network(plan, x, rev, cfg):
+    """net(x) / net(x, rev=True).  Everything is launched on x's device and on that device's current stream: the
+    kernels take raw pointers and the library uses the current CUDA device (stream, SM count, function attributes),
+    so the device is made current for the duration of the call (the reference loads checkpoints onto cuda:{gpu_ids[0]}
+    while another device may be current, main.py:127)."""
+    latent = x if isinstance(x, LatentInput) else None
+    if latent is not None:
+        x = latent.lr
+    require_cuda(x, "network input")
     params = plan.parameters()
-    needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
-    if not needs_grad:
-        return plan.execute(x, rev, cfg)
-    return _INNFunction.apply(x, plan, bool(rev), cfg, *params)
+    for p in params:
+        if p.device != x.device:
+            raise SininnError(f"network parameters live on {p.device} but the input is on {x.device}")
+    needs_grad = torch.is_grad_enabled() and ((x.requires_grad and latent is None) or any(p.requires_grad for p in params))
+    with _device_ctx(x):
+        if not needs_grad:
+            return plan.execute(latent if latent is not None else x, rev, cfg)
+        return _INNFunction.apply(x, plan, bool(rev), cfg, latent, *params)

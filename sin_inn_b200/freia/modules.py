@@ -77,8 +77,20 @@ class GLOWCouplingBlock(_PlanModule):
         return E.glow_op(self.dims_in[0], self.s1, self.s2, self.clamp)
 
     def jacobian(self, x, c=[], rev=False):
-        raise E.SininnError("log-Jacobian is not tracked: the reference never reads it "
-                            "(last_jac is written and never consumed; loss.py:38-39 uses mean(z^2))")
+        """log|det J| per sample of the block evaluated at x in direction `rev` (FrEIA returns the `last_jac` its
+        forward stored: sum over channels and pixels of the clamped log-scales of both halves, negated for rev).
+        The reference never reads it (loss.py:38-39 uses mean(z^2)); it is computed here on demand by re-running
+        the block's value pass with one reduction launch per half."""
+        x0 = x[0] if isinstance(x, (list, tuple)) else x
+        E.require_cuda(x0, "jacobian input")
+        cfg = E.default_config()
+        with torch.no_grad(), E._device_ctx(x0):
+            U, _ = E.K.nchw_to_nhwc(x0.detach(), None, None)
+            tr = E.Trunk(U)
+            logdet = torch.zeros(x0.shape[0], dtype=torch.float32, device=x0.device)
+            op = self._plan().core[0]
+            op.run(E.RunCtx(cfg, packs=None), tr, rev, logdet=logdet)
+        return logdet
 
 
 class PermuteRandom(_PlanModule):
@@ -102,6 +114,41 @@ class PermuteRandom(_PlanModule):
 
     def jacobian(self, x, rev=False):
         return 0.0
+
+
+class ActNorm(_PlanModule):
+    """Per-channel affine normalisation with data-dependent initialisation: forward x * exp(scale) + bias, reverse
+    (x - bias) / exp(scale); log|det J| = H*W * sum(scale).  Offered (commented out) at archs.py:40-44."""
+
+    def __init__(self, dims_in, init_data=None):
+        super().__init__()
+        self.dims_in = tuple(dims_in[0])
+        param_dims = [1, self.dims_in[0]] + [1] * (len(self.dims_in) - 1)
+        self.scale = nn.Parameter(torch.zeros(*param_dims))
+        self.bias = nn.Parameter(torch.zeros(*param_dims))
+        self.init_on_next_batch = True
+        if init_data is not None:
+            self.initialize_with_data(init_data)
+
+        def on_load_state_dict(*args):
+            self.init_on_next_batch = False
+        self._register_load_state_dict_pre_hook(on_load_state_dict)
+
+    def initialize_with_data(self, data):
+        with torch.no_grad():
+            flat = data.transpose(0, 1).contiguous().view(self.dims_in[0], -1)
+            self.scale.data.view(-1)[:] = torch.log(1 / flat.std(dim=-1))
+            scaled = data * self.scale.exp()
+            self.bias.data.view(-1)[:] = -scaled.transpose(0, 1).contiguous().view(self.dims_in[0], -1).mean(dim=-1)
+        self.init_on_next_batch = False
+
+    def _op(self):
+        return E.ActNormOp(self)
+
+    def jacobian(self, x, rev=False):
+        x0 = x[0] if isinstance(x, (list, tuple)) else x
+        j = self.scale.detach().sum() * (x0.shape[2] * x0.shape[3])
+        return (-j if rev else j).repeat(x0.shape[0])
 
 
 class Fixed1x1Conv(_PlanModule):

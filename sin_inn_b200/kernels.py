@@ -122,6 +122,78 @@ def nchw_to_nhwc(x, chan_map=None, bf16_range=None):
     return out, bf
 
 
+def latent_to_nhwc(lr, z, z_dims, chan_map=None, bf16_range=None, seed=0, offset=0, temp=1.0, z_out=None, step_state=None):
+    """cat((lr, z), 1) -> channels-last [B, h, w, L+Z] in one pass (lit_wrapper.py:41-42).  z=None: z = temp*N(0,1)
+    is drawn inside the kernel (counter offset + step_state[0] * z.numel() when a device step counter is given)."""
+    _lib.require_cuda(lr)
+    lr = lr.contiguous()
+    B, L, h, w = lr.shape
+    if z is not None:
+        z = z.contiguous()
+        if tuple(z.shape) != (B, z_dims, h, w):
+            raise _lib.SininnError(f"latent_to_nhwc: z must be {(B, z_dims, h, w)}, got {tuple(z.shape)}")
+    Cc = L + z_dims
+    out = torch.empty(B, h, w, Cc, dtype=torch.float32, device=lr.device)
+    bf, c0, c1 = None, 0, 0
+    if bf16_range is not None:
+        c0, c1 = bf16_range
+        bf = torch.empty(B * h * w, c1 - c0, dtype=torch.bfloat16, device=lr.device)
+    stride = B * z_dims * h * w
+    check(_run("layout", lambda: load().sininn_latent_to_nhwc(lr.data_ptr(), L, _p(z), z_dims, B, h * w, _p(chan_map), out.data_ptr(), _p(bf),
+                                                              c0, c1, int(seed) & (2**64 - 1), int(offset), float(temp), _p(z_out),
+                                                              _p(step_state), stride, stream_ptr()), 1, 0.0, 8.0 * out.numel()),
+          "latent_to_nhwc")
+    return out, bf
+
+
+def channel_affine(U, log_scale, bias, inverse):
+    """ActNorm on a channels-last fp32 tensor [..., C], in place."""
+    c = U.shape[-1]
+    check(_run("misc", lambda: load().sininn_channel_affine(U.data_ptr(), U.numel() // c, c, log_scale.data_ptr(), bias.data_ptr(),
+                                                            int(inverse), stream_ptr()), 1, 0.0, 8.0 * U.numel()), "channel_affine")
+    return U
+
+
+def channel_affine_bwd(U, dU, log_scale, bias, inverse, dls, dbias, accumulate):
+    """U: y -> x, dU: dy -> dx in place; dls / dbias [C] (+)= parameter gradients."""
+    c = U.shape[-1]
+    lib = load()
+    ws = _workspace(U.device, "affine_bwd", lib.sininn_channel_affine_bwd_workspace_bytes())
+    check(_run("misc", lambda: lib.sininn_channel_affine_bwd(U.data_ptr(), dU.data_ptr(), U.numel() // c, c, log_scale.data_ptr(),
+                                                             bias.data_ptr(), int(inverse), dls.data_ptr(), dbias.data_ptr(), int(accumulate),
+                                                             ws.data_ptr(), ws.numel(), stream_ptr()), 2, 0.0, 16.0 * U.numel()),
+          "channel_affine_bwd")
+
+
+def logscale_sum(s, B, kind, clamp, sign, out, accumulate):
+    """out[b] (+)= sign * sum_{pixels of sample b, channels} g(s);  s: [npix, L] fp32 view."""
+    s = _view2d(s)
+    npix, L = s.shape
+    check(_run("misc", lambda: load().sininn_logscale_sum(s.data_ptr(), s.stride(0), B, npix // B, L, kind, float(clamp), float(sign),
+                                                          out.data_ptr(), int(accumulate), stream_ptr()), 1), "logscale_sum")
+    return out
+
+
+def mmd(x, y, rev, scale, want_grad=False):
+    """scale * loss.mmd(x, y, rev) (loss.py:9-36) -> (0-dim loss, gradient w.r.t. x or None); x, y [b, ...] fp32."""
+    _lib.require_cuda(x)
+    x, y = x.contiguous(), y.contiguous()
+    b = x.shape[0]
+    D = x.numel() // b
+    if y.numel() != x.numel():
+        raise _lib.SininnError("mmd: x and y must have the same number of elements")
+    lib = load()
+    nbytes = lib.sininn_mmd_workspace_bytes(b, D)
+    if nbytes == 0:
+        raise _lib.SininnError(f"mmd: unsupported batch size {b} (1..64)")
+    ws = _workspace(x.device, "mmd", nbytes)
+    out = torch.empty((), dtype=torch.float32, device=x.device)
+    grad = torch.empty_like(x) if want_grad else None
+    check(_run("loss", lambda: lib.sininn_mmd(x.data_ptr(), y.data_ptr(), b, D, int(bool(rev)), float(scale), out.data_ptr(), _p(grad),
+                                              ws.data_ptr(), ws.numel(), stream_ptr()), 4 if want_grad else 3), "mmd")
+    return out, grad
+
+
 def nhwc_to_nchw(x, chan_map=None):
     _lib.require_cuda(x)
     B, h, w, c = x.shape
@@ -147,15 +219,25 @@ def permute_nhwc(x, chan_map, bf16_range=None):
     return out, bf
 
 
-def gather_windows_u8(video, centers, win, crop=None):
+def gather_windows_u8(video, centers, win, crop=None, crops_yx=None, patch=None):
     """video: uint8 [T, H, W, C] on the device; centers: int32 [B] on the device; crop = (y0, x0, ph, pw) or None.
-    Returns fp32 [B, (2*win+1)*C, ph, pw] = the frame windows / 255 (data.py:31-45 without the PNG decode)."""
+    Returns fp32 [B, (2*win+1)*C, ph, pw] = the frame windows / 255 (data.py:31-45 without the PNG decode).
+    crops_yx (int32 [B, 2] on the device) + patch = (ph, pw): one patch origin per sample instead of one crop."""
     _lib.require_cuda(video)
     if video.dtype != torch.uint8 or video.dim() != 4 or not video.is_contiguous():
         raise _lib.SininnError("gather_windows_u8: video must be a contiguous uint8 [T, H, W, C] tensor")
     T, H, W, Cc = video.shape
-    y0, x0, ph, pw = crop if crop is not None else (0, 0, H, W)
     B = centers.numel()
+    if crops_yx is not None:
+        ph, pw = patch
+        if crops_yx.dtype != torch.int32 or tuple(crops_yx.shape) != (B, 2) or not crops_yx.is_contiguous():
+            raise _lib.SininnError("gather_windows_u8: crops_yx must be a contiguous int32 [B, 2] tensor")
+        out = torch.empty(B, (2 * win + 1) * Cc, ph, pw, dtype=torch.float32, device=video.device)
+        check(_run("misc", lambda: load().sininn_gather_windows_u8_crops(video.data_ptr(), T, H, W, Cc, centers.data_ptr(), B, int(win),
+                                                                         crops_yx.data_ptr(), int(ph), int(pw), out.data_ptr(), stream_ptr()),
+                   1, 0.0, 5.0 * out.numel()), "gather_windows_u8_crops")
+        return out
+    y0, x0, ph, pw = crop if crop is not None else (0, 0, H, W)
     out = torch.empty(B, (2 * win + 1) * Cc, ph, pw, dtype=torch.float32, device=video.device)
     check(_run("misc", lambda: load().sininn_gather_windows_u8(video.data_ptr(), T, H, W, Cc, centers.data_ptr(), B, int(win), int(y0),
                                           int(x0), int(ph), int(pw), out.data_ptr(), stream_ptr()), 1, 0.0, 5.0 * out.numel()),
@@ -431,9 +513,11 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, st
                                   int(step), float(grad_scale), stream_ptr()), 1, 0.0, 28.0 * n), "adam_step")
 
 
-def adam_step_dev(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step_state, grad_scale=1.0):
-    """Adam with the step count on the device (int32[3] state tensor): replayable from a CUDA graph."""
+def adam_step_dev(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step_state, grad_scale=1.0, grad_b=None):
+    """Adam with the step count on the device (int32[3] state tensor): replayable from a CUDA graph.
+    grad_b: optional second gradient arena, added to grad inside the kernel."""
     n = param.numel()
-    check(_run("adam", lambda: load().sininn_adam_step_dev(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
-                                      n, float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
-                                      step_state.data_ptr(), float(grad_scale), stream_ptr()), 2, 0.0, 28.0 * n), "adam_step_dev")
+    check(_run("adam", lambda: load().sininn_adam_step_dev2(param.data_ptr(), grad.data_ptr(), _p(grad_b), exp_avg.data_ptr(),
+                                      exp_avg_sq.data_ptr(), n, float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                      step_state.data_ptr(), float(grad_scale), stream_ptr()), 2, 0.0, 28.0 * n + (4.0 * n if grad_b is not None else 0.0)),
+          "adam_step_dev")

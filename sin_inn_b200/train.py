@@ -2,8 +2,10 @@
 (lit_wrapper.py:29-77, 79-89, 91-128) on top of the drop-in nets, plus the data-parallel plumbing.
 
 Differences from the reference, all outside the INN kernels:
-  * loss.mmd is not evaluated (its lambdas default to 0, main.py:53,56, and the reference code
-    hard-codes .to('cuda'), loss.py:27-29);
+  * loss.mmd (loss.py:9-36) is a fused, device-agnostic kernel (kernels.mmd) and is only evaluated when its lambda
+    is non-zero (the defaults are 0, main.py:53,56; the reference evaluates it regardless and multiplies by 0);
+  * z is drawn on the device inside the kernel that concatenates (lr, z) into the inverse pass's input
+    (engine.LatentInput) unless the caller passes a z tensor;
   * parameters and gradients live in two flat fp32 arenas so that the optimizer is ONE fused Adam
     launch and data parallelism is ONE NCCL all-reduce per step (the reference gets an implicit DDP
     all-reduce inside each of its two manual_backward calls);
@@ -44,20 +46,25 @@ class _FusedLoss(torch.autograd.Function):
 
 
 def forward_half_loss(lr_z_hat, lr, w_rec, w_nll):
-    """lit_wrapper.py:45-48: w_rec * reconstruction(lr_z_hat[:, :lr_dims], lr) + w_nll * latent_nll(lr_z_hat[:, lr_dims:])."""
-    if not lr_z_hat.is_cuda:
-        loss = w_rec * reconstruction(lr_z_hat[:, :lr.shape[1]], lr)
-        return loss + w_nll * latent_nll(lr_z_hat[:, lr.shape[1]:]) if w_nll else loss
+    """lit_wrapper.py:45-48: w_rec * reconstruction(lr_z_hat[:, :lr_dims], lr) + w_nll * latent_nll(lr_z_hat[:, lr_dims:]).
+    One fused pass (value + gradient); CUDA tensors only, like everything on the product path."""
     loss, grad = K.inn_fwd_loss(lr_z_hat.detach(), lr, w_rec, w_nll)
     return _FusedLoss.apply(lr_z_hat, loss, grad)
 
 
 def inverse_half_loss(hr_hat, hr, w_rec):
     """lit_wrapper.py:53-55: w_rec * reconstruction(hr_hat, hr)."""
-    if not hr_hat.is_cuda:
-        return w_rec * reconstruction(hr_hat, hr)
     loss, grad = K.sqdiff(hr_hat.detach(), hr, w_rec / hr_hat.numel(), want_grad=True)
     return _FusedLoss.apply(hr_hat, loss, grad)
+
+
+def mmd(x, y, rev=False, weight=1.0):
+    """weight * loss.mmd(x, y, rev) (loss.py:9-36), differentiable w.r.t. x: Gram matrices, kernel sums and the
+    gradient come from kernels.mmd (no .to('cuda') hard-code, runs on whatever CUDA device x is on)."""
+    loss, grad = K.mmd(x.detach(), y.detach(), rev, weight, want_grad=x.requires_grad)
+    if grad is None:
+        return loss
+    return _FusedLoss.apply(x, loss, grad)
 
 
 class FlatParams:
@@ -107,10 +114,26 @@ class FusedAdam:
     def zero_grad(self):
         self.fp.zero_grad()
 
-    def step(self, grad_scale=1.0):
+    def state_dict(self):
+        """Moments, step count and hyper-parameters (what Lightning's resume_from_checkpoint restores for the reference,
+        main.py:115-116).  The flat parameter arena itself is saved through the module's own state_dict()."""
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "state": self.state.clone(),
+                "steps": self.steps, "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.wd}
+
+    def load_state_dict(self, sd):
+        if sd["exp_avg"].numel() != self.exp_avg.numel():
+            raise ValueError(f"optimizer state holds {sd['exp_avg'].numel()} elements, the model has {self.exp_avg.numel()}")
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.state.copy_(sd["state"])              # in place: a captured CUDA graph keeps reading this buffer
+        self.steps = int(sd["steps"])
+        self.lr, self.betas, self.eps, self.wd = sd["lr"], tuple(sd["betas"]), sd["eps"], sd["weight_decay"]
+
+    def step(self, grad_scale=1.0, grad_b=None):
+        """grad_b: optional second gradient arena added to the first inside the kernel (the two-stream step)."""
         self.steps += 1
         K.adam_step_dev(self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas, self.eps, self.wd,
-                        self.state, grad_scale)
+                        self.state, grad_scale, grad_b=grad_b)
         # the kernel wrote the parameters through raw pointers (no tensor version bump): drop the packed copies
         engine.invalidate_packs()
 
@@ -131,10 +154,12 @@ class SingleVideoTrainer:
         # partial waves of the other.  The second half accumulates into its own gradient arena (no read-modify-write
         # race on the shared .grad) and the two arenas are added before the all-reduce.  SININN_OVERLAP=0: one stream.
         self.overlap = (os.environ.get("SININN_OVERLAP", "1") != "0" and self.flat.flat.is_cuda and hasattr(inn, "plan"))
+        self.rank = dist.get_rank() if (world_size > 1 and dist.is_initialized()) else 0
         if self.overlap:
             inn.plan().side_wgrad = os.environ.get("SININN_SIDE_WGRAD", "1") != "0"
             self.grad_b = torch.zeros_like(self.flat.grad)
             self.side = torch.cuda.Stream(device=self.flat.flat.device)
+            self.comm = torch.cuda.Stream(device=self.flat.flat.device)
 
     def _point_grads(self, arena):
         off = 0
@@ -143,24 +168,59 @@ class SingleVideoTrainer:
             p.grad = arena[off:off + m].view(p.shape)
             off += m
 
+    def state_dict(self):
+        """Everything a restart needs: the network's parameters (reference key names) and the optimizer state."""
+        return {"inn": self.inn.state_dict(), "optim": self.optim.state_dict()}
+
+    def load_state_dict(self, sd):
+        self.inn.load_state_dict(sd["inn"])        # copies into the flat arena in place (parameter storage is unchanged)
+        self.optim.load_state_dict(sd["optim"])
+        engine.invalidate_packs()
+
     def broadcast_params(self):
         if self.world_size > 1:
             dist.broadcast(self.flat.flat, src=0)
 
-    def training_step(self, hr, lr, z):
-        """hr (b,3,H,W), lr (b,lr_dims,h,w), z (b,z_dims,h,w) on the GPU.  Returns the two loss tensors."""
+    def _latent(self, lr, z):
+        """(lr, z) as the inverse pass's input: concatenated -- and, for z=None, drawn (lit_wrapper.py:41) -- inside the
+        first kernel of that pass.  The optimizer's device-side step count advances the random stream, so a replayed
+        CUDA graph draws a new z every step."""
+        if not hasattr(self.inn, "plan"):
+            if z is None:
+                z = torch.randn(lr.shape[0], self.opt.z_dims, lr.shape[2], lr.shape[3], device=lr.device)
+            return torch.cat((lr, z), dim=1)
+        return engine.LatentInput(lr, z, z_dims=self.opt.z_dims, seed=getattr(self.opt, "seed", 0) + 7919 * self.rank,
+                                  step_state=self.optim.state)
+
+    def _fwd_loss(self, lr_z_hat, lr, z):
         o = self.opt
+        loss = forward_half_loss(lr_z_hat, lr, o.lambda_fwd_rec, o.lambda_latent_nll)
+        if getattr(o, "lambda_fwd_mmd", 0.0):              # lit_wrapper.py:47: + lambda * mmd(lr_z_hat, lr_z)
+            if z is None:
+                raise ValueError("lambda_fwd_mmd > 0 needs the z tensor (mmd compares against cat(lr, z))")
+            loss = loss + mmd(lr_z_hat, torch.cat((lr, z), dim=1), rev=False, weight=o.lambda_fwd_mmd)
+        return loss
+
+    def _bwd_loss(self, hr_hat, hr):
+        o = self.opt
+        loss = inverse_half_loss(hr_hat, hr, o.lambda_bwd_rec)
+        if getattr(o, "lambda_bwd_mmd", 0.0):              # lit_wrapper.py:55: + lambda * mmd(hr_hat, hr, rev=True)
+            loss = loss + mmd(hr_hat, hr, rev=True, weight=o.lambda_bwd_mmd)
+        return loss
+
+    def training_step(self, hr, lr, z=None):
+        """hr (b,3,H,W), lr (b,lr_dims,h,w) on the GPU; z (b,z_dims,h,w) or None (drawn on the device, as
+        lit_wrapper.py:41 does).  Returns the two loss tensors."""
         self.optim.zero_grad()
         if self.overlap:
             return self._training_step_two_streams(hr, lr, z)
-        lr_z = torch.cat((lr, z), dim=1)
         # forward pass HR -> (LR, z)                                   lit_wrapper.py:45-49
         lr_z_hat = self.inn(hr)
-        fwd_loss = forward_half_loss(lr_z_hat, lr, o.lambda_fwd_rec, o.lambda_latent_nll)
+        fwd_loss = self._fwd_loss(lr_z_hat, lr, z)
         fwd_loss.backward()
         # reverse pass (LR, z) -> HR                                    lit_wrapper.py:53-56
-        hr_hat = self.inn(lr_z, rev=True)
-        bwd_loss = inverse_half_loss(hr_hat, hr, o.lambda_bwd_rec)
+        hr_hat = self.inn(self._latent(lr, z), rev=True)
+        bwd_loss = self._bwd_loss(hr_hat, hr)
         bwd_loss.backward()
         if self.world_size > 1:
             dist.all_reduce(self.flat.grad)                            # one NCCL all-reduce per step
@@ -176,23 +236,30 @@ class SingleVideoTrainer:
         self.side.wait_stream(main)
         # forward pass HR -> (LR, z) and its backward on the current stream      lit_wrapper.py:45-49
         lr_z_hat = self.inn(hr)
-        fwd_loss = forward_half_loss(lr_z_hat, lr, o.lambda_fwd_rec, o.lambda_latent_nll)
+        fwd_loss = self._fwd_loss(lr_z_hat, lr, z)
         fwd_loss.backward()
+        if self.world_size > 1:
+            # the forward half's gradients are complete: all-reduce that arena now, on a communication stream, hidden
+            # behind the inverse half still running on the side stream; only the second arena's reduce is exposed
+            self.comm.wait_stream(main)
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(self.flat.grad)
         # reverse pass (LR, z) -> HR and its backward on the side stream         lit_wrapper.py:53-56
         self._point_grads(self.grad_b)
         try:
             with torch.cuda.stream(self.side):
-                lr_z = torch.cat((lr, z), dim=1)
-                hr_hat = self.inn(lr_z, rev=True)
-                bwd_loss = inverse_half_loss(hr_hat, hr, o.lambda_bwd_rec)
+                hr_hat = self.inn(self._latent(lr, z), rev=True)
+                bwd_loss = self._bwd_loss(hr_hat, hr)
                 bwd_loss.backward()
+                if self.world_size > 1:
+                    dist.all_reduce(self.grad_b)
         finally:
             self._point_grads(self.flat.grad)
         main.wait_stream(self.side)
-        self.flat.grad.add_(self.grad_b)
         if self.world_size > 1:
-            dist.all_reduce(self.flat.grad)
-        self.optim.step(grad_scale=1.0 / self.world_size)
+            main.wait_stream(self.comm)
+        # Adam reads g = flat.grad + grad_b (both already summed over the ranks): one pass instead of add_ + Adam
+        self.optim.step(grad_scale=1.0 / self.world_size, grad_b=self.grad_b)
         return fwd_loss.detach(), bwd_loss.detach()
 
     def capture(self, hr, lr, z, warmup=3):
@@ -202,9 +269,11 @@ class SingleVideoTrainer:
         step is no longer bounded by the Python/ctypes launch path.  `warmup` eager steps run first (allocator and
         workspaces reach steady state, function attributes are set, weight packs are built); they DO update the
         weights, exactly like `warmup` ordinary training steps."""
-        s_hr, s_lr, s_z = (torch.empty_like(t) for t in (hr, lr, z))
+        s_hr, s_lr = torch.empty_like(hr), torch.empty_like(lr)
+        s_z = torch.empty_like(z) if z is not None else None          # None: z is drawn on the device every replay
         for t, src in ((s_hr, hr), (s_lr, lr), (s_z, z)):
-            t.copy_(src)
+            if t is not None:
+                t.copy_(src)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -218,13 +287,19 @@ class SingleVideoTrainer:
             loss_pair = torch.stack(losses)          # both losses in one 8-byte buffer: one read-back per step
         self._graph = (graph, (s_hr, s_lr, s_z), losses)
 
-        def step(hr, lr, z):
+        def step(hr, lr, z=None):
+            if (z is None) != (s_z is None):
+                raise ValueError("the step was captured " + ("without" if s_z is None else "with") + " a z tensor")
             if hr.data_ptr() != s_hr.data_ptr():
                 s_hr.copy_(hr, non_blocking=True)
                 s_lr.copy_(lr, non_blocking=True)
-                s_z.copy_(z, non_blocking=True)
+                if s_z is not None:
+                    s_z.copy_(z, non_blocking=True)
             graph.replay()
             self.optim.steps += 1
+            # the replayed step packed the weights at its START and ran Adam at its end (through raw pointers): an eager
+            # validation_step / infer / newly captured inference graph must repack before it reads them
+            engine.invalidate_packs()
             return losses
 
         step.static_inputs = (s_hr, s_lr, s_z)
@@ -236,7 +311,7 @@ class SingleVideoTrainer:
         """lit_wrapper.py:79-89: lr_acc, hr_acc, z_nll."""
         o = self.opt
         lr_z_hat = self.inn(hr)
-        hr_hat = self.inn(torch.cat((lr, z), dim=1), rev=True)
+        hr_hat = self.inn(self._latent(lr, z), rev=True)
         return (reconstruction(lr_z_hat[:, :o.lr_dims], lr), reconstruction(hr_hat, hr),
                 latent_nll(lr_z_hat[:, o.lr_dims:]))
 
@@ -244,9 +319,15 @@ class SingleVideoTrainer:
     def infer(self, lr, temp=None, generator=None):
         """lit_wrapper.py:105-115: z = temp*N(0,1); hr_hat = inn(cat(lr, z), rev=True)."""
         o = self.opt
-        b, _, h, w = lr.shape
-        z = (o.temp if temp is None else temp) * torch.randn(b, o.z_dims, h, w, device=lr.device, generator=generator)
-        return self.inn(torch.cat((lr, z), dim=1), rev=True)
+        t = o.temp if temp is None else temp
+        if generator is not None or not hasattr(self.inn, "plan"):
+            b, _, h, w = lr.shape
+            z = t * torch.randn(b, o.z_dims, h, w, device=lr.device, generator=generator)
+            return self.inn(torch.cat((lr, z), dim=1), rev=True)
+        self._infer_calls = getattr(self, "_infer_calls", 0) + 1
+        lat = engine.LatentInput(lr, None, z_dims=o.z_dims, temp=t, seed=getattr(o, "seed", 0) + 104729,
+                                 offset=self._infer_calls * lr.shape[0] * o.z_dims * lr.shape[2] * lr.shape[3])
+        return self.inn(lat, rev=True)
 
 
 class HostBatchFeeder:
@@ -324,6 +405,22 @@ class VideoBatcher:
 
     def __len__(self):
         return self.centers.numel()
+
+    def random_patch_batch(self, batch, lr_patch, generator=None):
+        """A training batch of `batch` samples, each with its own random centre frame AND its own random patch
+        (lr_patch = (ph, pw) on the LR grid; the HR patch is the matching scale x larger window): the per-sample
+        patch sampler the north star's "trained on patches" implies (the reference's transform hook, data.py:43-44,
+        is never used).  Indices and origins are drawn on the device; two gather launches build (hr, lr)."""
+        dev = self.lr_video.device
+        ph, pw = lr_patch
+        h, w = self.lr_video.shape[1], self.lr_video.shape[2]
+        ids = torch.randint(0, len(self), (batch,), device=dev, generator=generator)
+        yx = torch.stack((torch.randint(0, h - ph + 1, (batch,), device=dev, generator=generator),
+                          torch.randint(0, w - pw + 1, (batch,), device=dev, generator=generator)), dim=1).to(torch.int32).contiguous()
+        lr = K.gather_windows_u8(self.lr_video, self.centers[ids].contiguous(), self.win, crops_yx=yx, patch=(ph, pw))
+        hr = K.gather_windows_u8(self.hr_frames, ids.to(torch.int32).contiguous(), 0, crops_yx=(yx * self.scale).contiguous(),
+                                 patch=(ph * self.scale, pw * self.scale))
+        return hr, lr, ids, yx
 
     def batch(self, ids, lr_crop=None):
         """ids: int64/int32 tensor of sample indices on the device; lr_crop = (y0, x0, ph, pw) on the LR grid."""

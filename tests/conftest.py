@@ -20,6 +20,8 @@ def fake_kernels(monkeypatch):
     import fake_kernels as FK
     monkeypatch.setattr(engine, "K", FK)
     monkeypatch.setattr(engine, "require_cuda", lambda t, what="tensor": None)
+    import contextlib
+    monkeypatch.setattr(engine, "_device_ctx", lambda t: contextlib.nullcontext())
     engine._pack_cache.clear()
     yield FK
     engine._pack_cache.clear()

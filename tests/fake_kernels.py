@@ -179,7 +179,7 @@ def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask
     cin = x.shape[1]
     taps = wpack.shape[0]
     x4 = x.float().reshape(B, H, W, cin)
-    acc = torch.zeros(B * H * W, cout, dtype=torch.float32)
+    acc = torch.zeros(B * H * W, cout, dtype=torch.float32, device=x.device)
     for tap in range(taps):
         dy, dx = (tap // 3 - 1, tap % 3 - 1) if taps == 9 else (0, 0)
         xs = _shift(x4, dy, dx).reshape(B * H * W, cin)
@@ -239,7 +239,7 @@ def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False, dbias=None
     cin, cout = x.shape[1], dy.shape[1]
     x4 = x.float().reshape(B, H, W, cin)
     dyf = dy.float()
-    res = torch.zeros(cout, cin, taps)
+    res = torch.zeros(cout, cin, taps, device=x.device)
     for tap in range(taps):
         oy, ox = (tap // 3 - 1, tap % 3 - 1) if taps == 9 else (0, 0)
         xs = _shift(x4, oy, ox).reshape(B * H * W, cin)
@@ -272,6 +272,57 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, st
     param.sub_((lr / bc1) * exp_avg / (exp_avg_sq.sqrt() / bc2 ** 0.5 + eps))
 
 
-def adam_step_dev(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step_state, grad_scale=1.0):
+def adam_step_dev(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step_state, grad_scale=1.0, grad_b=None):
     step_state[0] += 1
-    adam_step(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, int(step_state[0]), grad_scale)
+    g = grad if grad_b is None else grad + grad_b
+    adam_step(param, g, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, int(step_state[0]), grad_scale)
+
+
+def latent_to_nhwc(lr, z, z_dims, chan_map=None, bf16_range=None, seed=0, offset=0, temp=1.0, z_out=None, step_state=None):
+    if z is None:
+        g = torch.Generator().manual_seed(int(seed) + int(offset))
+        z = temp * torch.randn(lr.shape[0], z_dims, lr.shape[2], lr.shape[3], generator=g)
+        if z_out is not None:
+            z_out.copy_(z)
+    return nchw_to_nhwc(torch.cat((lr, z), 1), chan_map, bf16_range)
+
+
+def channel_affine(U, log_scale, bias, inverse):
+    if inverse:
+        U.copy_((U - bias) * torch.exp(-log_scale))
+    else:
+        U.copy_(U * torch.exp(log_scale) + bias)
+    return U
+
+
+def channel_affine_bwd(U, dU, log_scale, bias, inverse, dls, dbias, accumulate):
+    s = torch.exp(log_scale)
+    y, dy = U.clone(), dU.clone()
+    red = tuple(range(U.dim() - 1))
+    if not inverse:
+        U.copy_((y - bias) / s)
+        dU.copy_(dy * s)
+        a, b = (dy * (y - bias)).sum(red), dy.sum(red)
+    else:
+        U.copy_(y * s + bias)
+        dU.copy_(dy / s)
+        a, b = -(dy * y).sum(red), -(dy / s).sum(red)
+    if accumulate:
+        dls += a
+        dbias += b
+    else:
+        dls.copy_(a)
+        dbias.copy_(b)
+
+
+def logscale_sum(s, B, kind, clamp, sign, out, accumulate):
+    if kind == 0:
+        g = clamp * 0.636 * torch.atan(s / clamp)
+    else:
+        g = clamp * (2 * torch.sigmoid(s) - 1)
+    v = sign * g.reshape(B, -1).sum(1)
+    if accumulate:
+        out += v
+    else:
+        out.copy_(v)
+    return out

@@ -187,3 +187,57 @@ def test_fixed1x1conv_host(fake_kernels):
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from shared_checks import fixed1x1_checks
     fixed1x1_checks("cpu")
+
+
+def test_actnorm_latent_input_and_jacobian_host_logic(fake_kernels):
+    """Plan ops added for SURVEY 8a7 / 8f1 on the torch stand-in kernels (CPU): an ActNorm node inside a chain
+    (data-dependent init, parameter gradients through the recompute-from-inverse backward), the (lr, z) LatentInput
+    entry of the inverse pass, and the coupling log-determinant -- all against the oracle shim."""
+    OFf, OFm = R._freia()
+    from sin_inn_b200.freia import framework as Ff, modules as Fm
+
+    def build(Ff_, Fm_, conv):
+        torch.manual_seed(4)
+        nodes = [Ff_.InputNode(3, 16, 16, name="input")]
+        for name, cls, args in (("sq0", Fm_.IRevNetDownsampling, {}), ("sq1", Fm_.IRevNetDownsampling, {}),
+                                ("an0", Fm_.ActNorm, {}), ("g0", Fm_.GLOWCouplingBlock, {"subnet_constructor": conv, "clamp": 1.2}),
+                                ("p0", Fm_.PermuteRandom, {"seed": 1})):
+            nodes.append(Ff_.Node(nodes[-1], cls, args, name=name))
+        nodes.append(Ff_.OutputNode(nodes[-1], name="output"))
+        return Ff_.ReversibleGraphNet(nodes, verbose=False)
+
+    ora, net = build(OFf, OFm, R.subnet_conv), build(Ff, Fm, archs.subnet_conv)
+    net.engine_config = E.EngineConfig(precision="fp32")
+    x = torch.rand(2, 3, 16, 16, generator=torch.Generator().manual_seed(6))
+    res = {}
+    for tag, m in (("ora", ora), ("net", net)):
+        xi = x.clone().requires_grad_(True)
+        y = m(xi)
+        (y ** 2).mean().backward()
+        res[tag] = (y.detach(), xi.grad, {n: p.grad.clone() for n, p in m.named_parameters() if p.requires_grad})
+    (ya, dxa, ga), (yb, dxb, gb) = res["ora"], res["net"]
+    assert (ya - yb).abs().max() <= 1e-4 * max(1.0, ya.abs().max()) and (dxa - dxb).abs().max() <= 1e-4 * max(1.0, dxa.abs().max())
+    assert set(ga) == set(gb)
+    for n in ga:
+        assert (ga[n] - gb[n]).abs().max() <= 2e-4 * max(ga[n].abs().max().item(), 1e-3), n
+    # LatentInput: the cat happens in the entry kernel
+    lr, z = yb[:, :20].contiguous(), yb[:, 20:].contiguous()
+    with torch.no_grad():
+        a = net(torch.cat((lr, z), 1), rev=True)
+        b = net(E.LatentInput(lr, z), rev=True)
+    assert torch.equal(a, b) and (a - x).abs().max() <= 1e-5
+    # coupling log-determinant
+    torch.manual_seed(2)
+    ob = OFm.GLOWCouplingBlock([(48, 4, 4)], subnet_constructor=R.subnet_conv_1x1, clamp=1.2)
+    torch.manual_seed(2)
+    nb = Fm.GLOWCouplingBlock([(48, 4, 4)], subnet_constructor=archs.subnet_conv_1x1, clamp=1.2)
+    v = torch.randn(3, 48, 4, 4, generator=torch.Generator().manual_seed(1))
+    import os
+    os.environ["SININN_PRECISION"] = "fp32"
+    try:
+        for rev in (False, True):
+            with torch.no_grad():
+                ob([v], rev=rev)
+            assert (nb.jacobian([v], rev=rev) - ob.jacobian([v], rev=rev)).abs().max() <= 1e-4 * max(1.0, ob.last_jac.abs().max())
+    finally:
+        del os.environ["SININN_PRECISION"]

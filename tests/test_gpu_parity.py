@@ -327,3 +327,86 @@ def test_overlapped_step_matches_single_stream_step(arch):
         assert torch.equal(la[0], lb[0]) and torch.equal(la[1], lb[1])
     torch.cuda.synchronize()
     assert torch.equal(a.flat.flat, b.flat.flat)
+
+
+def test_fp32_overlapped_step_matches_single_stream_step():
+    """fp32 path: the weight-gradient operands are views of the live trunk, so they must NOT move to a side stream
+    (the next half-step rewrites that channel range in place).  The overlapped trainer step has to be bit-identical
+    to the single-stream one in this precision too."""
+    from sin_inn_b200 import archs, train
+    opt = R.make_opt(scale=4, num_coupling=2, lr_window=10, architecture="SRF", precision="fp32")
+
+    def make(overlap):
+        torch.manual_seed(0)
+        t = train.SingleVideoTrainer(archs.UncondSRFlow(3, 64, 64, opt).to(DEV), opt)
+        if not overlap:
+            t.overlap = False
+            t.inn.plan().side_wgrad = False
+        return t
+
+    batches = [tuple(t.to(DEV) for t in R.synthetic_batch(opt, 2, 64, 64, seed=s)) for s in range(2)]
+    a, b = make(True), make(False)
+    for i in range(3):
+        la, lb = a.training_step(*batches[i % 2]), b.training_step(*batches[i % 2])
+        assert torch.equal(la[0], lb[0]) and torch.equal(la[1], lb[1])
+    torch.cuda.synchronize()
+    assert torch.equal(a.flat.flat, b.flat.flat)
+
+
+def test_eager_inference_after_graph_replay_uses_current_weights():
+    """A replayed training graph updates the weights through raw pointers; an eager forward afterwards must see them
+    (not the packed copies made before the last Adam update)."""
+    from sin_inn_b200 import archs, train
+    opt = R.make_opt(scale=4, num_coupling=2, lr_window=10, architecture="SRF", precision="bf16")
+    torch.manual_seed(0)
+    tr = train.SingleVideoTrainer(archs.UncondSRFlow(3, 64, 64, opt).to(DEV), opt)
+    batch = tuple(t.to(DEV) for t in R.synthetic_batch(opt, 2, 64, 64, seed=0))
+    step = tr.capture(*batch, warmup=2)
+    for _ in range(3):
+        step(*batch)
+    with torch.no_grad():
+        y = tr.inn(batch[0])
+    torch.manual_seed(1)
+    fresh = archs.UncondSRFlow(3, 64, 64, opt).to(DEV)
+    fresh.load_state_dict(tr.inn.state_dict())
+    with torch.no_grad():
+        assert torch.equal(fresh(batch[0]), y)
+
+
+def test_trainer_state_dict_resumes_bit_identically():
+    """FusedAdam / SingleVideoTrainer state_dict: parameters + moments + device-side step count; a restored trainer
+    continues exactly like the original (the reference resumes through Lightning's resume_from_checkpoint)."""
+    from sin_inn_b200 import archs, train
+    opt = R.make_opt(scale=4, num_coupling=2, lr_window=10, architecture="SRF", precision="bf16")
+
+    def make(seed):
+        torch.manual_seed(seed)
+        return train.SingleVideoTrainer(archs.UncondSRFlow(3, 64, 64, opt).to(DEV), opt)
+
+    batches = [tuple(t.to(DEV) for t in R.synthetic_batch(opt, 2, 64, 64, seed=s)) for s in range(2)]
+    a = make(0)
+    for i in range(2):
+        a.training_step(*batches[i % 2])
+    sd = {k: ({kk: (vv.clone() if torch.is_tensor(vv) else vv) for kk, vv in v.items()}) for k, v in a.state_dict().items()}
+    for i in range(2):
+        la = a.training_step(*batches[i % 2])
+    b = make(7)                                   # different initial weights: everything must come from the state
+    b.load_state_dict(sd)
+    for i in range(2):
+        lb = b.training_step(*batches[i % 2])
+    assert torch.equal(la[0], lb[0]) and torch.equal(la[1], lb[1])
+    assert torch.equal(a.flat.flat, b.flat.flat) and a.optim.state[0].item() == b.optim.state[0].item() == 4
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_network_on_non_current_device():
+    """Inputs and parameters on cuda:1 while cuda:0 is current (main.py:127 loads onto cuda:{gpu_ids[0]})."""
+    opt, _, net0 = build_pair("SRF", 4, 2, 10, 64, 64, "bf16")
+    import copy
+    net1 = copy.deepcopy(net0).to("cuda:1")
+    x = torch.rand(2, 3, 64, 64)
+    with torch.no_grad():
+        y0 = net0(x.to("cuda:0"))
+        assert torch.cuda.current_device() == 0
+        y1 = net1(x.to("cuda:1"))
+    assert y1.device.index == 1 and torch.equal(y0.cpu(), y1.cpu())
