@@ -231,7 +231,10 @@ int sininn_subnet1x1_supported(int Cin, int hidden, int Cout);
 
 /* Re-layout nn.Conv2d OIHW fp32 weights for the implicit GEMMs above.
  *   mode 0 (fprop): out[tap][co][ci] = w[co][ci][tap]           rows = Cout, k = Cin
- *   mode 1 (dgrad): out[tap][ci][co] = w[co][ci][taps-1-tap]    rows = Cin,  k = Cout */
+ *   mode 1 (dgrad): out[tap][ci][co] = w[co][ci][taps-1-tap]    rows = Cin,  k = Cout
+ *   mode 2 / 3: the same two layouts for the fp32-accurate tensor-core path (bf16 only): K is six blocks of k_pad / 6
+ *               holding [wh | wh | wm | wh | wm | wl] (wh = bf16(w), wm = bf16(w - wh), wl = bf16(w - wh - wm));
+ *               pairs with sininn_split_bf16 operands */
 int sininn_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, int mode,
                             void* out, int out_dtype, int rows_pad, int k_pad, sininn_stream_t stream);
 
@@ -239,6 +242,15 @@ int sininn_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, in
  * {src fp32 OIHW ptr, dst ptr, Cout, Cin, taps, mode, rows_pad, k_pad}; all outputs share out_dtype. */
 int sininn_pack_conv_weights_batched(const void* jobs, int njobs, int out_dtype, sininn_stream_t stream);
 
+/* fp32-accurate tensor-core path: an fp32 activation matrix [npix][L] (pixel stride in_stride) as a bf16 matrix
+ * [npix][6 * Lp] of six channel blocks [h | m | h | l | m | h], h = bf16(s x), m = bf16(s x - h), l = bf16(s x - h - m)
+ * (s = scale; Lp >= L a multiple of 8, padding columns zero).  sininn_conv_tc over this operand and a mode 2 / 3 pack
+ * evaluates the fp32 convolution of archs.py:11-17 at fp32 accuracy on the bf16 tensor cores (6x the K: every product
+ * term of the three-term expansions down to second order).  blocks = 4 writes only [h | m | h | l]: against the first
+ * four K blocks of the same pack ([wh | wh | wm | wh]) that is the two-term-weight product, 2^-17 accurate at 4x the K --
+ * enough wherever no ReLU decision hangs on the result (second convolution of a subnet, data gradients). */
+int sininn_split_bf16(const float* in, int in_stride, long long npix, int L, float scale, void* out, int Lp, int blocks,
+                      sininn_stream_t stream);
 /* Weight gradient  dw[co][ci][tap] (+)= sum_p dy[p][co] * x[p+off(tap)][ci]  (OIHW fp32),
  * deterministic split over pixels + fixed-order reduction (no float atomics). */
 typedef struct {
@@ -251,6 +263,12 @@ typedef struct {
   /* tensor-core path only: NULL, or the bias gradient  dbias[co] (+)= sum_p dy[p][co]  computed in the same two
    * launches (column sums of the dy tiles the weight-gradient kernel streams through shared memory anyway) */
   float* dbias;   int dbias_accumulate;
+  /* fp32-accurate tensor-core path (CTA-pair kernel only; nterms = 0: off).  x and dy are split operands
+   * (sininn_split_bf16): the gradient is accumulated over nterms pairs of channel blocks, pair t reading x channels
+   * x_term_off[t] + [0, Cin) and dy channels dy_term_off[t] + [0, Cout) -- the products h*dh, h*dm, m*dh, m*dm, h*dl, l*dh
+   * of the three-term expansions, i.e. the pixel (K) dimension is walked nterms times.  bias_term_mask: bit t set = pair
+   * t's dy block enters the bias gradient (each of dh, dm, dl once). */
+  int nterms; int x_term_off[6]; int dy_term_off[6]; int bias_term_mask;
 } sininn_wgrad_desc;
 
 size_t sininn_wgrad_workspace_bytes(const sininn_wgrad_desc* d, int tensor_core);

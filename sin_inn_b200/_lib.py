@@ -47,6 +47,7 @@ class WgradDesc(C.Structure):
         ("dw", _vp), ("accumulate", C.c_int),
         ("workspace", _vp), ("workspace_bytes", C.c_size_t),
         ("dbias", _vp), ("dbias_accumulate", C.c_int),
+        ("nterms", C.c_int), ("x_term_off", C.c_int * 6), ("dy_term_off", C.c_int * 6), ("bias_term_mask", C.c_int),
     ]
 
 
@@ -107,6 +108,7 @@ SIGNATURES = {
     "sininn_subnet1x1_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "sininn_pack_conv_weight": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "sininn_pack_conv_weights_batched": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "sininn_split_bf16": (C.c_int, [_vp, C.c_int, _c_ll, C.c_int, C.c_float, _vp, C.c_int, C.c_int, _vp]),
     "sininn_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(WgradDesc), C.c_int]),
     "sininn_wgrad_simt": (C.c_int, [C.POINTER(WgradDesc), _vp]),
     "sininn_wgrad_tc": (C.c_int, [C.POINTER(WgradDesc), _vp]),

@@ -9,6 +9,8 @@
 
 namespace sininn {
 
+__device__ __forceinline__ bool aligned_dev16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 constexpr int BM = 64;   // pixels per CTA tile (8 x 8 spatial patch)
 constexpr int BN = 64;   // output channels per CTA tile
 constexpr int BK = 16;   // reduction slice
@@ -127,6 +129,25 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------- fp32-accurate tensor-core path ("split" operands)
+// An fp32 value x is carried as three bf16 terms h = bf16(x), m = bf16(x - h), l = bf16(x - h - m) (24 mantissa bits),
+// a weight w likewise as wh, wm, wl.  Activations are laid out as SIX channel blocks [h | m | h | l | m | h] and weights
+// as [wh | wh | wm | wh | wm | wl], so that the ordinary bf16 implicit GEMM over the 6x longer K computes every product
+// term down to second order,
+//     h*wh + m*wh + h*wm + l*wh + m*wm + h*wl  =  x*w - (third-order terms ~2^-26 |x w|),
+// i.e. fp32-level accuracy with fp32 accumulation in TMEM.  (Four blocks with two-term weights are 2^-17 accurate,
+// which passes value tolerances but flips ReLU decisions of near-zero hidden units ~30x more often than fp32 does,
+// and a flipped unit is a finite jump in the gradients -- measured on the parity nets, see DESIGN.md.)
+constexpr int SPLIT_BLOCKS = 6;
+__device__ __forceinline__ float split_weight_term(float w, int block) {
+  const float wh = __bfloat162float(__float2bfloat16_rn(w));
+  if (block == 0 || block == 1 || block == 3) return wh;
+  const float r1 = w - wh;
+  const float wm = __bfloat162float(__float2bfloat16_rn(r1));
+  return block == 5 ? r1 - wm : wm;       // the caller rounds to bf16
+}
+
 // ---------------------------------------------------------------- weight packing
 template <typename TO>
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int mode,
@@ -141,11 +162,14 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
     int row = (int)(r % rows_pad);
     int tap = (int)(r / rows_pad);
     float v = 0.f;
-    if (mode == 0) {            // fprop: row = co, k = ci
+    int blockk = 0;
+    if (mode >= 2) { const int kp = k_pad / SPLIT_BLOCKS; blockk = k / kp; k = k % kp; }   // split packs: six K blocks
+    if ((mode & 1) == 0) {      // fprop: row = co, k = ci
       if (row < Cout && k < Cin) v = w[((long long)row * Cin + k) * taps + tap];
     } else {                    // dgrad: row = ci, k = co, spatially flipped
       if (row < Cin && k < Cout) v = w[((long long)k * Cin + row) * taps + (taps - 1 - tap)];
     }
+    if (mode >= 2) v = split_weight_term(v, blockk);
     out[idx] = from_f32<TO>(v);
   }
 }
@@ -167,11 +191,14 @@ __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const long lon
     int row = (int)(r % rows_pad);
     int tap = (int)(r / rows_pad);
     float v = 0.f;
-    if (mode == 0) {
+    int blockk = 0;
+    if (mode >= 2) { const int kp = k_pad / SPLIT_BLOCKS; blockk = k / kp; k = k % kp; }
+    if ((mode & 1) == 0) {
       if (row < Cout && k < Cin) v = w[((long long)row * Cin + k) * taps + tap];
     } else {
       if (row < Cin && k < Cout) v = w[((long long)k * Cin + row) * taps + (taps - 1 - tap)];
     }
+    if (mode >= 2) v = split_weight_term(v, blockk);
     out[idx] = from_f32<TO>(v);
   }
 }
@@ -302,6 +329,47 @@ static inline int wgrad_splits(const sininn_wgrad_desc* d) {
   return (int)want;
 }
 
+// out[p][j * Lp + c] = term_j(scale * in[p][c]) for the six blocks [h | m | h | l | m | h]; columns c >= L of a block are zero
+__global__ void __launch_bounds__(256) split_slice_kernel(const float* __restrict__ in, int in_stride, long long npix, int L, int Lp,
+                                                          float scale, __nv_bfloat16* __restrict__ out, int blocks) {
+  pdl_wait();
+  pdl_trigger();
+  const int Lv = Lp / 4;
+  const long long total = npix * Lv;
+  const bool vec = (in_stride % 4) == 0 && aligned_dev16(in);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Lv) * 4;
+    const long long p = idx / Lv;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* src = in + p * in_stride + c;
+    if (vec && c + 3 < L) {
+      const float4 t = *reinterpret_cast<const float4*>(src);
+      x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (c + e < L) x[e] = src[e];
+    }
+    float h[4], m[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v = x[e] * scale;
+      h[e] = __bfloat162float(__float2bfloat16_rn(v));
+      const float r1 = v - h[e];
+      m[e] = __bfloat162float(__float2bfloat16_rn(r1));
+      l[e] = r1 - m[e];
+    }
+    __nv_bfloat16* o = out + p * (long long)(blocks * Lp) + c;
+    store4(o, make_float4(h[0], h[1], h[2], h[3]));
+    store4(o + Lp, make_float4(m[0], m[1], m[2], m[3]));
+    store4(o + 2 * Lp, make_float4(h[0], h[1], h[2], h[3]));
+    store4(o + 3 * Lp, make_float4(l[0], l[1], l[2], l[3]));
+    if (blocks == SPLIT_BLOCKS) {
+      store4(o + 4 * Lp, make_float4(m[0], m[1], m[2], m[3]));
+      store4(o + 5 * Lp, make_float4(h[0], h[1], h[2], h[3]));
+    }
+  }
+}
+
 }  // namespace sininn
 
 using namespace sininn;
@@ -351,9 +419,11 @@ int sininn_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, in
                             int rows_pad, int k_pad, sininn_stream_t stream) {
   SININN_CHECK_ARG(w_oihw && out && Cout > 0 && Cin > 0, "pack_conv_weight: bad arguments");
   SININN_CHECK_ARG(taps == 1 || taps == 9, "pack_conv_weight: taps must be 1 or 9");
-  SININN_CHECK_ARG(mode == 0 || mode == 1, "pack_conv_weight: mode must be 0 (fprop) or 1 (dgrad)");
-  const int rows = mode == 0 ? Cout : Cin, k = mode == 0 ? Cin : Cout;
-  SININN_CHECK_ARG(rows_pad >= rows && k_pad >= k, "pack_conv_weight: padding smaller than the matrix");
+  SININN_CHECK_ARG(mode >= 0 && mode <= 3, "pack_conv_weight: mode must be 0 (fprop), 1 (dgrad), 2 / 3 (their split forms)");
+  const int rows = (mode & 1) == 0 ? Cout : Cin, k = (mode & 1) == 0 ? Cin : Cout;
+  SININN_CHECK_ARG(rows_pad >= rows && (mode < 2 ? k_pad >= k : ((k_pad % SPLIT_BLOCKS) == 0 && k_pad / SPLIT_BLOCKS >= k)),
+                   "pack_conv_weight: padding smaller than the matrix");
+  SININN_CHECK_ARG(mode < 2 || out_dtype == SININN_BF16, "pack_conv_weight: split packs are bf16");
   const long long total = (long long)taps * rows_pad * k_pad;
   long long g = (total + 255) / 256;
   if (g > (long long)sm_count() * 16) g = (long long)sm_count() * 16;
@@ -372,6 +442,19 @@ int sininn_pack_conv_weights_batched(const void* jobs, int njobs, int out_dtype,
   else if (out_dtype == SININN_BF16) launch_k(pack_weight_batched_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(stream), (const long long*)jobs);
   else SININN_CHECK_ARG(false, "pack_conv_weights_batched: bad out_dtype");
   SININN_CHECK_LAUNCH("pack_conv_weights_batched");
+  return SININN_OK;
+}
+
+int sininn_split_bf16(const float* in, int in_stride, long long npix, int L, float scale, void* out, int Lp, int blocks,
+                      sininn_stream_t stream) {
+  SININN_CHECK_ARG(in && out && npix > 0 && L > 0, "split_bf16: bad arguments");
+  SININN_CHECK_ARG(blocks == 4 || blocks == SPLIT_BLOCKS, "split_bf16: 4 or 6 channel blocks");
+  SININN_CHECK_ARG(Lp >= L && (Lp % 8) == 0 && aligned8(out), "split_bf16: block width must be a multiple of 8 channels >= L");
+  const long long total = npix * (Lp / 4);
+  long long g = (total + 255) / 256;
+  if (g > (long long)sm_count() * 32) g = (long long)sm_count() * 32;
+  launch_k(split_slice_kernel, dim3((int)g), dim3(256), 0, as_stream(stream), in, in_stride, npix, L, Lp, scale, (__nv_bfloat16*)out, blocks);
+  SININN_CHECK_LAUNCH("split_bf16");
   return SININN_OK;
 }
 

@@ -45,6 +45,9 @@ struct WgPairParams {
   float* partial;                // [split][tap][Cw][Cn]
   int bias_mode;                 // 0 off, 1 dy is the wide operand, 2 dy is the narrow operand
   float* bias_partial;           // [split][Cout]
+  int nterms;                    // split operands: channel-block pairs the K walk is repeated over (1 = plain operands)
+  int woff[6], noff[6];          // channel offsets of pair t in the wide / narrow operand
+  int bias_terms;                // bit t: pair t's dy block is summed into the bias gradient
   int tma_out;                   // 1: partial tiles leave through TMA tensor stores (needs Cn % 4 == 0)
   long long* trace;              // debugging aid (sininn_debug_set_trace): clock64 stamps of pair 0's roles, or NULL
 };
@@ -152,17 +155,20 @@ wgrad_pair_kernel(const __grid_constant__ WgTensorMaps T, const __grid_constant_
       const int bh = (int)(blk % p.blocks_h);
       const int b = (int)(blk / p.blocks_h);
       const int w0 = bw * WP_BLK, h0 = bh * WP_BLK;
-      mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
-      if (elect_one()) {
-        if (rank == 0) mbar_expect_tx(smem_u32(&bars->full[stage]), 2u * p.tx_bytes);
-        const uint32_t full_l = mapa_u32(smem_u32(&bars->full[stage]), 0);     // the leader's barrier
-        const uint32_t dst = ring_u32 + stage * p.stage_bytes;
-        tma_load_4d_2sm(dst, &tmW, full_l, wch, w0, h0, b);
-        tma_load_4d_2sm(dst + WP_WIDE_BYTES / 2, &tmW, full_l, wch + 64, w0, h0, b);
-        tma_load_4d_2sm(dst + WP_WIDE_BYTES, &tmN, full_l, nch, w0 - ho, h0 - ho, b);
+      for (int term = 0; term < p.nterms; ++term) {          // all channel-block pairs of a pixel block back to back
+        mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(smem_u32(&bars->full[stage]), 2u * p.tx_bytes);
+          const uint32_t full_l = mapa_u32(smem_u32(&bars->full[stage]), 0);     // the leader's barrier
+          const uint32_t dst = ring_u32 + stage * p.stage_bytes;
+          const int wc = wch + p.woff[term], nc = nch + p.noff[term];
+          tma_load_4d_2sm(dst, &tmW, full_l, wc, w0, h0, b);
+          tma_load_4d_2sm(dst + WP_WIDE_BYTES / 2, &tmW, full_l, wc + 64, w0, h0, b);
+          tma_load_4d_2sm(dst + WP_WIDE_BYTES, &tmN, full_l, nc, w0 - ho, h0 - ho, b);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
     wp_stamp(p, 3, lane);
   } else if (warp == 1) {
@@ -196,9 +202,11 @@ wgrad_pair_kernel(const __grid_constant__ WgTensorMaps T, const __grid_constant_
       const uint32_t center_off = halo ? (uint32_t)(p.halo_w + 1) * 8u : 0u;
       const uint32_t stage_step = p.stage_bytes >> 4;
       const uint32_t d_bias = tmem_base + (uint32_t)(ntap * p.n_pair);
-      const int bias_mode = do_bias ? p.bias_mode : 0;
       int stage = 0; uint32_t phase = 0;
-      for (long long i = 0; i < nblk; ++i) {
+      const long long nsteps = nblk * p.nterms;
+      int term = 0;
+      uint32_t bias_acc = 0u;
+      for (long long i = 0; i < nsteps; ++i) {
         mbar_wait(smem_u32(&bars->full[stage]), phase);
         tc_fence_after();
         if (i == 0) wp_stamp(p, 4, lane);
@@ -207,6 +215,8 @@ wgrad_pair_kernel(const __grid_constant__ WgTensorMaps T, const __grid_constant_
         const uint64_t ad = a_desc0 + (uint64_t)(stage * stage_step);
         const uint64_t bs = b_desc0 + (uint64_t)(stage * stage_step);
         const uint32_t acc = i != 0 ? 1u : 0u;
+        const int bias_mode = (do_bias && ((p.bias_terms >> term) & 1)) ? p.bias_mode : 0;
+        if (++term == p.nterms) term = 0;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           if (t < ntap) {
@@ -219,17 +229,18 @@ wgrad_pair_kernel(const __grid_constant__ WgTensorMaps T, const __grid_constant_
           }
         }
         if (bias_mode == 1) {                 // colsum of the wide operand: D[m][0..15] += sum_k Wide[k][m] * 1
-          umma_bf16_2sm_p(lead, d_bias, ad, one_b, idesc_b1, acc);
+          umma_bf16_2sm_p(lead, d_bias, ad, one_b, idesc_b1, bias_acc);
           umma_bf16_2sm_p(lead, d_bias, ad + 128, one_b, idesc_b1, 1u);
           umma_bf16_2sm_p(lead, d_bias, ad + 256, one_b, idesc_b1, 1u);
           umma_bf16_2sm_p(lead, d_bias, ad + 384, one_b, idesc_b1, 1u);
         } else if (bias_mode == 2) {          // colsum of the narrow operand (unshifted): D[*][n] += sum_k 1 * Narrow[k][n]
           const uint64_t bd = bs + center_off;
-          umma_bf16_2sm_p(lead, d_bias, one_a, bd, idesc, acc);
+          umma_bf16_2sm_p(lead, d_bias, one_a, bd, idesc, bias_acc);
           umma_bf16_2sm_p(lead, d_bias, one_a, bd + b_kstep, idesc, 1u);
           umma_bf16_2sm_p(lead, d_bias, one_a, bd + 2 * b_kstep, idesc, 1u);
           umma_bf16_2sm_p(lead, d_bias, one_a, bd + 3 * b_kstep, idesc, 1u);
         }
+        if (bias_mode != 0) bias_acc = 1u;
         umma_commit_2sm_p(lead, smem_u32(&bars->empty[stage]), 3);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
@@ -529,6 +540,7 @@ static void set_splits(WgPairPlan& w, long long pairs_budget) {
 static bool plan_wgrad_pair(const sininn_wgrad_desc* d, bool with_bias, WgPairPlan& w) {
   if (!wgrad_pair_enabled()) return false;
   if (d->x_dtype != SININN_BF16 || d->dy_dtype != SININN_BF16 || (d->taps != 1 && d->taps != 9)) return false;
+  if (d->nterms < 0 || d->nterms > 6) return false;
   w.wide_is_dy = d->Cout >= d->Cin ? 1 : 0;
   w.Cw = w.wide_is_dy ? d->Cout : d->Cin;
   w.Cn = w.wide_is_dy ? d->Cin : d->Cout;
@@ -591,7 +603,7 @@ int launch_wgrad_pair_group(const sininn_wgrad_desc* ds, int n, void* workspace,
   int items = 0;
   for (int i = 0; i < n; ++i) {
     if (!plan_wgrad_pair(&ds[i], ds[i].dbias != nullptr, w[i])) return SININN_EUNSUPPORTED;
-    work[i] = (double)w[i].num_blocks * w[i].items * w[i].kstep_cycles;
+    work[i] = (double)w[i].num_blocks * w[i].items * w[i].kstep_cycles * (ds[i].nterms > 0 ? ds[i].nterms : 1);
     total += work[i];
     items += w[i].items;
   }
@@ -652,8 +664,9 @@ int launch_wgrad_pair_group(const sininn_wgrad_desc* ds, int n, void* workspace,
     const int narrow_stride = wi.wide_is_dy ? d->x_stride : d->dy_stride;
     for (int which = 0; which < 2; ++which) {
       const void* ptr = which == 0 ? wide : narrow;
-      const int C = which == 0 ? wi.Cw : wi.Cn;
       const int stride = which == 0 ? wide_stride : narrow_stride;
+      // split operands: the channel extent is the whole row of blocks (the pixel stride); plain: the true channel count
+      const int C = d->nterms > 0 ? stride : (which == 0 ? wi.Cw : wi.Cn);
       cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
       cuuint64_t strides[3] = {(cuuint64_t)stride * 2, (cuuint64_t)d->W * stride * 2, (cuuint64_t)d->H * d->W * stride * 2};
       const bool halo = which == 1 && d->taps == 9;
@@ -684,6 +697,13 @@ int launch_wgrad_pair_group(const sininn_wgrad_desc* ds, int n, void* workspace,
     }
     WgPairParams& p = G.prob[i];
     p.tma_out = tma_out;
+    p.nterms = d->nterms > 0 ? d->nterms : 1;
+    p.bias_terms = d->nterms > 0 ? d->bias_term_mask : 1;
+    for (int t = 0; t < 6; ++t) {
+      const int xo = (d->nterms > 0 && t < d->nterms) ? d->x_term_off[t] : 0, yo = (d->nterms > 0 && t < d->nterms) ? d->dy_term_off[t] : 0;
+      p.woff[t] = wi.wide_is_dy ? yo : xo;
+      p.noff[t] = wi.wide_is_dy ? xo : yo;
+    }
     p.trace = i == 0 ? g_wg_trace : nullptr;
     p.B = d->B; p.H = d->H; p.W = d->W; p.taps = d->taps;
     p.narrow_is_x = wi.wide_is_dy;

@@ -375,6 +375,10 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
     const int rc = launch_wgrad_pair_group(d, 1, d->workspace, d->workspace_bytes, as_stream(stream));
     if (rc != SININN_EUNSUPPORTED) return rc;
   }
+  if (d->nterms > 0) {
+    set_error("wgrad_tc: split-operand term lists are only taken by the CTA-pair kernel (wide operand > 128 channels)");
+    return SININN_EUNSUPPORTED;
+  }
   WgradPlan w;
   if (!plan_wgrad(d, w)) {
     set_error("wgrad_tc: unsupported shape (Cin=%d Cout=%d)", d->Cin, d->Cout);

@@ -26,8 +26,12 @@ from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, GLOW, IRN, SininnError, require
 
 @dataclass(frozen=True)
 class EngineConfig:
-    precision: str = "bf16"      # "fp32": CUDA-core fp32 subnets (1e-4 parity); "bf16": bf16 operands, fp32 accumulate
-    tensor_core: bool = True     # tcgen05 kernels for the subnets (bf16 only)
+    # "bf16":   bf16 operands, fp32 accumulate (tcgen05 kernels; the headline path)
+    # "fp32":   CUDA-core fp32 subnets: the reference-accurate path (1e-4 parity on outputs AND gradients)
+    # "fp32tc": fp32 activations, subnet GEMMs on the tensor cores over bf16 hi/mid/lo split operands: outputs 1e-5,
+    #           round trip 2e-6, ~6.5x the speed of "fp32"; gradients are limited by ReLU-kink flips
+    precision: str = "bf16"
+    tensor_core: bool = True     # tcgen05 kernels for the subnets (bf16 / fp32tc)
 
     @property
     def act_dtype(self):
@@ -37,11 +41,20 @@ class EngineConfig:
     def tc(self):
         return self.tensor_core and self.precision == "bf16"
 
+    @property
+    def split(self):
+        """fp32-accurate path on the tensor cores: fp32 activations / gradients, every subnet GEMM evaluated on bf16
+        hi/mid/lo splits of its operands (kernels.split_bf16, pack modes 2 / 3)."""
+        return self.tensor_core and self.precision == "fp32tc"
+
+
+PRECISIONS = ("bf16", "fp32", "fp32tc")
+
 
 def default_config():
     prec = os.environ.get("SININN_PRECISION", "bf16")
-    if prec not in ("bf16", "fp32"):
-        raise SininnError(f"SININN_PRECISION must be bf16 or fp32, got {prec!r}")
+    if prec not in PRECISIONS:
+        raise SininnError(f"SININN_PRECISION must be one of {PRECISIONS}, got {prec!r}")
     tc = os.environ.get("SININN_TENSOR_CORE", "1") != "0"
     return EngineConfig(precision=prec, tensor_core=tc)
 
@@ -125,8 +138,8 @@ def packed(w, mode, dtype):
     if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
         return hit[2]
     co, ci = w.shape[0], w.shape[1]
-    rows, k = (co, ci) if mode == 0 else (ci, co)
-    p = K.pack_weight(w, mode, dtype, _round_up(rows, 16), _round_up(k, 16))
+    rows, k = (co, ci) if mode % 2 == 0 else (ci, co)
+    p = K.pack_weight(w, mode, dtype, _round_up(rows, 16), _round_up(k, 16) if mode < 2 else K.SPLIT_BLOCKS * _round_up(k, 8))
     ent[1][(mode, dtype)] = (w._version, w.data_ptr(), p)
     return p
 
@@ -138,8 +151,8 @@ class PackSet:
     """All conv weights of one plan, re-laid-out for the implicit GEMMs by ONE batched kernel launch whenever any
     of them changed (fprop and dgrad layouts).  Outputs and the device-side job table are allocated once."""
 
-    def __init__(self, weights, dtype):
-        self.weights, self.dtype = list(weights), dtype
+    def __init__(self, weights, dtype, split=False):
+        self.weights, self.dtype, self.split = list(weights), dtype, split
         self.out, self.jobs, self.sig, self.ptrs = {}, None, None, None
 
     def _build(self, dev):
@@ -150,9 +163,11 @@ class PackSet:
             for mode in (0, 1):
                 r, k = (co, ci) if mode == 0 else (ci, co)
                 rp, kp = _round_up(r, 16), _round_up(k, 16)
+                if self.split:                       # pack modes 2 / 3: K = six blocks of round8(k)
+                    kp = K.SPLIT_BLOCKS * _round_up(k, 8)
                 t = torch.empty(kh * kw, rp, kp, dtype=self.dtype, device=dev)
                 self.out[(id(w), mode)] = t
-                rows.append([w.data_ptr(), t.data_ptr(), co, ci, kh * kw, mode, rp, kp])
+                rows.append([w.data_ptr(), t.data_ptr(), co, ci, kh * kw, mode + (2 if self.split else 0), rp, kp])
         self.jobs = torch.tensor(rows, dtype=torch.int64).to(dev)
         self.ptrs = tuple(w.data_ptr() for w in self.weights)
 
@@ -208,6 +223,16 @@ class Trunk:
         for key in [k for k in self.bf if not (k[1] <= c0 or k[0] >= c1)]:
             del self.bf[key]
 
+    def split_operand(self, rng):
+        """Channel range as a split bf16 operand [npix, 6*round8(L)] (fp32-accurate tensor-core path); cached like the
+        plain bf16 copies and dropped by invalidate()."""
+        key = (rng[0], rng[1], "split")
+        hit = self.bf.get(key)
+        if hit is None:
+            hit = K.split_bf16(self.mat()[:, rng[0]:rng[1]])
+            self.bf[key] = hit
+        return hit
+
     def operand(self, rng, dtype):
         """Channel range as a GEMM operand of `dtype` ([npix, L] view)."""
         c0, c1 = rng
@@ -222,10 +247,12 @@ class Trunk:
 
 
 class RunCtx:
-    def __init__(self, cfg, want_grads=False, packs=None, direct_grad=False):
+    def __init__(self, cfg, want_grads=False, packs=None, direct_grad=False, split_packs=None):
         self.cfg = cfg
         self.adt = cfg.act_dtype
         self.tc = cfg.tc
+        self.split = cfg.split
+        self.split_packs = split_packs
         self.grads = {} if want_grads else None
         self.packs = packs
         self.direct_grad = direct_grad      # accumulate weight gradients straight into param.grad (no autograd add)
@@ -255,6 +282,12 @@ class RunCtx:
             return self.packs.get(w, mode)
         return packed(w, mode, self.adt)
 
+    def pack_split(self, w, mode):
+        """bf16 hi/lo split layout (pack modes 2 / 3) for the fp32-accurate tensor-core path."""
+        if self.split_packs is not None:
+            return self.split_packs.get(w, mode)
+        return packed(w, mode + 2, torch.bfloat16)
+
     def add_grad(self, param, g):
         if param is None or not param.requires_grad:
             return
@@ -281,6 +314,25 @@ def flush_param_grads(ctx):
                 t.record_stream(ctx.wstream)      # keep the operands alive until the side stream has consumed them
         return
     K.wgrad_group(jobs)
+
+
+def _param_grads_split(ctx, conv, xs, dys, cinp, coutp, geom, taps):
+    """fp32-accurate weight/bias gradient on the tensor cores: the weight-gradient kernel walks the pixels once per
+    product term of the three-term expansions x = h+m+l, dy = dh+dm+dl (h*dh, h*dm, m*dh, m*dm, h*dl, l*dh: everything down
+    to second order), reading the matching channel blocks of the split operands; the bias gradient sums dh, dm, dl."""
+    wants_w = conv.weight.requires_grad
+    wants_b = conv.bias is not None and conv.bias.requires_grad
+    if not (wants_w or wants_b):
+        return
+    g, acc = ctx.grad_out(conv.weight) if wants_w else (torch.empty_like(conv.weight), False)
+    gb, accb = ctx.grad_out(conv.bias) if wants_b else (None, False)
+    H_, M_, L_ = 0, 1, 3                      # block index of each term in [h | m | h | l (| m | h)]
+    xo = [H_ * cinp, H_ * cinp, M_ * cinp, M_ * cinp, H_ * cinp, L_ * cinp]
+    yo = [H_ * coutp, M_ * coutp, H_ * coutp, M_ * coutp, L_ * coutp, H_ * coutp]
+    terms = (xo, yo, 0b010011)                # dh (pair 0), dm (pair 1), dl (pair 4) enter the bias sum once each
+    ctx.pending.append((xs[:, :conv.in_channels], dys[:, :conv.out_channels], geom, taps, g, acc, gb, accb, terms))
+    if len(ctx.pending) >= WGRAD_GROUP:
+        flush_param_grads(ctx)
 
 
 def _param_grads(ctx, conv, x, dy, geom, taps):
@@ -343,7 +395,35 @@ class ConvSubnet:
     def parameters(self):
         return [p for p in (self.c1.weight, self.c1.bias, self.c2.weight, self.c2.bias) if p is not None]
 
+    def _fwd_split(self, ctx, tr, src, keep):
+        """fp32-accurate forward on the tensor cores: both convolutions on split operands, hidden activation in fp32.
+        The first convolution takes the full six-block product (its output decides the ReLUs); everything downstream
+        of the ReLU -- second convolution, both data gradients -- takes the four-block (two-term-weight) product."""
+        dev = tr.U.device
+        xs = tr.split_operand(src)
+        h = torch.empty(tr.npix, self.hidden, dtype=torch.float32, device=dev)
+        bits = torch.empty(tr.npix, (self.hidden + 31) // 32, dtype=torch.int32, device=dev) if keep else None
+        K.conv(xs, ctx.pack_split(self.c1.weight, 0), tr.geom, self.hidden, h, bias=self.c1.bias, act=ACT_RELU, tensor_core=True,
+               bits_out=bits)
+        hs = K.split_bf16(h, blocks=4)
+        a = torch.empty(tr.npix, self.cout, dtype=torch.float32, device=dev)
+        K.conv(hs, ctx.pack_split(self.c2.weight, 0), tr.geom, self.cout, a, bias=self.c2.bias, tensor_core=True)
+        return a, (xs, hs, bits)
+
+    def _bwd_split(self, ctx, tr, saved, da, dsrc):
+        xs, hs, bits = saved
+        dev = xs.device
+        das = K.split_bf16(da, blocks=4)
+        dh = torch.empty(tr.npix, self.hidden, dtype=torch.float32, device=dev)
+        K.conv(das, ctx.pack_split(self.c2.weight, 1), tr.geom, self.hidden, dh, mask_bits=bits, tensor_core=True)
+        _param_grads_split(ctx, self.c2, hs, das, _round_up(self.hidden, 8), _round_up(self.cout, 8), tr.geom, self.taps)
+        dhs = K.split_bf16(dh, blocks=4)
+        K.conv(dhs, ctx.pack_split(self.c1.weight, 1), tr.geom, self.cin, dsrc, accumulate=True, tensor_core=True)
+        _param_grads_split(ctx, self.c1, xs, dhs, _round_up(self.cin, 8), _round_up(self.hidden, 8), tr.geom, self.taps)
+
     def fwd(self, ctx, tr, src, keep=False):
+        if ctx.split:
+            return self._fwd_split(ctx, tr, src, keep)
         x = tr.operand(src, ctx.adt)
         dev = x.device
         if (ctx.tc and self.taps == 1 and FUSE_1X1 and K.subnet1x1_supported(self.cin, self.hidden, self.cout)
@@ -368,6 +448,8 @@ class ConvSubnet:
 
     def bwd(self, ctx, tr, saved, da, dsrc):
         """da: dL/d(output) [npix, cout] in the activation dtype; accumulates dL/d(input) into dsrc (fp32 view)."""
+        if ctx.split:
+            return self._bwd_split(ctx, tr, saved, da, dsrc)
         x, h, bits = saved
         dev = x.device
         dh = torch.empty_like(h)
@@ -533,12 +615,25 @@ class LinearOp:
             self._packs[key] = K.pack_weight(w, 0, torch.float32, _round_up(self.C, 16), _round_up(self.C, 16))
         return self._packs[key]
 
-    def apply(self, U, rev, grad=False):
-        """U: channels-last [B,h,w,C] fp32 -> new tensor of the same shape."""
+    def pack_split(self, device, rev, grad=False):
+        key = (device.type, device.index, bool(rev), bool(grad), "split")
+        if key not in self._packs:
+            w = self.mats[(bool(rev), bool(grad))].to(torch.float32).reshape(self.C, self.C, 1, 1).to(device)
+            self._packs[key] = K.pack_weight(w, 2, torch.bfloat16, _round_up(self.C, 16), K.SPLIT_BLOCKS * _round_up(self.C, 8))
+        return self._packs[key]
+
+    def apply(self, U, rev, grad=False, split=False):
+        """U: channels-last [B,h,w,C] fp32 -> new tensor of the same shape.  split: on the tensor cores with bf16
+        hi/mid/lo operands (north-star item 3: the invertible 1x1 convolution as a tcgen05 GEMM at fp32 accuracy);
+        otherwise the CUDA-core fp32 GEMM."""
         out = torch.empty_like(U)
         npix = U.numel() // self.C
-        K.conv(U.view(npix, self.C), self.pack(U.device, rev, grad), tuple(U.shape[:3]), self.C, out.view(npix, self.C),
-               tensor_core=False)
+        if split:
+            K.conv(K.split_bf16(U.view(npix, self.C)), self.pack_split(U.device, rev, grad), tuple(U.shape[:3]), self.C,
+                   out.view(npix, self.C), tensor_core=True)
+        else:
+            K.conv(U.view(npix, self.C), self.pack(U.device, rev, grad), tuple(U.shape[:3]), self.C, out.view(npix, self.C),
+                   tensor_core=False)
         return out
 
     def parameters(self):
@@ -753,13 +848,20 @@ class Plan:
                     out.append(p)
         return out
 
-    def packs(self, dtype):
+    def packs(self, dtype, split=False):
         """The plan's conv weights packed for `dtype`, refreshed (one launch) if any weight changed."""
-        ps = self._packsets.get(dtype)
+        key = (dtype, split)
+        ps = self._packsets.get(key)
         if ps is None:
-            ps = self._packsets[dtype] = PackSet([p for p in self.parameters() if p.dim() == 4], dtype)
+            convs = [p for o in self.ops if o.kind == "coupling" for p in o.parameters() if p.dim() == 4]
+            ps = self._packsets[key] = PackSet(convs, dtype, split)
         ps.ensure()
         return ps
+
+    def _ctx_packs(self, cfg, t):
+        if not (self.body and K.__name__ == "sin_inn_b200.kernels" and t.is_cuda):
+            return None, None
+        return self.packs(cfg.act_dtype), (self.packs(torch.bfloat16, True) if cfg.split else None)
 
     def _check_input(self, x, rev):
         if isinstance(x, LatentInput):
@@ -789,7 +891,8 @@ class Plan:
     # ---- value pass ---------------------------------------------------------------------------
     def execute(self, x, rev, cfg):
         self._check_input(x, rev)
-        ctx = RunCtx(cfg, packs=self.packs(cfg.act_dtype) if (self.body and K.__name__ == "sin_inn_b200.kernels" and x.is_cuda) else None)
+        p_plain, p_split = self._ctx_packs(cfg, x)
+        ctx = RunCtx(cfg, packs=p_plain, split_packs=p_split)
         if not self.body:
             seq = self.prefix[::-1] if rev else self.prefix
             for op in seq:
@@ -826,7 +929,7 @@ class Plan:
                 U, bf = K.permute_nhwc(tr.U, op.gather_map(dev, rev), hint)
                 tr.set(U, None, {hint: bf} if bf is not None else None)
             elif op.kind == "linear":
-                tr.set(op.apply(tr.U, rev))
+                tr.set(op.apply(tr.U, rev, split=ctx.split))
             elif op.kind == "actnorm":
                 op.apply(tr, rev)
             else:
@@ -844,8 +947,8 @@ class Plan:
     def backward(self, y, dy, rev, cfg, need_dx=True):
         """y: the output execute(x, rev) produced; dy: dL/dy.  Returns (dL/dx or None, {id(param): grad})."""
         require_cuda(dy, "grad_output")
-        ctx = RunCtx(cfg, want_grads=True, direct_grad=self.direct_grad,
-                     packs=self.packs(cfg.act_dtype) if (self.body and K.__name__ == "sin_inn_b200.kernels" and dy.is_cuda) else None)
+        p_plain, p_split = self._ctx_packs(cfg, dy)
+        ctx = RunCtx(cfg, want_grads=True, direct_grad=self.direct_grad, packs=p_plain, split_packs=p_split)
         dy = dy.contiguous()
         if dy.dtype != torch.float32:
             raise SininnError("grad_output must be fp32")
@@ -895,7 +998,7 @@ class Plan:
                 tr.set(U, dU, {hint: bf} if bf is not None else None)
             elif op.kind == "linear":
                 # executed y = A x (A = W or W^-1): the input is A^-1 y, its gradient A^T dy
-                tr.set(op.apply(tr.U, not rev), op.apply(tr.dU, rev, grad=True))
+                tr.set(op.apply(tr.U, not rev, split=ctx.split), op.apply(tr.dU, rev, grad=True, split=ctx.split))
             elif op.kind == "actnorm":
                 op.backward(ctx, tr, rev)
             else:

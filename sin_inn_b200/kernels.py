@@ -12,6 +12,7 @@ from . import _lib
 from ._lib import F32, BF16, ConvDesc, Subnet1x1Desc, WgradDesc, check, dtype_code, load, stream_ptr
 
 _workspaces = {}
+SPLIT_BLOCKS = 6          # channel blocks of a split operand / K blocks of a split weight pack (conv_simt.cu)
 
 # ---- launch accounting / optional CUDA-event profiling (used by bench.py; off by default)
 LAUNCHES = 0          # kernels launched through this module since last reset
@@ -308,6 +309,19 @@ def cast_slice(src, out, scale=1.0):
     return out
 
 
+def split_bf16(src, scale=1.0, blocks=None):
+    """fp32 view [npix, L] -> bf16 [npix, 6*Lp] of the channel blocks [h | m | h | l | m | h] (Lp = L rounded up to 8):
+    the operand form of the fp32-accurate tensor-core path (sininn_split_bf16)."""
+    src = _view2d(src)
+    npix, L = src.shape
+    Lp = (L + 7) // 8 * 8
+    blocks = SPLIT_BLOCKS if blocks is None else blocks       # 4: [h | m | h | l] only (two-term-weight product)
+    out = torch.empty(npix, blocks * Lp, dtype=torch.bfloat16, device=src.device)
+    check(_run("split", lambda: load().sininn_split_bf16(src.data_ptr(), src.stride(0), npix, L, float(scale), out.data_ptr(), Lp,
+                                                         blocks, stream_ptr()), 1, 0.0, (4.0 + 2.0 * blocks) * npix * L), "split_bf16")
+    return out
+
+
 def act_bwd(d, y, out, act, slope=0.0):
     """out = d * act'(y); d fp32 view, y the activation output, out fp32/bf16 view (may be d itself)."""
     d, y, out = _view2d(d), _view2d(y), _view2d(out)
@@ -441,6 +455,7 @@ def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False, dbias=None
     if dbias is not None and not tensor_core:
         raise _lib.SininnError("wgrad: the fused bias gradient is a tensor-core-path feature (use colsum)")
     d.dbias, d.dbias_accumulate = _p(dbias), int(dbias_accumulate)
+    d.nterms = 0
     lib = load()
     nbytes = lib.sininn_wgrad_workspace_bytes(C.byref(d), int(tensor_core))
     ws = _workspace(x.device, "wgrad", nbytes)
@@ -453,11 +468,20 @@ def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False, dbias=None
 
 def wgrad_group(jobs):
     """Several tensor-core weight (+ bias) gradients in ONE pair of launches (sininn_wgrad_tc_group).
-    jobs: list of (x, dy, geom, taps, dw, accumulate, dbias, dbias_accumulate) as for wgrad()."""
+    jobs: list of (x, dy, geom, taps, dw, accumulate, dbias, dbias_accumulate[, terms]) as for wgrad(); terms (split
+    operands of the fp32-accurate path) = (x block offsets, dy block offsets, bias mask), see sininn_wgrad_desc."""
     n = len(jobs)
     arr = (WgradDesc * n)()
     flops = 0.0
-    for d, (x, dy, geom, taps, dw, acc, dbias, dbacc) in zip(arr, jobs):
+    for d, job in zip(arr, jobs):
+        x, dy, geom, taps, dw, acc, dbias, dbacc = job[:8]
+        terms = job[8] if len(job) > 8 else None
+        d.nterms = 0
+        if terms is not None:
+            xo, yo, mask = terms
+            d.nterms, d.bias_term_mask = len(xo), int(mask)
+            for t in range(len(xo)):
+                d.x_term_off[t], d.dy_term_off[t] = int(xo[t]), int(yo[t])
         x, dy = _view2d(x), _view2d(dy)
         d.B, d.H, d.W = geom
         d.Cin, d.Cout, d.taps = x.shape[1], dy.shape[1], taps
@@ -466,7 +490,7 @@ def wgrad_group(jobs):
         d.dw, d.accumulate = dw.data_ptr(), int(acc)
         d.dbias, d.dbias_accumulate = _p(dbias), int(dbacc)
         d.workspace, d.workspace_bytes = 0, 0
-        flops += 2.0 * geom[0] * geom[1] * geom[2] * d.Cin * d.Cout * taps
+        flops += 2.0 * geom[0] * geom[1] * geom[2] * d.Cin * d.Cout * taps * max(1, d.nterms)
     lib = load()
     ws = _workspace(jobs[0][0].device, "wgrad", lib.sininn_wgrad_group_workspace_bytes(arr, n))
     check(_run("wgrad", lambda: lib.sininn_wgrad_tc_group(arr, n, ws.data_ptr(), ws.numel(), stream_ptr()), 2, flops),

@@ -134,16 +134,36 @@ def axpy_slice(out, a, alpha):
     out.add_(a.float() * alpha)
 
 
+SPLIT_BLOCKS = 6
+
+
 def pack_weight(w, mode, dtype, rows_pad, k_pad):
     co, ci, kh, kw = w.shape
     taps = kh * kw
     wt = w.detach().reshape(co, ci, taps)
+    if mode >= 2:                        # split packs: K = six blocks [wh | wh | wm | wh | wm | wl]
+        kp = k_pad // SPLIT_BLOCKS
+        base = pack_weight(w, mode - 2, torch.float32, rows_pad, kp)
+        wh = base.to(torch.bfloat16).float()
+        wm = (base - wh).to(torch.bfloat16).float()
+        return torch.cat((wh, wh, wm, wh, wm, base - wh - wm), dim=2).to(torch.bfloat16)
     out = torch.zeros(taps, rows_pad, k_pad, dtype=torch.float32, device=w.device)
     if mode == 0:
         out[:, :co, :ci] = wt.permute(2, 0, 1)
     else:
         out[:, :ci, :co] = wt.flip(2).permute(2, 1, 0)
     return out.to(dtype)
+
+
+def split_bf16(src, scale=1.0, blocks=None):
+    npix, L = src.shape
+    Lp = (L + 7) // 8 * 8
+    x = torch.zeros(npix, Lp, dtype=torch.float32, device=src.device)
+    x[:, :L] = src.float() * scale
+    h = x.to(torch.bfloat16).float()
+    m = (x - h).to(torch.bfloat16).float()
+    l = x - h - m
+    return torch.cat((h, m, h, l, m, h) if blocks in (None, 6) else (h, m, h, l), dim=1).to(torch.bfloat16)
 
 
 def pack_weights_batched(jobs, njobs, dtype):
@@ -227,7 +247,19 @@ def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None, mas
 
 
 def wgrad_group(jobs):
-    for x, dy, geom, taps, dw, acc, dbias, dbacc in jobs:
+    for job in jobs:
+        x, dy, geom, taps, dw, acc, dbias, dbacc = job[:8]
+        if len(job) > 8 and job[8] is not None:       # split operands: sum over the channel-block pairs
+            xo, yo, mask = job[8]
+            cin, cout = x.shape[1], dy.shape[1]
+            xb, yb = x.data_ptr(), dy.data_ptr()
+            xfull = torch.as_strided(x, (x.shape[0], x.stride(0)), (x.stride(0), 1))
+            yfull = torch.as_strided(dy, (dy.shape[0], dy.stride(0)), (dy.stride(0), 1))
+            for t in range(len(xo)):
+                use_b = dbias is not None and (mask >> t) & 1
+                wgrad(xfull[:, xo[t]:xo[t] + cin], yfull[:, yo[t]:yo[t] + cout], geom, taps, dw, accumulate=acc or t > 0,
+                      tensor_core=True, dbias=dbias if use_b else None, dbias_accumulate=dbacc or (use_b and t > 0))
+            continue
         wgrad(x, dy, geom, taps, dw, accumulate=acc, tensor_core=True, dbias=dbias, dbias_accumulate=dbacc)
 
 

@@ -44,14 +44,22 @@ def fixed1x1_checks(dev):
     nodes.append(Ff.Node(nodes[-1], Fm.PermuteRandom, {"seed": 0}, name="perm"))
     nodes.append(Ff.OutputNode(nodes[-1], name="out"))
     net = Ff.ReversibleGraphNet(nodes, verbose=False).to(dev)
-    net.engine_config = E.EngineConfig(precision="fp32")
-    img = torch.rand(2, 3, 8, 8, generator=g).to(dev).requires_grad_(True)
-    out = net(img)
-    assert (net(out.detach(), rev=True) - img.detach()).abs().max() < 1e-5
-    out.square().mean().backward()
-    # gradient check against finite differences of the same network (fp32 path)
-    with torch.no_grad():
-        d = torch.randn(img.shape, generator=g).to(dev)
-        eps = 1e-2
-        num = (net(img.detach() + eps * d).square().mean() - net(img.detach() - eps * d).square().mean()) / (2 * eps)
-    assert abs(float(num) - float((img.grad * d).sum())) < 2e-3 * max(1.0, abs(float(num)))
+    img0 = torch.rand(2, 3, 8, 8, generator=g).to(dev)
+    d = torch.randn(img0.shape, generator=g).to(dev)
+    outs = {}
+    # "fp32": the 1x1 convolution on the CUDA-core fp32 GEMM; "fp32tc": on the tensor cores over split operands (north-star
+    # item 3: the invertible 1x1 convolution as a tcgen05 GEMM, at fp32 accuracy)
+    for precision in ("fp32", "fp32tc"):
+        net.engine_config = E.EngineConfig(precision=precision)
+        net.zero_grad()
+        img = img0.clone().requires_grad_(True)
+        out = net(img)
+        outs[precision] = out.detach()
+        assert (net(out.detach(), rev=True) - img.detach()).abs().max() < 1e-5
+        out.square().mean().backward()
+        # gradient check against finite differences of the same network
+        with torch.no_grad():
+            eps = 1e-2
+            num = (net(img.detach() + eps * d).square().mean() - net(img.detach() - eps * d).square().mean()) / (2 * eps)
+        assert abs(float(num) - float((img.grad * d).sum())) < 2e-3 * max(1.0, abs(float(num)))
+    assert (outs["fp32"] - outs["fp32tc"]).abs().max() < 1e-4 * max(1.0, float(outs["fp32"].abs().max()))

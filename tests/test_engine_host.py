@@ -10,8 +10,8 @@ from oracle import ref_torch as R
 from sin_inn_b200 import archs, engine as E
 
 
-def _pair(arch, scale, nc, lr_window, H, W, seed=5):
-    opt = R.make_opt(scale=scale, num_coupling=nc, lr_window=lr_window, architecture=arch, precision="fp32")
+def _pair(arch, scale, nc, lr_window, H, W, seed=5, precision="fp32"):
+    opt = R.make_opt(scale=scale, num_coupling=nc, lr_window=lr_window, architecture=arch, precision=precision)
     torch.manual_seed(seed)
     ora = R.build(arch, 3, H, W, opt)
     torch.manual_seed(seed)
@@ -32,10 +32,13 @@ def test_same_seed_same_init_and_keys(arch, scale, nc, lrw):
     net.load_state_dict(sa)
 
 
-@pytest.mark.parametrize("arch,scale,nc,lrw,H,W", [("SRF", 2, 2, 1, 16, 24), ("SRF", 4, 2, 10, 16, 32),
-                                                   ("IRN", 2, 1, 1, 16, 16), ("IRN", 4, 1, 10, 16, 24)])
-def test_forward_inverse_backward_match_oracle(fake_kernels, arch, scale, nc, lrw, H, W):
-    opt, ora, net = _pair(arch, scale, nc, lrw, H, W)
+@pytest.mark.parametrize("arch,scale,nc,lrw,H,W,precision", [("SRF", 2, 2, 1, 16, 24, "fp32"), ("SRF", 4, 2, 10, 16, 32, "fp32"),
+                                                             ("IRN", 2, 1, 1, 16, 16, "fp32"), ("IRN", 4, 1, 10, 16, 24, "fp32"),
+                                                             # split-operand plumbing of the fp32 tensor-core path (six-block
+                                                             # products, term-list weight gradients) on the torch stand-ins
+                                                             ("SRF", 2, 2, 1, 16, 24, "fp32tc"), ("SRF", 4, 2, 10, 16, 16, "fp32tc")])
+def test_forward_inverse_backward_match_oracle(fake_kernels, arch, scale, nc, lrw, H, W, precision):
+    opt, ora, net = _pair(arch, scale, nc, lrw, H, W, precision=precision)
     hr, lr, z = R.synthetic_batch(opt, 2, H, W, seed=3)
     lrz = torch.cat((lr, z), 1)
     res = {}

@@ -353,6 +353,72 @@ def test_wgrad_tc(K, taps, cin, cout, geom):
     assert (db2.cpu() - bsum).abs().max().item() <= tolb
 
 
+@pytest.mark.parametrize("taps,cin,cout,geom", [(9, 24, 256, (2, 16, 16)), (9, 256, 192, (1, 16, 32)), (1, 96, 256, (2, 6, 6)), (1, 256, 48, (1, 5, 9)),
+                                                (9, 48, 256, (1, 17, 33))])
+def test_split_operand_conv_is_fp32_accurate(K, taps, cin, cout, geom):
+    """fp32-accurate tensor-core convolution: bf16 hi/mid/lo split operands (split_bf16) x split weight packs (modes
+    2 / 3) through the ordinary tcgen05 kernels, against an fp64 evaluation: the error must be at fp32 level (the plain
+    bf16 path sits at ~3e-3), fprop and dgrad layouts, plus the split weight gradient (two-term blocks + combine)."""
+    B, H, W = geom
+    npix = B * H * W
+    k = 3 if taps == 9 else 1
+    x = rnd(npix, cin, seed=21)
+    w = rnd(cout, cin, k, k, seed=22) * 0.05
+    bias = rnd(cout, seed=23)
+    SB = K.SPLIT_BLOCKS
+    xs = K.split_bf16(x.to(DEV))
+    assert xs.shape == (npix, SB * ((cin + 7) // 8 * 8))
+    wp = K.pack_weight(w.to(DEV), 2, torch.bfloat16, (cout + 15) // 16 * 16, SB * ((cin + 7) // 8 * 8))
+    out = torch.empty(npix, cout, device=DEV)
+    K.conv(xs, wp, geom, cout, out, bias=bias.to(DEV), tensor_core=True)
+    import torch.nn.functional as F
+
+    def nchw(t, c):
+        return t.double().view(B, H, W, c).permute(0, 3, 1, 2)
+
+    def flat(t, c):
+        return t.permute(0, 2, 3, 1).reshape(npix, c)
+
+    ref = flat(F.conv2d(nchw(x, cin), w.double(), bias.double(), padding=k // 2), cout)
+    err = (out.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+    # the TMEM accumulators do not round to nearest: the error grows by ~6e-8 per accumulated MMA step (measured
+    # 2.5e-5 over the 864 steps of a 256-channel 3x3 conv), so the bound scales with the step count
+    steps = taps * ((SB * ((cin + 7) // 8 * 8) + 63) // 64) * 4
+    assert err <= 2e-6 + 6e-8 * steps, err
+    # four-block form (two-term weights): the first four channel blocks against the same pack, 2^-17 accurate
+    xs4 = K.split_bf16(x.to(DEV), blocks=4)
+    assert torch.equal(xs4, xs[:, :xs4.shape[1]])
+    out4 = torch.empty(npix, cout, device=DEV)
+    K.conv(xs4, wp, geom, cout, out4, bias=bias.to(DEV), tensor_core=True)
+    assert (out4.cpu().double() - ref).abs().max().item() / ref.abs().max().item() <= 2e-5 + 6e-8 * steps
+    # data gradient: dx = conv(dy, dgrad pack)
+    dy = rnd(npix, cout, seed=24) * 1e-3
+    dys = K.split_bf16(dy.to(DEV))
+    wpd = K.pack_weight(w.to(DEV), 3, torch.bfloat16, (cin + 15) // 16 * 16, SB * ((cout + 7) // 8 * 8))
+    dx = torch.zeros(npix, cin, device=DEV)
+    K.conv(dys, wpd, geom, cin, dx, tensor_core=True)
+    refd = flat(F.conv_transpose2d(nchw(dy, cout), w.double(), padding=k // 2), cin)
+    errd = (dx.cpu().double() - refd).abs().max().item() / refd.abs().max().item()
+    assert errd <= 2e-6 + 6e-8 * taps * ((SB * ((cout + 7) // 8 * 8) + 63) // 64) * 4, errd
+    # weight + bias gradient: the pixels are walked once per product term of the three-term expansions
+    cinp, coutp = (cin + 7) // 8 * 8, (cout + 7) // 8 * 8
+    xo = [0, 0, cinp, cinp, 0, 3 * cinp]
+    yo = [0, coutp, 0, coutp, 3 * coutp, 0]
+    dw = torch.full((cout, cin, k, k), 0.5, device=DEV)
+    db = torch.full((cout,), 0.25, device=DEV)
+    if max(cin, cout) > 128:              # (term lists are a CTA-pair kernel feature)
+        K.wgrad_group([(xs[:, :cin], dys[:, :cout], geom, taps, dw, True, db, True, (xo, yo, 0b010011))])
+        refw = torch.nn.grad.conv2d_weight(nchw(x, cin), (cout, cin, k, k), nchw(dy, cout), padding=k // 2)
+        errw = (dw.cpu().double() - 0.5 - refw).abs().max().item() / refw.abs().max().item()
+        errb = (db.cpu().double() - 0.25 - dy.double().sum(0)).abs().max().item() / dy.double().sum(0).abs().max().item()
+        assert errw <= 1e-4 and errb <= 1e-4, (errw, errb)          # (0.5 / 0.25 offsets cost a few fp32 ulps of the sum)
+        dw2, db2 = torch.empty_like(dw), torch.empty_like(db)
+        K.wgrad_group([(xs[:, :cin], dys[:, :cout], geom, taps, dw2, False, db2, False, (xo, yo, 0b010011))])
+        errw = (dw2.cpu().double() - refw).abs().max().item() / refw.abs().max().item()
+        errb = (db2.cpu().double() - dy.double().sum(0)).abs().max().item() / dy.double().sum(0).abs().max().item()
+        assert errw <= 6e-6 and errb <= 6e-6, (errw, errb)              # (6x the accumulation steps of one walk)
+
+
 @pytest.mark.parametrize("group", [[(9, 24, 256), (9, 256, 48)], [(1, 96, 256), (1, 256, 192), (9, 96, 256), (9, 256, 192)],
                                    [(9, 56, 32), (9, 256, 48)], [(9, 512, 192), (1, 24, 256), (9, 236, 108)]])
 def test_wgrad_tc_group(K, group):
