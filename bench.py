@@ -78,13 +78,14 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- reference / CPU arm
-def cpu_reference_run(steps, warmup, batch, threads=None, patch=WORKLOAD["patch"]):
+def cpu_reference_run(steps, warmup, batch, threads=None, patch=WORKLOAD["patch"], scale=WORKLOAD["scale"],
+                      lr_window=WORKLOAD["lr_window"]):
     """The reference's own CPU implementation of the path: its archs.py restated in oracle/ref_torch.py
     (the reference cannot travel to the GPU box and needs the un-installable FrEIA), fp32, all host threads."""
     from oracle import ref_torch as R
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    opt = R.make_opt(scale=WORKLOAD["scale"], num_coupling=WORKLOAD["num_coupling"], lr_window=WORKLOAD["lr_window"])
+    opt = R.make_opt(scale=scale, num_coupling=WORKLOAD["num_coupling"], lr_window=lr_window)
     torch.manual_seed(0)
     net = R.build_srf(3, patch, patch, opt)
     optim = R.make_optimizer(net, opt)
@@ -121,8 +122,8 @@ def run_reference(args):
 # ----------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch.distributed as dist
-    from oracle import ref_torch as R            # only for make_opt/synthetic_batch helpers + cpu_baseline leg
     from sin_inn_b200 import archs, kernels, train
+    from sin_inn_b200 import config as R         # make_opt / synthetic_batch (the oracle is only used by the CPU legs)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -139,10 +140,11 @@ def run_ours(args):
     trainer = train.SingleVideoTrainer(net, opt, world_size=world)
     trainer.broadcast_params()
     # synthetic data: a pool of pinned host batches (per-rank seed), copied H2D inside the e2e region
+    # (z is drawn on the device inside the step, as lit_wrapper.py:41 does: a batch is (hr, lr))
     pool = []
     for i in range(2):
-        hr, lr, z = R.synthetic_batch(opt, B, P, P, seed=1000 * rank + i)
-        pool.append(tuple(t.pin_memory() for t in (hr, lr, z)))
+        hr, lr, _ = R.synthetic_batch(opt, B, P, P, seed=1000 * rank + i, with_z=False)
+        pool.append(tuple(t.pin_memory() for t in (hr, lr)))
     dev_batches = [tuple(t.to(dev, non_blocking=True) for t in b) for b in pool]
     h2d = sum(t.numel() * 4 for t in pool[0])
     flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
@@ -160,7 +162,7 @@ def run_ours(args):
     graphed = None
     if not args.no_graph:
         try:
-            graphed = trainer.capture(*dev_batches[0], warmup=2)
+            graphed = trainer.capture(*dev_batches[0], None, warmup=2)
         except Exception as e:                      # keep measuring (eagerly) if stream capture is refused on this box
             print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running the step eagerly", file=sys.stderr, flush=True)
             torch.cuda.synchronize()
@@ -243,80 +245,210 @@ def run_ours(args):
         trainer._graph = None
         trainer.optim.zero_grad()
         torch.cuda.empty_cache()
-        inf = inference_1080p(net, opt, dev, args.infer_batch, iters=args.infer_iters, use_graph=not args.no_graph)
-    t = torch.tensor([ms, ms_e2e] + ([inf["fwd_ms"], inf["inv_ms"]] if inf else [0.0, 0.0]), dtype=torch.float64, device=dev)
+        inf = inference_1080p(net, opt, dev, args.infer_batch, iters=args.infer_iters, use_graph=not args.no_graph, world=world, rank=rank)
+    t = torch.tensor([ms, ms_e2e] + ([inf["fwd_ms"], inf["inv_ms"], inf["e2e_ms"]] if inf else [0.0, 0.0, 0.0]), dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, inf_fwd_ms, inf_inv_ms = t.tolist()
+    ms, ms_e2e, inf_fwd_ms, inf_inv_ms, inf_e2e_ms = t.tolist()
+    extras = {}
+    if world == 1 and not args.no_extras:
+        graphed = feeder = None
+        trainer._graph = None
+        del trainer, net
+        torch.cuda.empty_cache()
+        extras = extra_configs(dev, args)
     if rank == 0:
         pk = peaks()
         value = world * B * args.steps / (ms / 1e3)
         e2e = world * B * args.steps / (ms_e2e / 1e3)
-        # roofline of the dominant kernel (conv_tc_pair_kernel = every 3x3 subnet convolution, ~30 % of the step's
-        # device time): algorithmic FLOPs of its launches / their summed CUDA-event duration in the eager pass
-        zero = {"ms": 0.0, "flops": 0.0, "n": 0}
-        c3 = prof.get("conv3x3", zero)
-        fams = [prof.get(k, zero) for k in ("conv3x3", "conv1x1", "subnet1x1", "wgrad")]
-        tc_ms, tc_fl, tc_n = sum(f["ms"] for f in fams), sum(f["flops"] for f in fams), sum(f["n"] for f in fams)
-        achieved = c3["flops"] / (c3["ms"] / 1e3) / 1e12 if c3["ms"] > 0 else 0.0
-        achieved_all = tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
-        traffic, traffic_detail = None, None
-        tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        zero = {"ms": 0.0, "flops": 0.0, "n": 0, "bytes": 0.0}
+        # Tensor-bound kernel families of the eager single-stream pass: algorithmic FLOPs as passed by the wrappers
+        # (2 * pixels * Cin * Cout * taps per launch; the recompute launches inside the backward pass are executed work
+        # and are counted as such) / summed CUDA-event time.  The family with the largest share of the step is the one the
+        # roofline object describes; every family is listed in roofline.families.
+        tens = {k: prof.get(k, zero) for k in ("conv3x3", "wgrad", "subnet1x1", "conv1x1")}
+        tot_ms = sum(v["ms"] for v in prof.values())
+        top = max(tens, key=lambda k: tens[k]["ms"])
+        names = {"conv3x3": "conv_tc_pair_kernel (3x3 subnet convolutions: fprop, recompute, dgrad)",
+                 "wgrad": "wgrad_pair_kernel + wgrad_reduce_kernel (weight and bias gradients, grouped per coupling block)",
+                 "subnet1x1": "subnet1x1_fwd_kernel (fused 1x1 subnets: forward, recompute, data gradients)",
+                 "conv1x1": "conv_tc_kernel (1x1 convolutions outside the fused kernel)"}
+
+        def fam(v):
+            tf = v["flops"] / (v["ms"] / 1e3) / 1e12 if v["ms"] > 0 else 0.0
+            return {"achieved": tf, "frac": tf / pk["tf_burst"], "frac_of_sustained": tf / pk["tf_sustained"],
+                    "ms_per_step": v["ms"] / args.steps, "launches_per_step": v["n"] / args.steps,
+                    "share_of_step": v["ms"] / tot_ms if tot_ms > 0 else 0.0}
+        fams = {k: fam(v) for k, v in tens.items()}
+        tc_ms, tc_fl = sum(v["ms"] for v in tens.values()), sum(v["flops"] for v in tens.values())
+        traffic, tnote = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic_r2.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            per = [v["dram_read"] + v["dram_write"] for v in tj["shapes"].values()]
-            traffic, traffic_detail = sum(per) / len(per), tj
+            ent = tj.get("families", {}).get(top)
+            if ent:
+                traffic, tnote = ent["dram_bytes_per_launch"], ent["note"]
         alg_flops_step = 6 * 2 * conv_macs_per_patch(P) * B
+        # algorithmic-only: 4 of the 6 conv3x3/1x1 passes per direction are algorithmic (fprop, dgrad; + wgrad), the
+        # recomputed fprop is not: algorithmic FLOPs of the step / time of ALL tensor-bound launches
+        alg_only = alg_flops_step * args.steps / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
         line = {
             "metric": "INN train-step patches/sec", "value": value, "unit": "patches/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_per_step_spread": spread, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp32": "f32", "fp32tc": "f32 (bf16 split operands)"}[args.precision],
             "data": "synthetic",
             "config": {"workload": f"SRF scale4 c4 lr_window10 {P}x{P} train step, batch {B}/GPU", **WORKLOAD,
                        "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision, "tensor_core": not args.no_tensor_core,
                        "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2",
-                       "backward": "recompute-from-inverse", "cuda_graph": used_graph},
+                       "backward": "recompute-from-inverse", "cuda_graph": used_graph, "z": "drawn on the device inside the step"},
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tf_sustained"], "traffic": traffic, "peak_source": pk["source"] + " (sustained)",
-                         "kernel": "conv_tc_pair_kernel (3x3 subnet convolutions: fprop, recompute, dgrad)",
-                         "kernel_ms_per_step": c3["ms"] / args.steps, "kernel_launches": c3["n"],
-                         "traffic_note": "mean DRAM bytes per launch over the three ncu --set full captures in profiles/traffic_r1.json",
-                         "all_subnet_gemms": {"achieved": achieved_all, "frac": achieved_all / pk["tf_sustained"],
-                                              "ms_per_step": tc_ms / args.steps, "launches": tc_n},
-                         "whole_step_algorithmic_tflops": alg_flops_step / (ms / args.steps / 1e3) / 1e12},
+            "roofline": {"bound": "tensor", "achieved": fams[top]["achieved"], "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                         "frac": fams[top]["frac"], "frac_of_sustained": fams[top]["frac_of_sustained"],
+                         "peak_sustained": pk["tf_sustained"], "traffic": traffic, "traffic_note": tnote,
+                         "peak_source": pk["source"] + " (burst bf16; the sustained figure is alongside)",
+                         "kernel": names[top], "kernel_ms_per_step": fams[top]["ms_per_step"],
+                         "kernel_launches": tens[top]["n"], "kernel_share_of_step": fams[top]["share_of_step"],
+                         "families": fams,
+                         "all_subnet_gemms": {"achieved": tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0,
+                                              "frac": (tc_fl / (tc_ms / 1e3) / 1e12 / pk["tf_burst"]) if tc_ms > 0 else 0.0,
+                                              "ms_per_step": tc_ms / args.steps},
+                         "algorithmic_only_tflops": alg_only, "algorithmic_only_frac": alg_only / pk["tf_burst"],
+                         "whole_step_algorithmic_tflops": alg_flops_step / (ms / args.steps / 1e3) / 1e12,
+                         "whole_step_frac": alg_flops_step / (ms / args.steps / 1e3) / 1e12 / pk["tf_burst"],
+                         "timing_note": "family times come from a second, eager single-stream pass of the same K steps with a CUDA-event "
+                                        "pair around every launch (launch gaps included); the headline step is the graph-replayed, "
+                                        "stream-overlapped schedule of the same launches, tested bit-identical"},
             # bandwidth-bound kernel families: algorithmic bytes of their launches / CUDA-event time, vs measured HBM peak
-            "roofline_hbm": {fam: {"achieved": prof[fam]["bytes"] / (prof[fam]["ms"] / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                                   "frac": prof[fam]["bytes"] / (prof[fam]["ms"] / 1e3) / 1e9 / pk["hbm"],
-                                   "launches": prof[fam]["n"], "ms_per_step": prof[fam]["ms"] / args.steps}
-                             for fam in ("coupling_bwd", "coupling", "permute", "resample", "layout")
-                             if fam in prof and prof[fam]["ms"] > 0 and prof[fam]["bytes"] > 0},
+            "roofline_hbm": {fam_: {"achieved": prof[fam_]["bytes"] / (prof[fam_]["ms"] / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                    "frac": prof[fam_]["bytes"] / (prof[fam_]["ms"] / 1e3) / 1e9 / pk["hbm"],
+                                    "launches": prof[fam_]["n"], "ms_per_step": prof[fam_]["ms"] / args.steps}
+                             for fam_ in ("coupling_bwd", "coupling", "permute", "resample", "layout", "split")
+                             if fam_ in prof and prof[fam_]["ms"] > 0 and prof[fam_]["bytes"] > 0},
             "clocks": sampler.summary(),
             "profile_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
         }
         if inf:
             fr = world * inf["frames"]
+            # bf16 round trip inverse(forward(x)): the inverse re-evaluates every subnet on bf16-rounded inputs that differ in
+            # the last fp32 bits, so single bf16 roundings flip; bounds asserted here: max 6e-2, mean 1e-3
+            rt_ok = inf["roundtrip"] <= 6e-2 and inf["roundtrip_mean"] <= 1e-3
             line["inference_1080p"] = {
                 "workload": "SRF scale4 c4 1920x1080 frames, forward + inverse, no_grad, micro-batch %d/GPU (two in flight), frame-sharded" % args.infer_batch,
                 "fwd_inv_frames_per_s": fr / ((inf_fwd_ms + inf_inv_ms) / 1e3),
                 "fwd_frames_per_s": fr / (inf_fwd_ms / 1e3), "inv_frames_per_s": fr / (inf_inv_ms / 1e3),
                 "frames_timed_per_gpu": inf["frames"], "roundtrip_max_abs_err": inf["roundtrip"],
-                "algorithmic_tflops": 2 * 382.2e9 * fr / ((inf_fwd_ms + inf_inv_ms) / 1e3) / 1e12}
+                "roundtrip_mean_abs_err": inf["roundtrip_mean"], "roundtrip_within_bounds": rt_ok,
+                "algorithmic_tflops": 2 * 382.2e9 * fr / ((inf_fwd_ms + inf_inv_ms) / 1e3) / 1e12,
+                # BASELINE.json configs[3] end to end: a 120-frame clip sharded over the ranks; per frame the LR window comes
+                # from pinned host memory, z is drawn on the device (lit_wrapper.py:110), the inverse runs as a replayed graph,
+                # the frame is quantised to uint8 HWC on the device and copied to pinned host memory (lit_wrapper.py:117-121)
+                "e2e_120_frames": {"frames_per_s": world * inf["e2e_frames"] / (inf_e2e_ms / 1e3), "frames_per_gpu": inf["e2e_frames"],
+                                   "h2d_bytes_per_frame": inf["e2e_h2d"], "d2h_bytes_per_frame": inf["e2e_d2h"],
+                                   "direction": "inverse (LR, z) -> HR = the reference's infer"}}
+            assert rt_ok, f"bf16 round trip out of bounds: max {inf['roundtrip']}, mean {inf['roundtrip_mean']}"
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(steps=3, warmup=1, batch=2)
             line["cpu_baseline"] = {"value": r["value"], "unit": "patches/s", "cores": r["cores"], "kind": "port",
                                     "sample": "3 steps x 2 patches of 256x256, same model, oracle port of archs.py on host cores"}
+            r0 = cpu_reference_run(steps=5, warmup=1, batch=4, patch=64, scale=2, lr_window=1)
+            line["config0_cpu"] = {"workload": "BASELINE.json configs[0]: SRF scale 2, 4 couplings, 8-frame 64x64 clip (batch 4), fp32, "
+                                               "oracle port on host cores, full step", "patches_per_s": r0["value"],
+                                   "ms_per_step": r0["ms_per_step"], "cores": r0["cores"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def inference_1080p(net, opt, dev, micro_batch, iters, use_graph=True):
+def _time_steps(step, n, warm=2):
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def extra_configs(dev, args):
+    """Numbers for the BASELINE.json configurations the headline does not cover (N = 1 only; a few seconds each):
+    configs[1] "fp32 vs bf16" (both fp32 paths), configs[4] deep variant (throughput + peak memory), the IRN architecture."""
+    from sin_inn_b200 import archs, train
+    from sin_inn_b200 import config as R
+    out = {}
+    P, B = WORKLOAD["patch"], args.batch
+
+    def trainer_for(opt, ctor, patch, batch, graph=True):
+        torch.manual_seed(0)
+        net = ctor(3, patch, patch, opt).to(dev)
+        if opt.architecture == "IRN":             # conv5 is zero-initialised in the reference: a fresh IRN is the identity
+            g = torch.Generator(device="cpu").manual_seed(1)
+            for m in net.modules():
+                if isinstance(m, archs.DenseBlock):
+                    m.conv5.weight.data.copy_(0.02 * torch.randn(m.conv5.weight.shape, generator=g))
+        tr = train.SingleVideoTrainer(net, opt)
+        hr, lr, _ = (t.to(dev) if t is not None else None for t in R.synthetic_batch(opt, batch, patch, patch, seed=0, with_z=False))
+        step = None
+        if graph and not args.no_graph:
+            try:
+                g_ = tr.capture(hr, lr, None, warmup=2)
+                step = lambda: g_(hr, lr)
+            except Exception as e:
+                print(f"[bench] capture failed for an extra config ({e}); eager", file=sys.stderr, flush=True)
+        if step is None:
+            step = lambda: tr.training_step(hr, lr)
+        return tr, step
+
+    for prec, key, batch, steps in (("fp32tc", "fp32_path", B, 5), ("fp32", "fp32_cuda_core_path", 8, 2)):
+        opt = R.make_opt(scale=WORKLOAD["scale"], num_coupling=WORKLOAD["num_coupling"], lr_window=WORKLOAD["lr_window"], precision=prec)
+        tr, step = trainer_for(opt, archs.UncondSRFlow, P, batch)
+        msv = _time_steps(step, steps)
+        out[key] = {"workload": f"configs[1] in precision {prec!r}: " + ("fp32 activations, subnet GEMMs on the tensor cores over bf16 hi/mid/lo "
+                    "split operands" if prec == "fp32tc" else "CUDA-core fp32 kernels, the reference-accurate path"),
+                    "batch": batch, "value": batch / (msv / 1e3), "unit": "patches/s", "ms_per_step": msv}
+        del tr, step
+        torch.cuda.empty_cache()
+    # configs[4]: deep variant, 512x512 patches, recompute-from-inverse backward: throughput and peak memory
+    opt = R.make_opt(scale=4, num_coupling=8, lr_window=10, precision="bf16", hidden=512)
+    tr, step = trainer_for(opt, archs.UncondSRFlow, 512, 8, graph=False)
+    step()
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    msv = _time_steps(step, 3, warm=1)
+    peak = torch.cuda.max_memory_allocated() - base
+    npix0 = 8 * 128 * 128
+    stored = 2 * (16 * 2 * npix0 * 512 * 2 + 16 * 2 * (npix0 // 4) * 512 * 2)
+    out["deep_variant"] = {"workload": "configs[4]: SRF scale 4, 8 couplings per level, hidden 512, 512x512 patches, batch 8, bf16, eager step",
+                           "value": 8 / (msv / 1e3), "unit": "patches/s", "ms_per_step": msv,
+                           "peak_extra_memory_GiB": peak / 2 ** 30,
+                           "stored_activation_hiddens_GiB": stored / 2 ** 30,
+                           "note": "the backward pass keeps only the network output; an autograd graph of the same net stores every "
+                                   "512-wide hidden tensor (bf16 estimate, both passes)"}
+    del tr, step
+    torch.cuda.empty_cache()
+    opt = R.make_opt(scale=WORKLOAD["scale"], num_coupling=WORKLOAD["num_coupling"], lr_window=WORKLOAD["lr_window"], precision="bf16",
+                     architecture="IRN")
+    tr, step = trainer_for(opt, archs.InvRescaleNet, P, B)
+    msv = _time_steps(step, 5)
+    out["irn_arch"] = {"workload": f"InvRescaleNet (archs.py:201-233) scale 4, 4 InvBlockExp per level, {P}x{P}, batch {B}, bf16",
+                       "value": B / (msv / 1e3), "unit": "patches/s", "ms_per_step": msv,
+                       "algorithmic_tflops": 6 * 20.18e9 * B / (msv / 1e3) / 1e12}
+    del tr, step
+    torch.cuda.empty_cache()
+    return out
+
+
+def inference_1080p(net, opt, dev, micro_batch, iters, use_graph=True, world=1, rank=0):
     """Times `iters` micro-batches of 1920x1080 frames through net(x) and net(lr_z, rev=True) (CUDA events); each
-    direction is one replayed CUDA graph (train.GraphedInference) unless use_graph is False."""
-    from sin_inn_b200 import train
+    direction is one replayed CUDA graph (train.GraphedInference) unless use_graph is False.  Then BASELINE.json
+    configs[3] end to end: this rank's share of a 120-frame clip, host LR windows in, uint8 frames out."""
+    from sin_inn_b200 import engine, train
     H, W = 1080, 1920
     g = torch.Generator(device="cpu").manual_seed(7)
     hr = torch.rand(micro_batch, 3, H, W, generator=g).to(dev)
@@ -325,6 +457,7 @@ def inference_1080p(net, opt, dev, micro_batch, iters, use_graph=True):
         lrz = net(hr)
         back = net(lrz, rev=True)
         out["roundtrip"] = float((back - hr).abs().max())
+        out["roundtrip_mean"] = float((back - hr).abs().mean())
         del back
         if use_graph:
             # two independent micro-batches in flight on two streams: the replayed graphs fill each other's kernel tails
@@ -361,7 +494,76 @@ def inference_1080p(net, opt, dev, micro_batch, iters, use_graph=True):
             e1.record()
             torch.cuda.synchronize()
             out[tag] = e0.elapsed_time(e1)
-    out["frames"] = per_call * iters
+        out["frames"] = per_call * iters
+        # ---- configs[3] end to end: LR windows of this rank's frames from pinned host memory -> device, z drawn on the
+        # device (temp 0.8), inverse pass (graph replay over static lr / z-free LatentInput), uint8 HWC on the device,
+        # one pinned D2H copy per micro-batch; H2D of micro-batch i+1 overlaps the compute of i (side stream)
+        del gfs, gis
+        torch.cuda.empty_cache()
+        frames = list(train.shard_frames(120, rank, world))
+        mb = micro_batch
+        n_mb = (len(frames) + mb - 1) // mb
+        h, w = H // (2 * opt.scale), W // (2 * opt.scale)
+        host_lr = [torch.rand(mb, opt.lr_dims, h, w, generator=g).pin_memory() for _ in range(2)]
+        host_out = [torch.empty(mb, H, W, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        slots = [torch.empty(mb, opt.lr_dims, h, w, device=dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        step_state = torch.zeros(3, dtype=torch.int32, device=dev)          # advances the z stream per micro-batch
+
+        def run_mb(slot):
+            lat = engine.LatentInput(slots[slot], None, z_dims=opt.z_dims, temp=opt.temp, seed=1234 + rank, step_state=step_state)
+            return net(lat, rev=True)
+
+        graphs = None
+        if use_graph:
+            graphs = []
+            for slot in range(2):
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        run_mb(slot)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph):
+                    o = run_mb(slot)
+                    q = train.K.quantize_u8_hwc(o)
+                graphs.append((gph, q))
+
+        def submit(i):
+            with torch.cuda.stream(copy_stream):
+                slots[i % 2].copy_(host_lr[i % 2], non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def clip():
+            submit(0)
+            for i in range(n_mb):
+                if i + 1 < n_mb:
+                    submit(i + 1)
+                torch.cuda.current_stream().wait_event(ready[i % 2])
+                if graphs is not None:
+                    graphs[i % 2][0].replay()
+                    q = graphs[i % 2][1]
+                else:
+                    q = train.K.quantize_u8_hwc(run_mb(i % 2))
+                step_state[0:1].add_(1)
+                host_out[i % 2].copy_(q, non_blocking=True)
+                copy_stream.wait_stream(torch.cuda.current_stream())        # slot i % 2 is reused by micro-batch i + 2
+            torch.cuda.current_stream().synchronize()
+
+        clip()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        clip()
+        e1.record()
+        torch.cuda.synchronize()
+        out["e2e_ms"] = e0.elapsed_time(e1)
+        out["e2e_frames"] = n_mb * mb
+        out["e2e_h2d"] = opt.lr_dims * h * w * 4
+        out["e2e_d2h"] = H * W * 3
     return out
 
 
@@ -375,6 +577,7 @@ def main():
     ap.add_argument("--batch", type=int, default=WORKLOAD["batch_per_gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true", help="skip the 1080p forward+inverse measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp32 / deep-variant / IRN measurements (N = 1 only)")
     ap.add_argument("--infer-batch", type=int, default=2, help="1080p frames per micro-batch and GPU")
     ap.add_argument("--infer-iters", type=int, default=8)
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
