@@ -583,3 +583,18 @@ def test_gather_windows_u8_matches_data_py_arithmetic(K):
     hr, lr = vb.batch(torch.tensor([2, 0]), lr_crop=(2, 4, 8, 8))
     assert torch.equal(lr.cpu(), ref[[2, 0]][:, :, 2:10, 4:12])
     assert torch.equal(hr.cpu(), hr_frames[[2, 0]].permute(0, 3, 1, 2).float()[:, :, 4:20, 8:24] / 255.)
+
+
+@pytest.mark.parametrize("env", [{"SININN_PAIR": "0"}, {"SININN_PAIR": "0", "SININN_HALO": "0"}, {"SININN_WG_PAIR": "0"},
+                                 {"SININN_WGRAD_GROUP": "1"}, {"SININN_WG_HALO": "16"}, {"SININN_PDL": "0"}])
+def test_kernel_selection_switches(env):
+    """The environment switches select the older kernels (single-CTA halo / per-tap 3x3 convolutions, single-CTA weight
+    gradients, ungrouped weight gradients, 16-pixel halo rows, no programmatic dependent launch).  They are read once per
+    process, so each setting runs the convolution / weight-gradient / one network parity test in a subprocess."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sel = "test_conv_tc or test_wgrad_tc or (test_bf16_path_matches_oracle and SRF-4-2-10-1-72-104)"
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_kernels.py", "tests/test_gpu_parity.py", "-q", "-x", "-m", "gpu",
+                        "-k", sel, "-p", "no:cacheprovider"], cwd=root, env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout

@@ -52,6 +52,20 @@ elif case in ("coupling_bwd", "coupling_apply", "permute", "resample", "colsum")
             K.resample_nchw(x4, 0, 0)
         else:
             K.colsum(da, torch.zeros(2 * L, device=DEV))
+elif case.startswith("wgg_"):
+    # grouped weight gradients of one coupling block (what the training step launches): the four convolutions of a 3x3 or
+    # 1x1 GLOW block at level 0 / level 1, bias gradients included
+    lvl, taps = {"wgg_l0_3x3": (0, 9), "wgg_l1_3x3": (1, 9), "wgg_l0_1x1": (0, 1), "wgg_l1_1x1": (1, 1)}[case]
+    hw, c = (64, 48) if lvl == 0 else (32, 192)
+    npix, k = B * hw * hw, 3 if taps == 9 else 1
+    jobs = []
+    for _ in range(2):
+        for cin, cout in ((256, c), (c // 2, 256)):
+            x = torch.randn(npix, cin, device=DEV).to(torch.bfloat16)
+            dy = torch.randn(npix, cout, device=DEV).to(torch.bfloat16)
+            jobs.append((x, dy, (B, hw, hw), taps, torch.zeros(cout, cin, k, k, device=DEV), True, torch.zeros(cout, device=DEV), True))
+    for _ in range(3):
+        K.wgrad_group(jobs)
 elif case.startswith("wg_"):
     hw, cin, cout, taps = {"wg_l0c2": (64, 256, 48, 9), "wg_l1c2": (32, 256, 192, 9), "wg_l0c1": (64, 24, 256, 9)}[case]
     npix = B * hw * hw
