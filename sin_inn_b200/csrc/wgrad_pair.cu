@@ -748,11 +748,7 @@ int launch_wgrad_pair_group(const sininn_wgrad_desc* ds, int n, void* workspace,
 size_t wgrad_pair_group_workspace_bytes(const sininn_wgrad_desc* ds, int n) {
   // every problem may end up with all the pairs of the device (upper bound of its splits)
   size_t tot = 0;
-  for (int i = 0; i < n; ++i) {
-    const size_t b = wgrad_pair_workspace_bytes(&ds[i]);
-    if (b == 0) return 0;
-    tot += b;
-  }
+  for (int i = 0; i < n; ++i) tot += wgrad_pair_workspace_bytes(&ds[i]);     // (0 for problems the pair kernel does not take)
   return tot;
 }
 

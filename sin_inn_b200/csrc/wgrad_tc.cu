@@ -352,12 +352,33 @@ int sininn_wgrad_tc_group(const sininn_wgrad_desc* descs, int n, void* workspace
     const int rc = sininn::tc::launch_wgrad_pair_group(descs, n, workspace, workspace_bytes, sininn::as_stream(stream));
     if (rc != SININN_EUNSUPPORTED) return rc;
   }
-  for (int i = 0; i < n; ++i) {       // not a group the pair kernel takes: one by one (stream order makes sharing the workspace safe)
+  // Mixed group (e.g. a DenseBlock, archs.py:77-81: its first convolutions have <= 128 input channels): the problems the
+  // CTA-pair kernel takes still share one launch, the others run one by one.  Stream order makes sharing the workspace safe.
+  sininn_wgrad_desc pairable[4];
+  int np = 0;
+  for (int i = 0; i < n; ++i) {
+    if (np < 4 && sininn::tc::wgrad_pair_workspace_bytes(&descs[i]) > 0) {
+      pairable[np++] = descs[i];
+      continue;
+    }
     sininn_wgrad_desc d = descs[i];
     d.workspace = workspace;
     d.workspace_bytes = workspace_bytes;
     const int rc = sininn_wgrad_tc(&d, stream);
     if (rc != SININN_OK) return rc;
+  }
+  if (np > 0) {
+    const int rc = sininn::tc::launch_wgrad_pair_group(pairable, np, workspace, workspace_bytes, sininn::as_stream(stream));
+    if (rc == SININN_EUNSUPPORTED) {
+      for (int i = 0; i < np; ++i) {
+        pairable[i].workspace = workspace;
+        pairable[i].workspace_bytes = workspace_bytes;
+        const int r2 = sininn_wgrad_tc(&pairable[i], stream);
+        if (r2 != SININN_OK) return r2;
+      }
+    } else if (rc != SININN_OK) {
+      return rc;
+    }
   }
   return SININN_OK;
 }
