@@ -217,7 +217,12 @@ def run_ours(args):
     trainer.training_step(*dev_batches[0])
     kernels.profile_begin()
     for i in range(args.steps):
+        # Eager launching is host-bound (~10 ms of enqueue work per step): without a head start the GPU idles between
+        # launches and every event pair would also time the host's gap.  A 40 ms spin kernel goes first, the host queues the
+        # step behind it, and the GPU then runs the launches back to back: the pairs time kernel + launch latency only.
+        torch.cuda._sleep(int(0.04 * 1.9e9))
         trainer.training_step(*dev_batches[i % 2])     # eager: events cannot be recorded inside a graph replay
+        torch.cuda.synchronize()
     prof = kernels.profile_end()
     trainer.overlap, net.plan().side_wgrad = saved
     sampler.stop_flag = True

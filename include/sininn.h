@@ -189,6 +189,18 @@ typedef struct {
   /* tensor-core path only: 1 bit per element, uint32 [npix][ceil(Cout/32)], bit c%32 of word c/32 */
   const void* mask_bits;          /* NULL, or sign bits of the ReLU output the gradient flows through: result zeroed where 0 */
   void* bits_out;                 /* NULL, or receives the sign bits (value > 0) of this call's own output */
+  /* Affine coupling fused into the epilogue (3x3 tensor-core path; cpl_mode 0 = off).  The convolution is the SECOND
+   * conv of a GLOW subnet (archs.py:11-13 inside GLOWCouplingBlock, archs.py:61-64) packed with sininn_pack_conv_weight
+   * mode 4 (output rows interleaved s_0, t_0, s_1, t_1, ...), Cout = 2 * cpl_L; its output [s | t] is consumed in
+   * registers and never written (`out` may be NULL):
+   *   cpl_mode 1: the half-step of sininn_coupling_apply on cpl_u [npix][cpl_L] (pixel stride cpl_u_stride), in place,
+   *               direction cpl_inverse; cpl_bf16 (may be NULL) receives the compact bf16 copy of the result.
+   *   cpl_mode 2: the half-step of sininn_coupling_bwd: cpl_u holds y -> x, cpl_du holds dL/dy -> dL/dx (in place),
+   *               cpl_da (bf16 [npix][2 * cpl_L]) receives [dL/ds | dL/dt], cpl_bf16 the bf16 copy of x. */
+  int cpl_mode; int cpl_L; int cpl_inverse; float cpl_clamp;
+  float* cpl_u; int cpl_u_stride;
+  float* cpl_du; int cpl_du_stride;
+  void* cpl_bf16; void* cpl_da;
 } sininn_conv_desc;
 
 /* Debugging aid: when set to a device buffer of 4 x 512 int64, the CTA-pair 3x3 kernel records clock64() stamps of
@@ -223,6 +235,13 @@ typedef struct {
    * out (+)= W1^T dL/dh is the gradient w.r.t. the subnet input. */
   const void* mask_bits;                 /* NULL, or uint32 [npix][hidden/32]: first stage = zero where the bit is 0 */
   int accumulate;                        /* 1: out += result */
+  /* GLOW affine coupling in the second epilogue, exactly as the cpl_* fields of sininn_conv_desc: w2pack in the
+   * interleaved mode-4 layout, Cout = 2 * cpl_L, `out` unused (may be NULL); cpl_mode 1 = half-step on cpl_u, cpl_mode 2 =
+   * its backward (with h_out / bits_out stored for the subnet's backward pass, as in the recompute pass). */
+  int cpl_mode; int cpl_L; int cpl_inverse; float cpl_clamp;
+  float* cpl_u; int cpl_u_stride;
+  float* cpl_du; int cpl_du_stride;
+  void* cpl_bf16; void* cpl_da;
 } sininn_subnet1x1_desc;
 
 int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stream);
@@ -232,6 +251,8 @@ int sininn_subnet1x1_supported(int Cin, int hidden, int Cout);
 /* Re-layout nn.Conv2d OIHW fp32 weights for the implicit GEMMs above.
  *   mode 0 (fprop): out[tap][co][ci] = w[co][ci][tap]           rows = Cout, k = Cin
  *   mode 1 (dgrad): out[tap][ci][co] = w[co][ci][taps-1-tap]    rows = Cin,  k = Cout
+ *   mode 4 (fprop, rows interleaved): row 2c = output channel c, row 2c+1 = output channel Cout/2 + c -- the layout of a
+ *               GLOW subnet's second convolution whose [s | t] halves are consumed pairwise by the fused coupling epilogue
  *   mode 2 / 3: the same two layouts for the fp32-accurate tensor-core path (bf16 only): K is six blocks of k_pad / 6
  *               holding [wh | wh | wm | wh | wm | wl] (wh = bf16(w), wm = bf16(w - wh), wl = bf16(w - wh - wm));
  *               pairs with sininn_split_bf16 operands */

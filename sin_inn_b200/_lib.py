@@ -35,6 +35,10 @@ class ConvDesc(C.Structure):
         ("mask", _vp), ("mask_stride", C.c_int), ("mask_act", C.c_int),
         ("accumulate", C.c_int), ("alpha", C.c_float),
         ("mask_bits", _vp), ("bits_out", _vp),
+        ("cpl_mode", C.c_int), ("cpl_L", C.c_int), ("cpl_inverse", C.c_int), ("cpl_clamp", C.c_float),
+        ("cpl_u", _vp), ("cpl_u_stride", C.c_int),
+        ("cpl_du", _vp), ("cpl_du_stride", C.c_int),
+        ("cpl_bf16", _vp), ("cpl_da", _vp),
     ]
 
 
@@ -64,6 +68,10 @@ class Subnet1x1Desc(C.Structure):
         ("h_out", _vp), ("h_stride", C.c_int),
         ("bits_out", _vp),
         ("mask_bits", _vp), ("accumulate", C.c_int),
+        ("cpl_mode", C.c_int), ("cpl_L", C.c_int), ("cpl_inverse", C.c_int), ("cpl_clamp", C.c_float),
+        ("cpl_u", _vp), ("cpl_u_stride", C.c_int),
+        ("cpl_du", _vp), ("cpl_du_stride", C.c_int),
+        ("cpl_bf16", _vp), ("cpl_da", _vp),
     ]
 
 

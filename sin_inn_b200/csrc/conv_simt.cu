@@ -163,13 +163,16 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
     int tap = (int)(r / rows_pad);
     float v = 0.f;
     int blockk = 0;
-    if (mode >= 2) { const int kp = k_pad / SPLIT_BLOCKS; blockk = k / kp; k = k % kp; }   // split packs: six K blocks
-    if ((mode & 1) == 0) {      // fprop: row = co, k = ci
+    if (mode == 2 || mode == 3) { const int kp = k_pad / SPLIT_BLOCKS; blockk = k / kp; k = k % kp; }   // split packs: six K blocks
+    if (mode == 4) {            // fprop, output rows interleaved: (s_0, t_0, s_1, t_1, ...)
+      const int co = (row & 1) ? Cout / 2 + (row >> 1) : (row >> 1);
+      if (row < Cout && k < Cin) v = w[((long long)co * Cin + k) * taps + tap];
+    } else if ((mode & 1) == 0) {      // fprop: row = co, k = ci
       if (row < Cout && k < Cin) v = w[((long long)row * Cin + k) * taps + tap];
     } else {                    // dgrad: row = ci, k = co, spatially flipped
       if (row < Cin && k < Cout) v = w[((long long)k * Cin + row) * taps + (taps - 1 - tap)];
     }
-    if (mode >= 2) v = split_weight_term(v, blockk);
+    if (mode == 2 || mode == 3) v = split_weight_term(v, blockk);
     out[idx] = from_f32<TO>(v);
   }
 }
@@ -192,13 +195,16 @@ __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const long lon
     int tap = (int)(r / rows_pad);
     float v = 0.f;
     int blockk = 0;
-    if (mode >= 2) { const int kp = k_pad / SPLIT_BLOCKS; blockk = k / kp; k = k % kp; }
-    if ((mode & 1) == 0) {
+    if (mode == 2 || mode == 3) { const int kp = k_pad / SPLIT_BLOCKS; blockk = k / kp; k = k % kp; }
+    if (mode == 4) {
+      const int co = (row & 1) ? Cout / 2 + (row >> 1) : (row >> 1);
+      if (row < Cout && k < Cin) v = w[((long long)co * Cin + k) * taps + tap];
+    } else if ((mode & 1) == 0) {
       if (row < Cout && k < Cin) v = w[((long long)row * Cin + k) * taps + tap];
     } else {
       if (row < Cin && k < Cout) v = w[((long long)k * Cin + row) * taps + (taps - 1 - tap)];
     }
-    if (mode >= 2) v = split_weight_term(v, blockk);
+    if (mode == 2 || mode == 3) v = split_weight_term(v, blockk);
     out[idx] = from_f32<TO>(v);
   }
 }
@@ -419,11 +425,13 @@ int sininn_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, in
                             int rows_pad, int k_pad, sininn_stream_t stream) {
   SININN_CHECK_ARG(w_oihw && out && Cout > 0 && Cin > 0, "pack_conv_weight: bad arguments");
   SININN_CHECK_ARG(taps == 1 || taps == 9, "pack_conv_weight: taps must be 1 or 9");
-  SININN_CHECK_ARG(mode >= 0 && mode <= 3, "pack_conv_weight: mode must be 0 (fprop), 1 (dgrad), 2 / 3 (their split forms)");
+  SININN_CHECK_ARG(mode >= 0 && mode <= 4, "pack_conv_weight: mode must be 0 (fprop), 1 (dgrad), 2 / 3 (their split forms), 4 (interleaved fprop)");
+  SININN_CHECK_ARG(mode != 4 || (Cout % 2) == 0, "pack_conv_weight: the interleaved layout needs an even Cout");
+  const bool split = mode == 2 || mode == 3;
   const int rows = (mode & 1) == 0 ? Cout : Cin, k = (mode & 1) == 0 ? Cin : Cout;
-  SININN_CHECK_ARG(rows_pad >= rows && (mode < 2 ? k_pad >= k : ((k_pad % SPLIT_BLOCKS) == 0 && k_pad / SPLIT_BLOCKS >= k)),
+  SININN_CHECK_ARG(rows_pad >= rows && (!split ? k_pad >= k : ((k_pad % SPLIT_BLOCKS) == 0 && k_pad / SPLIT_BLOCKS >= k)),
                    "pack_conv_weight: padding smaller than the matrix");
-  SININN_CHECK_ARG(mode < 2 || out_dtype == SININN_BF16, "pack_conv_weight: split packs are bf16");
+  SININN_CHECK_ARG(!split || out_dtype == SININN_BF16, "pack_conv_weight: split packs are bf16");
   const long long total = (long long)taps * rows_pad * k_pad;
   long long g = (total + 255) / 256;
   if (g > (long long)sm_count() * 16) g = (long long)sm_count() * 16;

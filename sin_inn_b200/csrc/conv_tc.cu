@@ -153,7 +153,19 @@ extern "C" {
 
 int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream) {
   using namespace sininn::tc;
-  SININN_CHECK_ARG(d != nullptr && d->in && d->wpack && d->out, "conv_tc: null pointer");
+  SININN_CHECK_ARG(d != nullptr && d->in && d->wpack && (d->out || d->cpl_mode != 0), "conv_tc: null pointer");
+  if (d->cpl_mode != 0) {
+    SININN_CHECK_ARG(d->cpl_mode == 1 || d->cpl_mode == 2, "conv_tc: cpl_mode must be 0, 1 or 2");
+    SININN_CHECK_ARG(d->taps == 9 && d->Cout == 2 * d->cpl_L && d->rows_pad <= 256 && (d->cpl_L % 8) == 0,
+                     "conv_tc: the fused coupling epilogue needs a 3x3 convolution with Cout = 2 L <= 256, L %% 8 == 0 (Cout=%d L=%d)",
+                     d->Cout, d->cpl_L);
+    SININN_CHECK_ARG(d->cpl_u && aligned16(d->cpl_u) && (d->cpl_u_stride % 4) == 0 && d->cpl_clamp > 0.f, "conv_tc: bad coupling slice");
+    SININN_CHECK_ARG(d->cpl_mode == 1 || (d->cpl_du && aligned16(d->cpl_du) && (d->cpl_du_stride % 4) == 0 && d->cpl_da && aligned8(d->cpl_da)),
+                     "conv_tc: the coupling backward epilogue needs the gradient slice and the [ds | dt] output");
+    SININN_CHECK_ARG(!d->cpl_bf16 || aligned8(d->cpl_bf16), "conv_tc: misaligned bf16 copy");
+    SININN_CHECK_ARG(d->act == SININN_ACT_NONE && !d->mask && !d->mask_bits && !d->bits_out && !d->accumulate && d->alpha == 1.0f,
+                     "conv_tc: the coupling epilogue replaces every other epilogue option");
+  }
   SININN_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "conv_tc: bad shape");
   SININN_CHECK_ARG(d->taps == 1 || d->taps == 9, "conv_tc: taps must be 1 or 9");
   SININN_CHECK_ARG(d->in_dtype == SININN_BF16, "conv_tc: operands must be bf16");
@@ -199,9 +211,12 @@ int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream) {
   p.bits_out = reinterpret_cast<uint32_t*>(d->bits_out);
   p.bit_words = bit_words;
   p.accumulate = d->accumulate; p.alpha = d->alpha;
+  p.cpl.mode = d->cpl_mode; p.cpl.L = d->cpl_L; p.cpl.inverse = d->cpl_inverse; p.cpl.clamp = d->cpl_clamp;
+  p.cpl.u = d->cpl_u; p.cpl.u_stride = d->cpl_u_stride; p.cpl.du = d->cpl_du; p.cpl.du_stride = d->cpl_du_stride;
+  p.cpl.bf16 = reinterpret_cast<__nv_bfloat16*>(d->cpl_bf16); p.cpl.da = reinterpret_cast<__nv_bfloat16*>(d->cpl_da);
   const int esz = p.out_f32 ? 4 : 2;
   // TMA epilogue needs a 16-byte aligned output slice / pixel stride and no per-element mask tensor
-  p.tma_out = (aligned16(d->out) && ((long long)d->out_stride * esz) % 16 == 0 && d->mask == nullptr) ? 1 : 0;
+  p.tma_out = (d->out && aligned16(d->out) && ((long long)d->out_stride * esz) % 16 == 0 && d->mask == nullptr) ? 1 : 0;
 
   // 3x3 with 64-channel slabs: halo-reuse kernel (activation patch loaded once per slab instead of nine times)
   // (SININN_HALO=0 disables it; measured on B200: the UMMA swizzle XOR is taken from the absolute shared-memory
@@ -215,6 +230,10 @@ int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream) {
   if (pair_mode > 0 && d->taps == 9) {
     const int rc = launch_conv_pair(d, p, as_stream(stream));
     if (rc != SININN_EUNSUPPORTED) return rc;
+  }
+  if (d->cpl_mode != 0) {
+    set_error("conv_tc: the fused coupling epilogue is a CTA-pair kernel feature (shape not taken, or SININN_PAIR=0)");
+    return SININN_EUNSUPPORTED;
   }
   static int halo_mode = -1;
   if (halo_mode < 0) {

@@ -259,10 +259,19 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int b, h0, w0, n0;
       pair_item(hp, it, rank, b, h0, w0, n0);
       epilogue_load_bias(p, bias_s, n0, etid, bias_n0);
+      bool row_ok = false; long long pix = 0;
+      CplRegs cpl;
+      if (p.cpl.mode != 0) {                 // the coupling operands of this thread's first slab travel while the MMAs run
+        cpl_row<PT_W>(p, b, h0, w0, quarter, lane, row_ok, pix);
+        cpl_prefetch(p.cpl, cpl, pix, half * 16, row_ok);
+      }
       mbar_wait(smem_u32(&bars->acc_full[acc]), acc_phase);
       tc_fence_after();
       trace_stamp(hp, 2, ti, tl);
       const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE;
+      if (p.cpl.mode != 0) {
+        epilogue_tile_coupling(p.cpl, bias_s, t_base, row_ok, pix, half, 2, cpl);
+      } else {
 #ifdef SININN_PAIR_TRACE
       // stamps inside the first two tiles of warp 2 of CTA 0 go to role slot 2 from word 256 on
       long long* et = (hp.trace != nullptr && blockIdx.x == 0 && warp == 2 && ti < 6) ? hp.trace + 2 * TRACE_ROLE_WORDS + 256 + 16 * (ti / 2) : nullptr;
@@ -270,6 +279,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #else
       epilogue_tile<PT_W>(p, &tmO, stg, bias_s, t_base, b, h0, w0, n0, quarter, half, lane);
 #endif
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->acc_empty[acc]), 0));

@@ -57,6 +57,7 @@ struct S1Params {
   // data-gradient use of the same pipeline (x := dL/d(out), W1 := conv2 dgrad pack, W2 := conv1 dgrad pack):
   const uint32_t* bits_in;      // non-NULL: first epilogue = zero where the stored ReLU sign bit is 0 (no bias, no ReLU)
   int accumulate;               // 1: out += result (TMA reduce-add) instead of out = result
+  CplParams cpl;                // GLOW coupling (apply / backward) in the second epilogue; W2 rows interleaved (pack mode 4)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -124,7 +125,10 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   if (warp >= 2) {      // biases -> shared memory (zero beyond the real channel counts)
     const int e = threadIdx.x - 64;
     if (e < 256) b1_s[e] = (p.b1 != nullptr && e < p.hidden) ? __ldg(p.b1 + e) : 0.f;
-    if (e < 256) b2_s[e] = (p.b2 != nullptr && e < p.cout) ? __ldg(p.b2 + e) : 0.f;
+    if (e < 256) {
+      const int co = p.cpl.mode != 0 ? ((e & 1) ? p.cpl.L + (e >> 1) : (e >> 1)) : e;      // interleaved rows (s_0, t_0, ...)
+      b2_s[e] = (p.b2 != nullptr && e < p.cout) ? __ldg(p.b2 + co) : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -305,6 +309,18 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
       }
       // ---------------- epi2: D2 -> +b2 -> fp32 staging (own rows of the hidden tile) -> TMA store ----------------
+      if (p.cpl.mode != 0) {
+        // ... or the GLOW half-step on the output held in registers (tc_epilogue.cuh): operands of this warp's first
+        // slab are fetched before the wait for MMA2; the subnet output is never stored
+        CplRegs cpl;
+        cpl_prefetch(p.cpl, cpl, pix, half * 16, row_ok);
+        mbar_wait(smem_u32(&bars->d2_full), dph);
+        dph ^= 1;
+        tc_fence_after();
+        epilogue_tile_coupling(p.cpl, b2_s, d2_tmem + lane_base, row_ok, pix, half, S1_SUBS, cpl);
+        tc_fence_before();
+        continue;
+      }
       mbar_wait(smem_u32(&bars->d2_full), dph);
       dph ^= 1;
       tc_fence_after();
@@ -387,13 +403,24 @@ int sininn_subnet1x1_supported(int Cin, int hidden, int Cout) {
 
 int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stream) {
   using namespace sininn::tc;
-  SININN_CHECK_ARG(d != nullptr && d->x && d->w1pack && d->w2pack && d->out, "subnet1x1: null pointer");
+  SININN_CHECK_ARG(d != nullptr && d->x && d->w1pack && d->w2pack && (d->out || d->cpl_mode != 0), "subnet1x1: null pointer");
+  if (d->cpl_mode != 0) {
+    SININN_CHECK_ARG(d->cpl_mode == 1 || d->cpl_mode == 2, "subnet1x1: cpl_mode must be 0, 1 or 2");
+    SININN_CHECK_ARG(d->Cout == 2 * d->cpl_L && (d->cpl_L % 8) == 0, "subnet1x1: the coupling epilogue needs Cout = 2 L, L %% 8 == 0 (Cout=%d L=%d)",
+                     d->Cout, d->cpl_L);
+    SININN_CHECK_ARG(d->cpl_u && aligned16(d->cpl_u) && (d->cpl_u_stride % 4) == 0 && d->cpl_clamp > 0.f, "subnet1x1: bad coupling slice");
+    SININN_CHECK_ARG(d->cpl_mode == 1 || (d->cpl_du && aligned16(d->cpl_du) && (d->cpl_du_stride % 4) == 0 && d->cpl_da && aligned8(d->cpl_da)),
+                     "subnet1x1: the coupling backward epilogue needs the gradient slice and the [ds | dt] output");
+    SININN_CHECK_ARG(!d->cpl_bf16 || aligned8(d->cpl_bf16), "subnet1x1: misaligned bf16 copy");
+    SININN_CHECK_ARG(!d->mask_bits && !d->accumulate, "subnet1x1: the coupling epilogue is a forward-mode option");
+  }
   SININN_CHECK_ARG(d->npix > 0 && d->Cin > 0 && d->Cout > 0, "subnet1x1: bad shape");
   SININN_CHECK_ARG(d->hidden % 64 == 0 && d->hidden >= 64 && d->hidden <= 256, "subnet1x1: hidden width must be 64..256 in steps of 64 (got %d)", d->hidden);
   SININN_CHECK_ARG(d->Cout <= 256 && d->n2_pad % 16 == 0 && d->n2_pad >= d->Cout && d->n2_pad <= 256, "subnet1x1: bad Cout / n2_pad");
   SININN_CHECK_ARG(d->k1_pad % 16 == 0 && d->k1_pad >= d->Cin, "subnet1x1: bad k1_pad");
   SININN_CHECK_ARG(aligned16(d->x) && (d->x_stride * 2) % 16 == 0, "subnet1x1: x must be 16-byte aligned with a pixel stride that is a multiple of 8");
-  SININN_CHECK_ARG(aligned16(d->out) && (d->out_stride * 4) % 16 == 0, "subnet1x1: out must be 16-byte aligned with a pixel stride that is a multiple of 4");
+  SININN_CHECK_ARG(d->cpl_mode != 0 || (aligned16(d->out) && (d->out_stride * 4) % 16 == 0),
+                   "subnet1x1: out must be 16-byte aligned with a pixel stride that is a multiple of 4");
   SININN_CHECK_ARG(aligned16(d->w1pack) && aligned16(d->w2pack), "subnet1x1: packed weights misaligned");
   SININN_CHECK_ARG(d->h_out == nullptr || (aligned16(d->h_out) && (d->h_stride * 2) % 16 == 0), "subnet1x1: h_out misaligned");
   SININN_CHECK_ARG(d->npix < (1ll << 31) - 256, "subnet1x1: too many pixels");
@@ -416,6 +443,9 @@ int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stre
   p.w1_slab_bytes = (uint32_t)d->hidden * row1;
   p.w2_slab_bytes = (uint32_t)p.n2pad * 128u;
   p.b1 = d->b1; p.b2 = d->b2;
+  p.cpl.mode = d->cpl_mode; p.cpl.L = d->cpl_L; p.cpl.inverse = d->cpl_inverse; p.cpl.clamp = d->cpl_clamp;
+  p.cpl.u = d->cpl_u; p.cpl.u_stride = d->cpl_u_stride; p.cpl.du = d->cpl_du; p.cpl.du_stride = d->cpl_du_stride;
+  p.cpl.bf16 = reinterpret_cast<__nv_bfloat16*>(d->cpl_bf16); p.cpl.da = reinterpret_cast<__nv_bfloat16*>(d->cpl_da);
   p.bits_out = reinterpret_cast<uint32_t*>(d->bits_out);
   p.store_h = d->h_out != nullptr ? 1 : 0;
   p.bits_in = reinterpret_cast<const uint32_t*>(d->mask_bits);
@@ -446,7 +476,9 @@ int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stre
   if (!encode_2d(encode, &tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->w2pack, d->hidden, p.n2pad, d->hidden, 64, p.n2pad, CU_TENSOR_MAP_SWIZZLE_128B)) {
     set_error("subnet1x1: tensor map (W2) failed"); return SININN_ECUDA;
   }
-  if (!encode_2d(encode, &tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->out, d->Cout, d->npix, d->out_stride, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) {
+  if (d->cpl_mode != 0) {
+    tmO = tmX;                 // (never used: the coupling epilogue consumes the output in registers)
+  } else if (!encode_2d(encode, &tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->out, d->Cout, d->npix, d->out_stride, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) {
     set_error("subnet1x1: tensor map (out) failed (Cout=%d stride=%d)", d->Cout, d->out_stride); return SININN_ECUDA;
   }
   if (p.store_h) {

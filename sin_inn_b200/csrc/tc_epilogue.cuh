@@ -13,6 +13,16 @@ constexpr int STAGING_BYTES = 32 * 128;  // one epilogue warp: 32 rows x 128 B
 constexpr int EPI_SMEM_BYTES = 256 * 4 + NUM_EPI_WARPS * STAGING_BYTES;
 constexpr int SMEM_RING_BUDGET = 227 * 1024 - EPI_SMEM_BYTES - BARRIER_BYTES - 1024;   // 1024: worst-case alignment pad
 
+// affine coupling fused into an epilogue (sininn_conv_desc / sininn_subnet1x1_desc cpl_*): mode 0 off, 1 apply, 2 backward
+struct CplParams {
+  int mode, L, inverse;
+  float clamp;
+  float* u; int u_stride;
+  float* du; int du_stride;
+  __nv_bfloat16* bf16;
+  __nv_bfloat16* da;
+};
+
 struct Params {
   int B, H, W, Cin, Cout;
   int taps, kc, k_chunks;        // kc = channels per K step (16/32/64), k_chunks = ceil(Cin / kc)
@@ -33,6 +43,7 @@ struct Params {
   int bit_words;
   int accumulate; float alpha;
   int tma_out;                   // 1: TMA-store epilogue; 0: per-thread fallback (unaligned output slices)
+  CplParams cpl;                 // conv_tc_pair only
 };
 
 template <int TW>
@@ -136,8 +147,10 @@ __device__ __forceinline__ void epilogue_load_bias(const Params& p, float* bias_
   if (n0 == bias_n0) return;
   asm volatile("bar.sync 1, 256;" ::: "memory");           // everyone done with the previous slice
   {
-    const int co = n0 + etid;
-    bias_s[etid] = (p.bias != nullptr && co < p.Cout) ? __ldg(p.bias + co) : 0.f;
+    int co = n0 + etid;
+    const bool ok = p.bias != nullptr && co < p.Cout;
+    if (p.cpl.mode != 0) co = (co & 1) ? p.cpl.L + (co >> 1) : (co >> 1);     // rows interleaved (s_0, t_0, s_1, t_1, ...)
+    bias_s[etid] = ok ? __ldg(p.bias + co) : 0.f;
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");
   bias_n0 = n0;
@@ -248,6 +261,130 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
       if (p.out_f32) epilogue_chunk<float>(p, v, pix, n0 + c, row_ok);
       else epilogue_chunk<__nv_bfloat16>(p, v, pix, n0 + c, row_ok);
     }
+  }
+}
+
+// Affine coupling in the epilogue (GLOW, archs.py:61-64; equations SURVEY.md 8a).  The accumulator columns are the
+// interleaved subnet output (s_0, t_0, s_1, t_1, ...): one 32-column slab = 16 channels of this thread's pixel.
+//   cpl_mode 1:  u <- e(s) u + t   or   (u - t) / e(s);   optional compact bf16 copy
+//   cpl_mode 2:  y, dy -> x, dx in place; [ds | dt] as bf16; optional bf16 copy of x
+// The subnet output never reaches memory.  Rows are 64 contiguous bytes per thread and tensor (16-byte vector accesses).
+// Only 8 warps per SM do this math (the standalone kernels spread it over 64), so it uses the fast forms below: a
+// degree-7 polynomial in t^2 for atan (1.6e-7 absolute on [0, 1], reciprocal argument beyond 1), ex2.approx, approximate
+// division -- errors at fp32 rounding level, far inside the bf16 path's tolerance; the fp32 paths never take this epilogue.
+__device__ __forceinline__ float fast_atan(float r) {
+  const float a = fabsf(r);
+  const bool inv = a > 1.0f;
+  const float t = inv ? __fdividef(1.0f, a) : a;
+  const float z = t * t;
+  float p = -0.004668773151934147f;
+  p = fmaf(p, z, 0.02416618913412094f);
+  p = fmaf(p, z, -0.0593671016395092f);
+  p = fmaf(p, z, 0.09906096756458282f);
+  p = fmaf(p, z, -0.14016585052013397f);
+  p = fmaf(p, z, 0.19969235360622406f);
+  p = fmaf(p, z, -0.33331960439682007f);
+  p = fmaf(p, z, 0.9999998807907104f);
+  p *= t;
+  p = inv ? 1.5707963267948966f - p : p;
+  return copysignf(p, r);
+}
+// e = exp(g(s)), dg = g'(s) for the GLOW clamp (common.cuh log_scale)
+__device__ __forceinline__ void glow_scale_fast(float clamp, float inv_clamp, float sv, float& ex, float& dg) {
+  const float r = sv * inv_clamp;
+  ex = __expf(clamp * 0.636f * fast_atan(r));
+  dg = __fdividef(0.636f, fmaf(r, r, 1.0f));
+}
+
+struct CplRegs { float4 u[4], d[4]; };
+__device__ __forceinline__ void cpl_prefetch(const CplParams& p, CplRegs& R, long long pix, int ch0, bool row_ok) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const bool ok = row_ok && ch0 + 4 * q < p.L;
+    R.u[q] = ok ? *reinterpret_cast<const float4*>(p.u + pix * p.u_stride + ch0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    R.d[q] = (ok && p.mode == 2) ? *reinterpret_cast<const float4*>(p.du + pix * p.du_stride + ch0 + 4 * q)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int TW>
+__device__ __forceinline__ void cpl_row(const Params& p, int b, int h0, int w0, int quarter, int lane, bool& row_ok, long long& pix) {
+  const int row = quarter * 32 + lane;
+  const int oh = h0 + row / TW, ow = w0 + row % TW;
+  row_ok = (oh < p.H) && (ow < p.W) && (b < p.B);
+  pix = ((long long)b * p.H + oh) * p.W + ow;
+}
+
+// One slab: v = 32 accumulator columns (s_k, t_k interleaved) of this thread's pixel, bs = their biases, cur = the 16
+// channels of u (and du) loaded earlier; channels ch0 .. ch0+15.
+__device__ __forceinline__ void cpl_slab(const CplParams& p, const uint32_t (&v)[32], const float* bs, long long pix, int ch0,
+                                         const CplRegs& cur) {
+  const int L = p.L;
+  const float inv_clamp = 1.0f / p.clamp;
+  float* up = p.u + pix * p.u_stride + ch0;
+  float* dp = p.du + pix * p.du_stride + ch0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {           // four channels at a time
+    if (ch0 + 4 * q < L) {
+      const float uu[4] = {cur.u[q].x, cur.u[q].y, cur.u[q].z, cur.u[q].w};
+      float y[4];
+      if (p.mode == 1) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float sv = __uint_as_float(v[8 * q + 2 * e]) + bs[8 * q + 2 * e];
+          const float tv = __uint_as_float(v[8 * q + 2 * e + 1]) + bs[8 * q + 2 * e + 1];
+          float ex, dg;
+          glow_scale_fast(p.clamp, inv_clamp, sv, ex, dg);
+          y[e] = p.inverse ? __fdividef(uu[e] - tv, ex) : fmaf(ex, uu[e], tv);
+        }
+        *reinterpret_cast<float4*>(up + 4 * q) = make_float4(y[0], y[1], y[2], y[3]);
+      } else {
+        const float dy[4] = {cur.d[q].x, cur.d[q].y, cur.d[q].z, cur.d[q].w};
+        float dx[4], dsv[4], dtv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float sv = __uint_as_float(v[8 * q + 2 * e]) + bs[8 * q + 2 * e];
+          const float tv = __uint_as_float(v[8 * q + 2 * e + 1]) + bs[8 * q + 2 * e + 1];
+          float ex, dg;
+          glow_scale_fast(p.clamp, inv_clamp, sv, ex, dg);
+          if (!p.inverse) {                  // y = ex*x + t
+            y[e] = __fdividef(uu[e] - tv, ex);
+            dx[e] = dy[e] * ex;
+            dsv[e] = dy[e] * y[e] * ex * dg;
+            dtv[e] = dy[e];
+          } else {                           // y = (x - t)/ex
+            y[e] = fmaf(uu[e], ex, tv);
+            const float qv = __fdividef(dy[e], ex);
+            dx[e] = qv;
+            dsv[e] = -dy[e] * uu[e] * dg;
+            dtv[e] = -qv;
+          }
+        }
+        *reinterpret_cast<float4*>(up + 4 * q) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(dp + 4 * q) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+        __nv_bfloat16* da = p.da + pix * (2 * L) + ch0 + 4 * q;
+        store4(da, make_float4(dsv[0], dsv[1], dsv[2], dsv[3]));
+        store4(da + L, make_float4(dtv[0], dtv[1], dtv[2], dtv[3]));
+      }
+      if (p.bf16 != nullptr) store4(p.bf16 + pix * L + ch0 + 4 * q, make_float4(y[0], y[1], y[2], y[3]));
+    }
+  }
+}
+
+// `first` holds the operands of this warp's first slab, loaded BEFORE the wait for the accumulator; the operands of the
+// warp's next slab are loaded while the current one is computed.  The `nsub` warps of a lane quarter take alternate slabs.
+__device__ __forceinline__ void epilogue_tile_coupling(const CplParams& p, const float* bias_s, uint32_t t_base, bool row_ok, long long pix,
+                                                       int sub, int nsub, CplRegs& first) {
+  const int n_slabs = (2 * p.L + 31) / 32;
+  CplRegs cur = first;
+  for (int s = sub; s < n_slabs; s += nsub) {
+    uint32_t v[32];
+    tmem_ld32(t_base + s * 32, v);
+    CplRegs nxt;
+    if (s + nsub < n_slabs) cpl_prefetch(p, nxt, pix, (s + nsub) * 16, row_ok);
+    tmem_ld_wait();
+    if (row_ok) cpl_slab(p, v, bias_s + s * 32, pix, s * 16, cur);
+    cur = nxt;
   }
 }
 

@@ -64,6 +64,12 @@ def _round_up(v, m):
 
 
 FUSE_1X1 = os.environ.get("SININN_FUSE_1X1", "1") != "0"     # fused 1x1 subnet kernel (subnet1x1_tc.cu)
+# GLOW affine coupling (value pass / backward pass) inside the epilogue of the 3x3 subnet's second convolution
+# bit 0: value passes; bit 1: backward passes; bit 2: backward passes only where the subnet output is <= 64 columns wide
+# (level 0: that convolution is bound by its small-N MMAs and its epilogue has slack; at level 1 the extra loads, stores
+# and transcendental math of the backward half-step make the epilogue warps the bottleneck)
+FUSE_COUPLING = int(os.environ.get("SININN_FUSE_COUPLING", "5"))
+FUSE_COUPLING_1X1 = int(os.environ.get("SININN_FUSE_COUPLING_1X1", "1"))     # the same bits for the fused 1x1 subnet kernel
 
 TRACE = None     # debugging aid: set to a list to collect (label, trunk copy) after every executed op
 
@@ -138,8 +144,8 @@ def packed(w, mode, dtype):
     if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
         return hit[2]
     co, ci = w.shape[0], w.shape[1]
-    rows, k = (co, ci) if mode % 2 == 0 else (ci, co)
-    p = K.pack_weight(w, mode, dtype, _round_up(rows, 16), _round_up(k, 16) if mode < 2 else K.SPLIT_BLOCKS * _round_up(k, 8))
+    rows, k = (co, ci) if mode % 2 == 0 else (ci, co)      # (mode 4 = fprop with interleaved rows)
+    p = K.pack_weight(w, mode, dtype, _round_up(rows, 16), _round_up(k, 16) if mode not in (2, 3) else K.SPLIT_BLOCKS * _round_up(k, 8))
     ent[1][(mode, dtype)] = (w._version, w.data_ptr(), p)
     return p
 
@@ -168,6 +174,12 @@ class PackSet:
                 t = torch.empty(kh * kw, rp, kp, dtype=self.dtype, device=dev)
                 self.out[(id(w), mode)] = t
                 rows.append([w.data_ptr(), t.data_ptr(), co, ci, kh * kw, mode + (2 if self.split else 0), rp, kp])
+            if not self.split and self.dtype == torch.bfloat16 and co % 2 == 0 and co <= 256:
+                # interleaved fprop pack (rows s_0, t_0, s_1, t_1, ...) for the fused coupling epilogue
+                rp, kp = _round_up(co, 16), _round_up(ci, 16)
+                t = torch.empty(kh * kw, rp, kp, dtype=self.dtype, device=dev)
+                self.out[(id(w), 4)] = t
+                rows.append([w.data_ptr(), t.data_ptr(), co, ci, kh * kw, 4, rp, kp])
         self.jobs = torch.tensor(rows, dtype=torch.int64).to(dev)
         self.ptrs = tuple(w.data_ptr() for w in self.weights)
 
@@ -394,6 +406,45 @@ class ConvSubnet:
 
     def parameters(self):
         return [p for p in (self.c1.weight, self.c1.bias, self.c2.weight, self.c2.bias) if p is not None]
+
+    def can_fuse_coupling(self, ctx, L, backward):
+        mask = FUSE_COUPLING if self.taps == 9 else FUSE_COUPLING_1X1
+        on = (mask & 1) if not backward else ((mask & 2) or ((mask & 4) and self.cout <= 64))
+        if not (ctx.tc and self.cout == 2 * L and L % 8 == 0 and self.cout <= 256 and bool(on) and not getattr(self, "_no_fuse", False)):
+            return False
+        return self.taps == 9 or (FUSE_1X1 and K.subnet1x1_supported(self.cin, self.hidden, self.cout))
+
+    def fwd_coupled(self, ctx, tr, src, u, clamp, rev, want_bf, du=None):
+        """Subnet forward with the GLOW half-step (du None) or its backward (du given) applied to u in the second
+        convolution's epilogue: the subnet output [s | t] never leaves the SM.  Returns (bf16 copy of the new u or None,
+        saved tensors for bwd() or None, da or None); None altogether if the kernel does not take the shape."""
+        x = tr.operand(src, ctx.adt)
+        dev = x.device
+        L = u.shape[1]
+        keep = du is not None
+        bf = torch.empty(tr.npix, L, dtype=torch.bfloat16, device=dev) if want_bf else None
+        da = torch.empty(tr.npix, 2 * L, dtype=torch.bfloat16, device=dev) if keep else None
+        cpl = dict(mode=2 if keep else 1, u=u, clamp=clamp, inverse=rev, bf16=bf, du=du, da=da)
+        if self.taps == 1:
+            if x.stride(0) % 8 != 0:
+                return None
+            # fused 1x1 subnet: the hidden tile stays in shared memory AND the subnet output stays in registers
+            h = torch.empty(tr.npix, self.hidden, dtype=ctx.adt, device=dev) if keep else None
+            bits = torch.empty(tr.npix, self.hidden // 32, dtype=torch.int32, device=dev) if keep else None
+            K.subnet1x1_fwd(x, ctx.pack(self.c1.weight, 0), self.c1.bias, ctx.pack(self.c2.weight, 4), self.c2.bias, None,
+                            h_out=h, bits_out=bits, coupling=cpl)
+            return bf, ((x, h, bits) if keep else None), da
+        h = torch.empty(tr.npix, self.hidden, dtype=ctx.adt, device=dev)
+        bits = torch.empty(tr.npix, (self.hidden + 31) // 32, dtype=torch.int32, device=dev) if keep else None
+        K.conv(x, ctx.pack(self.c1.weight, 0), tr.geom, self.hidden, h, bias=self.c1.bias, act=ACT_RELU, tensor_core=True, bits_out=bits)
+        try:
+            K.conv(h, ctx.pack(self.c2.weight, 4), tr.geom, self.cout, None, bias=self.c2.bias, tensor_core=True, coupling=cpl)
+        except SininnError as e:
+            if "code -3" not in str(e):
+                raise
+            self._no_fuse = True                     # shape not taken by the CTA-pair kernel: unfused path from now on
+            return None
+        return bf, ((x, h, bits) if keep else None), da
 
     def _fwd_split(self, ctx, tr, src, keep):
         """fp32-accurate forward on the tensor cores: both convolutions on split operands, hidden activation in fp32.
@@ -720,11 +771,18 @@ class CouplingOp:
             want_bf = ctx.adt == torch.bfloat16 and nxt == st.dst and L % 8 == 0
             u = tr.mat()[:, st.dst[0]:st.dst[1]]
             if st.kind == "glow":
-                a, _ = st.nets[0].fwd(ctx, tr, st.src)
-                tr.invalidate(*st.dst)
-                if logdet is not None:
-                    K.logscale_sum(a[:, :L], B, GLOW, st.clamp, -1.0 if rev else 1.0, logdet, True)
-                bf = K.coupling_apply(u, a[:, :L], a[:, L:], GLOW, st.clamp, rev, want_bf)
+                fused = None
+                if logdet is None and st.nets[0].can_fuse_coupling(ctx, L, False):
+                    tr.invalidate(*st.dst)
+                    fused = st.nets[0].fwd_coupled(ctx, tr, st.src, u, st.clamp, rev, want_bf)
+                if fused is not None:
+                    bf = fused[0]
+                else:
+                    a, _ = st.nets[0].fwd(ctx, tr, st.src)
+                    tr.invalidate(*st.dst)
+                    if logdet is not None:
+                        K.logscale_sum(a[:, :L], B, GLOW, st.clamp, -1.0 if rev else 1.0, logdet, True)
+                    bf = K.coupling_apply(u, a[:, :L], a[:, L:], GLOW, st.clamp, rev, want_bf)
             elif st.kind == "irn_affine":
                 s, _ = st.nets[0].fwd(ctx, tr, st.src)
                 t, _ = st.nets[1].fwd(ctx, tr, st.src)
@@ -754,10 +812,17 @@ class CouplingOp:
             dsrc = tr.dmat()[:, st.src[0]:st.src[1]]
             dev = u.device
             if st.kind == "glow":
-                a, saved = st.nets[0].fwd(ctx, tr, st.src, keep=True)
-                da = torch.empty(tr.npix, 2 * L, dtype=ctx.adt, device=dev)
-                tr.invalidate(*st.dst)
-                bf = K.coupling_bwd(u, du, a[:, :L], a[:, L:], GLOW, st.clamp, rev, da[:, :L], da[:, L:], want_bf)
+                fused = None
+                if st.nets[0].can_fuse_coupling(ctx, L, True):
+                    tr.invalidate(*st.dst)
+                    fused = st.nets[0].fwd_coupled(ctx, tr, st.src, u, st.clamp, rev, want_bf, du=du)
+                if fused is not None:
+                    bf, saved, da = fused
+                else:
+                    a, saved = st.nets[0].fwd(ctx, tr, st.src, keep=True)
+                    da = torch.empty(tr.npix, 2 * L, dtype=ctx.adt, device=dev)
+                    tr.invalidate(*st.dst)
+                    bf = K.coupling_bwd(u, du, a[:, :L], a[:, L:], GLOW, st.clamp, rev, da[:, :L], da[:, L:], want_bf)
                 st.nets[0].bwd(ctx, tr, saved, da, dsrc)
             elif st.kind == "irn_affine":
                 s, saved_s = st.nets[0].fwd(ctx, tr, st.src, keep=True)

@@ -371,10 +371,16 @@ def pack_weights_batched(jobs, njobs, dtype):
 
 
 def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask_act=0, accumulate=False, alpha=1.0,
-         tensor_core=False, mask_bits=None, bits_out=None):
+         tensor_core=False, mask_bits=None, bits_out=None, coupling=None):
     """Implicit-GEMM 1x1 / 3x3 convolution on channels-last views.
-    x: [npix, Cin] view; wpack: [taps, rows_pad, k_pad]; geom = (B, H, W); out: [npix, cout] view."""
-    x, out = _view2d(x), _view2d(out)
+    x: [npix, Cin] view; wpack: [taps, rows_pad, k_pad]; geom = (B, H, W); out: [npix, cout] view.
+    coupling (3x3 tensor-core path, wpack in the interleaved mode-4 layout, out = None): the GLOW affine coupling runs in the
+    epilogue on the subnet output held in registers -- dict(mode=1|2, u=, clamp=, inverse=, bf16=None, du=None, da=None),
+    see sininn_conv_desc."""
+    x = _view2d(x)
+    if coupling is not None:
+        return _conv_coupled(x, wpack, geom, cout, bias, coupling)
+    out = _view2d(out)
     B, H, W = geom
     d = ConvDesc()
     d.B, d.H, d.W = B, H, W
@@ -405,26 +411,68 @@ def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask
     return out
 
 
+def _conv_coupled(x, wpack, geom, cout, bias, cp):
+    B, H, W = geom
+    u = _view2d(cp["u"])
+    L = u.shape[1]
+    d = ConvDesc()
+    d.B, d.H, d.W = B, H, W
+    d.Cin, d.Cout, d.taps = x.shape[1], cout, wpack.shape[0]
+    d.inp, d.in_dtype, d.in_stride = x.data_ptr(), dtype_code(x), x.stride(0)
+    d.wpack, d.rows_pad, d.k_pad = wpack.data_ptr(), wpack.shape[1], wpack.shape[2]
+    d.bias = _p(bias)
+    d.out, d.out_dtype, d.out_stride = 0, F32, 0
+    d.act, d.slope, d.mask, d.mask_stride, d.mask_act = 0, 0.0, 0, 0, 0
+    d.accumulate, d.alpha, d.mask_bits, d.bits_out = 0, 1.0, 0, 0
+    d.cpl_mode, d.cpl_L, d.cpl_inverse, d.cpl_clamp = int(cp["mode"]), L, int(bool(cp["inverse"])), float(cp["clamp"])
+    d.cpl_u, d.cpl_u_stride = u.data_ptr(), u.stride(0)
+    du = cp.get("du")
+    if du is not None:
+        du = _view2d(du)
+        d.cpl_du, d.cpl_du_stride = du.data_ptr(), du.stride(0)
+    else:
+        d.cpl_du, d.cpl_du_stride = 0, 0
+    d.cpl_bf16, d.cpl_da = _p(cp.get("bf16")), _p(cp.get("da"))
+    flops = 2.0 * B * H * W * d.Cin * d.Cout * d.taps
+    check(_run("conv3x3", lambda: load().sininn_conv_tc(C.byref(d), stream_ptr()), 1, flops), "conv_tc(coupling)")
+
+
 def subnet1x1_supported(cin, hidden, cout):
     """Shapes the fused 1x1 subnet kernel takes (everything else runs as two conv launches)."""
     return bool(load().sininn_subnet1x1_supported(int(cin), int(hidden), int(cout)))
 
 
-def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None, mask_bits=None, accumulate=False):
+def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None, mask_bits=None, accumulate=False, coupling=None):
     """out = W2 relu(W1 x + b1) + b2 per pixel, one launch (tcgen05; hidden activation stays on chip).
     x: bf16 [npix, Cin] view; w1pack [1, hidden, k1_pad]; w2pack [1, n2_pad, hidden]; out: fp32 [npix, Cout] view;
     h_out (bf16 [npix, hidden]) / bits_out (int32 [npix, hidden/32]) optionally receive the hidden activation."""
-    x, out = _view2d(x), _view2d(out)
+    x = _view2d(x)
     d = Subnet1x1Desc()
     d.npix = x.shape[0]
-    d.Cin, d.hidden, d.Cout = x.shape[1], w1pack.shape[1], out.shape[1]
+    if coupling is not None:             # GLOW half-step in the second epilogue: w2pack interleaved (mode 4), out unused
+        u = _view2d(coupling["u"])
+        cout = 2 * u.shape[1]
+        d.cpl_mode, d.cpl_L, d.cpl_inverse, d.cpl_clamp = int(coupling["mode"]), u.shape[1], int(bool(coupling["inverse"])), float(coupling["clamp"])
+        d.cpl_u, d.cpl_u_stride = u.data_ptr(), u.stride(0)
+        du = coupling.get("du")
+        if du is not None:
+            du = _view2d(du)
+            d.cpl_du, d.cpl_du_stride = du.data_ptr(), du.stride(0)
+        else:
+            d.cpl_du, d.cpl_du_stride = 0, 0
+        d.cpl_bf16, d.cpl_da = _p(coupling.get("bf16")), _p(coupling.get("da"))
+    else:
+        out = _view2d(out)
+        cout = out.shape[1]
+        d.cpl_mode = 0
+    d.Cin, d.hidden, d.Cout = x.shape[1], w1pack.shape[1], cout
     d.x, d.x_stride = x.data_ptr(), x.stride(0)
     d.w1pack, d.k1_pad = w1pack.data_ptr(), w1pack.shape[2]
     d.b1 = _p(b1)
     d.w2pack, d.n2_pad = w2pack.data_ptr(), w2pack.shape[1]
     d.b2 = _p(b2)
-    d.out, d.out_stride = out.data_ptr(), out.stride(0)
-    if x.dtype != torch.bfloat16 or out.dtype != torch.float32 or w1pack.dtype != torch.bfloat16 or w2pack.dtype != torch.bfloat16:
+    d.out, d.out_stride = (out.data_ptr(), out.stride(0)) if coupling is None else (0, 0)
+    if x.dtype != torch.bfloat16 or (coupling is None and out.dtype != torch.float32) or w1pack.dtype != torch.bfloat16 or w2pack.dtype != torch.bfloat16:
         raise _lib.SininnError("subnet1x1_fwd: bf16 operands and an fp32 output are required")
     if w2pack.shape[2] != d.hidden or w1pack.shape[0] != 1 or w2pack.shape[0] != 1:
         raise _lib.SininnError("subnet1x1_fwd: packed weights do not describe a 1x1 Cin->hidden->Cout subnet")

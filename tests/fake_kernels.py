@@ -141,14 +141,18 @@ def pack_weight(w, mode, dtype, rows_pad, k_pad):
     co, ci, kh, kw = w.shape
     taps = kh * kw
     wt = w.detach().reshape(co, ci, taps)
-    if mode >= 2:                        # split packs: K = six blocks [wh | wh | wm | wh | wm | wl]
+    if mode in (2, 3):                   # split packs: K = six blocks [wh | wh | wm | wh | wm | wl]
         kp = k_pad // SPLIT_BLOCKS
         base = pack_weight(w, mode - 2, torch.float32, rows_pad, kp)
         wh = base.to(torch.bfloat16).float()
         wm = (base - wh).to(torch.bfloat16).float()
         return torch.cat((wh, wh, wm, wh, wm, base - wh - wm), dim=2).to(torch.bfloat16)
     out = torch.zeros(taps, rows_pad, k_pad, dtype=torch.float32, device=w.device)
-    if mode == 0:
+    if mode == 4:                        # fprop, rows interleaved (s_0, t_0, s_1, t_1, ...)
+        base = wt.permute(2, 0, 1)
+        out[:, 0:co:2, :ci] = base[:, :co // 2]
+        out[:, 1:co:2, :ci] = base[:, co // 2:]
+    elif mode == 0:
         out[:, :co, :ci] = wt.permute(2, 0, 1)
     else:
         out[:, :ci, :co] = wt.flip(2).permute(2, 1, 0)
@@ -194,7 +198,26 @@ def _pack_bits(vals):
 
 
 def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask_act=0, accumulate=False, alpha=1.0,
-         tensor_core=False, mask_bits=None, bits_out=None):
+         tensor_core=False, mask_bits=None, bits_out=None, coupling=None):
+    if coupling is not None:            # interleaved pack (mode 4) + GLOW half-step in the "epilogue"
+        L = cout // 2
+        a = torch.empty(x.shape[0], cout, dtype=torch.float32, device=x.device)
+        il_bias = None
+        if bias is not None:
+            il_bias = torch.empty(cout, dtype=torch.float32, device=x.device)
+            il_bias[0::2], il_bias[1::2] = bias.detach()[:L], bias.detach()[L:]
+        conv(x, wpack, geom, cout, a, bias=il_bias, tensor_core=tensor_core)
+        s_, t_ = a[:, 0::2].contiguous(), a[:, 1::2].contiguous()
+        u = coupling["u"]
+        if coupling["mode"] == 1:
+            bf = coupling_apply(u, s_, t_, 0, coupling["clamp"], coupling["inverse"], coupling.get("bf16") is not None)
+        else:
+            da = coupling["da"]
+            bf = coupling_bwd(u, coupling["du"], s_, t_, 0, coupling["clamp"], coupling["inverse"], da[:, :L], da[:, L:],
+                              coupling.get("bf16") is not None)
+        if coupling.get("bf16") is not None:
+            coupling["bf16"].copy_(bf)
+        return
     B, H, W = geom
     cin = x.shape[1]
     taps = wpack.shape[0]
@@ -228,7 +251,19 @@ def subnet1x1_supported(cin, hidden, cout):
     return hidden % 64 == 0 and 64 <= hidden <= 256 and cout <= 256 and cout % 4 == 0 and cin % 8 == 0
 
 
-def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None, mask_bits=None, accumulate=False):
+def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None, mask_bits=None, accumulate=False, coupling=None):
+    if coupling is not None:
+        geom = (1, 1, x.shape[0])
+        hidden = w1pack.shape[1]
+        h = torch.empty(x.shape[0], hidden, dtype=torch.bfloat16, device=x.device)
+        bits = torch.empty(x.shape[0], hidden // 32, dtype=torch.int32, device=x.device)
+        conv(x, w1pack, geom, hidden, h, bias=b1, act=1, tensor_core=True, bits_out=bits)
+        if h_out is not None:
+            h_out.copy_(h)
+        if bits_out is not None:
+            bits_out.copy_(bits)
+        conv(h, w2pack, geom, 2 * coupling["u"].shape[1], None, bias=b2, tensor_core=True, coupling=coupling)
+        return None
     npix, cin = x.shape
     hidden, cout = w1pack.shape[1], out.shape[1]
     h = x.float() @ w1pack[0, :hidden, :cin].float().t()

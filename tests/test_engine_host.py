@@ -107,12 +107,15 @@ def test_cpu_input_fails_loudly():
         net(torch.rand(1, 3, 16, 16))
 
 
-@pytest.mark.parametrize("arch,scale,nc,lrw", [("SRF", 4, 2, 10), ("IRN", 4, 1, 10)])
-def test_bf16_operand_path_bookkeeping(fake_kernels, arch, scale, nc, lrw):
+@pytest.mark.parametrize("arch,scale,nc,lrw,tc", [("SRF", 4, 2, 10, False), ("IRN", 4, 1, 10, False),
+                                                  # tensor-core plumbing on the stand-ins: fused 1x1 subnet, sign-bit masks,
+                                                  # grouped weight gradients, coupling fused into the 3x3 conv-2 epilogue
+                                                  ("SRF", 4, 2, 10, True), ("IRN", 4, 1, 10, True)])
+def test_bf16_operand_path_bookkeeping(fake_kernels, arch, scale, nc, lrw, tc):
     """bf16 operand copies (cached per channel range, emitted by producer kernels) must stay coherent with
     the fp32 trunk: outputs/gradients stay within the bf16 tolerance of the fp32 oracle."""
     opt, ora, net = _pair(arch, scale, nc, lrw, 16, 32)
-    net.engine_config = E.EngineConfig(precision="bf16", tensor_core=False)
+    net.engine_config = E.EngineConfig(precision="bf16", tensor_core=tc)
     hr, lr, z = R.synthetic_batch(opt, 2, 16, 32, seed=4)
     lrz = torch.cat((lr, z), 1)
     out = {}

@@ -598,3 +598,83 @@ def test_kernel_selection_switches(env):
                         "-k", sel, "-p", "no:cacheprovider"], cwd=root, env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
     assert " passed" in r.stdout
+
+
+@pytest.mark.parametrize("L,geom", [(24, (2, 16, 16)), (96, (1, 12, 20)), (24, (1, 17, 33)), (96, (3, 7, 5))])
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_coupling_fused_into_conv_epilogue(K, L, geom, inverse):
+    """GLOW half-step (value pass, cpl_mode 1) and its backward (cpl_mode 2) in the epilogue of the subnet's second 3x3
+    convolution (interleaved mode-4 pack) == the unfused convolution followed by coupling_apply / coupling_bwd, bit for bit
+    on the subnet output (same accumulation order per column) and to fp32 rounding on the coupled values."""
+    B, H, W = geom
+    npix, hid, cout, C = B * H * W, 256, 2 * L, 2 * L
+    bf = torch.bfloat16
+    h = rnd(npix, hid, seed=31).abs().to(bf).to(DEV)
+    w = (rnd(cout, hid, 3, 3, seed=32) * 0.03).to(DEV)
+    bias = rnd(cout, seed=33).to(DEV)
+    U0, dU0 = rnd(npix, C, seed=34).to(DEV), (rnd(npix, C, seed=35) * 1e-2).to(DEV)
+    wp = K.pack_weight(w, 0, bf, (cout + 15) // 16 * 16, hid)
+    wpi = K.pack_weight(w, 4, bf, (cout + 15) // 16 * 16, hid)
+    a = torch.empty(npix, cout, device=DEV)
+    K.conv(h, wp, geom, cout, a, bias=bias, tensor_core=True)
+    for c0 in (0, L):                                  # the slice may be either half of the trunk
+        # value pass
+        Ur, Uf = U0.clone(), U0.clone()
+        bfr = K.coupling_apply(Ur[:, c0:c0 + L], a[:, :L], a[:, L:], 0, 1.2, inverse, True)
+        bff = torch.empty(npix, L, dtype=bf, device=DEV)
+        K.conv(h, wpi, geom, cout, None, bias=bias, tensor_core=True,
+               coupling=dict(mode=1, u=Uf[:, c0:c0 + L], clamp=1.2, inverse=inverse, bf16=bff))
+        assert (Ur - Uf).abs().max().item() <= 2e-6 * Ur.abs().max().item()
+        assert torch.equal(Ur[:, :c0], Uf[:, :c0]) and torch.equal(Ur[:, c0 + L:], Uf[:, c0 + L:])     # the other half is untouched
+        assert (bfr.float() - bff.float()).abs().max().item() <= 1e-2 * bfr.float().abs().max().item()
+        # backward pass
+        Ur, Uf, dUr, dUf = U0.clone(), U0.clone(), dU0.clone(), dU0.clone()
+        dar = torch.empty(npix, 2 * L, dtype=bf, device=DEV)
+        xr = K.coupling_bwd(Ur[:, c0:c0 + L], dUr[:, c0:c0 + L], a[:, :L], a[:, L:], 0, 1.2, inverse, dar[:, :L], dar[:, L:], True)
+        daf = torch.empty(npix, 2 * L, dtype=bf, device=DEV)
+        xf = torch.empty(npix, L, dtype=bf, device=DEV)
+        K.conv(h, wpi, geom, cout, None, bias=bias, tensor_core=True,
+               coupling=dict(mode=2, u=Uf[:, c0:c0 + L], clamp=1.2, inverse=inverse, bf16=xf, du=dUf[:, c0:c0 + L], da=daf))
+        assert (Ur - Uf).abs().max().item() <= 2e-6 * Ur.abs().max().item()
+        assert (dUr - dUf).abs().max().item() <= 2e-6 * dUr.abs().max().item()
+        assert (dar.float() - daf.float()).abs().max().item() <= 1e-2 * dar.float().abs().max().item()
+        assert (xr.float() - xf.float()).abs().max().item() <= 1e-2 * xr.float().abs().max().item()
+
+
+@pytest.mark.parametrize("L,npix", [(24, 128), (24, 5000), (96, 45), (96, 33 * 40)])
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_coupling_fused_into_1x1_subnet_kernel(K, L, npix, inverse):
+    """The fused 1x1 subnet kernel with the GLOW half-step (and its backward) in its second epilogue == the same kernel
+    writing the subnet output, followed by coupling_apply / coupling_bwd."""
+    bf = torch.bfloat16
+    cin, hid, cout, C = L, 256, 2 * L, 2 * L
+    x = rnd(npix, cin, seed=41).to(bf).to(DEV)
+    w1, w2 = (rnd(hid, cin, 1, 1, seed=42) * 0.2).to(DEV), (rnd(cout, hid, 1, 1, seed=43) * 0.05).to(DEV)
+    b1, b2 = rnd(hid, seed=44).to(DEV), rnd(cout, seed=45).to(DEV)
+    w1p = K.pack_weight(w1, 0, bf, hid, (cin + 15) // 16 * 16)
+    w2p = K.pack_weight(w2, 0, bf, (cout + 15) // 16 * 16, hid)
+    w2pi = K.pack_weight(w2, 4, bf, (cout + 15) // 16 * 16, hid)
+    U0, dU0 = rnd(npix, C, seed=46).to(DEV), (rnd(npix, C, seed=47) * 1e-2).to(DEV)
+    a = torch.empty(npix, cout, device=DEV)
+    h_ref = torch.empty(npix, hid, dtype=bf, device=DEV)
+    bits_ref = torch.empty(npix, hid // 32, dtype=torch.int32, device=DEV)
+    K.subnet1x1_fwd(x, w1p, b1, w2p, b2, a, h_out=h_ref, bits_out=bits_ref)
+    c0 = L
+    Ur, Uf = U0.clone(), U0.clone()
+    bfr = K.coupling_apply(Ur[:, c0:c0 + L], a[:, :L], a[:, L:], 0, 1.2, inverse, True)
+    bff = torch.empty(npix, L, dtype=bf, device=DEV)
+    K.subnet1x1_fwd(x, w1p, b1, w2pi, b2, None, coupling=dict(mode=1, u=Uf[:, c0:c0 + L], clamp=1.2, inverse=inverse, bf16=bff))
+    assert (Ur - Uf).abs().max().item() <= 2e-6 * Ur.abs().max().item()
+    assert (bfr.float() - bff.float()).abs().max().item() <= 1e-2 * bfr.float().abs().max().item()
+    Ur, Uf, dUr, dUf = U0.clone(), U0.clone(), dU0.clone(), dU0.clone()
+    dar = torch.empty(npix, 2 * L, dtype=bf, device=DEV)
+    K.coupling_bwd(Ur[:, c0:c0 + L], dUr[:, c0:c0 + L], a[:, :L], a[:, L:], 0, 1.2, inverse, dar[:, :L], dar[:, L:], False)
+    daf = torch.empty(npix, 2 * L, dtype=bf, device=DEV)
+    h2 = torch.empty_like(h_ref)
+    bits2 = torch.empty_like(bits_ref)
+    K.subnet1x1_fwd(x, w1p, b1, w2pi, b2, None, h_out=h2, bits_out=bits2,
+                    coupling=dict(mode=2, u=Uf[:, c0:c0 + L], clamp=1.2, inverse=inverse, du=dUf[:, c0:c0 + L], da=daf))
+    assert torch.equal(h2, h_ref) and torch.equal(bits2, bits_ref)
+    assert (Ur - Uf).abs().max().item() <= 2e-6 * Ur.abs().max().item()
+    assert (dUr - dUf).abs().max().item() <= 2e-6 * dUr.abs().max().item()
+    assert (dar.float() - daf.float()).abs().max().item() <= 1e-2 * dar.float().abs().max().item()
