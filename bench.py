@@ -134,7 +134,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     P, B = WORKLOAD["patch"], args.batch
     opt = R.make_opt(scale=WORKLOAD["scale"], num_coupling=WORKLOAD["num_coupling"], lr_window=WORKLOAD["lr_window"],
-                     precision=args.precision, tensor_core=not args.no_tensor_core)
+                     precision=args.precision, tensor_core=not args.no_tensor_core, activations=args.activations)
     torch.manual_seed(0)
     net = archs.UncondSRFlow(3, P, P, opt).to(dev)
     trainer = train.SingleVideoTrainer(net, opt, world_size=world)
@@ -255,6 +255,12 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e, inf_fwd_ms, inf_inv_ms, inf_e2e_ms = t.tolist()
+    # what the differentiable passes kept for their backward (engine.EngineConfig.activations, resolved by the plan)
+    plan_, cfg_ = net.plan(), net.engine_config
+    stores = any(plan_._store_choice.values()) if cfg_.activations == "auto" else cfg_.activations == "store"
+    f_ = 2 * opt.scale
+    stash_b = (plan_.stash_bytes((B, 3, P, P), False, cfg_)
+               + plan_.stash_bytes((B, opt.lr_dims + opt.z_dims, P // f_, P // f_), True, cfg_)) if stores else 0
     extras = {}
     if world == 1 and not args.no_extras:
         graphed = feeder = None
@@ -274,9 +280,9 @@ def run_ours(args):
         tens = {k: prof.get(k, zero) for k in ("conv3x3", "wgrad", "subnet1x1", "conv1x1")}
         tot_ms = sum(v["ms"] for v in prof.values())
         top = max(tens, key=lambda k: tens[k]["ms"])
-        names = {"conv3x3": "conv_tc_pair_kernel (3x3 subnet convolutions: fprop, recompute, dgrad)",
+        names = {"conv3x3": "conv_tc_pair_kernel (3x3 subnet convolutions: fprop, dgrad; their re-evaluation when activations='recompute')",
                  "wgrad": "wgrad_pair_kernel + wgrad_reduce_kernel (weight and bias gradients, grouped per coupling block)",
-                 "subnet1x1": "subnet1x1_fwd_kernel (fused 1x1 subnets: forward, recompute, data gradients)",
+                 "subnet1x1": "subnet1x1_fwd_kernel (fused 1x1 subnets: forward, data gradients; re-evaluation when activations='recompute')",
                  "conv1x1": "conv_tc_kernel (1x1 convolutions outside the fused kernel)"}
 
         def fam(v):
@@ -294,6 +300,7 @@ def run_ours(args):
             if ent:
                 traffic, tnote = ent["dram_bytes_per_launch"], ent["note"]
         alg_flops_step = 6 * 2 * conv_macs_per_patch(P) * B
+
         # algorithmic-only: 4 of the 6 conv3x3/1x1 passes per direction are algorithmic (fprop, dgrad; + wgrad), the
         # recomputed fprop is not: algorithmic FLOPs of the step / time of ALL tensor-bound launches
         alg_only = alg_flops_step * args.steps / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
@@ -305,7 +312,10 @@ def run_ours(args):
             "config": {"workload": f"SRF scale4 c4 lr_window10 {P}x{P} train step, batch {B}/GPU", **WORKLOAD,
                        "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision, "tensor_core": not args.no_tensor_core,
                        "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2",
-                       "backward": "recompute-from-inverse", "cuda_graph": used_graph, "z": "drawn on the device inside the step"},
+                       "backward": "trunk restored block by block from the exact inverse (never stored); coupling-subnet internals "
+                                   + ("kept from the value pass" if stores else "re-evaluated during backward"),
+                       "activations": args.activations, "subnet_state_bytes_per_step": stash_b,
+                       "cuda_graph": used_graph, "z": "drawn on the device inside the step"},
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
@@ -418,25 +428,35 @@ def extra_configs(dev, args):
                     "batch": batch, "value": batch / (msv / 1e3), "unit": "patches/s", "ms_per_step": msv}
         del tr, step
         torch.cuda.empty_cache()
-    # configs[4]: deep variant, 512x512 patches, recompute-from-inverse backward: throughput and peak memory
-    opt = R.make_opt(scale=4, num_coupling=8, lr_window=10, precision="bf16", hidden=512)
-    tr, step = trainer_for(opt, archs.UncondSRFlow, 512, 8, graph=False)
-    step()
-    torch.cuda.synchronize()
-    torch.cuda.reset_peak_memory_stats()
-    base = torch.cuda.memory_allocated()
-    msv = _time_steps(step, 3, warm=1)
-    peak = torch.cuda.max_memory_allocated() - base
-    npix0 = 8 * 128 * 128
-    stored = 2 * (16 * 2 * npix0 * 512 * 2 + 16 * 2 * (npix0 // 4) * 512 * 2)
-    out["deep_variant"] = {"workload": "configs[4]: SRF scale 4, 8 couplings per level, hidden 512, 512x512 patches, batch 8, bf16, eager step",
-                           "value": 8 / (msv / 1e3), "unit": "patches/s", "ms_per_step": msv,
-                           "peak_extra_memory_GiB": peak / 2 ** 30,
-                           "stored_activation_hiddens_GiB": stored / 2 ** 30,
-                           "note": "the backward pass keeps only the network output; an autograd graph of the same net stores every "
-                                   "512-wide hidden tensor (bf16 estimate, both passes)"}
-    del tr, step
-    torch.cuda.empty_cache()
+    # configs[1] with the subnets re-evaluated during backward instead of kept (activations="recompute")
+    def mem_and_time(opt, patch, batch, steps, graph):
+        tr, step = trainer_for(opt, archs.UncondSRFlow, patch, batch, graph=graph)
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        msv = _time_steps(step, steps, warm=1)
+        peak = torch.cuda.max_memory_allocated() - base
+        del tr, step
+        torch.cuda.empty_cache()
+        return msv, peak
+    opt = R.make_opt(scale=WORKLOAD["scale"], num_coupling=WORKLOAD["num_coupling"], lr_window=WORKLOAD["lr_window"], precision="bf16",
+                     activations="recompute")
+    msv, peak = mem_and_time(opt, P, B, 5, False)
+    out["recompute_variant"] = {"workload": "configs[1], bf16, eager step, activations='recompute': every coupling subnet is re-evaluated "
+                                            "from the restored trunk during backward; nothing but the network output is kept",
+                                "value": B / (msv / 1e3), "unit": "patches/s", "ms_per_step": msv, "peak_extra_memory_GiB": peak / 2 ** 30}
+    # configs[4]: deep variant, 512x512 patches: throughput and peak memory in both modes
+    out["deep_variant"] = {"workload": "configs[4]: SRF scale 4, 8 couplings per level, hidden 512, 512x512 patches, batch 8, bf16, eager step"}
+    for mode in ("recompute", "store"):
+        opt = R.make_opt(scale=4, num_coupling=8, lr_window=10, precision="bf16", hidden=512, activations=mode)
+        msv, peak = mem_and_time(opt, 512, 8, 3, False)
+        out["deep_variant"][mode] = {"value": 8 / (msv / 1e3), "unit": "patches/s", "ms_per_step": msv, "peak_extra_memory_GiB": peak / 2 ** 30}
+    out["deep_variant"]["value"] = out["deep_variant"]["store"]["value"]
+    out["deep_variant"]["unit"] = "patches/s"
+    out["deep_variant"]["note"] = ("'recompute' = fused recompute-from-inverse backward (only the network output is kept: the memory figure is "
+                                   "the working set of one coupling block); 'store' keeps the subnets' operand copy, hidden activation, sign "
+                                   "bits and output per block (the trunk is still rebuilt from the inverse)")
     opt = R.make_opt(scale=WORKLOAD["scale"], num_coupling=WORKLOAD["num_coupling"], lr_window=WORKLOAD["lr_window"], precision="bf16",
                      architecture="IRN")
     tr, step = trainer_for(opt, archs.InvRescaleNet, P, B)
@@ -579,6 +599,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32tc"])
+    ap.add_argument("--activations", default="auto", choices=["auto", "store", "recompute"],
+                    help="coupling-subnet internals for backward: kept from the value pass, or re-evaluated (engine.EngineConfig)")
     ap.add_argument("--batch", type=int, default=WORKLOAD["batch_per_gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true", help="skip the 1080p forward+inverse measurement")

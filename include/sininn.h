@@ -194,13 +194,15 @@ typedef struct {
    * mode 4 (output rows interleaved s_0, t_0, s_1, t_1, ...), Cout = 2 * cpl_L; its output [s | t] is consumed in
    * registers and never written (`out` may be NULL):
    *   cpl_mode 1: the half-step of sininn_coupling_apply on cpl_u [npix][cpl_L] (pixel stride cpl_u_stride), in place,
-   *               direction cpl_inverse; cpl_bf16 (may be NULL) receives the compact bf16 copy of the result.
+   *               direction cpl_inverse; cpl_bf16 (may be NULL) receives the compact bf16 copy of the result; cpl_a (may
+   *               be NULL; fp32 [npix][2 * cpl_L], 16-byte aligned) receives the subnet output [s | t] (bias included,
+   *               natural channel order) for a backward pass that keeps it instead of re-evaluating the subnet.
    *   cpl_mode 2: the half-step of sininn_coupling_bwd: cpl_u holds y -> x, cpl_du holds dL/dy -> dL/dx (in place),
    *               cpl_da (bf16 [npix][2 * cpl_L]) receives [dL/ds | dL/dt], cpl_bf16 the bf16 copy of x. */
   int cpl_mode; int cpl_L; int cpl_inverse; float cpl_clamp;
   float* cpl_u; int cpl_u_stride;
   float* cpl_du; int cpl_du_stride;
-  void* cpl_bf16; void* cpl_da;
+  void* cpl_bf16; void* cpl_da; float* cpl_a;
 } sininn_conv_desc;
 
 /* Debugging aid: when set to a device buffer of 4 x 512 int64, the CTA-pair 3x3 kernel records clock64() stamps of
@@ -241,7 +243,7 @@ typedef struct {
   int cpl_mode; int cpl_L; int cpl_inverse; float cpl_clamp;
   float* cpl_u; int cpl_u_stride;
   float* cpl_du; int cpl_du_stride;
-  void* cpl_bf16; void* cpl_da;
+  void* cpl_bf16; void* cpl_da; float* cpl_a;
 } sininn_subnet1x1_desc;
 
 int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stream);

@@ -38,7 +38,7 @@ class ConvDesc(C.Structure):
         ("cpl_mode", C.c_int), ("cpl_L", C.c_int), ("cpl_inverse", C.c_int), ("cpl_clamp", C.c_float),
         ("cpl_u", _vp), ("cpl_u_stride", C.c_int),
         ("cpl_du", _vp), ("cpl_du_stride", C.c_int),
-        ("cpl_bf16", _vp), ("cpl_da", _vp),
+        ("cpl_bf16", _vp), ("cpl_da", _vp), ("cpl_a", _vp),
     ]
 
 
@@ -71,7 +71,7 @@ class Subnet1x1Desc(C.Structure):
         ("cpl_mode", C.c_int), ("cpl_L", C.c_int), ("cpl_inverse", C.c_int), ("cpl_clamp", C.c_float),
         ("cpl_u", _vp), ("cpl_u_stride", C.c_int),
         ("cpl_du", _vp), ("cpl_du_stride", C.c_int),
-        ("cpl_bf16", _vp), ("cpl_da", _vp),
+        ("cpl_bf16", _vp), ("cpl_da", _vp), ("cpl_a", _vp),
     ]
 
 

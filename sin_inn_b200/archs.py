@@ -8,7 +8,8 @@ names / shapes / initialisation (so reference checkpoints load and ``lit_wrapper
   subnet_fc / subnet_conv / subnet_conv_1x1                 archs.py:7-17
 
 ``opt`` fields read: scale, num_coupling, lr_dims (as the reference) plus the optional extensions
-``hidden`` (subnet width, reference hard-codes 256) and ``precision`` ("bf16" | "fp32").
+``hidden`` (subnet width, reference hard-codes 256), ``precision`` ("bf16" | "fp32" | "fp32tc") and ``activations``
+("auto" | "store" | "recompute": what a differentiable pass keeps of the coupling subnets, engine.EngineConfig).
 Inputs must be CUDA tensors: there is no CPU implementation in this package.
 """
 import numpy as np
@@ -42,7 +43,8 @@ def _config_from(opt):
     prec = getattr(opt, "precision", None)
     if prec is None:
         return None
-    return E.EngineConfig(precision=prec, tensor_core=getattr(opt, "tensor_core", True))
+    return E.EngineConfig(precision=prec, tensor_core=getattr(opt, "tensor_core", True),
+                          activations=getattr(opt, "activations", E.default_config().activations))
 
 
 class UncondSRFlow:

@@ -163,6 +163,7 @@ int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream) {
     SININN_CHECK_ARG(d->cpl_mode == 1 || (d->cpl_du && aligned16(d->cpl_du) && (d->cpl_du_stride % 4) == 0 && d->cpl_da && aligned8(d->cpl_da)),
                      "conv_tc: the coupling backward epilogue needs the gradient slice and the [ds | dt] output");
     SININN_CHECK_ARG(!d->cpl_bf16 || aligned8(d->cpl_bf16), "conv_tc: misaligned bf16 copy");
+    SININN_CHECK_ARG(!d->cpl_a || (d->cpl_mode == 1 && aligned16(d->cpl_a)), "conv_tc: cpl_a needs cpl_mode 1 and 16-byte alignment");
     SININN_CHECK_ARG(d->act == SININN_ACT_NONE && !d->mask && !d->mask_bits && !d->bits_out && !d->accumulate && d->alpha == 1.0f,
                      "conv_tc: the coupling epilogue replaces every other epilogue option");
   }
@@ -214,6 +215,7 @@ int sininn_conv_tc(const sininn_conv_desc* d, sininn_stream_t stream) {
   p.cpl.mode = d->cpl_mode; p.cpl.L = d->cpl_L; p.cpl.inverse = d->cpl_inverse; p.cpl.clamp = d->cpl_clamp;
   p.cpl.u = d->cpl_u; p.cpl.u_stride = d->cpl_u_stride; p.cpl.du = d->cpl_du; p.cpl.du_stride = d->cpl_du_stride;
   p.cpl.bf16 = reinterpret_cast<__nv_bfloat16*>(d->cpl_bf16); p.cpl.da = reinterpret_cast<__nv_bfloat16*>(d->cpl_da);
+  p.cpl.a = d->cpl_mode == 1 ? d->cpl_a : nullptr;
   const int esz = p.out_f32 ? 4 : 2;
   // TMA epilogue needs a 16-byte aligned output slice / pixel stride and no per-element mask tensor
   p.tma_out = (d->out && aligned16(d->out) && ((long long)d->out_stride * esz) % 16 == 0 && d->mask == nullptr) ? 1 : 0;

@@ -412,6 +412,7 @@ int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stre
     SININN_CHECK_ARG(d->cpl_mode == 1 || (d->cpl_du && aligned16(d->cpl_du) && (d->cpl_du_stride % 4) == 0 && d->cpl_da && aligned8(d->cpl_da)),
                      "subnet1x1: the coupling backward epilogue needs the gradient slice and the [ds | dt] output");
     SININN_CHECK_ARG(!d->cpl_bf16 || aligned8(d->cpl_bf16), "subnet1x1: misaligned bf16 copy");
+    SININN_CHECK_ARG(!d->cpl_a || (d->cpl_mode == 1 && aligned16(d->cpl_a)), "subnet1x1: cpl_a needs cpl_mode 1 and 16-byte alignment");
     SININN_CHECK_ARG(!d->mask_bits && !d->accumulate, "subnet1x1: the coupling epilogue is a forward-mode option");
   }
   SININN_CHECK_ARG(d->npix > 0 && d->Cin > 0 && d->Cout > 0, "subnet1x1: bad shape");
@@ -446,6 +447,7 @@ int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stre
   p.cpl.mode = d->cpl_mode; p.cpl.L = d->cpl_L; p.cpl.inverse = d->cpl_inverse; p.cpl.clamp = d->cpl_clamp;
   p.cpl.u = d->cpl_u; p.cpl.u_stride = d->cpl_u_stride; p.cpl.du = d->cpl_du; p.cpl.du_stride = d->cpl_du_stride;
   p.cpl.bf16 = reinterpret_cast<__nv_bfloat16*>(d->cpl_bf16); p.cpl.da = reinterpret_cast<__nv_bfloat16*>(d->cpl_da);
+  p.cpl.a = d->cpl_mode == 1 ? d->cpl_a : nullptr;
   p.bits_out = reinterpret_cast<uint32_t*>(d->bits_out);
   p.store_h = d->h_out != nullptr ? 1 : 0;
   p.bits_in = reinterpret_cast<const uint32_t*>(d->mask_bits);

@@ -21,6 +21,7 @@ struct CplParams {
   float* du; int du_stride;
   __nv_bfloat16* bf16;
   __nv_bfloat16* da;
+  float* a;                      // mode 1: optional copy of the subnet output [s | t], fp32 [npix][2L]
 };
 
 struct Params {
@@ -329,6 +330,7 @@ __device__ __forceinline__ void cpl_slab(const CplParams& p, const uint32_t (&v)
       const float uu[4] = {cur.u[q].x, cur.u[q].y, cur.u[q].z, cur.u[q].w};
       float y[4];
       if (p.mode == 1) {
+        float sk[4], tk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float sv = __uint_as_float(v[8 * q + 2 * e]) + bs[8 * q + 2 * e];
@@ -336,8 +338,14 @@ __device__ __forceinline__ void cpl_slab(const CplParams& p, const uint32_t (&v)
           float ex, dg;
           glow_scale_fast(p.clamp, inv_clamp, sv, ex, dg);
           y[e] = p.inverse ? __fdividef(uu[e] - tv, ex) : fmaf(ex, uu[e], tv);
+          sk[e] = sv; tk[e] = tv;
         }
         *reinterpret_cast<float4*>(up + 4 * q) = make_float4(y[0], y[1], y[2], y[3]);
+        if (p.a != nullptr) {
+          float* ap = p.a + pix * (2 * L) + ch0 + 4 * q;
+          *reinterpret_cast<float4*>(ap) = make_float4(sk[0], sk[1], sk[2], sk[3]);
+          *reinterpret_cast<float4*>(ap + L) = make_float4(tk[0], tk[1], tk[2], tk[3]);
+        }
       } else {
         const float dy[4] = {cur.d[q].x, cur.d[q].y, cur.d[q].z, cur.d[q].w};
         float dx[4], dsv[4], dtv[4];

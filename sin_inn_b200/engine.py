@@ -32,6 +32,14 @@ class EngineConfig:
     #           round trip 2e-6, ~6.5x the speed of "fp32"; gradients are limited by ReLU-kink flips
     precision: str = "bf16"
     tensor_core: bool = True     # tcgen05 kernels for the subnets (bf16 / fp32tc)
+    # What a differentiable pass keeps for its backward.  The TRUNK is never kept: it is rebuilt block by block from the
+    # exact inverse.  The coupling subnets' internals (operand copy, hidden activation, ReLU sign bits, output) cannot be
+    # rebuilt from the inverse, only re-evaluated:
+    #   "recompute": re-evaluate every subnet during backward (memory of one block at a time),
+    #   "store":     keep them from the value pass (what autograd does in the reference; ~100 B per pixel and subnet at the
+    #                headline shape, 3.3 GB per step at B=32 256x256 -- against 180 GB), no forward GEMMs in backward,
+    #   "auto":      store when the estimate fits in STORE_FRACTION of the memory the process has not allocated.
+    activations: str = "auto"
 
     @property
     def act_dtype(self):
@@ -49,6 +57,8 @@ class EngineConfig:
 
 
 PRECISIONS = ("bf16", "fp32", "fp32tc")
+ACTIVATION_MODES = ("auto", "store", "recompute")
+STORE_FRACTION = float(os.environ.get("SININN_STORE_FRACTION", "0.25"))
 
 
 def default_config():
@@ -56,7 +66,10 @@ def default_config():
     if prec not in PRECISIONS:
         raise SininnError(f"SININN_PRECISION must be one of {PRECISIONS}, got {prec!r}")
     tc = os.environ.get("SININN_TENSOR_CORE", "1") != "0"
-    return EngineConfig(precision=prec, tensor_core=tc)
+    keep = os.environ.get("SININN_ACTIVATIONS", "auto")
+    if keep not in ACTIVATION_MODES:
+        raise SininnError(f"SININN_ACTIVATIONS must be one of {ACTIVATION_MODES}, got {keep!r}")
+    return EngineConfig(precision=prec, tensor_core=tc, activations=keep)
 
 
 def _round_up(v, m):
@@ -70,6 +83,10 @@ FUSE_1X1 = os.environ.get("SININN_FUSE_1X1", "1") != "0"     # fused 1x1 subnet 
 # and transcendental math of the backward half-step make the epilogue warps the bottleneck)
 FUSE_COUPLING = int(os.environ.get("SININN_FUSE_COUPLING", "5"))
 FUSE_COUPLING_1X1 = int(os.environ.get("SININN_FUSE_COUPLING_1X1", "1"))     # the same bits for the fused 1x1 subnet kernel
+# "store" mode value passes: 1 = fused epilogue that also writes the subnet output for backward (cpl_a).  Measured on the
+# B200 at the headline shape: 5.60-5.64 ms / step fused against 5.57 unfused (the extra 25 MB store per subnet in the
+# epilogue costs what the separate coupling kernel did), so the default keeps the plain convolution + coupling_apply.
+FUSE_STORE = os.environ.get("SININN_FUSE_STORE", "0") != "0"
 
 TRACE = None     # debugging aid: set to a list to collect (label, trunk copy) after every executed op
 
@@ -259,8 +276,10 @@ class Trunk:
 
 
 class RunCtx:
-    def __init__(self, cfg, want_grads=False, packs=None, direct_grad=False, split_packs=None):
+    def __init__(self, cfg, want_grads=False, packs=None, direct_grad=False, split_packs=None, stash=None):
         self.cfg = cfg
+        # "store" mode: the value pass appends every subnet's (output, saved tensors) here, backward pops them
+        self.stash = stash
         self.adt = cfg.act_dtype
         self.tc = cfg.tc
         self.split = cfg.split
@@ -407,6 +426,12 @@ class ConvSubnet:
     def parameters(self):
         return [p for p in (self.c1.weight, self.c1.bias, self.c2.weight, self.c2.bias) if p is not None]
 
+    def stash_bytes_per_pixel(self, cfg):
+        if cfg.split:
+            return 12 * _round_up(self.cin, 8) + 8 * self.hidden + self.hidden // 8 + 4 * self.cout
+        e = 2 if cfg.tc else 4
+        return e * (self.cin + self.hidden) + self.hidden // 8 + 4 * self.cout
+
     def can_fuse_coupling(self, ctx, L, backward):
         mask = FUSE_COUPLING if self.taps == 9 else FUSE_COUPLING_1X1
         on = (mask & 1) if not backward else ((mask & 2) or ((mask & 4) and self.cout <= 64))
@@ -414,17 +439,20 @@ class ConvSubnet:
             return False
         return self.taps == 9 or (FUSE_1X1 and K.subnet1x1_supported(self.cin, self.hidden, self.cout))
 
-    def fwd_coupled(self, ctx, tr, src, u, clamp, rev, want_bf, du=None):
+    def fwd_coupled(self, ctx, tr, src, u, clamp, rev, want_bf, du=None, store=False):
         """Subnet forward with the GLOW half-step (du None) or its backward (du given) applied to u in the second
-        convolution's epilogue: the subnet output [s | t] never leaves the SM.  Returns (bf16 copy of the new u or None,
-        saved tensors for bwd() or None, da or None); None altogether if the kernel does not take the shape."""
+        convolution's epilogue: the subnet output [s | t] never leaves the SM -- unless `store` asks for the copy a
+        backward pass in "store" mode reads.  Returns (bf16 copy of the new u or None, saved tensors for bwd() or None,
+        da (backward) / a (store) or None); None altogether if the kernel does not take the shape."""
         x = tr.operand(src, ctx.adt)
         dev = x.device
         L = u.shape[1]
-        keep = du is not None
+        keep = du is not None or store
         bf = torch.empty(tr.npix, L, dtype=torch.bfloat16, device=dev) if want_bf else None
-        da = torch.empty(tr.npix, 2 * L, dtype=torch.bfloat16, device=dev) if keep else None
-        cpl = dict(mode=2 if keep else 1, u=u, clamp=clamp, inverse=rev, bf16=bf, du=du, da=da)
+        da = torch.empty(tr.npix, 2 * L, dtype=torch.bfloat16, device=dev) if du is not None else None
+        cpl = dict(mode=2 if du is not None else 1, u=u, clamp=clamp, inverse=rev, bf16=bf, du=du, da=da)
+        if store:
+            da = cpl["a"] = torch.empty(tr.npix, 2 * L, dtype=torch.float32, device=dev)
         if self.taps == 1:
             if x.stride(0) % 8 != 0:
                 return None
@@ -495,6 +523,8 @@ class ConvSubnet:
                tensor_core=ctx.tc, bits_out=bits)
         a = torch.empty(tr.npix, self.cout, dtype=torch.float32, device=dev)
         K.conv(h, ctx.pack(self.c2.weight, 0), tr.geom, self.cout, a, bias=self.c2.bias, tensor_core=ctx.tc)
+        if ctx.stash is not None and x.dtype == torch.float32:
+            x = x.clone()                            # fp32 operands are views of the live trunk; a stored one must be private
         return a, (x, h, bits)
 
     def bwd(self, ctx, tr, saved, da, dsrc):
@@ -546,6 +576,9 @@ class DenseSubnet:
         for c in self.convs:
             out += [p for p in (c.weight, c.bias) if p is not None]
         return out
+
+    def stash_bytes_per_pixel(self, cfg):
+        return (2 if cfg.tc else 4) * _round_up(self.ctot, 8) + 4 * self.cout
 
     def fwd(self, ctx, tr, src, keep=False):
         dev = tr.U.device
@@ -756,6 +789,9 @@ class CouplingOp:
     def first_src(self, rev):
         return (self.steps[-1] if rev else self.steps[0]).src
 
+    def stash_bytes_per_pixel(self, cfg):
+        return sum(n.stash_bytes_per_pixel(cfg) for st in self.steps for n in st.nets)
+
     def first_step_backward(self, rev):
         """The half-step whose subnet the backward pass of a value pass `rev` evaluates first."""
         return self.steps[0] if rev else self.steps[-1]
@@ -770,28 +806,37 @@ class CouplingOp:
             nxt = steps[i + 1].src if i + 1 < len(steps) else None
             want_bf = ctx.adt == torch.bfloat16 and nxt == st.dst and L % 8 == 0
             u = tr.mat()[:, st.dst[0]:st.dst[1]]
+            keep = ctx.stash is not None
             if st.kind == "glow":
                 fused = None
-                if logdet is None and st.nets[0].can_fuse_coupling(ctx, L, False):
+                if logdet is None and (FUSE_STORE or not keep) and st.nets[0].can_fuse_coupling(ctx, L, False):
                     tr.invalidate(*st.dst)
-                    fused = st.nets[0].fwd_coupled(ctx, tr, st.src, u, st.clamp, rev, want_bf)
+                    fused = st.nets[0].fwd_coupled(ctx, tr, st.src, u, st.clamp, rev, want_bf, store=keep)
                 if fused is not None:
                     bf = fused[0]
+                    if keep:
+                        ctx.stash.append((fused[2], fused[1]))
                 else:
-                    a, _ = st.nets[0].fwd(ctx, tr, st.src)
+                    a, saved = st.nets[0].fwd(ctx, tr, st.src, keep=keep)
+                    if keep:
+                        ctx.stash.append((a, saved))
                     tr.invalidate(*st.dst)
                     if logdet is not None:
                         K.logscale_sum(a[:, :L], B, GLOW, st.clamp, -1.0 if rev else 1.0, logdet, True)
                     bf = K.coupling_apply(u, a[:, :L], a[:, L:], GLOW, st.clamp, rev, want_bf)
             elif st.kind == "irn_affine":
-                s, _ = st.nets[0].fwd(ctx, tr, st.src)
-                t, _ = st.nets[1].fwd(ctx, tr, st.src)
+                s, saved_s = st.nets[0].fwd(ctx, tr, st.src, keep=keep)
+                t, saved_t = st.nets[1].fwd(ctx, tr, st.src, keep=keep)
+                if keep:
+                    ctx.stash.append((s, saved_s, t, saved_t))
                 tr.invalidate(*st.dst)
                 if logdet is not None:
                     K.logscale_sum(s, B, IRN, st.clamp, -1.0 if rev else 1.0, logdet, True)
                 bf = K.coupling_apply(u, s, t, IRN, st.clamp, rev, want_bf)
             else:
-                f, _ = st.nets[0].fwd(ctx, tr, st.src)
+                f, saved = st.nets[0].fwd(ctx, tr, st.src, keep=keep)
+                if keep:
+                    ctx.stash.append((f, saved))
                 tr.invalidate(*st.dst)
                 K.axpy_slice(u, f, -1.0 if rev else 1.0)
                 bf = None
@@ -806,27 +851,32 @@ class CouplingOp:
         for i, st in enumerate(undo):
             L = st.dst[1] - st.dst[0]
             nxt = undo[i + 1].src if i + 1 < len(undo) else None
-            want_bf = ctx.adt == torch.bfloat16 and nxt == st.dst and L % 8 == 0
+            stored = ctx.stash.pop() if ctx.stash is not None else None
+            # with stored subnet internals nothing in backward reads a bf16 copy of the restored trunk
+            want_bf = ctx.adt == torch.bfloat16 and nxt == st.dst and L % 8 == 0 and stored is None
             u = tr.mat()[:, st.dst[0]:st.dst[1]]
             du = tr.dmat()[:, st.dst[0]:st.dst[1]]
             dsrc = tr.dmat()[:, st.src[0]:st.src[1]]
             dev = u.device
             if st.kind == "glow":
                 fused = None
-                if st.nets[0].can_fuse_coupling(ctx, L, True):
+                if stored is None and st.nets[0].can_fuse_coupling(ctx, L, True):
                     tr.invalidate(*st.dst)
                     fused = st.nets[0].fwd_coupled(ctx, tr, st.src, u, st.clamp, rev, want_bf, du=du)
                 if fused is not None:
                     bf, saved, da = fused
                 else:
-                    a, saved = st.nets[0].fwd(ctx, tr, st.src, keep=True)
+                    a, saved = stored if stored is not None else st.nets[0].fwd(ctx, tr, st.src, keep=True)
                     da = torch.empty(tr.npix, 2 * L, dtype=ctx.adt, device=dev)
                     tr.invalidate(*st.dst)
                     bf = K.coupling_bwd(u, du, a[:, :L], a[:, L:], GLOW, st.clamp, rev, da[:, :L], da[:, L:], want_bf)
                 st.nets[0].bwd(ctx, tr, saved, da, dsrc)
             elif st.kind == "irn_affine":
-                s, saved_s = st.nets[0].fwd(ctx, tr, st.src, keep=True)
-                t, saved_t = st.nets[1].fwd(ctx, tr, st.src, keep=True)
+                if stored is not None:
+                    s, saved_s, t, saved_t = stored
+                else:
+                    s, saved_s = st.nets[0].fwd(ctx, tr, st.src, keep=True)
+                    t, saved_t = st.nets[1].fwd(ctx, tr, st.src, keep=True)
                 Lp = _round_up(L, 8)
                 ds = torch.empty(tr.npix, Lp, dtype=ctx.adt, device=dev)[:, :L]
                 dt = torch.empty(tr.npix, Lp, dtype=ctx.adt, device=dev)[:, :L]
@@ -836,7 +886,7 @@ class CouplingOp:
                 st.nets[1].bwd(ctx, tr, saved_t, dt, dsrc)
             else:
                 sign = -1.0 if rev else 1.0
-                f, saved = st.nets[0].fwd(ctx, tr, st.src, keep=True)
+                f, saved = stored if stored is not None else st.nets[0].fwd(ctx, tr, st.src, keep=True)
                 tr.invalidate(*st.dst)
                 K.axpy_slice(u, f, -sign)                       # restore dst
                 df = torch.empty(tr.npix, _round_up(L, 8), dtype=ctx.adt, device=dev)[:, :L]
@@ -896,6 +946,7 @@ class Plan:
         # opt-in with direct_grad: weight/bias gradient launches run on a side stream next to the data-gradient chain
         self.side_wgrad = False
         self._wstreams = {}
+        self._store_choice = {}
 
     def _wgrad_stream(self):
         cur = torch.cuda.current_stream()
@@ -954,10 +1005,42 @@ class Plan:
             (op.steps[-1] if rev else op.steps[0]).nets[0], DenseSubnet) else None
 
     # ---- value pass ---------------------------------------------------------------------------
-    def execute(self, x, rev, cfg):
+    def stash_bytes(self, shape, rev, cfg):
+        """Bytes a differentiable value pass keeps in "store" mode for an input of `shape` (per-pixel figures of the
+        subnets x the pixel count of the level each coupling block runs at)."""
+        npix = shape[0] * shape[2] * shape[3]
+        if not rev:
+            npix //= 4 ** len(self.prefix)
+        total = 0
+        for op in (self.core[::-1] if rev else self.core):
+            if op.kind == "resample":
+                npix = npix * 4 if rev else npix // 4
+            elif op.kind == "coupling":
+                total += npix * op.stash_bytes_per_pixel(cfg)
+        return total
+
+    def wants_store(self, x, rev, cfg):
+        """EngineConfig.activations resolved for this call: True = keep the subnet internals of the value pass."""
+        if cfg.activations not in ACTIVATION_MODES:
+            raise SininnError(f"EngineConfig.activations must be one of {ACTIVATION_MODES}, got {cfg.activations!r}")
+        if cfg.activations != "auto" or not self.body:
+            return cfg.activations == "store" and bool(self.body)
+        key = (tuple(x.shape), bool(rev), cfg.precision, cfg.tensor_core)
+        hit = self._store_choice.get(key)
+        if hit is None:
+            dev = x.device
+            if dev.type != "cuda":
+                return True
+            avail = torch.cuda.get_device_properties(dev).total_memory - torch.cuda.memory_allocated(dev)
+            hit = self.stash_bytes(x.shape, rev, cfg) <= STORE_FRACTION * avail
+            self._store_choice[key] = hit
+        return hit
+
+    def execute(self, x, rev, cfg, stash=None):
+        """stash: a list to fill with the subnet internals a later backward(..., stash=) consumes ("store" mode)."""
         self._check_input(x, rev)
         p_plain, p_split = self._ctx_packs(cfg, x)
-        ctx = RunCtx(cfg, packs=p_plain, split_packs=p_split)
+        ctx = RunCtx(cfg, packs=p_plain, split_packs=p_split, stash=stash)
         if not self.body:
             seq = self.prefix[::-1] if rev else self.prefix
             for op in seq:
@@ -1009,11 +1092,12 @@ class Plan:
         return y
 
     # ---- backward from the output ----------------------------------------------------------------
-    def backward(self, y, dy, rev, cfg, need_dx=True):
-        """y: the output execute(x, rev) produced; dy: dL/dy.  Returns (dL/dx or None, {id(param): grad})."""
+    def backward(self, y, dy, rev, cfg, need_dx=True, stash=None):
+        """y: the output execute(x, rev) produced; dy: dL/dy; stash: what execute(..., stash=) kept, consumed here.
+        Returns (dL/dx or None, {id(param): grad})."""
         require_cuda(dy, "grad_output")
         p_plain, p_split = self._ctx_packs(cfg, dy)
-        ctx = RunCtx(cfg, want_grads=True, direct_grad=self.direct_grad, packs=p_plain, split_packs=p_split)
+        ctx = RunCtx(cfg, want_grads=True, direct_grad=self.direct_grad, packs=p_plain, split_packs=p_split, stash=stash)
         dy = dy.contiguous()
         if dy.dtype != torch.float32:
             raise SininnError("grad_output must be fp32")
@@ -1091,7 +1175,9 @@ class _INNFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, plan, rev, cfg, latent, *params):
-        y = plan.execute(latent if latent is not None else x.detach(), rev, cfg)
+        inp = latent if latent is not None else x.detach()
+        ctx.stash = [] if plan.wants_store(inp, rev, cfg) else None
+        y = plan.execute(inp, rev, cfg, stash=ctx.stash)
         ctx.plan, ctx.rev, ctx.cfg = plan, rev, cfg
         ctx.params = params
         ctx.need_dx = x.requires_grad and latent is None
@@ -1101,8 +1187,9 @@ class _INNFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         (y,) = ctx.saved_tensors
+        stash, ctx.stash = ctx.stash, None             # consumed: a second backward through this node is not supported
         with _device_ctx(y):
-            dx, grads = ctx.plan.backward(y, dy, ctx.rev, ctx.cfg, need_dx=ctx.need_dx)
+            dx, grads = ctx.plan.backward(y, dy, ctx.rev, ctx.cfg, need_dx=ctx.need_dx, stash=stash)
         gl = [grads.get(id(p)) if p.requires_grad else None for p in ctx.params]
         return (dx, None, None, None, None, *gl)
 

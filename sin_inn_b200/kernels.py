@@ -432,7 +432,7 @@ def _conv_coupled(x, wpack, geom, cout, bias, cp):
         d.cpl_du, d.cpl_du_stride = du.data_ptr(), du.stride(0)
     else:
         d.cpl_du, d.cpl_du_stride = 0, 0
-    d.cpl_bf16, d.cpl_da = _p(cp.get("bf16")), _p(cp.get("da"))
+    d.cpl_bf16, d.cpl_da, d.cpl_a = _p(cp.get("bf16")), _p(cp.get("da")), _p(cp.get("a"))
     flops = 2.0 * B * H * W * d.Cin * d.Cout * d.taps
     check(_run("conv3x3", lambda: load().sininn_conv_tc(C.byref(d), stream_ptr()), 1, flops), "conv_tc(coupling)")
 
@@ -460,7 +460,7 @@ def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None, mas
             d.cpl_du, d.cpl_du_stride = du.data_ptr(), du.stride(0)
         else:
             d.cpl_du, d.cpl_du_stride = 0, 0
-        d.cpl_bf16, d.cpl_da = _p(coupling.get("bf16")), _p(coupling.get("da"))
+        d.cpl_bf16, d.cpl_da, d.cpl_a = _p(coupling.get("bf16")), _p(coupling.get("da")), _p(coupling.get("a"))
     else:
         out = _view2d(out)
         cout = out.shape[1]

@@ -211,6 +211,8 @@ def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask
         u = coupling["u"]
         if coupling["mode"] == 1:
             bf = coupling_apply(u, s_, t_, 0, coupling["clamp"], coupling["inverse"], coupling.get("bf16") is not None)
+            if coupling.get("a") is not None:
+                coupling["a"][:, :L], coupling["a"][:, L:] = s_, t_
         else:
             da = coupling["da"]
             bf = coupling_bwd(u, coupling["du"], s_, t_, 0, coupling["clamp"], coupling["inverse"], da[:, :L], da[:, L:],

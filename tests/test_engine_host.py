@@ -247,3 +247,32 @@ def test_actnorm_latent_input_and_jacobian_host_logic(fake_kernels):
             assert (nb.jacobian([v], rev=rev) - ob.jacobian([v], rev=rev)).abs().max() <= 1e-4 * max(1.0, ob.last_jac.abs().max())
     finally:
         del os.environ["SININN_PRECISION"]
+
+
+@pytest.mark.parametrize("arch,precision,tc", [("SRF", "fp32", False), ("SRF", "bf16", True), ("SRF", "fp32tc", True),
+                                               ("IRN", "fp32", False), ("IRN", "bf16", True)])
+def test_stored_and_recomputed_subnet_state_agree(fake_kernels, arch, precision, tc):
+    """EngineConfig.activations: "store" keeps every subnet's operand copy / hidden activation / output from the value
+    pass, "recompute" re-evaluates them from the trunk the inverse restores.  Same outputs; gradients equal up to the
+    round-off of the restored trunk (fp32: 1e-5; bf16 operands: their rounding decides a few copies differently)."""
+    res = {}
+    for mode in ("store", "recompute"):
+        opt, ora, net = _pair(arch, 4, 2 if arch == "SRF" else 1, 10, 16, 32)
+        net.engine_config = E.EngineConfig(precision=precision, tensor_core=tc, activations=mode)
+        hr, lr, z = R.synthetic_batch(opt, 2, 16, 32, seed=4)
+        x = hr.clone().requires_grad_(True)
+        y = net(x)
+        R.reconstruction(y[:, :opt.lr_dims], lr).backward()
+        u = torch.cat((lr, z), 1).requires_grad_(True)
+        R.reconstruction(net(u, rev=True), hr).backward()
+        res[mode] = (y.detach(), x.grad, u.grad, {n: p.grad for n, p in net.named_parameters() if p.requires_grad})
+    tol = 1e-5 if precision == "fp32" else (1e-4 if precision == "fp32tc" else 3e-2)
+    a, b = res["store"], res["recompute"]
+    assert torch.equal(a[0], b[0])
+    for i in (1, 2):
+        assert (a[i] - b[i]).norm() <= tol * max(1e-6, float(b[i].norm()))
+    for n, g in a[3].items():
+        assert (g - b[3][n]).norm() <= tol * max(1e-6, float(g.norm())), n
+    with pytest.raises(E.SininnError):
+        net.engine_config = E.EngineConfig(activations="sometimes")
+        net(hr.clone().requires_grad_(True))

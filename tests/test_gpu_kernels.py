@@ -622,8 +622,10 @@ def test_coupling_fused_into_conv_epilogue(K, L, geom, inverse):
         Ur, Uf = U0.clone(), U0.clone()
         bfr = K.coupling_apply(Ur[:, c0:c0 + L], a[:, :L], a[:, L:], 0, 1.2, inverse, True)
         bff = torch.empty(npix, L, dtype=bf, device=DEV)
+        af = torch.full((npix, cout), float("nan"), device=DEV)
         K.conv(h, wpi, geom, cout, None, bias=bias, tensor_core=True,
-               coupling=dict(mode=1, u=Uf[:, c0:c0 + L], clamp=1.2, inverse=inverse, bf16=bff))
+               coupling=dict(mode=1, u=Uf[:, c0:c0 + L], clamp=1.2, inverse=inverse, bf16=bff, a=af))
+        assert torch.equal(af, a)                       # the kept subnet output: same accumulation order per column
         assert (Ur - Uf).abs().max().item() <= 2e-6 * Ur.abs().max().item()
         assert torch.equal(Ur[:, :c0], Uf[:, :c0]) and torch.equal(Ur[:, c0 + L:], Uf[:, c0 + L:])     # the other half is untouched
         assert (bfr.float() - bff.float()).abs().max().item() <= 1e-2 * bfr.float().abs().max().item()
@@ -663,7 +665,9 @@ def test_coupling_fused_into_1x1_subnet_kernel(K, L, npix, inverse):
     Ur, Uf = U0.clone(), U0.clone()
     bfr = K.coupling_apply(Ur[:, c0:c0 + L], a[:, :L], a[:, L:], 0, 1.2, inverse, True)
     bff = torch.empty(npix, L, dtype=bf, device=DEV)
-    K.subnet1x1_fwd(x, w1p, b1, w2pi, b2, None, coupling=dict(mode=1, u=Uf[:, c0:c0 + L], clamp=1.2, inverse=inverse, bf16=bff))
+    af = torch.full((npix, cout), float("nan"), device=DEV)
+    K.subnet1x1_fwd(x, w1p, b1, w2pi, b2, None, coupling=dict(mode=1, u=Uf[:, c0:c0 + L], clamp=1.2, inverse=inverse, bf16=bff, a=af))
+    assert torch.equal(af, a)
     assert (Ur - Uf).abs().max().item() <= 2e-6 * Ur.abs().max().item()
     assert (bfr.float() - bff.float()).abs().max().item() <= 1e-2 * bfr.float().abs().max().item()
     Ur, Uf, dUr, dUf = U0.clone(), U0.clone(), dU0.clone(), dU0.clone()

@@ -16,10 +16,10 @@ DEV = "cuda:0"
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def build_pair(arch, scale, nc, lrw, H, W, precision, seed=11, tensor_core=True):
+def build_pair(arch, scale, nc, lrw, H, W, precision, seed=11, tensor_core=True, activations="auto"):
     from sin_inn_b200 import archs
     opt = R.make_opt(scale=scale, num_coupling=nc, lr_window=lrw, architecture=arch, precision=precision,
-                     tensor_core=tensor_core)
+                     tensor_core=tensor_core, activations=activations)
     torch.manual_seed(seed)
     ora = R.build(arch, 3, H, W, opt)
     torch.manual_seed(seed)
@@ -154,6 +154,35 @@ def test_bf16_path_matches_oracle(arch, scale, nc, lrw, B, H, W, tc):
     opt, ora, net = build_pair(arch, scale, nc, lrw, H, W, "bf16", tensor_core=tc)
     hr, out = run_both(opt, ora, net, B, H, W)
     check(hr, out, 2e-2, 2e-2, norm_wise=True)
+
+
+@pytest.mark.parametrize("arch,precision,tol", [("SRF", "fp32", 1e-4), ("IRN", "fp32", 1e-4), ("SRF", "bf16", 2e-2),
+                                                ("IRN", "bf16", 2e-2), ("SRF", "fp32tc", 1e-4)])
+def test_recompute_mode_matches_oracle_and_store_mode(arch, precision, tol):
+    """engine.EngineConfig.activations: every other test runs "auto" (= "store" at test sizes: the subnets' operand copy,
+    hidden activation, sign bits and output are kept from the value pass).  Here the same nets run in "recompute" mode
+    (subnets re-evaluated from the trunk the inverse restores) against the oracle, and the two modes against each other."""
+    res = {}
+    for mode in ("recompute", "store"):
+        opt, ora, net = build_pair(arch, 4, 2, 10, 64, 64, precision, activations=mode)
+        hr, out = run_both(opt, ora, net, 2, 64, 64)
+        if precision == "bf16":
+            check(hr, out, tol, 2e-2, norm_wise=True)
+        elif precision == "fp32":
+            check(hr, out, tol, 1e-5)
+        else:
+            _kink_aware_check(hr, out, 1e-4, 1e-5, 5e-3)
+        res[mode] = out["net"]
+    a, b = res["store"], res["recompute"]
+    if precision == "bf16":
+        # value passes differ too: "recompute" applies the coupling in the conv-2 epilogue (polynomial atan, __expf)
+        for k in ("y", "xr"):
+            assert (a[k] - b[k]).abs().max().item() <= 1e-3 * max(1.0, a[k].abs().max().item())
+    else:
+        assert torch.equal(a["y"], b["y"]) and torch.equal(a["xr"], b["xr"])
+    for n, g in a["g"].items():
+        rel = float((g - b["g"][n]).norm() / max(1e-12, float(g.norm())))
+        assert rel <= (4e-2 if precision == "bf16" else 5e-3 if precision == "fp32tc" else 1e-4), (n, rel)
 
 
 @pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLD, "*.npz")) if "known" not in p))
