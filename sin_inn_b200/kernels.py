@@ -25,14 +25,15 @@ def profile_begin():
     _prof = []
 
 
-def profile_end():
-    """Stop profiling; returns {family: {"ms", "flops", "bytes", "n"}} (algorithmic flops/bytes as passed in)."""
+def profile_end(by_shape=False):
+    """Stop profiling; returns {family: {"ms", "flops", "bytes", "n"}} (algorithmic flops/bytes as passed in).
+    by_shape: key on "family shape-tag" (the tag the launch wrappers attach) instead of the family alone."""
     global _prof
     rec, _prof = _prof or [], None
     torch.cuda.synchronize()
     out = {}
-    for fam, e0, e1, nk, flops, nbytes in rec:
-        d = out.setdefault(fam, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+    for fam, e0, e1, nk, flops, nbytes, tag in rec:
+        d = out.setdefault(f"{fam} {tag}" if (by_shape and tag) else fam, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
         d["ms"] += e0.elapsed_time(e1)
         d["flops"] += flops
         d["bytes"] += nbytes
@@ -40,7 +41,7 @@ def profile_end():
     return out
 
 
-def _run(family, fn, nk=1, flops=0.0, nbytes=0.0):
+def _run(family, fn, nk=1, flops=0.0, nbytes=0.0, tag=None):
     global LAUNCHES
     LAUNCHES += nk
     if _prof is None:
@@ -49,7 +50,7 @@ def _run(family, fn, nk=1, flops=0.0, nbytes=0.0):
     e0.record()
     rc = fn()
     e1.record()
-    _prof.append((family, e0, e1, nk, flops, nbytes))
+    _prof.append((family, e0, e1, nk, flops, nbytes, tag() if callable(tag) else tag))
     return rc
 
 
@@ -407,7 +408,10 @@ def conv(x, wpack, geom, cout, out, bias=None, act=0, slope=0.0, mask=None, mask
     fn = lib.sininn_conv_tc if tensor_core else lib.sininn_conv_simt
     flops = 2.0 * B * H * W * d.Cin * d.Cout * d.taps
     fam = "conv3x3" if d.taps == 9 else "conv1x1"
-    check(_run(fam, lambda: fn(C.byref(d), stream_ptr()), 1, flops), "conv_tc" if tensor_core else "conv_simt")
+    tag = lambda: (f"{H}x{W} {d.Cin}->{d.Cout}" + (" relu" if act else "") + (" bits" if bits_out is not None else "")
+                   + (" masked" if (mask is not None or mask_bits is not None) else "") + (" acc" if accumulate else "")
+                   + (" f32" if out.dtype == torch.float32 else " bf16"))
+    check(_run(fam, lambda: fn(C.byref(d), stream_ptr()), 1, flops, tag=tag), "conv_tc" if tensor_core else "conv_simt")
     return out
 
 
@@ -434,7 +438,8 @@ def _conv_coupled(x, wpack, geom, cout, bias, cp):
         d.cpl_du, d.cpl_du_stride = 0, 0
     d.cpl_bf16, d.cpl_da, d.cpl_a = _p(cp.get("bf16")), _p(cp.get("da")), _p(cp.get("a"))
     flops = 2.0 * B * H * W * d.Cin * d.Cout * d.taps
-    check(_run("conv3x3", lambda: load().sininn_conv_tc(C.byref(d), stream_ptr()), 1, flops), "conv_tc(coupling)")
+    tag = lambda: f"{H}x{W} {d.Cin}->{d.Cout} cpl{d.cpl_mode}" + (" +a" if d.cpl_a else "")
+    check(_run("conv3x3", lambda: load().sininn_conv_tc(C.byref(d), stream_ptr()), 1, flops, tag=tag), "conv_tc(coupling)")
 
 
 def subnet1x1_supported(cin, hidden, cout):
@@ -485,7 +490,9 @@ def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None, mas
     # gradient use (see sininn.h): hidden stage masked by the forward's ReLU sign bits, output accumulated
     d.mask_bits, d.accumulate = _p(mask_bits), int(accumulate)
     flops = 2.0 * d.npix * d.hidden * (d.Cin + d.Cout)
-    check(_run("subnet1x1", lambda: load().sininn_subnet1x1_fwd_tc(C.byref(d), stream_ptr()), 1, flops), "subnet1x1_fwd_tc")
+    tag = lambda: (f"npix{d.npix} {d.Cin}->{d.hidden}->{d.Cout}" + (" keep" if d.h_out else "") + (" grad" if d.mask_bits else "")
+                   + (f" cpl{d.cpl_mode}" if d.cpl_mode else ""))
+    check(_run("subnet1x1", lambda: load().sininn_subnet1x1_fwd_tc(C.byref(d), stream_ptr()), 1, flops, tag=tag), "subnet1x1_fwd_tc")
     return out
 
 
@@ -541,7 +548,8 @@ def wgrad_group(jobs):
         flops += 2.0 * geom[0] * geom[1] * geom[2] * d.Cin * d.Cout * taps * max(1, d.nterms)
     lib = load()
     ws = _workspace(jobs[0][0].device, "wgrad", lib.sininn_wgrad_group_workspace_bytes(arr, n))
-    check(_run("wgrad", lambda: lib.sininn_wgrad_tc_group(arr, n, ws.data_ptr(), ws.numel(), stream_ptr()), 2, flops),
+    tag = lambda: " | ".join(f"{a.H}x{a.W} {a.Cin}x{a.Cout} t{a.taps}" for a in arr)
+    check(_run("wgrad", lambda: lib.sininn_wgrad_tc_group(arr, n, ws.data_ptr(), ws.numel(), stream_ptr()), 2, flops, tag=tag),
           "wgrad_tc_group")
 
 
