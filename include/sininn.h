@@ -208,7 +208,8 @@ typedef struct {
 /* Debugging aid: when set to a device buffer of 4 x 512 int64, the CTA-pair 3x3 kernel records clock64() stamps of
  * CTA 0's producer / MMA / epilogue roles into words 0..1535 (only when built with -DSININN_PAIR_TRACE) and the CTA-pair
  * weight-gradient kernel its phase stamps into words 1536..1543: {entry, prologue done, dependency wait done, producer
- * done, first stage landed, last MMA issued, accumulators ready, partials stored}.  NULL switches tracing off (default). */
+ * done, first stage landed, last MMA issued, accumulators ready, partials stored}; the fused 1x1 subnet backward kernel
+ * writes words 1600..1855 (MMA issuer, then epilogue warp 2: 16 tiles x 8 stamps each).  NULL switches tracing off (default). */
 int sininn_debug_set_trace(void* device_buf_3x512_int64);
 
 int sininn_conv_simt(const sininn_conv_desc* d, sininn_stream_t stream);   /* fp32-accurate CUDA-core path */
@@ -249,6 +250,34 @@ typedef struct {
 int sininn_subnet1x1_fwd_tc(const sininn_subnet1x1_desc* d, sininn_stream_t stream);
 /* 1 when the fused kernel takes a Cin -> hidden -> Cout subnet (channel multiples and shared-memory budget), else 0 */
 int sininn_subnet1x1_supported(int Cin, int hidden, int Cout);
+
+/* Fused 1x1 coupling subnet, BACKWARD (tcgen05/TMEM/TMA, bf16 operands, hidden = 256): everything autograd derives for
+ * subnet_conv_1x1 (archs.py:15-17) from x (the subnet input the forward pass read) and da = dL/d(subnet output), in one
+ * kernel launch + one reduction launch:
+ *   h = relu(W1 x + b1) (re-evaluated, bit-identical to sininn_subnet1x1_fwd_tc),  dh = (h > 0) * (W2^T da),
+ *   dsrc += W1^T dh,   dw2 (+)= sum_p da h^T,  db2 (+)= sum_p da,   dw1 (+)= sum_p dh x^T,  db1 (+)= sum_p dh.
+ * Neither h nor dh is written to memory.  w1pack: conv1 fprop pack (mode 0) [hidden][k1_pad]; w2dpack: conv2 dgrad pack
+ * (mode 1) [hidden][k2_pad]; w1dpack: conv1 dgrad pack (mode 1) [r1_pad][hidden]; dw1 / dw2: OIHW fp32 ([hidden][Cin],
+ * [Cout][hidden]).  Each CTA leaves one partial of the parameter gradients in `workspace`; they are summed in a fixed
+ * order (bit-reproducible).  Shapes: sininn_subnet1x1_bwd_supported (Cin % 8 == 0, Cin <= 32, Cout % 4 == 0, Cout <= 64). */
+typedef struct {
+  long long npix;
+  int Cin, hidden, Cout;
+  const void* x;  int x_stride;          /* bf16 [npix][Cin] */
+  const void* da; int da_stride;         /* bf16 [npix][Cout] */
+  const void* w1pack;  int k1_pad;
+  const float* b1;                       /* [hidden] or NULL */
+  const void* w2dpack; int k2_pad;
+  const void* w1dpack; int r1_pad;
+  float* dsrc;    int dsrc_stride;       /* fp32 [npix][Cin], accumulated into */
+  float* dw1; int dw1_accumulate; float* db1; int db1_accumulate;
+  float* dw2; int dw2_accumulate; float* db2; int db2_accumulate;
+  void* workspace; size_t workspace_bytes;
+} sininn_subnet1x1_bwd_desc;
+
+int sininn_subnet1x1_bwd_supported(int Cin, int hidden, int Cout);
+size_t sininn_subnet1x1_bwd_workspace_bytes(const sininn_subnet1x1_bwd_desc* d);
+int sininn_subnet1x1_bwd_tc(const sininn_subnet1x1_bwd_desc* d, sininn_stream_t stream);
 
 /* Re-layout nn.Conv2d OIHW fp32 weights for the implicit GEMMs above.
  *   mode 0 (fprop): out[tap][co][ci] = w[co][ci][tap]           rows = Cout, k = Cin

@@ -75,6 +75,23 @@ class Subnet1x1Desc(C.Structure):
     ]
 
 
+class Subnet1x1BwdDesc(C.Structure):
+    _fields_ = [
+        ("npix", _c_ll),
+        ("Cin", C.c_int), ("hidden", C.c_int), ("Cout", C.c_int),
+        ("x", _vp), ("x_stride", C.c_int),
+        ("da", _vp), ("da_stride", C.c_int),
+        ("w1pack", _vp), ("k1_pad", C.c_int),
+        ("b1", _vp),
+        ("w2dpack", _vp), ("k2_pad", C.c_int),
+        ("w1dpack", _vp), ("r1_pad", C.c_int),
+        ("dsrc", _vp), ("dsrc_stride", C.c_int),
+        ("dw1", _vp), ("dw1_accumulate", C.c_int), ("db1", _vp), ("db1_accumulate", C.c_int),
+        ("dw2", _vp), ("dw2_accumulate", C.c_int), ("db2", _vp), ("db2_accumulate", C.c_int),
+        ("workspace", _vp), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/sininn.h declares
 SIGNATURES = {
     "sininn_version": (C.c_int, []),
@@ -114,6 +131,9 @@ SIGNATURES = {
     "sininn_conv_tc": (C.c_int, [C.POINTER(ConvDesc), _vp]),
     "sininn_subnet1x1_fwd_tc": (C.c_int, [C.POINTER(Subnet1x1Desc), _vp]),
     "sininn_subnet1x1_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "sininn_subnet1x1_bwd_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "sininn_subnet1x1_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(Subnet1x1BwdDesc)]),
+    "sininn_subnet1x1_bwd_tc": (C.c_int, [C.POINTER(Subnet1x1BwdDesc), _vp]),
     "sininn_pack_conv_weight": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "sininn_pack_conv_weights_batched": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "sininn_split_bf16": (C.c_int, [_vp, C.c_int, _c_ll, C.c_int, C.c_float, _vp, C.c_int, C.c_int, _vp]),

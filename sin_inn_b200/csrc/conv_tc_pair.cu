@@ -417,6 +417,7 @@ int launch_conv_pair(const sininn_conv_desc* d, Params p, cudaStream_t st) {
 
 void set_pair_trace(long long* buf) { g_trace_buf = buf; }
 void set_wgrad_pair_trace(long long* buf);      // wgrad_pair.cu (its 8 stamps go to words 1536.. of the same buffer)
+void set_s1bwd_trace(long long* buf);           // subnet1x1_bwd.cu (2 roles x 16 tiles x 8 stamps at words 1600..1855)
 
 }  // namespace tc
 }  // namespace sininn
@@ -424,5 +425,6 @@ void set_wgrad_pair_trace(long long* buf);      // wgrad_pair.cu (its 8 stamps g
 extern "C" int sininn_debug_set_trace(void* device_buf_3x512_int64) {
   sininn::tc::set_pair_trace(reinterpret_cast<long long*>(device_buf_3x512_int64));
   sininn::tc::set_wgrad_pair_trace(device_buf_3x512_int64 ? reinterpret_cast<long long*>(device_buf_3x512_int64) + 3 * 512 : nullptr);
+  sininn::tc::set_s1bwd_trace(device_buf_3x512_int64 ? reinterpret_cast<long long*>(device_buf_3x512_int64) + 1600 : nullptr);
   return SININN_OK;
 }

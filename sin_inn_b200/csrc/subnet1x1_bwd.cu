@@ -1,0 +1,610 @@
+// Fused 1x1 coupling subnet, BACKWARD: for  a = W2 relu(W1 x + b1) + b2  (per pixel) and da = dL/da, ONE launch computes
+//
+//     dsrc += W1^T dh,   dh = (h > 0) * (W2^T da),   h = relu(W1 x + b1)  (re-evaluated here from x)
+//     dW2 (+)= sum_p da[p] h[p]^T,  db2 (+)= sum_p da[p],   dW1 (+)= sum_p dh[p] x[p]^T,  db1 (+)= sum_p dh[p]
+//
+// Replaces what autograd derives for subnet_conv_1x1 (/root/reference/archs.py:15-17) inside a GLOW coupling half
+// (call site archs.py:56-64).  Neither the hidden activation h nor its gradient dh ever reaches HBM (67 MB each per
+// subnet at the level-0 shape of the headline workload; the unfused path wrote h once, dh once and read each twice:
+// ncu showed the level-0 1x1 weight-gradient launch at 0.83 of the HBM peak doing nothing else).  HBM traffic per pixel:
+// x (Cin * 2 B) + da (Cout * 2 B) in, dsrc (Cin * 8 B, read-modify-write) -- and one partial of the weight gradients per CTA.
+//
+// One persistent CTA per SM, a tile = 128 consecutive pixels of the channels-last matrices.  Five GEMM families per tile
+// on tcgen05 (cta_group::1, M = 128), accumulators in TMEM:
+//     G1   Hpre [128 px x 256]    = X . W1^T           K = Cin     (A = x tile, K-major)          -> ACC_H
+//     G2   DHpre[128 px x 256]    = DA . W2            K = Cout    (A = da tile, K-major)         -> ACC_H (after h left it)
+//     G3   dsrc [128 px x Cin]    = DH . W1            K = 256     (A = dh tile in smem, K-major) -> ACC_S
+//     G4   dW2^T[256 x Cout]     += H^T . DA           K = 128 px  (A = h tile read MN-major, B = da tile MN-major) -> ACC_W2
+//     G4b  db2  [. x Cout]       += 1^T . DA                        (A = a tile of ones)           -> ACC_B2
+//     G5   dW1  [256 x Cin (+1)] += DH^T . X           K = 128 px  (A = dh tile MN-major, B = x tile MN-major) -> ACC_W1
+// The hidden tile is ONE 64 KB shared-memory buffer (four 128B-swizzled boxes of 64 channels x 128 pixels): the first
+// epilogue writes h into it, G4 reads it transposed, the second epilogue overwrites it with dh (each thread reads its own row of
+// h back for the ReLU mask: one HSET2 + one AND per two values), G3 reads that K-major and G5 transposed -- a 128B-swizzled
+// [pixels][64 channels] box is a legal K-major operand over the channels AND a legal MN-major operand over the pixels.
+// db1 costs nothing: the first zero-filled padding column of the x tile is overwritten with ones after it lands, so the
+// column Cin of ACC_W1 is sum_p dh[p] (G1 multiplies that column with a zero column of the W1 pack).
+// ACC_W2 / ACC_W1 / ACC_B2 persist over all tiles of the CTA; at the end every CTA stores one partial and
+// wgrad_reduce_kernel (wgrad_pair.cu) adds the partials in a fixed order: bit-deterministic, no float atomics.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-17 epilogue (four per TMEM lane quarter, one 64-column slab each).
+#include "tc_epilogue.cuh"
+
+namespace sininn {
+namespace tc {
+
+int launch_reduce_two(const sininn_wgrad_desc* d0, const float* partial0, int wide_is_dy0, const float* bias_partial0,
+                      const sininn_wgrad_desc* d1, const float* partial1, int wide_is_dy1, const float* bias_partial1,
+                      int splits, cudaStream_t st);      // wgrad_pair.cu
+
+constexpr int SB_EPI_WARPS = 16;
+constexpr int SB_THREADS = 64 + 32 * SB_EPI_WARPS;
+constexpr int SB_HID = 256;
+constexpr uint32_t SB_BOX = 128 * 128;             // one box: 128 rows (pixels, or weight rows) x 128 B (64 bf16)
+constexpr uint32_t SB_ONES_BYTES = 4096;
+constexpr uint32_t SB_STAGING_BYTES = 4 * 4096;    // dsrc tile: 128 pixels x 32 fp32 (one 32-row box per lane quarter)
+
+struct __align__(8) SbBarriers {
+  uint64_t w_full;
+  uint64_t x_full[2], x_empty[2], da_full[2], da_empty[2];
+  uint64_t d1_full;        // G1 retired: Hpre in ACC_H                                   (MMA -> epilogue)
+  uint64_t hacc_free;      // every epilogue warp has read Hpre out of ACC_H              (epilogue -> MMA: G2 may overwrite it)
+  uint64_t h_full;         // h tile (and the ones column of the x tile) in shared memory (epilogue -> MMA: G4)
+  uint64_t d2_full;        // G2 retired: DHpre in ACC_H                                  (MMA -> epilogue)
+  uint64_t g4_done;        // G4 / G4b retired: the h tile may be overwritten with dh     (MMA -> epilogue)
+  uint64_t dacc_free;      // every epilogue warp has read DHpre out of ACC_H             (epilogue -> MMA: next tile's G1)
+  uint64_t dh_full;        // dh tile in shared memory                                    (epilogue -> MMA: G3, G5)
+  uint64_t s_full;         // G3 / G5 retired: dsrc tile in ACC_S, hidden tile free       (MMA -> epilogue)
+  uint32_t tmem_base, pad;
+};
+
+struct SbParams {
+  long long npix;
+  int num_tiles;
+  int cin, cout;
+  int k1_steps, k2_steps;          // K = 16 steps of G1 / G2
+  int n3, n4, n5;                  // UMMA N of G3 (Cin padded to 16), G4 (Cout padded to 16), G5 (Cin + 1 padded to 16)
+  uint32_t col_s, col_w2, col_w1, col_b2;     // TMEM columns of the accumulators (ACC_H at 0)
+  uint32_t w1d_slab_bytes;         // n3 * 128
+  const float* b1;
+  float* p_w2;                     // [grid][cout][256]
+  float* p_w1;                     // [grid][cin][256]
+  float* p_b2;                     // [grid][cout]
+  float* p_b1;                     // [grid][256]
+  long long* trace;                // debugging aid (sininn_debug_set_trace): clock64 stamps of CTA 0's MMA / epilogue roles, or NULL
+};
+
+__device__ __forceinline__ void sb_tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void sb_tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+static long long* g_s1bwd_trace = nullptr;
+void set_s1bwd_trace(long long* buf) { g_s1bwd_trace = buf; }
+// role 0 = MMA issuer, 1 = epilogue warp 2; up to 16 tiles x 8 stamps each (tile 15 of the epilogue role: kernel phases)
+__device__ __forceinline__ void sb_stamp(const SbParams& p, int role, int tile_i, int slot, int lane) {
+  if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tile_i < 16) p.trace[role * 128 + tile_i * 8 + slot] = clock64();
+}
+
+// 0xFFFF in each half of the result whose bf16 half of h is > 0 (one HSET2)
+__device__ __forceinline__ uint32_t relu_mask(uint32_t h2) {
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&h2), __floats2bfloat162_rn(0.f, 0.f));
+}
+
+__global__ void __launch_bounds__(SB_THREADS, 1)
+subnet1x1_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDA,
+                     const __grid_constant__ CUtensorMap tmW1f, const __grid_constant__ CUtensorMap tmW2d,
+                     const __grid_constant__ CUtensorMap tmW1d, const __grid_constant__ CUtensorMap tmS, const SbParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* w1f_s = smem_raw + pad;                          // [256 rows][64 B]    conv1 fprop pack (B of G1), SWIZZLE_64B
+  uint8_t* w2d_s = w1f_s + SB_BOX;                          // [256 rows][128 B]   conv2 dgrad pack (B of G2)
+  uint8_t* w1d_s = w2d_s + 2 * SB_BOX;                      // [4 slabs][n3 rows][128 B]  conv1 dgrad pack (B of G3)
+  uint8_t* x_s = w1d_s + 4 * p.w1d_slab_bytes;              // [2 stages][128 px][128 B]
+  uint8_t* da_s = x_s + 2 * SB_BOX;                         // [2 stages][128 px][128 B]
+  uint8_t* h_s = da_s + 2 * SB_BOX;                         // [4 boxes][128 px][128 B]   h, then dh
+  uint8_t* stg_s = h_s + 4 * SB_BOX;                        // [4 quarters][32 px][128 B] fp32 dsrc tile
+  uint8_t* ones = stg_s + SB_STAGING_BYTES;
+  SbBarriers* bars = reinterpret_cast<SbBarriers*>(ones + SB_ONES_BYTES);
+  float* b1_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);       // [256]
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  sb_stamp(p, 1, 15, 0, threadIdx.x);
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars->w_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bars->x_full[s]), 1);
+      mbar_init(smem_u32(&bars->x_empty[s]), 1);
+      mbar_init(smem_u32(&bars->da_full[s]), 1);
+      mbar_init(smem_u32(&bars->da_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bars->d1_full), 1);
+    mbar_init(smem_u32(&bars->hacc_free), SB_EPI_WARPS);
+    mbar_init(smem_u32(&bars->h_full), SB_EPI_WARPS);
+    mbar_init(smem_u32(&bars->d2_full), 1);
+    mbar_init(smem_u32(&bars->g4_done), 1);
+    mbar_init(smem_u32(&bars->dacc_free), SB_EPI_WARPS);
+    mbar_init(smem_u32(&bars->dh_full), SB_EPI_WARPS);
+    mbar_init(smem_u32(&bars->s_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDA);
+    tma_prefetch_desc(&tmW1f);
+    tma_prefetch_desc(&tmW2d);
+    tma_prefetch_desc(&tmW1d);
+    tma_prefetch_desc(&tmS);
+  }
+  // constant tile of ones (bf16 1.0 = 0x3F80): the A operand of the db2 MMAs; all ones look the same under every swizzle
+  for (int i = threadIdx.x; i < (int)(SB_ONES_BYTES / 16); i += SB_THREADS)
+    reinterpret_cast<uint4*>(ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  fence_async_smem();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  sb_stamp(p, 1, 15, 1, threadIdx.x);
+  pdl_wait();       // prologue above overlaps the previous kernel's tail; global memory from here on
+  pdl_trigger();
+  if (warp >= 2) {
+    const int e = threadIdx.x - 64;
+    if (e < SB_HID) b1_s[e] = p.b1 != nullptr ? __ldg(p.b1 + e) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  sb_stamp(p, 1, 15, 2, threadIdx.x);
+  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t acc_h = tmem_base, acc_s = tmem_base + p.col_s, acc_w2 = tmem_base + p.col_w2, acc_w1 = tmem_base + p.col_w1,
+                 acc_b2 = tmem_base + p.col_b2;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (elect_one()) {
+      const uint32_t full = smem_u32(&bars->w_full);
+      mbar_expect_tx(full, 3u * SB_BOX + 4u * p.w1d_slab_bytes);
+      sb_tma_load_2d(smem_u32(w1f_s), &tmW1f, full, 0, 0);
+      sb_tma_load_2d(smem_u32(w1f_s) + SB_BOX / 2, &tmW1f, full, 0, 128);
+      sb_tma_load_2d(smem_u32(w2d_s), &tmW2d, full, 0, 0);
+      sb_tma_load_2d(smem_u32(w2d_s) + SB_BOX, &tmW2d, full, 0, 128);
+      for (int s = 0; s < 4; ++s) sb_tma_load_2d(smem_u32(w1d_s) + s * p.w1d_slab_bytes, &tmW1d, full, s * 64, 0);
+    }
+    __syncwarp();
+    int st = 0; uint32_t ph = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      mbar_wait(smem_u32(&bars->x_empty[st]), ph ^ 1);
+      if (elect_one()) {
+        const uint32_t full = smem_u32(&bars->x_full[st]);
+        mbar_expect_tx(full, SB_BOX);
+        sb_tma_load_2d(smem_u32(x_s) + st * SB_BOX, &tmX, full, 0, t * 128);
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(&bars->da_empty[st]), ph ^ 1);
+      if (elect_one()) {
+        const uint32_t full = smem_u32(&bars->da_full[st]);
+        mbar_expect_tx(full, SB_BOX);
+        sb_tma_load_2d(smem_u32(da_s) + st * SB_BOX, &tmDA, full, 0, t * 128);
+      }
+      __syncwarp();
+      if (++st == 2) { st = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (whole warp loops, predicated issue: state stays in uniform registers) ==========
+    // Per tile:  G2 as soon as the epilogue has read Hpre out of ACC_H;  G4 / G4b once the h tile is stored;  the NEXT tile's
+    // G1 as soon as the epilogue has read DHpre out of ACC_H;  G3 / G5 once the dh tile is stored.  The epilogue's arithmetic
+    // on tile i+1's Hpre therefore runs under G3 / G5 of tile i, and its arithmetic on DHpre under G4 / G4b.
+    const uint32_t kk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);        // D f32, A/B bf16 K-major, M = 128
+    const uint32_t mn = kk | (1u << 15) | (1u << 16);                                            // A and B MN-major
+    const uint32_t idesc12 = kk | ((uint32_t)(SB_HID >> 3) << 17);
+    const uint32_t idesc3 = kk | ((uint32_t)(p.n3 >> 3) << 17);
+    const uint32_t idesc4 = mn | ((uint32_t)(p.n4 >> 3) << 17);
+    const uint32_t idesc5 = mn | ((uint32_t)(p.n5 >> 3) << 17);
+    const uint64_t x_desc0 = make_desc(smem_u32(x_s), 1024, 2);
+    const uint64_t da_desc0 = make_desc(smem_u32(da_s), 1024, 2);
+    const uint64_t w1f_desc = make_desc(smem_u32(w1f_s), 512, 4);                                 // 64-byte rows, SWIZZLE_64B
+    const uint64_t w2d_desc = make_desc(smem_u32(w2d_s), 1024, 2);
+    const uint64_t w1d_desc0 = make_desc(smem_u32(w1d_s), 1024, 2);
+    const uint64_t h_k_desc0 = make_desc(smem_u32(h_s), 1024, 2);
+    // MN-major A over the hidden tile: LBO = distance between 64-channel boxes, SBO = distance between 8-pixel K groups
+    const uint64_t h_mn_desc0 = (h_k_desc0 & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)(SB_BOX >> 4) << 16);
+    uint64_t ones_desc = make_desc(smem_u32(ones), 1024, 2);                                      // 128 "channels" x 16 pixels
+    ones_desc = (ones_desc & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)(2048 >> 4) << 16);
+    const uint32_t stage_step = SB_BOX >> 4;
+    const uint32_t w1d_step = p.w1d_slab_bytes >> 4;
+    int st = 0; uint32_t ph = 0;
+    uint32_t tph = 0;                          // phase of the once-per-tile barriers
+    int ti = 0;
+    uint32_t first = 0u;                       // 0 on the CTA's first tile: the persistent accumulators start from zero
+
+    mbar_wait(smem_u32(&bars->w_full), 0);
+    if ((int)blockIdx.x < p.num_tiles) {
+      mbar_wait(smem_u32(&bars->x_full[0]), 0);
+      tc_fence_after();
+      __syncwarp();
+      const uint32_t lead = elect_pred();
+      for (int k = 0; k < p.k1_steps; ++k) umma_bf16_p(lead, acc_h, x_desc0 + 2 * k, w1f_desc + 2 * k, idesc12, k != 0 ? 1u : 0u);
+      umma_commit_p(lead, smem_u32(&bars->d1_full));
+    }
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const uint64_t xd = x_desc0 + (uint64_t)(st * stage_step);
+      const uint64_t dad = da_desc0 + (uint64_t)(st * stage_step);
+      // ---- Hpre has left ACC_H: DHpre = da . W2
+      sb_stamp(p, 0, ti, 0, lane);
+      mbar_wait(smem_u32(&bars->hacc_free), tph);
+      mbar_wait(smem_u32(&bars->da_full[st]), ph);
+      tc_fence_after();
+      __syncwarp();
+      sb_stamp(p, 0, ti, 1, lane);
+      uint32_t lead = elect_pred();
+      for (int k = 0; k < p.k2_steps; ++k) umma_bf16_p(lead, acc_h, dad + 2 * k, w2d_desc + 2 * k, idesc12, k != 0 ? 1u : 0u);
+      umma_commit_p(lead, smem_u32(&bars->d2_full));
+      // ---- h is in shared memory: weight gradient of conv2 and its bias gradient
+      mbar_wait(smem_u32(&bars->h_full), tph);
+      tc_fence_after();
+      __syncwarp();
+      sb_stamp(p, 0, ti, 2, lane);
+      lead = elect_pred();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint64_t ad = h_mn_desc0 + (uint64_t)(hh * 2 * stage_step);
+        const uint32_t d = acc_w2 + (uint32_t)(hh * p.n4);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16_p(lead, d, ad + 128 * k, dad + 128 * k, idesc4, k == 0 ? first : 1u);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) umma_bf16_p(lead, acc_b2, ones_desc, dad + 128 * k, idesc4, k == 0 ? first : 1u);
+      umma_commit_p(lead, smem_u32(&bars->g4_done));
+      umma_commit_p(lead, smem_u32(&bars->da_empty[st]));
+      sb_stamp(p, 0, ti, 3, lane);
+      // ---- DHpre has left ACC_H: the next tile's first layer
+      mbar_wait(smem_u32(&bars->dacc_free), tph);
+      if (t + (int)gridDim.x < p.num_tiles) {
+        const int sn = st ^ 1;
+        mbar_wait(smem_u32(&bars->x_full[sn]), sn == 0 ? ph ^ 1 : ph);
+        tc_fence_after();
+        __syncwarp();
+        lead = elect_pred();
+        const uint64_t xn = x_desc0 + (uint64_t)(sn * stage_step);
+        for (int k = 0; k < p.k1_steps; ++k) umma_bf16_p(lead, acc_h, xn + 2 * k, w1f_desc + 2 * k, idesc12, k != 0 ? 1u : 0u);
+        umma_commit_p(lead, smem_u32(&bars->d1_full));
+      }
+      sb_stamp(p, 0, ti, 4, lane);
+      // ---- dh is in shared memory: input gradient, weight (+ bias) gradient of conv1
+      mbar_wait(smem_u32(&bars->dh_full), tph);
+      tc_fence_after();
+      __syncwarp();
+      sb_stamp(p, 0, ti, 5, lane);
+      lead = elect_pred();
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const uint64_t ad = h_k_desc0 + (uint64_t)(s * stage_step);
+        const uint64_t bd = w1d_desc0 + (uint64_t)(s * w1d_step);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_p(lead, acc_s, ad + 2 * k, bd + 2 * k, idesc3, (s | k) != 0 ? 1u : 0u);
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint64_t ad = h_mn_desc0 + (uint64_t)(hh * 2 * stage_step);
+        const uint32_t d = acc_w1 + (uint32_t)(hh * p.n5);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16_p(lead, d, ad + 128 * k, xd + 128 * k, idesc5, k == 0 ? first : 1u);
+      }
+      umma_commit_p(lead, smem_u32(&bars->s_full));
+      umma_commit_p(lead, smem_u32(&bars->x_empty[st]));
+      sb_stamp(p, 0, ti, 6, lane);
+      ++ti;
+      first = 1u;
+      tph ^= 1;
+      if (++st == 2) { st = 0; ph ^= 1; }
+    }
+  } else {
+    // ======================= epilogue warps =======================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                    // TMEM lane quarter this warp may read (warp id % 4)
+    const int sub = ew >> 2;                         // 0..3: the 64-column slab of the hidden tile this warp owns
+    const int row = quarter * 32 + lane;             // pixel row inside the tile
+    const uint32_t lane_base = ((uint32_t)(quarter * 32) << 16);
+    uint8_t* hrow = h_s + sub * SB_BOX + row * 128;
+    uint8_t* stg = stg_s + quarter * 4096;           // fp32 staging of this quarter's 32 rows of dsrc (sub 0 only)
+    const float* bs = b1_s + sub * 64;
+    const int ones_chunk = p.cin >> 3;               // 16-byte piece of an x row that holds the first padding column
+    uint32_t tph = 0;
+    int st = 0;
+    int ti = 0;
+    int prev_t = -1;
+    const int tl = warp == 2 ? lane : 1;             // stamps come from warp 2, lane 0
+
+    // dsrc tile of the previous tile: ACC_S -> fp32 staging -> TMA reduce-add (G3 / G5 of that tile have retired)
+    auto epi3 = [&](int tprev) {
+      if (sub == 0) {
+        uint32_t v[32];
+        tmem_ld32(acc_s + lane_base, v);
+        tmem_ld_wait();
+        if (lane == 0) bulk_wait_read0();            // (the reduce-add issued a whole tile ago has long read its staging rows)
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          sb_tma_reduce_add_2d(&tmS, smem_u32(stg), 0, tprev * 128 + quarter * 32);
+          bulk_commit();
+        }
+      }
+    };
+
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      sb_stamp(p, 1, ti, 0, tl);
+      // ---------------- epi1: ACC_H -> h = relu(. + b1) as packed bf16 in registers ----------------
+      mbar_wait(smem_u32(&bars->d1_full), tph);
+      tc_fence_after();
+      sb_stamp(p, 1, ti, 1, tl);
+      uint4 hq[8];
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(acc_h + lane_base + sub * 64, v0);
+        tmem_ld32(acc_h + lane_base + sub * 64 + 32, v1);
+        tmem_ld_wait();
+        sb_stamp(p, 1, ti, 7, tl);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->hacc_free));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 ba = *reinterpret_cast<const float4*>(bs + 8 * q), bb = *reinterpret_cast<const float4*>(bs + 8 * q + 4);
+          hq[q].x = pack_bf16(fmaxf(__uint_as_float(v0[8 * q + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(v0[8 * q + 1]) + ba.y, 0.f));
+          hq[q].y = pack_bf16(fmaxf(__uint_as_float(v0[8 * q + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v0[8 * q + 3]) + ba.w, 0.f));
+          hq[q].z = pack_bf16(fmaxf(__uint_as_float(v0[8 * q + 4]) + bb.x, 0.f), fmaxf(__uint_as_float(v0[8 * q + 5]) + bb.y, 0.f));
+          hq[q].w = pack_bf16(fmaxf(__uint_as_float(v0[8 * q + 6]) + bb.z, 0.f), fmaxf(__uint_as_float(v0[8 * q + 7]) + bb.w, 0.f));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 ba = *reinterpret_cast<const float4*>(bs + 32 + 8 * q), bb = *reinterpret_cast<const float4*>(bs + 32 + 8 * q + 4);
+          hq[q + 4].x = pack_bf16(fmaxf(__uint_as_float(v1[8 * q + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(v1[8 * q + 1]) + ba.y, 0.f));
+          hq[q + 4].y = pack_bf16(fmaxf(__uint_as_float(v1[8 * q + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v1[8 * q + 3]) + ba.w, 0.f));
+          hq[q + 4].z = pack_bf16(fmaxf(__uint_as_float(v1[8 * q + 4]) + bb.x, 0.f), fmaxf(__uint_as_float(v1[8 * q + 5]) + bb.y, 0.f));
+          hq[q + 4].w = pack_bf16(fmaxf(__uint_as_float(v1[8 * q + 6]) + bb.z, 0.f), fmaxf(__uint_as_float(v1[8 * q + 7]) + bb.w, 0.f));
+        }
+      }
+      sb_stamp(p, 1, ti, 2, tl);
+      // the hidden tile is free once G3 / G5 of the previous tile have retired
+      if (prev_t >= 0) {
+        mbar_wait(smem_u32(&bars->s_full), tph ^ 1);
+        tc_fence_after();
+      }
+      sb_stamp(p, 1, ti, 3, tl);
+      if (sub == 0) {
+        // the x tile has landed (G1 has read it): ones into its first padding column (column Cin of ACC_W1 = db1)
+        *reinterpret_cast<uint4*>(x_s + st * SB_BOX + row * 128 + ((ones_chunk ^ (row & 7)) << 4)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(hrow + ((q ^ (row & 7)) << 4)) = hq[q];
+      fence_async_smem();                            // generic-proxy writes (h, the ones column) -> visible to tcgen05.mma
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->h_full));
+      // the previous tile's dsrc leaves now, under G4 (ACC_S is not written again before this warp arrives on dh_full)
+      if (prev_t >= 0) epi3(prev_t);
+      // ---------------- epi2: ACC_H -> dh = (h > 0) * . as packed bf16 (the mask from this thread's own h values) ----------------
+      mbar_wait(smem_u32(&bars->d2_full), tph);
+      tc_fence_after();
+      sb_stamp(p, 1, ti, 4, tl);
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(acc_h + lane_base + sub * 64, v0);
+        tmem_ld32(acc_h + lane_base + sub * 64 + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->dacc_free));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          hq[q].x = pack_bf16(__uint_as_float(v0[8 * q + 0]), __uint_as_float(v0[8 * q + 1])) & relu_mask(hq[q].x);
+          hq[q].y = pack_bf16(__uint_as_float(v0[8 * q + 2]), __uint_as_float(v0[8 * q + 3])) & relu_mask(hq[q].y);
+          hq[q].z = pack_bf16(__uint_as_float(v0[8 * q + 4]), __uint_as_float(v0[8 * q + 5])) & relu_mask(hq[q].z);
+          hq[q].w = pack_bf16(__uint_as_float(v0[8 * q + 6]), __uint_as_float(v0[8 * q + 7])) & relu_mask(hq[q].w);
+          hq[q + 4].x = pack_bf16(__uint_as_float(v1[8 * q + 0]), __uint_as_float(v1[8 * q + 1])) & relu_mask(hq[q + 4].x);
+          hq[q + 4].y = pack_bf16(__uint_as_float(v1[8 * q + 2]), __uint_as_float(v1[8 * q + 3])) & relu_mask(hq[q + 4].y);
+          hq[q + 4].z = pack_bf16(__uint_as_float(v1[8 * q + 4]), __uint_as_float(v1[8 * q + 5])) & relu_mask(hq[q + 4].z);
+          hq[q + 4].w = pack_bf16(__uint_as_float(v1[8 * q + 6]), __uint_as_float(v1[8 * q + 7])) & relu_mask(hq[q + 4].w);
+        }
+      }
+      // G4 / G4b have finished reading the h tile: dh over it
+      mbar_wait(smem_u32(&bars->g4_done), tph);
+      sb_stamp(p, 1, ti, 5, tl);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(hrow + ((q ^ (row & 7)) << 4)) = hq[q];
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->dh_full));
+      sb_stamp(p, 1, ti, 6, tl);
+      ++ti;
+      prev_t = t;
+      tph ^= 1;
+      st ^= 1;
+    }
+    sb_stamp(p, 1, 15, 3, tl);
+    if (prev_t >= 0) {
+      mbar_wait(smem_u32(&bars->s_full), tph ^ 1);
+      tc_fence_after();
+      epi3(prev_t);
+    }
+    // ---------------- the CTA's partial weight / bias gradients (every MMA has retired: s_full of the last tile) ----------------
+    {
+      const int hh = sub & 1;
+      const int m = hh * 128 + row;                  // hidden channel of this thread's accumulator row
+      // partials are stored transposed ([channel of the narrow side][hidden channel]): the 32 lanes of a warp hold 32
+      // consecutive hidden channels, so every store instruction writes one full 128-byte line
+      if (sub < 2) {
+        float* dst = p.p_w2 + (long long)blockIdx.x * SB_HID * p.cout + m;
+        for (int c = 0; c < p.cout; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(acc_w2 + lane_base + (uint32_t)(hh * p.n4 + c), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c + j < p.cout) dst[(long long)(c + j) * SB_HID] = __uint_as_float(v[j]);
+        }
+      } else {
+        float* dst = p.p_w1 + (long long)blockIdx.x * SB_HID * p.cin + m;
+        for (int c = 0; c < p.n5; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(acc_w1 + lane_base + (uint32_t)(hh * p.n5 + c), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (c + j < p.cin) dst[(long long)(c + j) * SB_HID] = __uint_as_float(v[j]);
+            if (c + j == p.cin) p.p_b1[(long long)blockIdx.x * SB_HID + m] = __uint_as_float(v[j]);
+          }
+        }
+      }
+      if (sub == 2 && quarter == 0) {                // every row of ACC_B2 holds the column sums of da: row 0 stores them
+        for (int c = 0; c < p.cout; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(acc_b2 + lane_base + (uint32_t)c, v);
+          tmem_ld_wait();
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c + j < p.cout) p.p_b2[(long long)blockIdx.x * p.cout + c + j] = __uint_as_float(v[j]);
+          }
+        }
+      }
+    }
+    sb_stamp(p, 1, 15, 4, tl);
+    if (lane == 0) bulk_wait_all();
+    tc_fence_before();
+    sb_stamp(p, 1, 15, 5, tl);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+  sb_stamp(p, 1, 15, 6, threadIdx.x);
+}
+
+static bool sb_encode_2d(EncodeTiledFn encode, CUtensorMap* tm, CUtensorMapDataType dt, int esz, const void* base, long long inner,
+                         long long outer, long long stride_elems, int box_inner, int box_outer,
+                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)stride_elems * esz};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  return encode(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct SbPlan { int n3, n4, n5, cols; size_t smem; };
+static bool sb_plan(int Cin, int hidden, int Cout, SbPlan& w) {
+  if (hidden != SB_HID || Cin <= 0 || Cout <= 0 || (Cin % 8) != 0 || (Cout % 4) != 0 || Cin > 32 || Cout > 64) return false;
+  w.n3 = (Cin + 15) / 16 * 16;
+  w.n4 = (Cout + 15) / 16 * 16;
+  w.n5 = (Cin + 1 + 15) / 16 * 16;
+  w.cols = SB_HID + w.n3 + 2 * w.n4 + 2 * w.n5 + w.n4;
+  if (w.cols > TMEM_COLS) return false;
+  w.smem = (size_t)(1 + 2 + 2 + 2 + 4) * SB_BOX + 4u * (size_t)w.n3 * 128u + SB_STAGING_BYTES + SB_ONES_BYTES + 256 + 1024 + 1024;
+  return w.smem <= 227 * 1024;
+}
+
+}  // namespace tc
+}  // namespace sininn
+
+using namespace sininn;
+
+extern "C" {
+
+int sininn_subnet1x1_bwd_supported(int Cin, int hidden, int Cout) {
+  sininn::tc::SbPlan w;
+  return sininn::tc::sb_plan(Cin, hidden, Cout, w) ? 1 : 0;
+}
+
+size_t sininn_subnet1x1_bwd_workspace_bytes(const sininn_subnet1x1_bwd_desc* d) {
+  if (d == nullptr) return 0;
+  return (size_t)sm_count() * ((size_t)d->hidden * (d->Cout + d->Cin + 1) + d->Cout) * sizeof(float) + 1024;
+}
+
+int sininn_subnet1x1_bwd_tc(const sininn_subnet1x1_bwd_desc* d, sininn_stream_t stream) {
+  using namespace sininn::tc;
+  SININN_CHECK_ARG(d != nullptr && d->x && d->da && d->w1pack && d->w2dpack && d->w1dpack && d->dsrc && d->dw1 && d->dw2 && d->db1 && d->db2,
+                   "subnet1x1_bwd: null pointer");
+  SbPlan w;
+  SININN_CHECK_ARG(d->npix > 0 && sb_plan(d->Cin, d->hidden, d->Cout, w),
+                   "subnet1x1_bwd: unsupported shape Cin=%d hidden=%d Cout=%d (hidden 256, Cin %% 8 == 0, Cin <= 32, Cout %% 4 == 0, Cout <= 64)",
+                   d->Cin, d->hidden, d->Cout);
+  SININN_CHECK_ARG(d->k1_pad % 16 == 0 && d->k1_pad >= d->Cin && d->k1_pad <= 32, "subnet1x1_bwd: bad k1_pad");
+  SININN_CHECK_ARG(d->k2_pad % 8 == 0 && d->k2_pad >= d->Cout && d->k2_pad <= 64, "subnet1x1_bwd: bad k2_pad");
+  SININN_CHECK_ARG(d->r1_pad == w.n3, "subnet1x1_bwd: r1_pad must be Cin rounded up to 16 (got %d)", d->r1_pad);
+  SININN_CHECK_ARG(aligned16(d->x) && (d->x_stride * 2) % 16 == 0 && aligned16(d->da) && (d->da_stride * 2) % 16 == 0,
+                   "subnet1x1_bwd: x / da must be 16-byte aligned with pixel strides that are multiples of 8");
+  SININN_CHECK_ARG(aligned16(d->dsrc) && (d->dsrc_stride * 4) % 16 == 0, "subnet1x1_bwd: dsrc must be 16-byte aligned with a pixel stride that is a multiple of 4");
+  SININN_CHECK_ARG(aligned16(d->w1pack) && aligned16(d->w2dpack) && aligned16(d->w1dpack), "subnet1x1_bwd: packed weights misaligned");
+  SININN_CHECK_ARG(d->npix < (1ll << 31) - 256, "subnet1x1_bwd: too many pixels");
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { set_error("subnet1x1_bwd: cuTensorMapEncodeTiled not available from the driver"); return SININN_ECUDA; }
+
+  SbParams p;
+  p.npix = d->npix;
+  p.num_tiles = (int)((d->npix + 127) / 128);
+  p.cin = d->Cin; p.cout = d->Cout;
+  p.k1_steps = (d->Cin + 15) / 16;
+  p.k2_steps = (d->Cout + 15) / 16;
+  p.n3 = w.n3; p.n4 = w.n4; p.n5 = w.n5;
+  p.col_s = SB_HID;
+  p.col_w2 = p.col_s + (uint32_t)w.n3;
+  p.col_w1 = p.col_w2 + 2u * (uint32_t)w.n4;
+  p.col_b2 = p.col_w1 + 2u * (uint32_t)w.n5;
+  p.w1d_slab_bytes = (uint32_t)w.n3 * 128u;
+  p.b1 = d->b1;
+  p.trace = g_s1bwd_trace;
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  const size_t need = ((size_t)grid * ((size_t)SB_HID * (d->Cout + d->Cin + 1) + d->Cout)) * sizeof(float);
+  if (!d->workspace || d->workspace_bytes < need) {
+    set_error("subnet1x1_bwd: workspace too small (%zu < %zu)", d->workspace_bytes, need);
+    return SININN_EWORKSPACE;
+  }
+  float* ws = reinterpret_cast<float*>(d->workspace);
+  p.p_w2 = ws;
+  p.p_w1 = p.p_w2 + (size_t)grid * SB_HID * d->Cout;
+  p.p_b1 = p.p_w1 + (size_t)grid * SB_HID * d->Cin;
+  p.p_b2 = p.p_b1 + (size_t)grid * SB_HID;
+
+  CUtensorMap tmX, tmDA, tmW1f, tmW2d, tmW1d, tmS;
+  const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  if (!sb_encode_2d(encode, &tmX, bf, 2, d->x, d->Cin, d->npix, d->x_stride, 64, 128) ||
+      !sb_encode_2d(encode, &tmDA, bf, 2, d->da, d->Cout, d->npix, d->da_stride, 64, 128) ||
+      !sb_encode_2d(encode, &tmW1f, bf, 2, d->w1pack, d->k1_pad, SB_HID, d->k1_pad, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B) ||
+      !sb_encode_2d(encode, &tmW2d, bf, 2, d->w2dpack, d->k2_pad, SB_HID, d->k2_pad, 64, 128) ||
+      !sb_encode_2d(encode, &tmW1d, bf, 2, d->w1dpack, SB_HID, d->r1_pad, SB_HID, 64, w.n3) ||
+      !sb_encode_2d(encode, &tmS, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->dsrc, d->Cin, d->npix, d->dsrc_stride, 32, 32)) {
+    set_error("subnet1x1_bwd: cuTensorMapEncodeTiled failed (Cin=%d Cout=%d strides %d %d %d)", d->Cin, d->Cout, d->x_stride, d->da_stride, d->dsrc_stride);
+    return SININN_ECUDA;
+  }
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(subnet1x1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("subnet1x1_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SININN_ECUDA; }
+    attr_set[dev] = true;
+  }
+  launch_k(subnet1x1_bwd_kernel, dim3((unsigned)grid), dim3(SB_THREADS), w.smem, as_stream(stream), tmX, tmDA, tmW1f, tmW2d, tmW1d, tmS, p);
+  SININN_CHECK_LAUNCH("subnet1x1_bwd");
+  // fixed-order reduction of the per-CTA partials into the gradients (conv2: the wide operand is its INPUT h; conv1: its output gradient dh)
+  sininn_wgrad_desc g2 = {}, g1 = {};
+  g2.taps = 1; g2.Cin = SB_HID; g2.Cout = d->Cout; g2.dw = d->dw2; g2.accumulate = d->dw2_accumulate; g2.dbias = d->db2; g2.dbias_accumulate = d->db2_accumulate;
+  g1.taps = 1; g1.Cin = d->Cin; g1.Cout = SB_HID; g1.dw = d->dw1; g1.accumulate = d->dw1_accumulate; g1.dbias = d->db1; g1.dbias_accumulate = d->db1_accumulate;
+  // (partials are [cout][hidden] and [cin][hidden]: the "wide" index of the reduction is the narrow channel here)
+  return launch_reduce_two(&g2, p.p_w2, 1, p.p_b2, &g1, p.p_w1, 0, p.p_b1, grid, as_stream(stream));
+}
+
+}  // extern "C"

@@ -368,14 +368,14 @@ struct WgReduceJob {
   const float* partial; int splits, taps, Cw, Cn, wide_is_dy, Cout, Cin;
   float* dw; int accumulate;
   const float* bias_partial; int bias_rows; float* dbias; int dbias_accumulate;
-  int block_begin, vec;
+  int block_begin, vec, ru;    // ru: output vectors per thread and pass (RU, or 1 for small problems: more blocks)
 };
 struct WgReduceParams { int njobs; WgReduceJob job[WG_MAX_PROBLEMS + 1]; };     // job[njobs].block_begin = grid size
 
 constexpr int RG = 8;          // split groups (one warp each)
-constexpr int RU = 4;          // output vectors per thread and pass: RU x ceil(splits / RG) independent loads in flight
-template <int VEC>
-__device__ __forceinline__ void reduce_job(const WgReduceJob& j, int bid, int nblocks, float (*red)[32 * RU][5]) {
+constexpr int RU_MAX = 4;      // output vectors per thread and pass: RU x ceil(splits / RG) independent loads in flight
+template <int VEC, int RU>
+__device__ __forceinline__ void reduce_job(const WgReduceJob& j, int bid, int nblocks, float (*red)[32 * RU_MAX][5]) {
   if (j.bias_partial != nullptr) {
     // per-split column sums of dy: one warp per channel (lane l adds rows l, l+32, ... in order, then a fixed xor tree)
     const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
@@ -396,6 +396,7 @@ __device__ __forceinline__ void reduce_job(const WgReduceJob& j, int bid, int nb
     for (int u = 0; u < RU; ++u)
 #pragma unroll
       for (int e = 0; e < VEC; ++e) s[u][e] = 0.f;
+#pragma unroll 4
     for (int k = g; k < j.splits; k += RG) {
 #pragma unroll
       for (int u = 0; u < RU; ++u) {
@@ -450,13 +451,13 @@ __device__ __forceinline__ void reduce_job(const WgReduceJob& j, int bid, int nb
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgReduceParams R) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float red[RG][32 * RU][5];
+  __shared__ float red[RG][32 * RU_MAX][5];
   int ji = 0;
   while (ji + 1 < R.njobs && (int)blockIdx.x >= R.job[ji + 1].block_begin) ++ji;
   const WgReduceJob& j = R.job[ji];
   const int bid = blockIdx.x - j.block_begin, nblocks = R.job[ji + 1].block_begin - j.block_begin;
-  if (j.vec == 4) reduce_job<4>(j, bid, nblocks, red);
-  else reduce_job<1>(j, bid, nblocks, red);
+  if (j.vec == 4) { if (j.ru == 1) reduce_job<4, 1>(j, bid, nblocks, red); else reduce_job<4, RU_MAX>(j, bid, nblocks, red); }
+  else reduce_job<1, RU_MAX>(j, bid, nblocks, red);
 }
 
 static void reduce_add_job(WgReduceParams& R, const sininn_wgrad_desc* d, const float* partial, int splits, int wide_is_dy,
@@ -470,6 +471,9 @@ static void reduce_add_job(WgReduceParams& R, const sininn_wgrad_desc* d, const 
   j.bias_partial = bias_partial; j.bias_rows = bias_rows; j.dbias = d->dbias; j.dbias_accumulate = d->dbias_accumulate;
   j.vec = (j.Cn % 4) == 0 ? 4 : 1;
   const long long per = (long long)d->taps * j.Cw * j.Cn;
+  // small problems (the 1x1 convolutions): one output vector per thread, so that the grid still covers the device
+  j.ru = (j.vec == 4 && per / j.vec < (long long)32 * RU_MAX * sm_count()) ? 1 : RU_MAX;
+  const int RU = j.ru;
   long long g = (per / j.vec + 32 * RU - 1) / (32 * RU);
   if (g > max_blocks) g = max_blocks;
   if (g < 1) g = 1;
@@ -495,6 +499,19 @@ int launch_reduce_single(const sininn_wgrad_desc* d, cudaStream_t st, const floa
   WgReduceParams R;
   R.njobs = 0;
   reduce_add_job(R, d, partial, splits, wide_is_dy, bias_partial, bias_rows, sm_count() * 8);
+  return launch_reduce_group(R, st);
+}
+
+// used by the fused 1x1 subnet backward (subnet1x1_bwd.cu): its two weight gradients (+ bias gradients) leave the kernel
+// as one partial per CTA; both are reduced by one launch.  d0 / d1 carry taps, Cout, Cin, dw, accumulate, dbias,
+// dbias_accumulate of the two convolutions; partials are [splits][Cw][Cn], bias partials [splits][Cout].
+int launch_reduce_two(const sininn_wgrad_desc* d0, const float* partial0, int wide_is_dy0, const float* bias_partial0,
+                      const sininn_wgrad_desc* d1, const float* partial1, int wide_is_dy1, const float* bias_partial1,
+                      int splits, cudaStream_t st) {
+  WgReduceParams R;
+  R.njobs = 0;
+  reduce_add_job(R, d0, partial0, splits, wide_is_dy0, bias_partial0, bias_partial0 ? splits : 0, sm_count() * 4);
+  reduce_add_job(R, d1, partial1, splits, wide_is_dy1, bias_partial1, bias_partial1 ? splits : 0, sm_count() * 4);
   return launch_reduce_group(R, st);
 }
 

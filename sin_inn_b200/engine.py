@@ -77,6 +77,9 @@ def _round_up(v, m):
 
 
 FUSE_1X1 = os.environ.get("SININN_FUSE_1X1", "1") != "0"     # fused 1x1 subnet kernel (subnet1x1_tc.cu)
+# fused 1x1 subnet BACKWARD kernel (subnet1x1_bwd.cu): hidden activation re-evaluated on chip, data gradient and both
+# weight / bias gradients in one launch -- the value pass then keeps only the subnet's bf16 operand copy
+FUSE_1X1_BWD = os.environ.get("SININN_FUSE_1X1_BWD", "1") != "0"
 # GLOW affine coupling (value pass / backward pass) inside the epilogue of the 3x3 subnet's second convolution
 # bit 0: value passes; bit 1: backward passes; bit 2: backward passes only where the subnet output is <= 64 columns wide
 # (level 0: that convolution is bound by its small-N MMAs and its epilogue has slack; at level 1 the extra loads, stores
@@ -422,6 +425,7 @@ class ConvSubnet:
         self.c1, self.c2 = mods[0], mods[2]
         self.taps = self.c1.kernel_size[0] ** 2
         self.cin, self.hidden, self.cout = self.c1.in_channels, self.c1.out_channels, self.c2.out_channels
+        self._fused_bwd = None
 
     def parameters(self):
         return [p for p in (self.c1.weight, self.c1.bias, self.c2.weight, self.c2.bias) if p is not None]
@@ -430,7 +434,23 @@ class ConvSubnet:
         if cfg.split:
             return 12 * _round_up(self.cin, 8) + 8 * self.hidden + self.hidden // 8 + 4 * self.cout
         e = 2 if cfg.tc else 4
+        if cfg.tc and self._bwd_fusable():
+            return e * self.cin + 4 * self.cout           # the hidden activation is re-evaluated on chip
         return e * (self.cin + self.hidden) + self.hidden // 8 + 4 * self.cout
+
+    def _bwd_fusable(self):
+        """Shape / parameter test for the fused backward kernel (the caller checks that the tensor-core path is on).
+        Decided when the value pass runs: a subnet whose backward is fused keeps no hidden activation to fall back on."""
+        if self._fused_bwd is None:
+            self._fused_bwd = bool(
+                FUSE_1X1_BWD and FUSE_1X1 and self.taps == 1 and self.c1.bias is not None and self.c2.bias is not None
+                and self.cin % 8 == 0 and self.cout % 8 == 0
+                and K.subnet1x1_supported(self.cin, self.hidden, self.cout)
+                and K.subnet1x1_bwd_supported(self.cin, self.hidden, self.cout))
+        return self._fused_bwd and all(q.requires_grad for q in self.parameters())
+
+    def fused_bwd(self, ctx):
+        return bool(ctx.tc and self._bwd_fusable())
 
     def can_fuse_coupling(self, ctx, L, backward):
         mask = FUSE_COUPLING if self.taps == 9 else FUSE_COUPLING_1X1
@@ -457,8 +477,9 @@ class ConvSubnet:
             if x.stride(0) % 8 != 0:
                 return None
             # fused 1x1 subnet: the hidden tile stays in shared memory AND the subnet output stays in registers
-            h = torch.empty(tr.npix, self.hidden, dtype=ctx.adt, device=dev) if keep else None
-            bits = torch.empty(tr.npix, self.hidden // 32, dtype=torch.int32, device=dev) if keep else None
+            keep_h = keep and not self.fused_bwd(ctx)       # (the fused backward kernel re-evaluates h from x on chip)
+            h = torch.empty(tr.npix, self.hidden, dtype=ctx.adt, device=dev) if keep_h else None
+            bits = torch.empty(tr.npix, self.hidden // 32, dtype=torch.int32, device=dev) if keep_h else None
             K.subnet1x1_fwd(x, ctx.pack(self.c1.weight, 0), self.c1.bias, ctx.pack(self.c2.weight, 4), self.c2.bias, None,
                             h_out=h, bits_out=bits, coupling=cpl)
             return bf, ((x, h, bits) if keep else None), da
@@ -510,8 +531,9 @@ class ConvSubnet:
             # one launch for the whole subnet: the hidden activation stays in shared memory (it is only written
             # out, with its ReLU sign bits, when the backward kernels need it)
             a = torch.empty(tr.npix, self.cout, dtype=torch.float32, device=dev)
-            h = torch.empty(tr.npix, self.hidden, dtype=ctx.adt, device=dev) if keep else None
-            bits = torch.empty(tr.npix, self.hidden // 32, dtype=torch.int32, device=dev) if keep else None
+            keep_h = keep and not self.fused_bwd(ctx)       # (the fused backward kernel re-evaluates h from x on chip)
+            h = torch.empty(tr.npix, self.hidden, dtype=ctx.adt, device=dev) if keep_h else None
+            bits = torch.empty(tr.npix, self.hidden // 32, dtype=torch.int32, device=dev) if keep_h else None
             K.subnet1x1_fwd(x, ctx.pack(self.c1.weight, 0), self.c1.bias, ctx.pack(self.c2.weight, 0), self.c2.bias, a,
                             h_out=h, bits_out=bits)
             return a, (x, h, bits)
@@ -533,6 +555,13 @@ class ConvSubnet:
             return self._bwd_split(ctx, tr, saved, da, dsrc)
         x, h, bits = saved
         dev = x.device
+        if h is None:
+            # 1x1 subnet, fused backward: h re-evaluated on chip, dsrc += W1^T dh and the four parameter gradients in one
+            # kernel (+ one fixed-order reduction); neither h nor dh exists in memory
+            K.subnet1x1_bwd(x, da, ctx.pack(self.c1.weight, 0), self.c1.bias, ctx.pack(self.c2.weight, 1), ctx.pack(self.c1.weight, 1),
+                            dsrc, ctx.grad_out(self.c1.weight) + ctx.grad_out(self.c1.bias),
+                            ctx.grad_out(self.c2.weight) + ctx.grad_out(self.c2.bias))
+            return
         dh = torch.empty_like(h)
         if (ctx.tc and self.taps == 1 and FUSE_1X1 and bits is not None and da.stride(0) % 8 == 0
                 and K.subnet1x1_supported(self.cout, self.hidden, self.cin) and dsrc.stride(0) % 4 == 0

@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import F32, BF16, ConvDesc, Subnet1x1Desc, WgradDesc, check, dtype_code, load, stream_ptr
+from ._lib import F32, BF16, ConvDesc, Subnet1x1BwdDesc, Subnet1x1Desc, WgradDesc, check, dtype_code, load, stream_ptr
 
 _workspaces = {}
 SPLIT_BLOCKS = 6          # channel blocks of a split operand / K blocks of a split weight pack (conv_simt.cu)
@@ -494,6 +494,47 @@ def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None, mas
                    + (f" cpl{d.cpl_mode}" if d.cpl_mode else ""))
     check(_run("subnet1x1", lambda: load().sininn_subnet1x1_fwd_tc(C.byref(d), stream_ptr()), 1, flops, tag=tag), "subnet1x1_fwd_tc")
     return out
+
+
+def subnet1x1_bwd_supported(cin, hidden, cout):
+    """Shapes the fused 1x1 subnet BACKWARD kernel takes (sininn_subnet1x1_bwd_tc)."""
+    return bool(load().sininn_subnet1x1_bwd_supported(int(cin), int(hidden), int(cout)))
+
+
+def subnet1x1_bwd(x, da, w1pack, b1, w2dpack, w1dpack, dsrc, grads1, grads2):
+    """Whole backward pass of a 1x1 subnet a = W2 relu(W1 x + b1) + b2 in one kernel (+ one reduction) launch: the hidden
+    activation is re-evaluated from x on chip, dsrc += W1^T dh, and the parameter gradients of both convolutions.
+    x: bf16 [npix, Cin] view; da: bf16 [npix, Cout] view; w1pack / w2dpack / w1dpack: conv1 fprop, conv2 dgrad, conv1 dgrad
+    packs; dsrc: fp32 [npix, Cin] view; grads1 / grads2 = (dw, accumulate, dbias, dbias_accumulate) of conv1 / conv2."""
+    x, da, dsrc = _view2d(x), _view2d(da), _view2d(dsrc)
+    d = Subnet1x1BwdDesc()
+    d.npix = x.shape[0]
+    d.Cin, d.hidden, d.Cout = x.shape[1], w1pack.shape[1], da.shape[1]
+    if (x.dtype != torch.bfloat16 or da.dtype != torch.bfloat16 or dsrc.dtype != torch.float32
+            or any(w.dtype != torch.bfloat16 or w.shape[0] != 1 for w in (w1pack, w2dpack, w1dpack))):
+        raise _lib.SininnError("subnet1x1_bwd: bf16 operands / packs (1 tap) and an fp32 input gradient are required")
+    if w2dpack.shape[1] != d.hidden or w1dpack.shape[2] != d.hidden or dsrc.shape[1] != d.Cin or da.shape[0] != d.npix:
+        raise _lib.SininnError("subnet1x1_bwd: packed weights / operands do not describe a 1x1 Cin->hidden->Cout subnet")
+    d.x, d.x_stride = x.data_ptr(), x.stride(0)
+    d.da, d.da_stride = da.data_ptr(), da.stride(0)
+    d.w1pack, d.k1_pad = w1pack.data_ptr(), w1pack.shape[2]
+    d.b1 = _p(b1)
+    d.w2dpack, d.k2_pad = w2dpack.data_ptr(), w2dpack.shape[2]
+    d.w1dpack, d.r1_pad = w1dpack.data_ptr(), w1dpack.shape[1]
+    d.dsrc, d.dsrc_stride = dsrc.data_ptr(), dsrc.stride(0)
+    (dw1, acc1, db1, accb1), (dw2, acc2, db2, accb2) = grads1, grads2
+    for t in (dw1, db1, dw2, db2):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise _lib.SininnError("subnet1x1_bwd: gradient tensors must be contiguous fp32")
+    d.dw1, d.dw1_accumulate, d.db1, d.db1_accumulate = dw1.data_ptr(), int(acc1), db1.data_ptr(), int(accb1)
+    d.dw2, d.dw2_accumulate, d.db2, d.db2_accumulate = dw2.data_ptr(), int(acc2), db2.data_ptr(), int(accb2)
+    lib = load()
+    ws = _workspace(x.device, "s1bwd", lib.sininn_subnet1x1_bwd_workspace_bytes(C.byref(d)))
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+    # recompute of h (Cin) + dh (Cout) + dsrc (Cin) + both weight gradients (Cin + Cout)
+    flops = 2.0 * d.npix * d.hidden * (3 * d.Cin + 2 * d.Cout)
+    tag = lambda: f"npix{d.npix} {d.Cin}->{d.hidden}->{d.Cout}"
+    check(_run("subnet1x1_bwd", lambda: lib.sininn_subnet1x1_bwd_tc(C.byref(d), stream_ptr()), 2, flops, tag=tag), "subnet1x1_bwd_tc")
 
 
 def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False, dbias=None, dbias_accumulate=False):

@@ -283,6 +283,23 @@ def subnet1x1_fwd(x, w1pack, b1, w2pack, b2, out, h_out=None, bits_out=None, mas
     return out
 
 
+def subnet1x1_bwd_supported(cin, hidden, cout):
+    return hidden == 256 and cin % 8 == 0 and cin <= 32 and cout % 4 == 0 and cout <= 64
+
+
+def subnet1x1_bwd(x, da, w1pack, b1, w2dpack, w1dpack, dsrc, grads1, grads2):
+    npix, cin = x.shape
+    hidden, cout = w1pack.shape[1], da.shape[1]
+    hb = torch.relu(x.float() @ w1pack[0, :hidden, :cin].float().t() + (0 if b1 is None else b1.detach().float())).to(torch.bfloat16)
+    dh = (da.float() @ w2dpack[0, :hidden, :cout].float().t()) * (hb.float() > 0)
+    dhb = dh.to(torch.bfloat16)
+    dsrc.add_(dhb.float() @ w1dpack[0, :cin, :hidden].float().t())
+    (dw1, acc1, db1, accb1), (dw2, acc2, db2, accb2) = grads1, grads2
+    for g, acc, val in ((dw2, acc2, (da.float().t() @ hb.float()).reshape(dw2.shape)), (db2, accb2, da.float().sum(0)),
+                        (dw1, acc1, (dhb.float().t() @ x.float()).reshape(dw1.shape)), (db1, accb1, dhb.float().sum(0))):
+        g.copy_(g + val if acc else val)
+
+
 def wgrad_group(jobs):
     for job in jobs:
         x, dy, geom, taps, dw, acc, dbias, dbacc = job[:8]

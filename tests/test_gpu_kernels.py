@@ -526,6 +526,54 @@ def test_subnet1x1_fused_data_gradient(K, cin, hidden, cout, npix):
     assert bool(((hfwd <= 0) <= (dhc == 0)).all())       # exactly zero wherever the forward ReLU was off
 
 
+@pytest.mark.parametrize("cin,cout,npix", [(24, 48, 128), (24, 48, 5000), (24, 48, 2 * 148 * 128 + 77), (16, 48, 3001), (32, 32, 1000),
+                                           (8, 16, 300)])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_subnet1x1_fused_backward(K, cin, cout, npix, accumulate):
+    """The whole backward pass of a 1x1 subnet in one kernel (hidden activation re-evaluated on chip, input gradient, both
+    weight and both bias gradients) against the torch restatement; operands are channel slices of wider matrices."""
+    bf, hidden = torch.bfloat16, 256
+    assert K.subnet1x1_bwd_supported(cin, hidden, cout)
+    w1 = rnd(hidden, cin, 1, 1, seed=90) * 0.2
+    w2 = rnd(cout, hidden, 1, 1, seed=91) * 0.1
+    b1 = rnd(hidden, seed=92) * 0.3
+    xw = rnd(npix, cin + 8, seed=93).to(bf)
+    daw = rnd(npix, cout + 8, seed=94).to(bf)
+    cip, cop = (cin + 15) // 16 * 16, (cout + 15) // 16 * 16
+    packs_ref = (FK.pack_weight(w1, 0, bf, hidden, cip), FK.pack_weight(w2, 1, bf, hidden, cop), FK.pack_weight(w1, 1, bf, cip, hidden))
+    packs_dev = (K.pack_weight(w1.to(DEV), 0, bf, hidden, cip), K.pack_weight(w2.to(DEV), 1, bf, hidden, cop),
+                 K.pack_weight(w1.to(DEV), 1, bf, cip, hidden))
+    base = rnd(npix, cin + 4, seed=95)
+    g0 = [rnd(hidden, cin, 1, 1, seed=96), rnd(hidden, seed=97), rnd(cout, hidden, 1, 1, seed=98), rnd(cout, seed=99)]
+    ref, gref = base.clone(), [g.clone() for g in g0]
+    FK.subnet1x1_bwd(xw[:, :cin], daw[:, :cout], packs_ref[0], b1, packs_ref[1], packs_ref[2], ref[:, :cin],
+                     (gref[0], accumulate, gref[1], accumulate), (gref[2], accumulate, gref[3], accumulate))
+    got, gg = base.clone().to(DEV), [g.clone().to(DEV) for g in g0]
+    xd, dad = xw.to(DEV), daw.to(DEV)
+
+    def run(out, grads):
+        K.subnet1x1_bwd(xd[:, :cin], dad[:, :cout], packs_dev[0], b1.to(DEV), packs_dev[1], packs_dev[2], out[:, :cin],
+                        (grads[0], accumulate, grads[1], accumulate), (grads[2], accumulate, grads[3], accumulate))
+    run(got, gg)
+    torch.cuda.synchronize()
+    gotc = got.cpu()
+    assert torch.equal(gotc[:, cin:], base[:, cin:]), "fused backward wrote outside its channel slice"
+    assert (gotc[:, :cin] - ref[:, :cin]).abs().max().item() <= 1e-2 * max(1.0, ref[:, :cin].abs().max().item())
+    for name, a, b in zip(("dw1", "db1", "dw2", "db2"), gg, gref):
+        err = (a.cpu() - b).abs().max().item()
+        assert err <= 2e-3 * max(1.0, b.abs().max().item()), (name, err, b.abs().max().item())
+    # bit-deterministic: fixed-order reduction of the per-CTA partials, no float atomics
+    got2, gg2 = base.clone().to(DEV), [g.clone().to(DEV) for g in g0]
+    run(got2, gg2)
+    assert torch.equal(got2.cpu(), gotc) and all(torch.equal(a, b) for a, b in zip(gg, gg2))
+
+
+def test_subnet1x1_backward_support_query(K):
+    assert K.subnet1x1_bwd_supported(24, 256, 48) and K.subnet1x1_bwd_supported(8, 256, 16)
+    assert not K.subnet1x1_bwd_supported(96, 256, 192)      # the persistent weight-gradient accumulators exceed 512 TMEM columns
+    assert not K.subnet1x1_bwd_supported(24, 128, 48) and not K.subnet1x1_bwd_supported(20, 256, 48)
+
+
 @pytest.mark.parametrize("B,C,L,hw,w_nll", [(3, 48, 12, (16, 16), 0.0), (2, 192, 84, (5, 9), 0.7), (1, 12, 12, (8, 8), 0.3)])
 def test_fused_forward_half_loss(K, B, C, L, hw, w_nll):
     """lit_wrapper.py:45-48 (loss.reconstruction on the LR channels + loss.latent_nll on the z channels) and the gradient

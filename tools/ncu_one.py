@@ -33,6 +33,20 @@ if case.startswith("s1x1"):
             keep = case == "s1x1_keep"
             K.subnet1x1_fwd(x, K.pack_weight(w1, 0, torch.bfloat16, 256, 32), b1, K.pack_weight(w2, 0, torch.bfloat16, 48, 256), b2, out,
                             h_out=h if keep else None, bits_out=bits if keep else None)
+elif case == "bwd1x1":
+    # fused 1x1 subnet backward at level 0 (subnet1x1_bwd.cu): recompute of h, dh, input gradient, both weight gradients
+    npix, cin, hid, cout = B * 64 * 64, 24, 256, 48
+    bf = torch.bfloat16
+    x = torch.randn(npix, cin, device=DEV).to(bf)
+    da = torch.randn(npix, cout, device=DEV).to(bf)
+    w1 = torch.randn(hid, cin, 1, 1, device=DEV) * 0.05
+    w2 = torch.randn(cout, hid, 1, 1, device=DEV) * 0.05
+    b1 = torch.randn(hid, device=DEV)
+    dsrc = torch.zeros(npix, cin, device=DEV)
+    g = [torch.zeros(hid, cin, 1, 1, device=DEV), torch.zeros(hid, device=DEV), torch.zeros(cout, hid, 1, 1, device=DEV), torch.zeros(cout, device=DEV)]
+    packs = (K.pack_weight(w1, 0, bf, 256, 32), K.pack_weight(w2, 1, bf, 256, 48), K.pack_weight(w1, 1, bf, 32, 256))
+    for _ in range(3):
+        K.subnet1x1_bwd(x, da, packs[0], b1, packs[1], packs[2], dsrc, (g[0], True, g[1], True), (g[2], True, g[3], True))
 elif case in ("coupling_bwd", "coupling_apply", "permute", "resample", "colsum"):
     # HBM-bound kernels at the bench workload's level-0 shapes (B=32: 131072 pixels x 48 channels fp32 trunk)
     npix, C, L = B * 64 * 64, 48, 24
