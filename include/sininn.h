@@ -186,7 +186,9 @@ typedef struct {
   const void* mask; int mask_stride; /* NULL, or activation OUTPUT (dtype=out_dtype): result *= act'(mask) */
   int mask_act;
   int accumulate; float alpha;    /* out = (accumulate ? out : 0) + alpha * f(acc + bias) */
-  /* tensor-core path only: 1 bit per element, uint32 [npix][ceil(Cout/32)], bit c%32 of word c/32 */
+  /* tensor-core path only: 1 bit per element, uint32 [npix][ceil(Cout/32)]; channel c sits in word c/32 at bit
+   * (e >> 1) + 16 * (e & 1), e = c % 32 (the two halves of a packed bf16x2 register map to bits j and 16 + j); an opaque
+   * format between the call that writes bits_out and the calls that read it as mask_bits */
   const void* mask_bits;          /* NULL, or sign bits of the ReLU output the gradient flows through: result zeroed where 0 */
   void* bits_out;                 /* NULL, or receives the sign bits (value > 0) of this call's own output */
   /* Affine coupling fused into the epilogue (3x3 tensor-core path; cpl_mode 0 = off).  The convolution is the SECOND

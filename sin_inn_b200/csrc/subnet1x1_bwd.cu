@@ -91,11 +91,6 @@ __device__ __forceinline__ void sb_stamp(const SbParams& p, int role, int tile_i
   if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tile_i < 16) p.trace[role * 128 + tile_i * 8 + slot] = clock64();
 }
 
-// 0xFFFF in each half of the result whose bf16 half of h is > 0 (one HSET2)
-__device__ __forceinline__ uint32_t relu_mask(uint32_t h2) {
-  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&h2), __floats2bfloat162_rn(0.f, 0.f));
-}
-
 __global__ void __launch_bounds__(SB_THREADS, 1)
 subnet1x1_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDA,
                      const __grid_constant__ CUtensorMap tmW1f, const __grid_constant__ CUtensorMap tmW2d,
@@ -405,14 +400,14 @@ subnet1x1_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (lane == 0) mbar_arrive(smem_u32(&bars->dacc_free));
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          hq[q].x = pack_bf16(__uint_as_float(v0[8 * q + 0]), __uint_as_float(v0[8 * q + 1])) & relu_mask(hq[q].x);
-          hq[q].y = pack_bf16(__uint_as_float(v0[8 * q + 2]), __uint_as_float(v0[8 * q + 3])) & relu_mask(hq[q].y);
-          hq[q].z = pack_bf16(__uint_as_float(v0[8 * q + 4]), __uint_as_float(v0[8 * q + 5])) & relu_mask(hq[q].z);
-          hq[q].w = pack_bf16(__uint_as_float(v0[8 * q + 6]), __uint_as_float(v0[8 * q + 7])) & relu_mask(hq[q].w);
-          hq[q + 4].x = pack_bf16(__uint_as_float(v1[8 * q + 0]), __uint_as_float(v1[8 * q + 1])) & relu_mask(hq[q + 4].x);
-          hq[q + 4].y = pack_bf16(__uint_as_float(v1[8 * q + 2]), __uint_as_float(v1[8 * q + 3])) & relu_mask(hq[q + 4].y);
-          hq[q + 4].z = pack_bf16(__uint_as_float(v1[8 * q + 4]), __uint_as_float(v1[8 * q + 5])) & relu_mask(hq[q + 4].z);
-          hq[q + 4].w = pack_bf16(__uint_as_float(v1[8 * q + 6]), __uint_as_float(v1[8 * q + 7])) & relu_mask(hq[q + 4].w);
+          hq[q].x = pack_bf16(__uint_as_float(v0[8 * q + 0]), __uint_as_float(v0[8 * q + 1])) & bf16x2_gt0_mask(hq[q].x);
+          hq[q].y = pack_bf16(__uint_as_float(v0[8 * q + 2]), __uint_as_float(v0[8 * q + 3])) & bf16x2_gt0_mask(hq[q].y);
+          hq[q].z = pack_bf16(__uint_as_float(v0[8 * q + 4]), __uint_as_float(v0[8 * q + 5])) & bf16x2_gt0_mask(hq[q].z);
+          hq[q].w = pack_bf16(__uint_as_float(v0[8 * q + 6]), __uint_as_float(v0[8 * q + 7])) & bf16x2_gt0_mask(hq[q].w);
+          hq[q + 4].x = pack_bf16(__uint_as_float(v1[8 * q + 0]), __uint_as_float(v1[8 * q + 1])) & bf16x2_gt0_mask(hq[q + 4].x);
+          hq[q + 4].y = pack_bf16(__uint_as_float(v1[8 * q + 2]), __uint_as_float(v1[8 * q + 3])) & bf16x2_gt0_mask(hq[q + 4].y);
+          hq[q + 4].z = pack_bf16(__uint_as_float(v1[8 * q + 4]), __uint_as_float(v1[8 * q + 5])) & bf16x2_gt0_mask(hq[q + 4].z);
+          hq[q + 4].w = pack_bf16(__uint_as_float(v1[8 * q + 6]), __uint_as_float(v1[8 * q + 7])) & bf16x2_gt0_mask(hq[q + 4].w);
         }
       }
       // G4 / G4b have finished reading the h tile: dh over it

@@ -252,34 +252,33 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         tmem_ld32(d1_tmem + lane_base + s * 64, v0);
         tmem_ld32(d1_tmem + lane_base + s * 64 + 32, v1);
         tmem_ld_wait();
-        float x[64];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { x[j] = __uint_as_float(v0[j]); x[32 + j] = __uint_as_float(v1[j]); }
+        // packed bf16x2 arithmetic (the epilogue is ALU-pipe bound, tc_epilogue.cuh): pk[j] = elements 2j, 2j+1 of the slab
+        uint32_t pk[32];
         if (p.bits_in != nullptr) {                  // gradient through the ReLU: keep where the forward output was > 0
           uint2 mb = make_uint2(0u, 0u);
           if (row_ok) mb = __ldg(reinterpret_cast<const uint2*>(p.bits_in + pix * bit_words + 2 * s));
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (!((mb.x >> j) & 1u)) x[j] = 0.f;
-            if (!((mb.y >> j) & 1u)) x[32 + j] = 0.f;
+          for (int j = 0; j < 16; ++j) {
+            pk[j] = pack_bf16(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1])) & sign_bits_expand(mb.x, j);
+            pk[16 + j] = pack_bf16(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1])) & sign_bits_expand(mb.y, j);
           }
         } else {
           const float* bs = b1_s + s * 64;
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float4 bq = *reinterpret_cast<const float4*>(bs + 4 * q);
-            x[4 * q + 0] = fmaxf(x[4 * q + 0] + bq.x, 0.f);
-            x[4 * q + 1] = fmaxf(x[4 * q + 1] + bq.y, 0.f);
-            x[4 * q + 2] = fmaxf(x[4 * q + 2] + bq.z, 0.f);
-            x[4 * q + 3] = fmaxf(x[4 * q + 3] + bq.w, 0.f);
+          for (int q = 0; q < 8; ++q) {
+            const float4 ba = *reinterpret_cast<const float4*>(bs + 4 * q), bb = *reinterpret_cast<const float4*>(bs + 32 + 4 * q);
+            pk[2 * q] = bf16x2_relu(pack_bf16(__uint_as_float(v0[4 * q]) + ba.x, __uint_as_float(v0[4 * q + 1]) + ba.y));
+            pk[2 * q + 1] = bf16x2_relu(pack_bf16(__uint_as_float(v0[4 * q + 2]) + ba.z, __uint_as_float(v0[4 * q + 3]) + ba.w));
+            pk[16 + 2 * q] = bf16x2_relu(pack_bf16(__uint_as_float(v1[4 * q]) + bb.x, __uint_as_float(v1[4 * q + 1]) + bb.y));
+            pk[16 + 2 * q + 1] = bf16x2_relu(pack_bf16(__uint_as_float(v1[4 * q + 2]) + bb.z, __uint_as_float(v1[4 * q + 3]) + bb.w));
           }
         }
         if (p.bits_out != nullptr) {
           uint32_t s0 = 0u, s1 = 0u;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            s0 |= (x[j] > 0.f ? 1u : 0u) << j;
-            s1 |= (x[32 + j] > 0.f ? 1u : 0u) << j;
+          for (int j = 0; j < 16; ++j) {
+            s0 |= bf16x2_gt0_mask(pk[j]) & ((1u << j) | (1u << (16 + j)));
+            s1 |= bf16x2_gt0_mask(pk[16 + j]) & ((1u << j) | (1u << (16 + j)));
           }
           if (row_ok) {
             uint2* dst = reinterpret_cast<uint2*>(p.bits_out + pix * bit_words + 2 * s);
@@ -288,14 +287,8 @@ subnet1x1_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
         uint8_t* hrow = h_s + s * 16384 + row * 128;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint4 o;
-          o.x = pack_bf16(x[8 * q + 0], x[8 * q + 1]);
-          o.y = pack_bf16(x[8 * q + 2], x[8 * q + 3]);
-          o.z = pack_bf16(x[8 * q + 4], x[8 * q + 5]);
-          o.w = pack_bf16(x[8 * q + 6], x[8 * q + 7]);
-          *reinterpret_cast<uint4*>(hrow + ((q ^ (row & 7)) << 4)) = o;
-        }
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(hrow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
       fence_async_smem();                            // generic-proxy writes -> visible to tcgen05.mma / TMA
       tc_fence_before();

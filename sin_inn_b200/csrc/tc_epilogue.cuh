@@ -77,6 +77,24 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ReLU sign-bit masks (bits_out / mask_bits of the C ABI): one bit per element, 32 elements per word.  Element e of a word
+// sits at bit (e >> 1) + 16 * (e & 1): the two halves of the packed bf16x2 register j of a word (elements 2j, 2j + 1) map to
+// bits j and 16 + j, so producing a word costs one HSET2 + one LOP3 per REGISTER and applying it one shift-AND, one multiply
+// (FMA pipe) and one AND per register.  The epilogues are bound by the ALU pipe (16 lanes per clock and scheduler for
+// FMNMX / FSETP / SEL / LOP3 / F2FP -- measured with in-kernel stamps), not by issue slots or TMEM reads.
+__host__ __device__ constexpr int sign_bit_pos(int e) { return (e >> 1) + 16 * (e & 1); }
+// max(v, 0) on both bf16 halves (relu(round(x)) == round(relu(x)): rounding keeps the sign)
+__device__ __forceinline__ uint32_t bf16x2_relu(uint32_t v) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&v), __floats2bfloat162_rn(0.f, 0.f));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+// 0xFFFF in each half of the result whose bf16 half of v is > 0
+__device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t v) {
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&v), __floats2bfloat162_rn(0.f, 0.f));
+}
+// the AND mask of packed register j (0..15) of a sign-bit word: 0xFFFF per half whose bit is set
+__device__ __forceinline__ uint32_t sign_bits_expand(uint32_t word, int j) { return ((word >> j) & 0x00010001u) * 0xFFFFu; }
+
 // per-thread fallback for output slices TMA cannot address (unaligned base / stride)
 template <typename TO>
 __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&v)[16], long long pix, int col0, bool row_ok) {
@@ -91,7 +109,7 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
     if (mask != nullptr) x *= act_grad(p.mask_act, p.slope, to_f32(mask[j]));
     if (p.bits_in != nullptr) {
       const uint32_t w = p.bits_in[pix * p.bit_words + ((col0 + j) >> 5)];
-      if (!((w >> ((col0 + j) & 31)) & 1u)) x = 0.f;
+      if (!((w >> sign_bit_pos((col0 + j) & 31)) & 1u)) x = 0.f;
     }
     x *= p.alpha;
     if (p.accumulate) x += to_f32(out[j]);
@@ -135,7 +153,7 @@ __device__ __forceinline__ void slab_math(const Params& p, float (&x)[NCOL], con
   if (mbits != nullptr) {
 #pragma unroll
     for (int j = 0; j < NCOL; ++j)
-      if (!((mbits[j >> 5] >> (j & 31)) & 1u)) x[j] = 0.f;
+      if (!((mbits[j >> 5] >> sign_bit_pos(j & 31)) & 1u)) x[j] = 0.f;
   }
   if (p.alpha != 1.0f) {
 #pragma unroll
@@ -205,7 +223,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
         slab_math<32>(p, x, bias_s + c, p.bits_in ? mb : nullptr);
         if (p.bits_out != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sign[0] |= (x[j] > 0.f ? 1u : 0u) << j;
+          for (int j = 0; j < 32; ++j) sign[0] |= (x[j] > 0.f ? 1u : 0u) << sign_bit_pos(j);
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q)                         // 16-byte piece q of the row, 128B swizzle: q ^ (row & 7)
@@ -217,25 +235,61 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
         tmem_ld32(t_base + c + 32, v1);                    // (columns past n_valid are clipped by the TMA store)
         tmem_ld_wait();
         EPI_STAMP();
-        float x[64];
+        // the two shapes that dominate a training step work on packed bf16x2 registers (half the ALU-pipe instructions):
+        //   conv1 of a subnet:            bias + ReLU (+ sign bits for the backward pass)
+        //   masked data gradient (conv2): nothing but the stored sign-bit mask
+        const bool fast_relu = p.act == SININN_ACT_RELU && p.bits_in == nullptr && p.alpha == 1.0f;
+        const bool fast_mask = p.act == SININN_ACT_NONE && p.bias == nullptr && p.bits_in != nullptr && p.bits_out == nullptr && p.alpha == 1.0f;
+        if (fast_relu || fast_mask) {
+          uint32_t pk[32];
+          if (fast_relu) {
+            const float* bsl = bias_s + c;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { x[j] = __uint_as_float(v0[j]); x[32 + j] = __uint_as_float(v1[j]); }
-        slab_math<64>(p, x, bias_s + c, p.bits_in ? mb : nullptr);
-        if (p.bits_out != nullptr) {
+            for (int q = 0; q < 8; ++q) {
+              const float4 ba = *reinterpret_cast<const float4*>(bsl + 4 * q), bb = *reinterpret_cast<const float4*>(bsl + 32 + 4 * q);
+              pk[2 * q] = bf16x2_relu(pack_bf16(__uint_as_float(v0[4 * q]) + ba.x, __uint_as_float(v0[4 * q + 1]) + ba.y));
+              pk[2 * q + 1] = bf16x2_relu(pack_bf16(__uint_as_float(v0[4 * q + 2]) + ba.z, __uint_as_float(v0[4 * q + 3]) + ba.w));
+              pk[16 + 2 * q] = bf16x2_relu(pack_bf16(__uint_as_float(v1[4 * q]) + bb.x, __uint_as_float(v1[4 * q + 1]) + bb.y));
+              pk[16 + 2 * q + 1] = bf16x2_relu(pack_bf16(__uint_as_float(v1[4 * q + 2]) + bb.z, __uint_as_float(v1[4 * q + 3]) + bb.w));
+            }
+            if (p.bits_out != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            sign[0] |= (x[j] > 0.f ? 1u : 0u) << j;
-            sign[1] |= (x[32 + j] > 0.f ? 1u : 0u) << j;
+              for (int j = 0; j < 16; ++j) {
+                sign[0] |= bf16x2_gt0_mask(pk[j]) & ((1u << j) | (1u << (16 + j)));
+                sign[1] |= bf16x2_gt0_mask(pk[16 + j]) & ((1u << j) | (1u << (16 + j)));
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              pk[j] = pack_bf16(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1])) & sign_bits_expand(mb[0], j);
+              pk[16 + j] = pack_bf16(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1])) & sign_bits_expand(mb[1], j);
+            }
           }
-        }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint4 o;
-          o.x = pack_bf16(x[8 * q + 0], x[8 * q + 1]);
-          o.y = pack_bf16(x[8 * q + 2], x[8 * q + 3]);
-          o.z = pack_bf16(x[8 * q + 4], x[8 * q + 5]);
-          o.w = pack_bf16(x[8 * q + 6], x[8 * q + 7]);
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        } else {
+          float x[64];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { x[j] = __uint_as_float(v0[j]); x[32 + j] = __uint_as_float(v1[j]); }
+          slab_math<64>(p, x, bias_s + c, p.bits_in ? mb : nullptr);
+          if (p.bits_out != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              sign[0] |= (x[j] > 0.f ? 1u : 0u) << sign_bit_pos(j);
+              sign[1] |= (x[32 + j] > 0.f ? 1u : 0u) << sign_bit_pos(j);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint4 o;
+            o.x = pack_bf16(x[8 * q + 0], x[8 * q + 1]);
+            o.y = pack_bf16(x[8 * q + 2], x[8 * q + 3]);
+            o.z = pack_bf16(x[8 * q + 4], x[8 * q + 5]);
+            o.w = pack_bf16(x[8 * q + 6], x[8 * q + 7]);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+          }
         }
       }
       EPI_STAMP();

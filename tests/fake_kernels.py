@@ -181,10 +181,14 @@ def _shift(x4, dy, dx):
     return xp[:, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W]
 
 
+# ReLU sign-bit masks: element e of a 32-element word sits at bit (e >> 1) + 16 * (e & 1) (include/sininn.h: the two halves of
+# packed bf16x2 register j map to bits j and 16 + j)
+_BIT_POS = torch.tensor([(e >> 1) + 16 * (e & 1) for e in range(32)])
+
+
 def _unpack_bits(bits, cout):
     w = bits.to(torch.int64) & 0xffffffff
-    sh = torch.arange(32)
-    return ((w.unsqueeze(-1) >> sh) & 1).reshape(bits.shape[0], -1)[:, :cout].float()
+    return ((w.unsqueeze(-1) >> _BIT_POS) & 1).reshape(bits.shape[0], -1)[:, :cout].float()
 
 
 def _pack_bits(vals):
@@ -192,7 +196,7 @@ def _pack_bits(vals):
     words = (c + 31) // 32
     b = torch.zeros(npix, words * 32, dtype=torch.int64)
     b[:, :c] = (vals > 0).to(torch.int64)
-    w = (b.reshape(npix, words, 32) << torch.arange(32)).sum(-1)
+    w = (b.reshape(npix, words, 32) << _BIT_POS).sum(-1)
     w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)
     return w.to(torch.int32)
 
