@@ -53,7 +53,7 @@ def test_resample_nhwc(K, mode, shape):
     assert (xr.cpu() - x).abs().max() <= 1e-6 * x.abs().max()
 
 
-@pytest.mark.parametrize("C,hw", [(48, (8, 8)), (192, (5, 9)), (7, (3, 11))])
+@pytest.mark.parametrize("C,hw", [(48, (8, 8)), (192, (5, 9)), (7, (3, 11)), (48, (20, 13)), (64, (16, 16)), (72, (9, 15))])
 def test_layout_and_permute(K, C, hw):
     x = rnd(2, C, *hw, seed=3)
     perm = torch.randperm(C, generator=torch.Generator().manual_seed(4)).to(torch.int32)
@@ -65,6 +65,9 @@ def test_layout_and_permute(K, C, hw):
         assert torch.equal(bf.cpu(), rbf)
     back = K.nhwc_to_nchw(y, None)
     assert torch.equal(back.cpu(), x[:, perm.long()])
+    inv = torch.empty_like(perm)
+    inv[perm.long()] = torch.arange(C, dtype=torch.int32)
+    assert torch.equal(K.nhwc_to_nchw(y, inv.to(DEV)).cpu(), x)          # out channel i <- in channel map[i]
     z, zbf = K.permute_nhwc(y, perm.to(DEV), rng)
     rz, rzbf = FK.permute_nhwc(ry, perm, rng)
     assert torch.equal(z.cpu(), rz)
