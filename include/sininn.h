@@ -136,10 +136,11 @@ int sininn_logscale_sum(const float* s, int s_stride, int B, long long pix_per_s
  *   inverse=1:  u <- (u - t) / exp(g(s))      (archs.py:157 and GLOW rev)
  * s,t: fp32 [npix][L] with their own strides (GLOW: both halves of one subnet
  * output; IRN: outputs of H and G).  u_bf16 (may be NULL): compact bf16 copy of
- * the updated slice. */
+ * the updated slice.  fast_math = 1 (bf16 path): polynomial atan, ex2.approx and approximate division (errors at fp32
+ * rounding level) instead of the accurate libm forms, whose ~60 instructions per element make the kernel ALU-bound. */
 int sininn_coupling_apply(float* u, int u_stride, const float* s, int s_stride, const float* t, int t_stride,
                           long long npix, int L, int kind, float clamp, int inverse,
-                          void* u_bf16, sininn_stream_t stream);
+                          void* u_bf16, int fast_math, sininn_stream_t stream);
 /* Backward of one coupling half from its OUTPUT (recompute-from-inverse, the
  * equations of SURVEY.md section 8a).  On entry u holds y and du holds dL/dy;
  * on exit u holds the reconstructed input x and du holds dL/dx.  Writes
@@ -149,7 +150,7 @@ int sininn_coupling_bwd(float* u, int u_stride, float* du, int du_stride,
                         const float* s, int s_stride, const float* t, int t_stride,
                         long long npix, int L, int kind, float clamp, int inverse,
                         void* ds_out, int ds_stride, void* dt_out, int dt_stride, int out_dtype,
-                        void* x_bf16, sininn_stream_t stream);
+                        void* x_bf16, int fast_math, sininn_stream_t stream);
 
 /* small helpers around the subnets */
 /* out[p][c] = scale * in[p][c] converted to out_dtype */

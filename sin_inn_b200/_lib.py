@@ -117,9 +117,9 @@ SIGNATURES = {
     "sininn_mmd": (C.c_int, [_vp, _vp, C.c_int, _c_ll, C.c_int, C.c_float, _vp, _vp, _vp, C.c_size_t, _vp]),
     "sininn_quantize_u8_hwc": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "sininn_coupling_apply": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _c_ll, C.c_int, C.c_int, C.c_float,
-                                        C.c_int, _vp, _vp]),
+                                        C.c_int, _vp, C.c_int, _vp]),
     "sininn_coupling_bwd": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _c_ll, C.c_int, C.c_int,
-                                      C.c_float, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp]),
+                                      C.c_float, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),
     "sininn_cast_slice": (C.c_int, [_vp, C.c_int, _c_ll, C.c_int, C.c_float, _vp, C.c_int, C.c_int, _vp]),
     "sininn_act_bwd": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _c_ll, C.c_int, C.c_int,
                                  C.c_float, _vp]),

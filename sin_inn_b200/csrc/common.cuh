@@ -101,6 +101,59 @@ __device__ __forceinline__ void log_scale(int kind, float clamp, float raw, floa
   }
 }
 
+// ---- fast forms for the bf16 path (standalone coupling kernels with fast_math = 1 and the coupling epilogues of the tcgen05
+// kernels): a degree-7 polynomial in t^2 for atan (1.6e-7 absolute on [0, 1], reciprocal argument beyond 1), ex2.approx,
+// approximate division -- errors at fp32 rounding level, far inside that path's tolerance.  The accurate libm forms above cost
+// ~60 ALU instructions per element, which makes the "bandwidth-bound" coupling kernels ALU-bound (16 lanes per clock and
+// scheduler): measured 15 / 21 us per launch against 8 / 14 us of HBM time at the headline shape.
+__device__ __forceinline__ float fast_atan(float r) {
+  const float a = fabsf(r);
+  const bool inv = a > 1.0f;
+  const float t = inv ? __fdividef(1.0f, a) : a;
+  const float z = t * t;
+  float p = -0.004668773151934147f;
+  p = fmaf(p, z, 0.02416618913412094f);
+  p = fmaf(p, z, -0.0593671016395092f);
+  p = fmaf(p, z, 0.09906096756458282f);
+  p = fmaf(p, z, -0.14016585052013397f);
+  p = fmaf(p, z, 0.19969235360622406f);
+  p = fmaf(p, z, -0.33331960439682007f);
+  p = fmaf(p, z, 0.9999998807907104f);
+  p *= t;
+  p = inv ? 1.5707963267948966f - p : p;
+  return copysignf(p, r);
+}
+// e = exp(g(s)), dg = g'(s) for the GLOW clamp (log_scale above)
+__device__ __forceinline__ void glow_scale_fast(float clamp, float inv_clamp, float sv, float& ex, float& dg) {
+  const float r = sv * inv_clamp;
+  ex = __expf(clamp * 0.636f * fast_atan(r));
+  dg = __fdividef(0.636f, fmaf(r, r, 1.0f));
+}
+
+// e = exp(g), dg = g' for either coupling kind
+__device__ __forceinline__ void scale_fast(int kind, float clamp, float inv_clamp, float raw, float& ex, float& dg) {
+  if (kind == SININN_GLOW) {
+    glow_scale_fast(clamp, inv_clamp, raw, ex, dg);
+  } else {
+    const float sg = __fdividef(1.0f, 1.0f + __expf(-raw));
+    ex = __expf(clamp * (2.0f * sg - 1.0f));
+    dg = 2.0f * clamp * sg * (1.0f - sg);
+  }
+}
+
+// idx = p * n + c (0 <= c < n): 32-bit arithmetic whenever the index space allows it -- a 64-bit division is a ~100-instruction
+// subroutine, several times the rest of an elementwise kernel's body
+__device__ __forceinline__ void split_index(long long idx, int n, long long& p, int& c) {
+  if (idx <= 0xffffffffLL) {
+    const unsigned q = (unsigned)idx / (unsigned)n;
+    p = q;
+    c = (int)((unsigned)idx - q * (unsigned)n);
+  } else {
+    p = idx / n;
+    c = (int)(idx - p * n);
+  }
+}
+
 __device__ __forceinline__ float act_fwd(int act, float slope, float v) {
   if (act == SININN_ACT_RELU) return v > 0.f ? v : 0.f;
   if (act == SININN_ACT_LRELU) return v > 0.f ? v : slope * v;

@@ -38,7 +38,7 @@ __device__ __forceinline__ void stv(__nv_bfloat16* p, const Pack<VEC>& r) {
   else *p = __float2bfloat16_rn(r.v[0]);
 }
 
-template <int VEC>
+template <int VEC, bool FAST>
 __global__ void __launch_bounds__(256) coupling_apply_kernel(float* __restrict__ u, int u_stride, const float* __restrict__ s,
                                                              int s_stride, const float* __restrict__ t, int t_stride,
                                                              long long npix, int L, int kind, float clamp, int inverse,
@@ -47,27 +47,36 @@ __global__ void __launch_bounds__(256) coupling_apply_kernel(float* __restrict__
   pdl_trigger();
   const int Lv = L / VEC;
   const long long total = npix * Lv;
+  const float inv_clamp = 1.0f / clamp;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(idx % Lv) * VEC;
-    long long p = idx / Lv;
+    int c;
+    long long p;
+    split_index(idx, Lv, p, c);
+    c *= VEC;
     Pack<VEC> x = ldv<VEC>(u + p * u_stride + c);
     Pack<VEC> sv = ldv<VEC>(s + p * s_stride + c);
     Pack<VEC> tv = ldv<VEC>(t + p * t_stride + c);
     Pack<VEC> y;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      float g, dg;
-      log_scale(kind, clamp, sv.v[e], g, dg);
-      float ex = expf(g);
-      y.v[e] = inverse ? (x.v[e] - tv.v[e]) / ex : ex * x.v[e] + tv.v[e];
+      float ex, dg;
+      if (FAST) {
+        scale_fast(kind, clamp, inv_clamp, sv.v[e], ex, dg);
+        y.v[e] = inverse ? __fdividef(x.v[e] - tv.v[e], ex) : fmaf(ex, x.v[e], tv.v[e]);
+      } else {
+        float g;
+        log_scale(kind, clamp, sv.v[e], g, dg);
+        ex = expf(g);
+        y.v[e] = inverse ? (x.v[e] - tv.v[e]) / ex : ex * x.v[e] + tv.v[e];
+      }
     }
     stv<VEC>(u + p * u_stride + c, y);
     if (ubf != nullptr) stv<VEC>(ubf + p * L + c, y);
   }
 }
 
-template <int VEC, typename TO>
+template <int VEC, typename TO, bool FAST>
 __global__ void __launch_bounds__(256) coupling_bwd_kernel(float* __restrict__ u, int u_stride, float* __restrict__ du, int du_stride,
                                                            const float* __restrict__ s, int s_stride, const float* __restrict__ t,
                                                            int t_stride, long long npix, int L, int kind, float clamp, int inverse,
@@ -79,8 +88,10 @@ __global__ void __launch_bounds__(256) coupling_bwd_kernel(float* __restrict__ u
   const long long total = npix * Lv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(idx % Lv) * VEC;
-    long long p = idx / Lv;
+    int c;
+    long long p;
+    split_index(idx, Lv, p, c);
+    c *= VEC;
     Pack<VEC> y = ldv<VEC>(u + p * u_stride + c);
     Pack<VEC> dy = ldv<VEC>(du + p * du_stride + c);
     Pack<VEC> sv = ldv<VEC>(s + p * s_stride + c);
@@ -88,17 +99,22 @@ __global__ void __launch_bounds__(256) coupling_bwd_kernel(float* __restrict__ u
     Pack<VEC> x, dx, dsv, dtv;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      float g, dg;
-      log_scale(kind, clamp, sv.v[e], g, dg);
-      float ex = expf(g);
+      float ex, dg;
+      if (FAST) {
+        scale_fast(kind, clamp, 1.0f / clamp, sv.v[e], ex, dg);
+      } else {
+        float g;
+        log_scale(kind, clamp, sv.v[e], g, dg);
+        ex = expf(g);
+      }
       if (!inverse) {            // y = ex*x + t
-        x.v[e] = (y.v[e] - tv.v[e]) / ex;
+        x.v[e] = FAST ? __fdividef(y.v[e] - tv.v[e], ex) : (y.v[e] - tv.v[e]) / ex;
         dx.v[e] = dy.v[e] * ex;
         dsv.v[e] = dy.v[e] * x.v[e] * ex * dg;
         dtv.v[e] = dy.v[e];
       } else {                   // y = (x - t)/ex
         x.v[e] = y.v[e] * ex + tv.v[e];
-        float q = dy.v[e] / ex;
+        float q = FAST ? __fdividef(dy.v[e], ex) : dy.v[e] / ex;
         dx.v[e] = q;
         dsv.v[e] = -dy.v[e] * y.v[e] * dg;
         dtv.v[e] = -q;
@@ -121,8 +137,10 @@ __global__ void __launch_bounds__(256) cast_slice_kernel(const float* __restrict
   const long long total = npix * Lv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(idx % Lv) * VEC;
-    long long p = idx / Lv;
+    int c;
+    long long p;
+    split_index(idx, Lv, p, c);
+    c *= VEC;
     Pack<VEC> v = ldv<VEC>(in + p * in_stride + c);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) v.v[e] *= scale;
@@ -138,8 +156,9 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* d, int d_stri
   const long long total = npix * L;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(idx % L);
-    long long p = idx / L;
+    int c;
+    long long p;
+    split_index(idx, L, p, c);
     float g = act_grad(act, slope, to_f32(y[p * y_stride + c]));
     out[p * out_stride + c] = from_f32<TO>(d[p * d_stride + c] * g);
   }
@@ -153,8 +172,9 @@ __global__ void __launch_bounds__(256) axpy_slice_kernel(float* __restrict__ out
   const long long total = npix * L;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(idx % L);
-    long long p = idx / L;
+    int c;
+    long long p;
+    split_index(idx, L, p, c);
     out[p * out_stride + c] += alpha * to_f32(a[p * a_stride + c]);
   }
 }
@@ -300,7 +320,9 @@ __global__ void __launch_bounds__(256) inn_fwd_loss_partial_kernel(const float* 
   float a_rec = 0.f, a_nll = 0.f;
   const long long chw = (long long)C * HW, lhw = (long long)L * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / chw, r = i - b * chw;
+    long long b, r;
+    if (chw <= 0x7fffffffLL) { int r32; split_index(i, (int)chw, b, r32); r = r32; }
+    else { b = i / chw; r = i - b * chw; }
     const float v = y[i];
     float g;
     if (r < lhw) {
@@ -327,24 +349,37 @@ __global__ void __launch_bounds__(256) inn_fwd_loss_partial_kernel(const float* 
     partial[nblk + blockIdx.x] = s1;
   }
 }
-__global__ void inn_fwd_loss_finish_kernel(const float* __restrict__ partial, int n, float s_rec, float s_nll, float* __restrict__ out) {
+// Sum of n block partials in double by ONE block of 256 threads: thread t adds partials t, t + 256, ... in order, then a
+// fixed-order tree through shared memory (bit-reproducible; a single thread walking thousands of partials cost 25-80 us
+// on the critical path of a step).
+__device__ __forceinline__ double block_sum_256(const float* __restrict__ partial, int n, double (*red)[8]) {
+  double a = 0.0;
+  for (int k = threadIdx.x; k < n; k += 256) a += (double)partial[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  __syncthreads();                                   // (red may still be read from a previous call)
+  if ((threadIdx.x & 31) == 0) (*red)[threadIdx.x >> 5] = a;
+  __syncthreads();
+  double s = 0.0;
+  for (int k = 0; k < 8; ++k) s += (*red)[k];
+  return s;
+}
+__global__ void __launch_bounds__(256) inn_fwd_loss_finish_kernel(const float* __restrict__ partial, int n, float s_rec, float s_nll,
+                                                                  float* __restrict__ out) {
   pdl_wait();
   pdl_trigger();
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double a = 0.0, b = 0.0;
-    for (int k = 0; k < n; ++k) { a += (double)partial[k]; b += (double)partial[n + k]; }
-    out[0] = (float)(a * (double)s_rec + b * (double)s_nll);
-  }
+  __shared__ double red[8];
+  const double a = block_sum_256(partial, n, &red);
+  const double b = block_sum_256(partial + n, n, &red);
+  if (threadIdx.x == 0) out[0] = (float)(a * (double)s_rec + b * (double)s_nll);
 }
 
-__global__ void sqdiff_finish_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) sqdiff_finish_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
   pdl_wait();
   pdl_trigger();
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0;
-    for (int k = 0; k < n; ++k) s += (double)partial[k];
-    out[0] = (float)(s * (double)scale);
-  }
+  __shared__ double red[8];
+  const double s = block_sum_256(partial, n, &red);
+  if (threadIdx.x == 0) out[0] = (float)(s * (double)scale);
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -410,7 +445,7 @@ using namespace sininn;
 extern "C" {
 
 int sininn_coupling_apply(float* u, int u_stride, const float* s, int s_stride, const float* t, int t_stride,
-                          long long npix, int L, int kind, float clamp, int inverse, void* u_bf16,
+                          long long npix, int L, int kind, float clamp, int inverse, void* u_bf16, int fast_math,
                           sininn_stream_t stream) {
   SININN_CHECK_ARG(u && s && t && npix > 0 && L > 0, "coupling_apply: bad arguments");
   SININN_CHECK_ARG(kind == SININN_GLOW || kind == SININN_IRN, "coupling_apply: unknown kind %d", kind);
@@ -420,15 +455,18 @@ int sininn_coupling_apply(float* u, int u_stride, const float* s, int s_stride, 
             aligned16(s) && aligned16(t) && (!bf || aligned8(bf));
   const long long total = npix * (v4 ? L / 4 : L);
   const int block = 256, grid = grid_for(total, block);
-  if (v4) launch_k(coupling_apply_kernel<4>, dim3(grid), dim3(block), 0, as_stream(stream), u, u_stride, s, s_stride, t, t_stride, npix, L, kind, clamp, inverse, bf);
-  else launch_k(coupling_apply_kernel<1>, dim3(grid), dim3(block), 0, as_stream(stream), u, u_stride, s, s_stride, t, t_stride, npix, L, kind, clamp, inverse, bf);
+#define LAUNCH(V, F) launch_k(coupling_apply_kernel<V, F>, dim3(grid), dim3(block), 0, as_stream(stream), u, u_stride, s, s_stride, t, t_stride, npix, L, kind, clamp, inverse, bf)
+  if (fast_math) { if (v4) LAUNCH(4, true); else LAUNCH(1, true); }
+  else           { if (v4) LAUNCH(4, false); else LAUNCH(1, false); }
+#undef LAUNCH
   SININN_CHECK_LAUNCH("coupling_apply");
   return SININN_OK;
 }
 
 int sininn_coupling_bwd(float* u, int u_stride, float* du, int du_stride, const float* s, int s_stride, const float* t,
                         int t_stride, long long npix, int L, int kind, float clamp, int inverse, void* ds_out,
-                        int ds_stride, void* dt_out, int dt_stride, int out_dtype, void* x_bf16, sininn_stream_t stream) {
+                        int ds_stride, void* dt_out, int dt_stride, int out_dtype, void* x_bf16, int fast_math,
+                        sininn_stream_t stream) {
   SININN_CHECK_ARG(u && du && s && t && ds_out && dt_out && npix > 0 && L > 0, "coupling_bwd: bad arguments");
   SININN_CHECK_ARG(kind == SININN_GLOW || kind == SININN_IRN, "coupling_bwd: unknown kind %d", kind);
   SININN_CHECK_ARG(out_dtype == SININN_F32 || out_dtype == SININN_BF16, "coupling_bwd: bad out_dtype");
@@ -440,13 +478,15 @@ int sininn_coupling_bwd(float* u, int u_stride, float* du, int du_stride, const 
   const long long total = npix * (v4 ? L / 4 : L);
   const int block = 256, grid = grid_for(total, block);
   cudaStream_t st = as_stream(stream);
-#define LAUNCH(V, T)                                                                                                    \
-  launch_k(coupling_bwd_kernel<V, T>, dim3(grid), dim3(block), 0, st, u, u_stride, du, du_stride, s, s_stride, t, t_stride, npix, L, kind, \
+#define LAUNCH2(V, T, F)                                                                                                \
+  launch_k(coupling_bwd_kernel<V, T, F>, dim3(grid), dim3(block), 0, st, u, u_stride, du, du_stride, s, s_stride, t, t_stride, npix, L, kind, \
                                                     clamp, inverse, reinterpret_cast<T*>(ds_out), ds_stride,            \
                                                     reinterpret_cast<T*>(dt_out), dt_stride, bf)
+#define LAUNCH(V, T) do { if (fast_math) LAUNCH2(V, T, true); else LAUNCH2(V, T, false); } while (0)
   if (f32) { if (v4) LAUNCH(4, float); else LAUNCH(1, float); }
   else     { if (v4) LAUNCH(4, __nv_bfloat16); else LAUNCH(1, __nv_bfloat16); }
 #undef LAUNCH
+#undef LAUNCH2
   SININN_CHECK_LAUNCH("coupling_bwd");
   return SININN_OK;
 }
@@ -548,7 +588,7 @@ int sininn_sqdiff_nchw(const float* a, const float* b, long long n, float scale,
   }
   cudaStream_t st = as_stream(stream);
   launch_k(sqdiff_partial_kernel, dim3(grid), dim3(256), 0, st, a, b, n, 2.f * scale, grad_out, (float*)workspace);
-  launch_k(sqdiff_finish_kernel, dim3(1), dim3(32), 0, st, (const float*)workspace, grid, scale, loss_out);
+  launch_k(sqdiff_finish_kernel, dim3(1), dim3(256), 0, st, (const float*)workspace, grid, scale, loss_out);
   SININN_CHECK_LAUNCH("sqdiff");
   return SININN_OK;
 }
@@ -569,7 +609,7 @@ int sininn_inn_fwd_loss(const float* y, const float* lr, int B, int C, int L, lo
   cudaStream_t st = as_stream(stream);
   launch_k(inn_fwd_loss_partial_kernel, dim3(grid), dim3(256), 0, st, y, lr, C, L, HW, total, 2.f * s_rec, 2.f * s_nll, grad_out,
            (float*)workspace, grid);
-  launch_k(inn_fwd_loss_finish_kernel, dim3(1), dim3(32), 0, st, (const float*)workspace, grid, s_rec, s_nll, loss_out);
+  launch_k(inn_fwd_loss_finish_kernel, dim3(1), dim3(256), 0, st, (const float*)workspace, grid, s_rec, s_nll, loss_out);
   SININN_CHECK_LAUNCH("inn_fwd_loss");
   return SININN_OK;
 }

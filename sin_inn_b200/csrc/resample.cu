@@ -51,12 +51,13 @@ __global__ void __launch_bounds__(256) resample_nchw_fwd_kernel(const float* __r
   const int Ho = H >> 1, Wo = W >> 1, Wv = Wo / VEC;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int jv = (int)(idx % Wv);
-    long long r = idx / Wv;
-    int i = (int)(r % Ho);
-    long long plane = r / Ho;          // b*C + c
-    int c = (int)(plane % C);
-    long long b = plane / C;
+    int jv;
+    long long r;
+    split_index(idx, Wv, r, jv);
+    int i, c;
+    long long plane, b;                // plane = b*C + c
+    split_index(r, Ho, plane, i);
+    split_index(plane, C, b, c);
     const float* r0 = in + (plane * H + 2 * i) * (long long)W + 2 * jv * VEC;
     const float* r1 = r0 + W;
     __align__(16) float x0[2 * VEC], x1[2 * VEC];
@@ -91,12 +92,13 @@ __global__ void __launch_bounds__(256) resample_nchw_inv_kernel(const float* __r
   const int Ho = H >> 1, Wo = W >> 1, Wv = Wo / VEC;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int jv = (int)(idx % Wv);
-    long long r = idx / Wv;
-    int i = (int)(r % Ho);
-    long long plane = r / Ho;
-    int c = (int)(plane % C);
-    long long b = plane / C;
+    int jv;
+    long long r;
+    split_index(idx, Wv, r, jv);
+    int i, c;
+    long long plane, b;
+    split_index(r, Ho, plane, i);
+    split_index(plane, C, b, c);
     typedef typename VecT<VEC>::type ST;
     __align__(16) float o[4][VEC];
 #pragma unroll
@@ -133,12 +135,13 @@ __global__ void __launch_bounds__(256) resample_nhwc_kernel(const float* __restr
   typedef typename VecT<VEC>::type VT;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(idx % Cv);
-    long long r = idx / Cv;
-    int j = (int)(r % Wo);
-    r /= Wo;
-    int i = (int)(r % Ho);
-    long long b = r / Ho;
+    int cv;
+    long long r;
+    split_index(idx, Cv, r, cv);
+    int j, i;
+    long long r2, b;
+    split_index(r, Wo, r2, j);
+    split_index(r2, Ho, b, i);
     int c = cv * VEC;
     long long hi = ((b * H + 2 * i) * (long long)W + 2 * j) * C + c;   // full-res (2i,2j)
     long long lo = ((b * Ho + i) * (long long)Wo + j) * 4 * C + c;     // low-res pixel, band 0
@@ -235,8 +238,9 @@ __global__ void __launch_bounds__(256) permute_nhwc_kernel(const float* __restri
   const long long total = npix * Cv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(idx % Cv);
-    long long p = idx / Cv;
+    int cv;
+    long long p;
+    split_index(idx, Cv, p, cv);
     int c = cv * VEC;
     float v[VEC];
 #pragma unroll
@@ -267,8 +271,10 @@ __global__ void __launch_bounds__(256) permute_nhwc_pair_kernel(const float* __r
   const long long total = npix * Cv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % Cv) * 4;
-    const long long p = idx / Cv;
+    int c;
+    long long p;
+    split_index(idx, Cv, p, c);
+    c *= 4;
     const int m0 = __ldg(map + c), m1 = __ldg(map + c + 1), m2 = __ldg(map + c + 2), m3 = __ldg(map + c + 3);
     const float* ra = in_a + p * C;
     const float* rb = in_b + p * C;

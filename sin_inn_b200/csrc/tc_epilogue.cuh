@@ -327,30 +327,6 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
 // Only 8 warps per SM do this math (the standalone kernels spread it over 64), so it uses the fast forms below: a
 // degree-7 polynomial in t^2 for atan (1.6e-7 absolute on [0, 1], reciprocal argument beyond 1), ex2.approx, approximate
 // division -- errors at fp32 rounding level, far inside the bf16 path's tolerance; the fp32 paths never take this epilogue.
-__device__ __forceinline__ float fast_atan(float r) {
-  const float a = fabsf(r);
-  const bool inv = a > 1.0f;
-  const float t = inv ? __fdividef(1.0f, a) : a;
-  const float z = t * t;
-  float p = -0.004668773151934147f;
-  p = fmaf(p, z, 0.02416618913412094f);
-  p = fmaf(p, z, -0.0593671016395092f);
-  p = fmaf(p, z, 0.09906096756458282f);
-  p = fmaf(p, z, -0.14016585052013397f);
-  p = fmaf(p, z, 0.19969235360622406f);
-  p = fmaf(p, z, -0.33331960439682007f);
-  p = fmaf(p, z, 0.9999998807907104f);
-  p *= t;
-  p = inv ? 1.5707963267948966f - p : p;
-  return copysignf(p, r);
-}
-// e = exp(g(s)), dg = g'(s) for the GLOW clamp (common.cuh log_scale)
-__device__ __forceinline__ void glow_scale_fast(float clamp, float inv_clamp, float sv, float& ex, float& dg) {
-  const float r = sv * inv_clamp;
-  ex = __expf(clamp * 0.636f * fast_atan(r));
-  dg = __fdividef(0.636f, fmaf(r, r, 1.0f));
-}
-
 struct CplRegs { float4 u[4], d[4]; };
 __device__ __forceinline__ void cpl_prefetch(const CplParams& p, CplRegs& R, long long pix, int ch0, bool row_ok) {
 #pragma unroll

@@ -852,7 +852,7 @@ class CouplingOp:
                     tr.invalidate(*st.dst)
                     if logdet is not None:
                         K.logscale_sum(a[:, :L], B, GLOW, st.clamp, -1.0 if rev else 1.0, logdet, True)
-                    bf = K.coupling_apply(u, a[:, :L], a[:, L:], GLOW, st.clamp, rev, want_bf)
+                    bf = K.coupling_apply(u, a[:, :L], a[:, L:], GLOW, st.clamp, rev, want_bf, fast=ctx.tc)
             elif st.kind == "irn_affine":
                 s, saved_s = st.nets[0].fwd(ctx, tr, st.src, keep=keep)
                 t, saved_t = st.nets[1].fwd(ctx, tr, st.src, keep=keep)
@@ -861,7 +861,7 @@ class CouplingOp:
                 tr.invalidate(*st.dst)
                 if logdet is not None:
                     K.logscale_sum(s, B, IRN, st.clamp, -1.0 if rev else 1.0, logdet, True)
-                bf = K.coupling_apply(u, s, t, IRN, st.clamp, rev, want_bf)
+                bf = K.coupling_apply(u, s, t, IRN, st.clamp, rev, want_bf, fast=ctx.tc)
             else:
                 f, saved = st.nets[0].fwd(ctx, tr, st.src, keep=keep)
                 if keep:
@@ -898,7 +898,7 @@ class CouplingOp:
                     a, saved = stored if stored is not None else st.nets[0].fwd(ctx, tr, st.src, keep=True)
                     da = torch.empty(tr.npix, 2 * L, dtype=ctx.adt, device=dev)
                     tr.invalidate(*st.dst)
-                    bf = K.coupling_bwd(u, du, a[:, :L], a[:, L:], GLOW, st.clamp, rev, da[:, :L], da[:, L:], want_bf)
+                    bf = K.coupling_bwd(u, du, a[:, :L], a[:, L:], GLOW, st.clamp, rev, da[:, :L], da[:, L:], want_bf, fast=ctx.tc)
                 st.nets[0].bwd(ctx, tr, saved, da, dsrc)
             elif st.kind == "irn_affine":
                 if stored is not None:
@@ -910,7 +910,7 @@ class CouplingOp:
                 ds = torch.empty(tr.npix, Lp, dtype=ctx.adt, device=dev)[:, :L]
                 dt = torch.empty(tr.npix, Lp, dtype=ctx.adt, device=dev)[:, :L]
                 tr.invalidate(*st.dst)
-                bf = K.coupling_bwd(u, du, s, t, IRN, st.clamp, rev, ds, dt, want_bf)
+                bf = K.coupling_bwd(u, du, s, t, IRN, st.clamp, rev, ds, dt, want_bf, fast=ctx.tc)
                 st.nets[0].bwd(ctx, tr, saved_s, ds, dsrc)
                 st.nets[1].bwd(ctx, tr, saved_t, dt, dsrc)
             else:

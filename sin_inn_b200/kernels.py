@@ -278,17 +278,17 @@ def permute_nhwc_pair(xa, xb, chan_map, bf16_range=None):
 
 
 # ----------------------------------------------------------------------------- coupling
-def coupling_apply(u, s, t, kind, clamp, inverse, want_bf16=False):
+def coupling_apply(u, s, t, kind, clamp, inverse, want_bf16=False, fast=False):
     u, s, t = _view2d(u), _view2d(s), _view2d(t)
     npix, L = u.shape
     bf = torch.empty(npix, L, dtype=torch.bfloat16, device=u.device) if want_bf16 else None
     check(_run("coupling", lambda: load().sininn_coupling_apply(u.data_ptr(), u.stride(0), s.data_ptr(), s.stride(0), t.data_ptr(), t.stride(0),
-                                       npix, L, kind, float(clamp), int(inverse), _p(bf), stream_ptr()), 1, 0.0, 16.0 * npix * L),
+                                       npix, L, kind, float(clamp), int(inverse), _p(bf), int(fast), stream_ptr()), 1, 0.0, 16.0 * npix * L),
           "coupling_apply")
     return bf
 
 
-def coupling_bwd(u, du, s, t, kind, clamp, inverse, ds, dt, want_bf16=False):
+def coupling_bwd(u, du, s, t, kind, clamp, inverse, ds, dt, want_bf16=False, fast=False):
     u, du, s, t, ds, dt = map(_view2d, (u, du, s, t, ds, dt))
     npix, L = u.shape
     if ds.dtype != dt.dtype:
@@ -296,7 +296,7 @@ def coupling_bwd(u, du, s, t, kind, clamp, inverse, ds, dt, want_bf16=False):
     bf = torch.empty(npix, L, dtype=torch.bfloat16, device=u.device) if want_bf16 else None
     check(_run("coupling_bwd", lambda: load().sininn_coupling_bwd(u.data_ptr(), u.stride(0), du.data_ptr(), du.stride(0), s.data_ptr(), s.stride(0),
                                      t.data_ptr(), t.stride(0), npix, L, kind, float(clamp), int(inverse),
-                                     ds.data_ptr(), ds.stride(0), dt.data_ptr(), dt.stride(0), dtype_code(ds), _p(bf),
+                                     ds.data_ptr(), ds.stride(0), dt.data_ptr(), dt.stride(0), dtype_code(ds), _p(bf), int(fast),
                                      stream_ptr()), 1, 0.0, (24.0 + 2.0 * ds.element_size()) * npix * L), "coupling_bwd")
     return bf
 

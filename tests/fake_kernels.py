@@ -87,14 +87,14 @@ def _log_scale(kind, clamp, raw):
     return clamp * (2 * sg - 1), 2 * clamp * sg * (1 - sg)
 
 
-def coupling_apply(u, s, t, kind, clamp, inverse, want_bf16=False):
+def coupling_apply(u, s, t, kind, clamp, inverse, want_bf16=False, fast=False):
     g, _ = _log_scale(kind, clamp, s)
     e = torch.exp(g)
     u.copy_((u - t) / e if inverse else e * u + t)
     return u.to(torch.bfloat16).contiguous() if want_bf16 else None
 
 
-def coupling_bwd(u, du, s, t, kind, clamp, inverse, ds, dt, want_bf16=False):
+def coupling_bwd(u, du, s, t, kind, clamp, inverse, ds, dt, want_bf16=False, fast=False):
     g, dg = _log_scale(kind, clamp, s)
     e = torch.exp(g)
     y, dy = u.clone(), du.clone()

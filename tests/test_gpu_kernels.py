@@ -651,6 +651,31 @@ def test_kernel_selection_switches(env):
     assert " passed" in r.stdout
 
 
+@pytest.mark.parametrize("kind,clamp", [(0, 1.2), (1, 1.0)])
+@pytest.mark.parametrize("npix,C,L", [(1000, 48, 24), (333, 192, 108), (77, 10, 3)])
+def test_coupling_fast_math_variants(K, kind, clamp, npix, C, L):
+    """fast_math = 1 (what the bf16 path launches: polynomial atan, ex2.approx, approximate division) against the accurate
+    kernels: errors stay at fp32 rounding level, two orders of magnitude inside that path's bf16 operand rounding."""
+    U = rnd(npix, C, seed=5).to(DEV)
+    a = (rnd(npix, 2 * L, seed=6) * 2).to(DEV)
+    dU = rnd(npix, C, seed=7).to(DEV)
+    rel = lambda x, y: (x.float() - y.float()).abs().max().item() / max(1.0, y.float().abs().max().item())
+    for inverse in (0, 1):
+        ua, uf = U.clone(), U.clone()
+        K.coupling_apply(ua[:, :L], a[:, :L], a[:, L:], kind, clamp, inverse)
+        bf = K.coupling_apply(uf[:, :L], a[:, :L], a[:, L:], kind, clamp, inverse, want_bf16=True, fast=True)
+        assert rel(uf, ua) <= 4e-6 and torch.equal(uf[:, L:], U[:, L:])
+        assert rel(bf, ua[:, :L]) <= 8e-3
+        outs = []
+        for fast in (False, True):
+            y, dy = ua.clone(), dU.clone()
+            ds, dt = torch.empty(npix, L, device=DEV), torch.empty(npix, L, device=DEV)
+            K.coupling_bwd(y[:, :L], dy[:, :L], a[:, :L], a[:, L:], kind, clamp, inverse, ds, dt, fast=fast)
+            outs.append((y, dy, ds, dt))
+        for got, ref in zip(outs[1], outs[0]):
+            assert rel(got, ref) <= 1e-5
+
+
 @pytest.mark.parametrize("L,geom", [(24, (2, 16, 16)), (96, (1, 12, 20)), (24, (1, 17, 33)), (96, (3, 7, 5))])
 @pytest.mark.parametrize("inverse", [0, 1])
 def test_coupling_fused_into_conv_epilogue(K, L, geom, inverse):
