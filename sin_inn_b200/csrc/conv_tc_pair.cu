@@ -4,7 +4,7 @@
 // shows those kernels pinned at the L2 -> SM bandwidth, not at the tensor pipe.  Here two CTAs of a cluster (one TPC)
 // work on two pixel tiles at once with ONE M = 256 tcgen05.mma per K step:
 //   * each CTA loads the halo'd activation patch of its OWN pixel tile (A rows 0..127 / 128..255), as in
-//     conv_tc_halo.cu (box {64 ch, 16 w, 18 h}, every tap a shifted UMMA descriptor), and
+//     conv_tc_halo.cu (here a box {64 ch, 10 w, 18 h}; every tap a shifted UMMA descriptor), and
 //   * each CTA holds only HALF of the weight rows (B is split along N across the pair), so the weight bytes per
 //     pixel tile halve -- and when the per-CTA half of ALL taps and slabs fits in shared memory (every level-0
 //     shape) the weights are loaded ONCE per kernel and stay resident: L2 -> SM traffic is the activations only.
@@ -23,9 +23,14 @@ namespace sininn {
 namespace tc {
 
 constexpr int PT_W = 8, PT_H = 16;                               // pixel tile of one CTA (UMMA rows 128)
-constexpr int PH_W = 16, PH_H = PT_H + 2;                        // halo box
-constexpr uint32_t PHALO_BYTES = PH_W * PH_H * 128;              // 36864
-constexpr int P_MAX_A = 4, P_MAX_B = 8;
+// halo box: 10 pixels wide (tile + 1 on each side), not 16 -- the 128-byte swizzle of TMA and UMMA is a function of the
+// shared-memory address bits, so any 128-byte row pitch is a legal 8-row-group stride (SBO = 1280 B; verified on the B200 by
+// the weight-gradient kernel first).  The level-0 convolutions are bound by what an SM takes in from L2 per tile (~22 B/clk):
+// 180 instead of 288 halo pixels per 128 output pixels.
+constexpr int PH_W = PT_W + 2, PH_H = PT_H + 2;
+constexpr uint32_t PHALO_TX = PH_W * PH_H * 128;                 // 23040 bytes delivered per box
+constexpr uint32_t PHALO_BYTES = (PHALO_TX + 1023u) & ~1023u;    // stage pitch (stage bases stay 1024-aligned)
+constexpr int P_MAX_A = 6, P_MAX_B = 8;
 constexpr int PAIR_THREADS = NUM_THREADS + 32;                   // + warp 10: weight-ring producer
 
 struct __align__(8) PairBarriers {
@@ -148,7 +153,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(smem_u32(&bars->a_empty[sa]), pa ^ 1);
         trace_stamp(hp, 0, ti, lane);
         if (elect_one()) {
-          if (rank == 0) mbar_expect_tx(smem_u32(&bars->a_full[sa]), 2u * PHALO_BYTES);
+          if (rank == 0) mbar_expect_tx(smem_u32(&bars->a_full[sa]), 2u * PHALO_TX);
           tma_load_4d_2sm(a_u32 + sa * PHALO_BYTES, &tmA, mapa_u32(smem_u32(&bars->a_full[sa]), 0), kc * 64, w0 - 1, h0 - 1, b);
         }
         __syncwarp();
@@ -224,7 +229,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
               bdesc = b_desc0 + (uint64_t)((three ? sb * 3 + tap % 3 : sb) * b_step);
             }
-            // tap (dy, dx) in 0..2 (halo origin is (h0-1, w0-1)): start row dy*16 + dx of the halo box, 8 x 16 B per row
+            // tap (dy, dx) in 0..2 (halo origin is (h0-1, w0-1)): start row dy*PH_W + dx of the halo box, 8 x 16 B per row
             const uint64_t adesc = a_stage + (uint64_t)(((tap / 3) * PH_W + (tap % 3)) * 8);
             umma_bf16_2sm_p(lead, d_tmem, adesc, bdesc, idesc, (kc | tap) != 0 ? 1u : 0u);
             if (ksteps > 1) umma_bf16_2sm_p(lead, d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
@@ -252,13 +257,19 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int etid = threadIdx.x - 64;
     int acc = 0; uint32_t acc_phase = 0;
     int bias_n0 = -1;
+    // Cout <= 256: the whole bias vector is loaded once.  Reloading the slice of every N tile costs two 256-thread barriers per
+    // work item, which make the eight epilogue warps start every tile in lockstep with the slowest one (in-kernel stamps:
+    // ~1000 of the ~3700 cycles a level-0 24->256 tile took)
+    const bool bias_all = p.Cout <= 256;
+    if (bias_all) epilogue_load_bias(p, bias_s, 0, etid, bias_n0);
     int ti = 0;
     const int tl = warp == 2 ? lane : 1;
     trace_stamp(hp, 2, ti, tl);
     for (long long it = pair; it < hp.num_items; it += npairs) {
       int b, h0, w0, n0;
       pair_item(hp, it, rank, b, h0, w0, n0);
-      epilogue_load_bias(p, bias_s, n0, etid, bias_n0);
+      if (!bias_all) epilogue_load_bias(p, bias_s, n0, etid, bias_n0);
+      const float* bias_t = bias_all ? bias_s + n0 : bias_s;      // bias of this tile's first column
       bool row_ok = false; long long pix = 0;
       CplRegs cpl;
       if (p.cpl.mode != 0) {                 // the coupling operands of this thread's first slab travel while the MMAs run
@@ -270,14 +281,14 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       trace_stamp(hp, 2, ti, tl);
       const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE;
       if (p.cpl.mode != 0) {
-        epilogue_tile_coupling(p.cpl, bias_s, t_base, row_ok, pix, half, 2, cpl);
+        epilogue_tile_coupling(p.cpl, bias_t, t_base, row_ok, pix, half, 2, cpl);
       } else {
 #ifdef SININN_PAIR_TRACE
       // stamps inside the first two tiles of warp 2 of CTA 0 go to role slot 2 from word 256 on
       long long* et = (hp.trace != nullptr && blockIdx.x == 0 && warp == 2 && ti < 6) ? hp.trace + 2 * TRACE_ROLE_WORDS + 256 + 16 * (ti / 2) : nullptr;
-      epilogue_tile<PT_W>(p, &tmO, stg, bias_s, t_base, b, h0, w0, n0, quarter, half, lane, et);
+      epilogue_tile<PT_W>(p, &tmO, stg, bias_t, t_base, b, h0, w0, n0, quarter, half, lane, et);
 #else
-      epilogue_tile<PT_W>(p, &tmO, stg, bias_s, t_base, b, h0, w0, n0, quarter, half, lane);
+      epilogue_tile<PT_W>(p, &tmO, stg, bias_t, t_base, b, h0, w0, n0, quarter, half, lane);
 #endif
       }
       tc_fence_before();
@@ -334,7 +345,8 @@ int launch_conv_pair(const sininn_conv_desc* d, Params p, cudaStream_t st) {
       const long long room = total - fixed - wres;
       if (room >= 3LL * PHALO_BYTES) {
         n_tile = nt;
-        a_stages = room >= 4LL * PHALO_BYTES ? 4 : 3;
+        a_stages = (int)(room / PHALO_BYTES);
+        if (a_stages > P_MAX_A) a_stages = P_MAX_A;
       }
     }
   }

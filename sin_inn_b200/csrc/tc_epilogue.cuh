@@ -437,14 +437,16 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const CUtensorMap*
     const int etid = threadIdx.x - 64;                         // 0..255 among the epilogue threads
     int acc = 0; uint32_t acc_phase = 0;
     int bias_n0 = -1;
+    const bool bias_all = p.Cout <= 256;                       // whole bias vector loaded once: no per-tile barriers
+    if (bias_all) epilogue_load_bias(p, bias_s, 0, etid, bias_n0);
     for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       int b, h0, w0, n0;
       tile_coords<TW>(p, t, b, h0, w0, n0);
-      epilogue_load_bias(p, bias_s, n0, etid, bias_n0);
+      if (!bias_all) epilogue_load_bias(p, bias_s, n0, etid, bias_n0);
       mbar_wait(smem_u32(&bars->acc_full[acc]), acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE;
-      epilogue_tile<TW>(p, tmO, stg, bias_s, t_base, b, h0, w0, n0, quarter, half, lane);
+      epilogue_tile<TW>(p, tmO, stg, bias_all ? bias_s + n0 : bias_s, t_base, b, h0, w0, n0, quarter, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
