@@ -17,6 +17,7 @@
 //
 // Replaces cuDNN's 3x3 nn.Conv2d forward / data-gradient inside subnet_conv (/root/reference/archs.py:11-13) and
 // DenseBlock (/root/reference/archs.py:77-81,88-95).
+#include <stdlib.h>
 #include "tc_epilogue.cuh"
 
 namespace sininn {
@@ -78,9 +79,62 @@ __device__ __forceinline__ void pair_item(const PairParams& hp, long long it, in
   h0 = th * PT_H; w0 = tw * PT_W;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+// One 32-column half of a 128-byte bf16 output slab, for the 16-epilogue-warp variant: the two warps of a pair (same TMEM lane
+// quarter, hw = 0 / 1) drain columns c + 32 hw .. + 31 of the warp quarter's 32 rows, write their 64-byte halves of the shared
+// 128B-swizzled staging rows, meet on a named barrier, and the pair's leader sends the slab off as ONE tensor store.  Only the
+// two shapes that need it (launch_conv_pair): bias + ReLU (+ sign bits), or the stored sign-bit mask alone.
+template <int TW>
+__device__ __forceinline__ void epilogue_half_slab(const Params& p, const CUtensorMap* tmO, uint8_t* stg, const float* bias_c, uint32_t t_col,
+                                                   int b, int h0, int w0, int col0, int quarter, int hw, int lane, int pair_bar) {
+  const int row = quarter * 32 + lane;
+  const int oh = h0 + row / TW, ow = w0 + row % TW;
+  const bool row_ok = (oh < p.H) && (ow < p.W) && (b < p.B);
+  const long long pix = ((long long)b * p.H + oh) * p.W + ow;
+  const int wi = (col0 >> 5) + hw;                        // sign-bit word of this warp's 32 columns
+  uint32_t mb = 0xffffffffu;
+  if (p.bits_in != nullptr) mb = (row_ok && wi < p.bit_words) ? __ldg(p.bits_in + pix * p.bit_words + wi) : 0u;
+  uint32_t v[32];
+  tmem_ld32(t_col + 32 * hw, v);
+  tmem_ld_wait();
+  uint32_t pk[16];
+  uint32_t sign = 0u;
+  if (p.act == SININN_ACT_RELU) {
+    const float* bsl = bias_c + 32 * hw;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 ba = *reinterpret_cast<const float4*>(bsl + 4 * q);
+      pk[2 * q] = bf16x2_relu(pack_bf16(__uint_as_float(v[4 * q]) + ba.x, __uint_as_float(v[4 * q + 1]) + ba.y));
+      pk[2 * q + 1] = bf16x2_relu(pack_bf16(__uint_as_float(v[4 * q + 2]) + ba.z, __uint_as_float(v[4 * q + 3]) + ba.w));
+    }
+    if (p.bits_out != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sign |= bf16x2_gt0_mask(pk[j]) & ((1u << j) | (1u << (16 + j)));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) & sign_bits_expand(mb, j);
+  }
+  if (hw == 0 && lane == 0) bulk_wait_read0();             // the pair's previous tensor store has finished reading the staging rows
+  asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 * hw + q) ^ (lane & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  if (p.bits_out != nullptr && row_ok && wi < p.bit_words) p.bits_out[pix * p.bit_words + wi] = sign;
+  fence_async_smem();                                      // generic-proxy smem writes -> visible to the TMA engine
+  asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+  if (hw == 0 && lane == 0) {
+    tma_store_4d(tmO, smem_u32(stg), col0, w0, h0 + (32 / TW) * quarter, b);
+    bulk_commit();
+  }
+}
+
+// EW = epilogue warps per CTA: 8 (two per TMEM lane quarter, every epilogue variant) or 16 (four per quarter, the 256-wide bf16
+// outputs whose epilogue -- not the MMAs -- sets the tile period: with two warps per scheduler the ALU pipe sat at 16 %).
+template <int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW + 32, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const PairParams hp) {
+  constexpr int RING_WARP = 2 + EW;                        // weight-ring producer
   const Params& p = hp.p;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -109,7 +163,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bars->acc_full[a]), 1);
-      mbar_init(smem_u32(&bars->acc_empty[a]), 2 * NUM_EPI_WARPS);   // the epilogue warps of BOTH CTAs
+      mbar_init(smem_u32(&bars->acc_empty[a]), 2 * EW);              // the epilogue warps of BOTH CTAs
     }
     mbar_init(smem_u32(&bars->w_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -160,7 +214,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (++sa == hp.a_stages) { sa = 0; pa ^= 1; }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == RING_WARP) {
     // ======================= weight-ring producer (both CTAs; streaming mode only) =======================
     // its own warp so that the halo loads (one per slab, ~2500 cycles to land) run a_stages slabs ahead instead of
     // being paced by the much shallower weight ring
@@ -248,7 +302,35 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < 10) {
+  } else if (EW == 16 && warp < RING_WARP) {
+    // ======================= epilogue, 16 warps: pairs of warps share a 128-byte slab (epilogue_half_slab) =======================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int sub = ew >> 2;                                 // 0..3
+    const int pr = sub >> 1, hw = sub & 1;                   // pair of this quarter, half of the pair's slab
+    uint8_t* stg = staging + (quarter * 2 + pr) * STAGING_BYTES;
+    const int pair_bar = 2 + quarter * 2 + pr;               // named barriers 2..9 (0 = __syncthreads, 1 = bias load)
+    const int etid = threadIdx.x - 64;
+    if (etid < 256) bias_s[etid] = (p.bias != nullptr && etid < p.Cout) ? __ldg(p.bias + etid) : 0.f;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long long it = pair; it < hp.num_items; it += npairs) {
+      int b, h0, w0, n0;
+      pair_item(hp, it, rank, b, h0, w0, n0);
+      mbar_wait(smem_u32(&bars->acc_full[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE;
+      const int n_valid = min(p.n_tile, p.Cout - n0);
+      const int n_slabs = (n_valid + 63) / 64;
+      for (int sl = pr; sl < n_slabs; sl += 2)
+        epilogue_half_slab<PT_W>(p, &tmO, stg, bias_s + n0 + sl * 64, t_base + sl * 64, b, h0, w0, n0 + sl * 64, quarter, hw, lane, pair_bar);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->acc_empty[acc]), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) bulk_wait_all();
+  } else if (EW == 8 && warp < RING_WARP) {
     // ======================= epilogue (both CTAs, each on its own 128 accumulator rows) =======================
     const int ew = warp - 2;
     const int quarter = warp & 3;
@@ -307,6 +389,15 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+static bool pair_epi16_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SININN_PAIR_EPI16");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 // Host launcher, called by sininn_conv_tc for 3x3 convolutions.  Returns SININN_EUNSUPPORTED when the shape does
@@ -415,13 +506,21 @@ int launch_conv_pair(const sininn_conv_desc* d, Params p, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_pair_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_pair_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("conv_tc(pair): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SININN_ECUDA; }
     attr_set[dev] = true;
   }
   long long pairs = hp.num_items < npairs ? hp.num_items : npairs;
   if (b_stages == 0 && p.n_tiles > 1) pairs = npairs;            // resident N tile must be invariant per pair
-  launch_k(conv_tc_pair_kernel, dim3((unsigned)(2 * pairs)), dim3(PAIR_THREADS), smem, st, tmA, tmB, tmO, hp);
+  // 16 epilogue warps where the epilogue sets the pace: wide bf16 outputs that are bias + ReLU (+ sign bits) or the masked data
+  // gradient (the two packed-bf16x2 shapes of tc_epilogue.cuh); everything else keeps the general 8-warp epilogue
+  const bool relu_shape = p.act == SININN_ACT_RELU && p.bits_in == nullptr;
+  const bool mask_shape = p.act == SININN_ACT_NONE && p.bias == nullptr && p.bits_in != nullptr && p.bits_out == nullptr;
+  const bool wide16 = pair_epi16_enabled() && p.tma_out && !p.out_f32 && p.cpl.mode == 0 && p.alpha == 1.0f && !p.accumulate && p.mask == nullptr &&
+                      d->Cout >= 128 && d->Cout <= 256 && (d->Cout % 64) == 0 && (relu_shape || mask_shape);
+  if (wide16) launch_k(conv_tc_pair_kernel<16>, dim3((unsigned)(2 * pairs)), dim3(64 + 32 * 16 + 32), smem, st, tmA, tmB, tmO, hp);
+  else launch_k(conv_tc_pair_kernel<8>, dim3((unsigned)(2 * pairs)), dim3(PAIR_THREADS), smem, st, tmA, tmB, tmO, hp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv_tc(pair): launch failed: %s", cudaGetErrorString(e)); return SININN_ECUDA; }
   return SININN_OK;
