@@ -152,6 +152,22 @@ int sininn_coupling_bwd(float* u, int u_stride, float* du, int du_stride,
                         void* ds_out, int ds_stride, void* dt_out, int dt_stride, int out_dtype,
                         void* x_bf16, int fast_math, sininn_stream_t stream);
 
+/* The LAST half-step of a coupling block fused with the channel permutation that follows it (FrEIA GLOWCouplingBlock ->
+ * PermuteRandom, archs.py:61-68):  out[p][i] = f(in[p][chan_map[i]]),  f = the half-step of sininn_coupling_apply for source
+ * channels in [c0, c0 + L) (s, t indexed by channel - c0), identity for the others.  in / out: [npix][C] fp32 (C % 4 == 0),
+ * not in place.  bf16_out (may be NULL): compact bf16 copy of out[:, bc0:bc1].  Same arithmetic as the two separate calls. */
+int sininn_coupling_apply_permute(const float* in, float* out, long long npix, int C, const int32_t* chan_map, int c0, int L,
+                                  const float* s, int s_stride, const float* t, int t_stride, int kind, float clamp, int inverse,
+                                  void* bf16_out, int bc0, int bc1, int fast_math, sininn_stream_t stream);
+/* The undo of that permutation fused with sininn_coupling_bwd of the half-step: y_in / dy_in are the trunk and its gradient in
+ * the permuted layout, chan_map undoes the permutation (out channel i <- in channel chan_map[i]); output channels
+ * [c0, c0 + L) (multiples of 4) receive x and dL/dx of the half-step, the others are moved unchanged; ds_out / dt_out as
+ * in sininn_coupling_bwd. */
+int sininn_coupling_bwd_unpermute(const float* y_in, const float* dy_in, float* x_out, float* dx_out, long long npix, int C,
+                                  const int32_t* chan_map, int c0, int L, const float* s, int s_stride, const float* t, int t_stride,
+                                  int kind, float clamp, int inverse, void* ds_out, int ds_stride, void* dt_out, int dt_stride,
+                                  int out_dtype, int fast_math, sininn_stream_t stream);
+
 /* small helpers around the subnets */
 /* out[p][c] = scale * in[p][c] converted to out_dtype */
 int sininn_cast_slice(const float* in, int in_stride, long long npix, int L, float scale, void* out, int out_dtype,

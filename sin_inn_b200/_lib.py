@@ -120,6 +120,10 @@ SIGNATURES = {
                                         C.c_int, _vp, C.c_int, _vp]),
     "sininn_coupling_bwd": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _c_ll, C.c_int, C.c_int,
                                       C.c_float, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),
+    "sininn_coupling_apply_permute": (C.c_int, [_vp, _vp, _c_ll, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int,
+                                                C.c_float, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "sininn_coupling_bwd_unpermute": (C.c_int, [_vp, _vp, _vp, _vp, _c_ll, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int,
+                                                C.c_int, C.c_float, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "sininn_cast_slice": (C.c_int, [_vp, C.c_int, _c_ll, C.c_int, C.c_float, _vp, C.c_int, C.c_int, _vp]),
     "sininn_act_bwd": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _c_ll, C.c_int, C.c_int,
                                  C.c_float, _vp]),

@@ -128,6 +128,118 @@ __global__ void __launch_bounds__(256) coupling_bwd_kernel(float* __restrict__ u
   }
 }
 
+// ---- the last half-step of a coupling block fused with the channel permutation that follows it (value pass), and the
+// permutation's undo fused with the backward of that half-step (backward pass).  FrEIA: GLOWCouplingBlock followed by
+// PermuteRandom (/root/reference/archs.py:61-68).  Standalone, the half-step rewrites half of the trunk in place and the
+// permutation then moves all of it (4T bytes per block, 7T with the gradient in the backward pass); fused, every channel is
+// read once and written once to its permuted place (3T / 5T).  One thread = 4 consecutive OUTPUT channels of a pixel.
+//   out[p][i] = f(in[p][map[i]])   where f is the half-step if map[i] lies in the active range [c0, c0 + L), else identity
+template <bool FAST>
+__global__ void __launch_bounds__(256) coupling_apply_permute_kernel(const float* __restrict__ in, float* __restrict__ out, long long npix, int C,
+                                                                     const int32_t* __restrict__ map, int c0, int L,
+                                                                     const float* __restrict__ s, int s_stride, const float* __restrict__ t, int t_stride,
+                                                                     int kind, float clamp, int inverse, __nv_bfloat16* __restrict__ bf, int bc0, int bc1) {
+  pdl_wait();
+  pdl_trigger();
+  const int Cv = C / 4;
+  const long long total = npix * Cv;
+  const float inv_clamp = 1.0f / clamp;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int c;
+    long long p;
+    split_index(idx, Cv, p, c);
+    c *= 4;
+    const float* row = in + p * C;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int sc = __ldg(map + c + e);
+      float x = row[sc];
+      const int j = sc - c0;
+      if (j >= 0 && j < L) {
+        const float sv = s[p * s_stride + j], tv = t[p * t_stride + j];
+        float ex, dg;
+        if (FAST) {
+          scale_fast(kind, clamp, inv_clamp, sv, ex, dg);
+          x = inverse ? __fdividef(x - tv, ex) : fmaf(ex, x, tv);
+        } else {
+          float g;
+          log_scale(kind, clamp, sv, g, dg);
+          ex = expf(g);
+          x = inverse ? (x - tv) / ex : ex * x + tv;
+        }
+      }
+      v[e] = x;
+    }
+    const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+    store4(out + p * C + c, o);
+    if (bf != nullptr && c >= bc0 && c < bc1) store4(bf + p * (long long)(bc1 - bc0) + (c - bc0), o);
+  }
+}
+
+// y_in / dy_in: trunk and gradient in the PERMUTED layout (the block's output after the permutation); map undoes the
+// permutation (out channel i <- in channel map[i]).  Output channels [c0, c0 + L) (c0, L multiples of 4) are the half-step's:
+// coupling_bwd_kernel's arithmetic; the others are moved unchanged.
+template <typename TO, bool FAST>
+__global__ void __launch_bounds__(256) coupling_bwd_unpermute_kernel(const float* __restrict__ y_in, const float* __restrict__ dy_in,
+                                                                     float* __restrict__ x_out, float* __restrict__ dx_out, long long npix, int C,
+                                                                     const int32_t* __restrict__ map, int c0, int L,
+                                                                     const float* __restrict__ s, int s_stride, const float* __restrict__ t, int t_stride,
+                                                                     int kind, float clamp, int inverse, TO* __restrict__ ds, int ds_stride,
+                                                                     TO* __restrict__ dt, int dt_stride) {
+  pdl_wait();
+  pdl_trigger();
+  const int Cv = C / 4;
+  const long long total = npix * Cv;
+  const float inv_clamp = 1.0f / clamp;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int c;
+    long long p;
+    split_index(idx, Cv, p, c);
+    c *= 4;
+    const int m0 = __ldg(map + c), m1 = __ldg(map + c + 1), m2 = __ldg(map + c + 2), m3 = __ldg(map + c + 3);
+    const float* ry = y_in + p * C;
+    const float* rd = dy_in + p * C;
+    const float y[4] = {ry[m0], ry[m1], ry[m2], ry[m3]};
+    const float dy[4] = {rd[m0], rd[m1], rd[m2], rd[m3]};
+    const int j = c - c0;
+    if (j >= 0 && j < L) {
+      const Pack<4> sv = ldv<4>(s + p * s_stride + j), tv = ldv<4>(t + p * t_stride + j);
+      Pack<4> x, dx, dsv, dtv;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float ex, dg;
+        if (FAST) {
+          scale_fast(kind, clamp, inv_clamp, sv.v[e], ex, dg);
+        } else {
+          float g;
+          log_scale(kind, clamp, sv.v[e], g, dg);
+          ex = expf(g);
+        }
+        if (!inverse) {            // y = ex*x + t
+          x.v[e] = FAST ? __fdividef(y[e] - tv.v[e], ex) : (y[e] - tv.v[e]) / ex;
+          dx.v[e] = dy[e] * ex;
+          dsv.v[e] = dy[e] * x.v[e] * ex * dg;
+          dtv.v[e] = dy[e];
+        } else {                   // y = (x - t)/ex
+          x.v[e] = y[e] * ex + tv.v[e];
+          const float q = FAST ? __fdividef(dy[e], ex) : dy[e] / ex;
+          dx.v[e] = q;
+          dsv.v[e] = -dy[e] * y[e] * dg;
+          dtv.v[e] = -q;
+        }
+      }
+      stv<4>(x_out + p * C + c, x);
+      stv<4>(dx_out + p * C + c, dx);
+      stv<4>(ds + p * ds_stride + j, dsv);
+      stv<4>(dt + p * dt_stride + j, dtv);
+    } else {
+      store4(x_out + p * C + c, make_float4(y[0], y[1], y[2], y[3]));
+      store4(dx_out + p * C + c, make_float4(dy[0], dy[1], dy[2], dy[3]));
+    }
+  }
+}
+
 template <int VEC, typename TO>
 __global__ void __launch_bounds__(256) cast_slice_kernel(const float* __restrict__ in, int in_stride, long long npix, int L,
                                                          float scale, TO* __restrict__ out, int out_stride) {
@@ -488,6 +600,50 @@ int sininn_coupling_bwd(float* u, int u_stride, float* du, int du_stride, const 
 #undef LAUNCH
 #undef LAUNCH2
   SININN_CHECK_LAUNCH("coupling_bwd");
+  return SININN_OK;
+}
+
+int sininn_coupling_apply_permute(const float* in, float* out, long long npix, int C, const int32_t* chan_map, int c0, int L,
+                                  const float* s, int s_stride, const float* t, int t_stride, int kind, float clamp, int inverse,
+                                  void* bf16_out, int bc0, int bc1, int fast_math, sininn_stream_t stream) {
+  SININN_CHECK_ARG(in && out && chan_map && s && t && npix > 0 && C > 0 && in != out, "coupling_apply_permute: bad arguments");
+  SININN_CHECK_ARG(kind == SININN_GLOW || kind == SININN_IRN, "coupling_apply_permute: unknown kind %d", kind);
+  SININN_CHECK_ARG(clamp > 0.f && c0 >= 0 && L > 0 && c0 + L <= C, "coupling_apply_permute: bad active range / clamp");
+  SININN_CHECK_ARG((C % 4) == 0 && aligned16(out), "coupling_apply_permute: needs C %% 4 == 0 and a 16-byte aligned output");
+  __nv_bfloat16* bf = reinterpret_cast<__nv_bfloat16*>(bf16_out);
+  if (bf) SININN_CHECK_ARG(0 <= bc0 && bc0 < bc1 && bc1 <= C && (bc0 % 4) == 0 && (bc1 % 4) == 0 && aligned8(bf), "coupling_apply_permute: bad bf16 channel range");
+  const long long total = npix * (C / 4);
+  const int block = 256, grid = grid_for(total, block);
+  if (fast_math) launch_k(coupling_apply_permute_kernel<true>, dim3(grid), dim3(block), 0, as_stream(stream), in, out, npix, C, chan_map, c0, L, s, s_stride, t, t_stride, kind, clamp, inverse, bf, bc0, bc1);
+  else launch_k(coupling_apply_permute_kernel<false>, dim3(grid), dim3(block), 0, as_stream(stream), in, out, npix, C, chan_map, c0, L, s, s_stride, t, t_stride, kind, clamp, inverse, bf, bc0, bc1);
+  SININN_CHECK_LAUNCH("coupling_apply_permute");
+  return SININN_OK;
+}
+
+int sininn_coupling_bwd_unpermute(const float* y_in, const float* dy_in, float* x_out, float* dx_out, long long npix, int C,
+                                  const int32_t* chan_map, int c0, int L, const float* s, int s_stride, const float* t, int t_stride,
+                                  int kind, float clamp, int inverse, void* ds_out, int ds_stride, void* dt_out, int dt_stride,
+                                  int out_dtype, int fast_math, sininn_stream_t stream) {
+  SININN_CHECK_ARG(y_in && dy_in && x_out && dx_out && chan_map && s && t && ds_out && dt_out && npix > 0 && C > 0, "coupling_bwd_unpermute: bad arguments");
+  SININN_CHECK_ARG(y_in != x_out && dy_in != dx_out, "coupling_bwd_unpermute: cannot run in place");
+  SININN_CHECK_ARG(kind == SININN_GLOW || kind == SININN_IRN, "coupling_bwd_unpermute: unknown kind %d", kind);
+  SININN_CHECK_ARG(out_dtype == SININN_F32 || out_dtype == SININN_BF16, "coupling_bwd_unpermute: bad out_dtype");
+  const bool f32 = out_dtype == SININN_F32;
+  SININN_CHECK_ARG(clamp > 0.f && c0 >= 0 && L > 0 && c0 + L <= C && (C % 4) == 0 && (c0 % 4) == 0 && (L % 4) == 0,
+                   "coupling_bwd_unpermute: C, c0 and L must be multiples of 4 (C=%d c0=%d L=%d)", C, c0, L);
+  SININN_CHECK_ARG(aligned16(x_out) && aligned16(dx_out) && aligned16(s) && aligned16(t) && (s_stride % 4) == 0 && (t_stride % 4) == 0 &&
+                   (ds_stride % 4) == 0 && (dt_stride % 4) == 0 && (f32 ? (aligned16(ds_out) && aligned16(dt_out)) : (aligned8(ds_out) && aligned8(dt_out))),
+                   "coupling_bwd_unpermute: misaligned operands");
+  const long long total = npix * (C / 4);
+  const int block = 256, grid = grid_for(total, block);
+  cudaStream_t st = as_stream(stream);
+#define LAUNCH(T, F)                                                                                                                     \
+  launch_k(coupling_bwd_unpermute_kernel<T, F>, dim3(grid), dim3(block), 0, st, y_in, dy_in, x_out, dx_out, npix, C, chan_map, c0, L, s, s_stride, \
+           t, t_stride, kind, clamp, inverse, reinterpret_cast<T*>(ds_out), ds_stride, reinterpret_cast<T*>(dt_out), dt_stride)
+  if (f32) { if (fast_math) LAUNCH(float, true); else LAUNCH(float, false); }
+  else     { if (fast_math) LAUNCH(__nv_bfloat16, true); else LAUNCH(__nv_bfloat16, false); }
+#undef LAUNCH
+  SININN_CHECK_LAUNCH("coupling_bwd_unpermute");
   return SININN_OK;
 }
 

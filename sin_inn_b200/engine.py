@@ -90,6 +90,9 @@ FUSE_COUPLING_1X1 = int(os.environ.get("SININN_FUSE_COUPLING_1X1", "1"))     # t
 # B200 at the headline shape: 5.60-5.64 ms / step fused against 5.57 unfused (the extra 25 MB store per subnet in the
 # epilogue costs what the separate coupling kernel did), so the default keeps the plain convolution + coupling_apply.
 FUSE_STORE = os.environ.get("SININN_FUSE_STORE", "0") != "0"
+# A channel permutation next to a coupling block whose adjoining half-step runs as a standalone kernel is folded into that
+# kernel (coupling_apply_permute / coupling_bwd_unpermute): every channel moves once instead of twice
+FOLD_PERM = os.environ.get("SININN_FOLD_PERM", "1") != "0"
 
 TRACE = None     # debugging aid: set to a list to collect (label, trunk copy) after every executed op
 
@@ -826,8 +829,28 @@ class CouplingOp:
         return self.steps[0] if rev else self.steps[-1]
 
     # ---- value pass
-    def run(self, ctx, tr, rev, logdet=None):
-        """logdet (optional fp32 [B] tensor): accumulates the block's log|det J| per sample (FrEIA's last_jac)."""
+    def _uses_epilogue(self, ctx, st, L, keep, logdet):
+        """Value pass: will this GLOW half-step run inside the second convolution's epilogue?"""
+        return logdet is None and (FUSE_STORE or not keep) and st.nets[0].can_fuse_coupling(ctx, L, False)
+
+    def folds_perm_value(self, ctx, tr, rev, logdet=None):
+        """Can the permutation that follows this block be folded into its last half-step (value pass)?"""
+        st = (self.steps[::-1] if rev else self.steps)[-1]
+        L = st.dst[1] - st.dst[0]
+        return (FOLD_PERM and st.kind == "glow" and tr.C % 4 == 0
+                and not self._uses_epilogue(ctx, st, L, ctx.stash is not None, logdet))
+
+    def folds_perm_backward(self, ctx, tr, rev):
+        """Can the undo of the permutation that follows this block be folded into the backward of its last half-step?  Only
+        with stored subnet outputs: re-evaluating the subnet needs the un-permuted trunk first."""
+        st = (self.steps[::-1] if rev else self.steps)[-1]
+        L = st.dst[1] - st.dst[0]
+        return (FOLD_PERM and ctx.stash is not None and st.kind == "glow" and tr.C % 4 == 0 and L % 4 == 0 and st.dst[0] % 4 == 0)
+
+    def run(self, ctx, tr, rev, logdet=None, post_perm=None):
+        """logdet (optional fp32 [B] tensor): accumulates the block's log|det J| per sample (FrEIA's last_jac).
+        post_perm = (gather map, bf16 hint range or None): the permutation that follows the block, to be applied by the last
+        half-step's kernel (the caller has checked folds_perm_value)."""
         steps = self.steps[::-1] if rev else self.steps
         B = tr.U.shape[0]
         for i, st in enumerate(steps):
@@ -836,9 +859,20 @@ class CouplingOp:
             want_bf = ctx.adt == torch.bfloat16 and nxt == st.dst and L % 8 == 0
             u = tr.mat()[:, st.dst[0]:st.dst[1]]
             keep = ctx.stash is not None
+            if st.kind == "glow" and post_perm is not None and i == len(steps) - 1:
+                a, saved = st.nets[0].fwd(ctx, tr, st.src, keep=keep)
+                if keep:
+                    ctx.stash.append((a, saved))
+                if logdet is not None:
+                    K.logscale_sum(a[:, :L], B, GLOW, st.clamp, -1.0 if rev else 1.0, logdet, True)
+                cmap, hint = post_perm
+                U, bfh = K.coupling_apply_permute(tr.U, cmap, st.dst, a[:, :L], a[:, L:], GLOW, st.clamp, rev, hint, fast=ctx.tc)
+                tr.set(U, None, {hint: bfh} if bfh is not None else None)
+                _trace(f"half:{st.kind}:{st.src}->{st.dst}+perm", tr.U)
+                return
             if st.kind == "glow":
                 fused = None
-                if logdet is None and (FUSE_STORE or not keep) and st.nets[0].can_fuse_coupling(ctx, L, False):
+                if self._uses_epilogue(ctx, st, L, keep, logdet):
                     tr.invalidate(*st.dst)
                     fused = st.nets[0].fwd_coupled(ctx, tr, st.src, u, st.clamp, rev, want_bf, store=keep)
                 if fused is not None:
@@ -874,13 +908,23 @@ class CouplingOp:
             _trace(f"half:{st.kind}:{st.src}->{st.dst}", tr.U)
 
     # ---- backward from the output: restores the block input in tr.U and turns tr.dU into dL/d(input)
-    def backward(self, ctx, tr, rev):
+    def backward(self, ctx, tr, rev, pre_perm=None):
+        """pre_perm: gather map that undoes the permutation executed after this block; tr still holds the permuted trunk and
+        gradient, and the first half-step's kernel un-permutes them (the caller has checked folds_perm_backward)."""
         executed = self.steps[::-1] if rev else self.steps
         undo = executed[::-1]
         for i, st in enumerate(undo):
             L = st.dst[1] - st.dst[0]
             nxt = undo[i + 1].src if i + 1 < len(undo) else None
             stored = ctx.stash.pop() if ctx.stash is not None else None
+            if i == 0 and pre_perm is not None:
+                a, saved = stored
+                da = torch.empty(tr.npix, 2 * L, dtype=ctx.adt, device=tr.U.device)
+                U, dU = K.coupling_bwd_unpermute(tr.U, tr.dU, pre_perm, st.dst, a[:, :L], a[:, L:], GLOW, st.clamp, rev,
+                                                 da[:, :L], da[:, L:], fast=ctx.tc)
+                tr.set(U, dU)
+                st.nets[0].bwd(ctx, tr, saved, da, tr.dmat()[:, st.src[0]:st.src[1]])
+                continue
             # with stored subnet internals nothing in backward reads a bf16 copy of the restored trunk
             want_bf = ctx.adt == torch.bfloat16 and nxt == st.dst and L % 8 == 0 and stored is None
             u = tr.mat()[:, st.dst[0]:st.dst[1]]
@@ -1097,10 +1141,20 @@ class Plan:
         if bf is not None:
             tr.bf[hint] = bf
         _trace("to_nhwc", tr.U)
+        folded = False
         for i, op in enumerate(seq):
             nxt = seq[i + 1] if i + 1 < len(seq) else None
+            if folded:                     # this permutation was applied by the coupling block before it
+                folded = False
+                _trace(op.kind, tr.U)
+                continue
             if op.kind == "coupling":
-                op.run(ctx, tr, rev)
+                if nxt is not None and nxt.kind == "perm" and op.folds_perm_value(ctx, tr, rev):
+                    after = seq[i + 2] if i + 2 < len(seq) else None
+                    op.run(ctx, tr, rev, post_perm=(nxt.gather_map(dev, rev), self._hint(after, rev, ctx)))
+                    folded = True
+                else:
+                    op.run(ctx, tr, rev)
             elif op.kind == "perm":
                 hint = self._hint(nxt, rev, ctx)
                 U, bf = K.permute_nhwc(tr.U, op.gather_map(dev, rev), hint)
@@ -1155,12 +1209,19 @@ class Plan:
         if self.side_wgrad and self.direct_grad and dy.is_cuda and cfg.tc and K.__name__ == "sin_inn_b200.kernels":
             ctx.wstream = self._wgrad_stream()
         # 2. walk the executed ops backwards
+        pre_perm = None
         for i, op in enumerate(undo):
             if op.kind == "coupling":
-                op.backward(ctx, tr, rev)
+                op.backward(ctx, tr, rev, pre_perm=pre_perm)
+                pre_perm = None
             elif op.kind == "perm":
                 m_val = op.gather_map(dev, not rev)            # inverse of the executed value map
                 m_grad = op.gather_map(dev, rev, grad=True)
+                nxt_op = undo[i + 1] if i + 1 < len(undo) else None
+                if (m_val is m_grad and nxt_op is not None and nxt_op.kind == "coupling"
+                        and nxt_op.folds_perm_backward(ctx, tr, rev)):
+                    pre_perm = m_val                           # undone by the next block's first backward kernel
+                    continue
                 # the gather also emits the bf16 operand of the subnet the next block's backward evaluates first
                 hint = None
                 nxt = undo[i + 1] if i + 1 < len(undo) else None

@@ -301,6 +301,43 @@ def coupling_bwd(u, du, s, t, kind, clamp, inverse, ds, dt, want_bf16=False, fas
     return bf
 
 
+def coupling_apply_permute(U, chan_map, rng, s, t, kind, clamp, inverse, bf16_range=None, fast=False):
+    """Last half-step of a coupling block + the channel permutation after it in one pass: returns (U_new, bf16 copy of
+    U_new[..., bf16_range] or None) with U_new[..., i] = f(U[..., chan_map[i]]), f = the half-step on source channels rng."""
+    _lib.require_cuda(U)
+    C_ = U.shape[-1]
+    npix = U.numel() // C_
+    s, t = _view2d(s), _view2d(t)
+    out = torch.empty_like(U)
+    bf, b0, b1 = None, 0, 0
+    if bf16_range is not None:
+        b0, b1 = bf16_range
+        bf = torch.empty(npix, b1 - b0, dtype=torch.bfloat16, device=U.device)
+    c0, L = rng[0], rng[1] - rng[0]
+    check(_run("coupling", lambda: load().sininn_coupling_apply_permute(U.data_ptr(), out.data_ptr(), npix, C_, chan_map.data_ptr(), c0, L,
+                                       s.data_ptr(), s.stride(0), t.data_ptr(), t.stride(0), kind, float(clamp), int(inverse), _p(bf), b0, b1,
+                                       int(fast), stream_ptr()), 1, 0.0, 8.0 * U.numel() + 8.0 * npix * L), "coupling_apply_permute")
+    return out, bf
+
+
+def coupling_bwd_unpermute(Y, dY, chan_map, rng, s, t, kind, clamp, inverse, ds, dt, fast=False):
+    """Undo of a channel permutation on (trunk, gradient) + the backward of the half-step on channels rng of the result, one
+    pass: returns (X, dX) in the un-permuted layout; ds / dt receive the half-step's subnet-output gradients."""
+    _lib.require_cuda(Y)
+    C_ = Y.shape[-1]
+    npix = Y.numel() // C_
+    s, t, ds, dt = map(_view2d, (s, t, ds, dt))
+    if ds.dtype != dt.dtype:
+        raise _lib.SininnError("coupling_bwd_unpermute: ds and dt must share a dtype")
+    X, dX = torch.empty_like(Y), torch.empty_like(dY)
+    c0, L = rng[0], rng[1] - rng[0]
+    check(_run("coupling_bwd", lambda: load().sininn_coupling_bwd_unpermute(Y.data_ptr(), dY.data_ptr(), X.data_ptr(), dX.data_ptr(), npix, C_,
+                                       chan_map.data_ptr(), c0, L, s.data_ptr(), s.stride(0), t.data_ptr(), t.stride(0), kind, float(clamp),
+                                       int(inverse), ds.data_ptr(), ds.stride(0), dt.data_ptr(), dt.stride(0), dtype_code(ds), int(fast),
+                                       stream_ptr()), 1, 0.0, 16.0 * Y.numel() + (8.0 + 2.0 * ds.element_size()) * npix * L), "coupling_bwd_unpermute")
+    return X, dX
+
+
 def cast_slice(src, out, scale=1.0):
     """out[p][c] = scale*src[p][c]; src fp32 view, out fp32/bf16 view of the same shape."""
     src, out = _view2d(src), _view2d(out)

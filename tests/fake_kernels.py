@@ -112,6 +112,21 @@ def coupling_bwd(u, du, s, t, kind, clamp, inverse, ds, dt, want_bf16=False, fas
     return x.to(torch.bfloat16).contiguous() if want_bf16 else None
 
 
+def coupling_apply_permute(U, chan_map, rng, s, t, kind, clamp, inverse, bf16_range=None, fast=False):
+    C_ = U.shape[-1]
+    W = U.reshape(-1, C_).clone()
+    coupling_apply(W[:, rng[0]:rng[1]], s, t, kind, clamp, inverse)
+    return permute_nhwc(W.reshape(U.shape), chan_map, bf16_range)
+
+
+def coupling_bwd_unpermute(Y, dY, chan_map, rng, s, t, kind, clamp, inverse, ds, dt, fast=False):
+    X, dX, _ = permute_nhwc_pair(Y, dY, chan_map, None)
+    C_ = Y.shape[-1]
+    x2, dx2 = X.reshape(-1, C_), dX.reshape(-1, C_)
+    coupling_bwd(x2[:, rng[0]:rng[1]], dx2[:, rng[0]:rng[1]], s, t, kind, clamp, inverse, ds, dt)
+    return X, dX
+
+
 def cast_slice(src, out, scale=1.0):
     out.copy_((src * scale).to(out.dtype))
     return out

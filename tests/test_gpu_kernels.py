@@ -651,6 +651,43 @@ def test_kernel_selection_switches(env):
     assert " passed" in r.stdout
 
 
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("npix,C,c0,L", [(1000, 48, 24, 24), (1000, 48, 0, 24), (333, 192, 96, 96), (77, 12, 8, 4)])
+def test_coupling_folded_with_permutation(K, npix, C, c0, L, fast):
+    """The last half-step of a block + the permutation after it in one kernel (value pass), and the permutation's undo + the
+    half-step's backward in one kernel (backward pass) == the separate kernels, bit for bit (same arithmetic per element)."""
+    bf = torch.bfloat16
+    U = rnd(npix, C, seed=41).to(DEV)
+    dU = rnd(npix, C, seed=42).to(DEV)
+    a = (rnd(npix, 2 * L, seed=43) * 2).to(DEV)
+    perm = torch.randperm(C, generator=torch.Generator().manual_seed(44)).to(torch.int32).to(DEV)
+    hint = (C // 2, C) if (C // 2) % 4 == 0 else None
+    for inverse in (0, 1):
+        # value pass
+        ref = U.clone()
+        K.coupling_apply(ref[:, c0:c0 + L], a[:, :L], a[:, L:], 0, 1.2, inverse, fast=fast)
+        ref_p, ref_bf = K.permute_nhwc(ref.view(1, 1, npix, C), perm, hint)
+        got, got_bf = K.coupling_apply_permute(U.view(1, 1, npix, C), perm, (c0, c0 + L), a[:, :L], a[:, L:], 0, 1.2, inverse, hint, fast=fast)
+        assert torch.equal(got, ref_p)
+        if hint:
+            assert torch.equal(got_bf, ref_bf)
+        # backward pass: (ref_p, dU) are the permuted trunk / gradient; inv undoes the permutation
+        inv = torch.empty_like(perm)
+        inv[perm.long()] = torch.arange(C, dtype=torch.int32, device=DEV)
+        Yp = ref_p.view(npix, C)
+        X1, dX1, _ = K.permute_nhwc_pair(Yp.view(1, 1, npix, C), dU.view(1, 1, npix, C), inv, None)
+        X1, dX1 = X1.view(npix, C).clone(), dX1.view(npix, C).clone()
+        ds1, dt1 = torch.empty(npix, L, dtype=bf, device=DEV), torch.empty(npix, L, dtype=bf, device=DEV)
+        K.coupling_bwd(X1[:, c0:c0 + L], dX1[:, c0:c0 + L], a[:, :L], a[:, L:], 0, 1.2, inverse, ds1, dt1, fast=fast)
+        ds2, dt2 = torch.empty(npix, L, dtype=bf, device=DEV), torch.empty(npix, L, dtype=bf, device=DEV)
+        X2, dX2 = K.coupling_bwd_unpermute(Yp.view(1, 1, npix, C), dU.view(1, 1, npix, C), inv, (c0, c0 + L), a[:, :L], a[:, L:], 0, 1.2, inverse,
+                                           ds2, dt2, fast=fast)
+        assert torch.equal(X2.view(npix, C), X1) and torch.equal(dX2.view(npix, C), dX1)
+        assert torch.equal(ds2, ds1) and torch.equal(dt2, dt1)
+        if not fast:
+            assert (X1 - U).abs().max().item() <= 1e-5 * max(1.0, U.abs().max().item())      # the block input is back
+
+
 @pytest.mark.parametrize("kind,clamp", [(0, 1.2), (1, 1.0)])
 @pytest.mark.parametrize("npix,C,L", [(1000, 48, 24), (333, 192, 108), (77, 10, 3)])
 def test_coupling_fast_math_variants(K, kind, clamp, npix, C, L):

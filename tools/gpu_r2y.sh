@@ -2,7 +2,9 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 {
-make -C sin_inn_b200/csrc clean > /dev/null; make -C sin_inn_b200/csrc -j16 EXTRA=-DSININN_PAIR_TRACE 2>&1 | grep -E "error" 
-python tools/pair_trace.py c1 d2
+for V in 0 1; do
+  echo "== SININN_FUSE_STORE=$V"
+  SININN_FUSE_STORE=$V python bench.py --no-cpu-baseline --no-inference --no-extras 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], {k: round(v,3) for k,v in d['profile_ms_per_step'].items()})"
+done
 } > gpurun_out/r2y.log 2>&1
-tail -40 gpurun_out/r2y.log
+tail -50 gpurun_out/r2y.log
