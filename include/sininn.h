@@ -76,6 +76,14 @@ int sininn_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, const
                         void* bf16_out, int c0, int c1, sininn_stream_t stream);
 int sininn_nhwc_to_nchw(const float* in, float* out, int B, int C, int HW, const int32_t* chan_map,
                         sininn_stream_t stream);
+/* Two IRevNetDownsampling nodes (mode 0 of sininn_resample_nchw, archs.py:28-38) followed by the NCHW -> NHWC change, as ONE
+ * pass:  out[b][i][j][k2 * 4 C0 + k1 * C0 + c] = in[b][c][4 i + 2 (k2 >> 1) + (k1 >> 1)][4 j + 2 (k2 & 1) + (k1 & 1)]
+ * (in [B][C0][H][W], out [B][H/4][W/4][16 C0]; H, W multiples of 4), bit-identical to the three separate calls.
+ * bf16_out (may be NULL): compact bf16 copy of out channels [c0, c1).  sininn_nhwc_to_unsqueeze2 is the inverse map. */
+int sininn_squeeze2_to_nhwc(const float* in, float* out, int B, int C0, int H, int W, void* bf16_out, int c0, int c1,
+                            sininn_stream_t stream);
+int sininn_nhwc_to_unsqueeze2(const float* in, float* out, int B, int C0, int H, int W, sininn_stream_t stream);
+
 /* FrEIA PermuteRandom on channels-last data: out[p][i] = in[p][chan_map[i]] */
 int sininn_permute_nhwc(const float* in, float* out, long long npix, int C, const int32_t* chan_map,
                         void* bf16_out, int c0, int c1, sininn_stream_t stream);

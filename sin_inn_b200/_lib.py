@@ -101,6 +101,8 @@ SIGNATURES = {
     "sininn_resample_nhwc": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp]),
     "sininn_nchw_to_nhwc": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
     "sininn_nhwc_to_nchw": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "sininn_squeeze2_to_nhwc": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
+    "sininn_nhwc_to_unsqueeze2": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "sininn_permute_nhwc": (C.c_int, [_vp, _vp, _c_ll, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
     "sininn_permute_nhwc_pair": (C.c_int, [_vp, _vp, _vp, _vp, _c_ll, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
     "sininn_gather_windows_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -227,6 +227,71 @@ __global__ void __launch_bounds__(256) layout_kernel(const float* __restrict__ i
   }
 }
 
+// ---------------------------------------------------------------- two squeezes + NCHW -> NHWC in one pass (and back)
+// The SRF graph starts with two IRevNetDownsampling nodes (/root/reference/archs.py:28-38) before its first coupling block; as
+// three kernels (squeeze, squeeze, layout change) the input is read and written three times.  Composed index map:
+//   out[b][i][j][k2 * 4 C0 + k1 * C0 + c] = in[b][c][4 i + 2 dy(k2) + dy(k1)][4 j + 2 dx(k2) + dx(k1)],   dy(k) = k >> 1, dx(k) = k & 1.
+// One block = one output row segment of SQ_P pixels of one sample: 4 input rows x C0 channels are read as float4 (the four
+// values are the (dx2, dx1) positions of one output pixel), staged as [pixel][16 C0] in shared memory and written as one
+// contiguous run (TO_NHWC), or the other way round.
+constexpr int SQ_P = 64;
+template <bool TO_NHWC>
+__global__ void __launch_bounds__(256) squeeze2_layout_kernel(const float* __restrict__ in, float* __restrict__ out, int C0, int H, int W,
+                                                              __nv_bfloat16* __restrict__ bf, int bc0, int bc1) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float sq_tile[];                   // [SQ_P][C + 1], C = 16 * C0
+  const int C = 16 * C0, pitch = C + 1;
+  const int Ho = H >> 2, Wo = W >> 2;
+  const int j0 = blockIdx.x * SQ_P, i = blockIdx.y;
+  const long long b = blockIdx.z;
+  const int np = min(SQ_P, Wo - j0);
+  const int nvec = C0 * 4 * np;                        // float4 pieces of the full-resolution side: (c, row r, pixel jj)
+  const float* full = TO_NHWC ? in : out;              // (address arithmetic only)
+  (void)full;
+  if (TO_NHWC) {
+    for (int e = threadIdx.x; e < nvec; e += 256) {
+      const int jj = e % np, cr = e / np, r = cr & 3, c = cr >> 2;
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(in + ((b * C0 + c) * H + 4 * i + r) * (long long)W + 4 * (j0 + jj)));
+      const int dy2 = r >> 1, dy1 = r & 1;
+      float* t = sq_tile + jj * pitch + c;
+      // x offset 0..3 = 2 dx2 + dx1
+      t[((dy2 * 2 + 0) * 4 + (dy1 * 2 + 0)) * C0] = v.x;
+      t[((dy2 * 2 + 0) * 4 + (dy1 * 2 + 1)) * C0] = v.y;
+      t[((dy2 * 2 + 1) * 4 + (dy1 * 2 + 0)) * C0] = v.z;
+      t[((dy2 * 2 + 1) * 4 + (dy1 * 2 + 1)) * C0] = v.w;
+    }
+    __syncthreads();
+    const long long pix0 = (b * Ho + i) * (long long)Wo + j0;
+    float* o = out + pix0 * C;
+    const int L = bc1 - bc0;
+    for (int e = threadIdx.x; e < np * C; e += 256) {
+      const int jj = e / C, ch = e - jj * C;
+      const float v = sq_tile[jj * pitch + ch];
+      o[e] = v;
+      if (bf != nullptr && ch >= bc0 && ch < bc1) bf[(pix0 + jj) * L + (ch - bc0)] = __float2bfloat16_rn(v);
+    }
+  } else {
+    const float* src = in + ((b * Ho + i) * (long long)Wo + j0) * C;
+    for (int e = threadIdx.x; e < np * C; e += 256) {
+      const int jj = e / C, ch = e - jj * C;
+      sq_tile[jj * pitch + ch] = src[e];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nvec; e += 256) {
+      const int jj = e % np, cr = e / np, r = cr & 3, c = cr >> 2;
+      const int dy2 = r >> 1, dy1 = r & 1;
+      const float* t = sq_tile + jj * pitch + c;
+      float4 v;
+      v.x = t[((dy2 * 2 + 0) * 4 + (dy1 * 2 + 0)) * C0];
+      v.y = t[((dy2 * 2 + 0) * 4 + (dy1 * 2 + 1)) * C0];
+      v.z = t[((dy2 * 2 + 1) * 4 + (dy1 * 2 + 0)) * C0];
+      v.w = t[((dy2 * 2 + 1) * 4 + (dy1 * 2 + 1)) * C0];
+      __stcs(reinterpret_cast<float4*>(out + ((b * C0 + c) * H + 4 * i + r) * (long long)W + 4 * (j0 + jj)), v);
+    }
+  }
+}
+
 // out[p][i] = in[p][map[i]]  (+ optional compact bf16 copy of out[:, bc0:bc1])
 template <int VEC>
 __global__ void __launch_bounds__(256) permute_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, long long npix,
@@ -415,6 +480,32 @@ int sininn_nhwc_to_nchw(const float* in, float* out, int B, int C, int HW, const
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
   launch_k(layout_kernel<false>, dim3(grid), dim3(block), 0, as_stream(stream), in, out, C, HW, chan_map, nullptr, 0, 0);
   SININN_CHECK_LAUNCH("nhwc_to_nchw");
+  return SININN_OK;
+}
+
+int sininn_squeeze2_to_nhwc(const float* in, float* out, int B, int C0, int H, int W, void* bf16_out, int c0, int c1,
+                            sininn_stream_t stream) {
+  SININN_CHECK_ARG(in && out && B > 0 && C0 > 0 && H > 0 && W > 0, "squeeze2_to_nhwc: bad arguments");
+  SININN_CHECK_ARG((H % 4) == 0 && (W % 4) == 0 && aligned16(in), "squeeze2_to_nhwc: H and W must be multiples of 4 and the input 16-byte aligned (got %dx%d)", H, W);
+  SININN_CHECK_ARG(B <= 65535 && H / 4 <= 65535 && 16 * C0 <= 192, "squeeze2_to_nhwc: batch / height / channels out of range");
+  if (bf16_out) SININN_CHECK_ARG(0 <= c0 && c0 < c1 && c1 <= 16 * C0, "squeeze2_to_nhwc: bad bf16 channel range");
+  const int Wo = W / 4;
+  dim3 grid((Wo + SQ_P - 1) / SQ_P, H / 4, B);
+  launch_k(squeeze2_layout_kernel<true>, grid, dim3(256), (size_t)SQ_P * (16 * C0 + 1) * sizeof(float), as_stream(stream), in, out, C0, H, W,
+           reinterpret_cast<__nv_bfloat16*>(bf16_out), c0, c1);
+  SININN_CHECK_LAUNCH("squeeze2_to_nhwc");
+  return SININN_OK;
+}
+
+int sininn_nhwc_to_unsqueeze2(const float* in, float* out, int B, int C0, int H, int W, sininn_stream_t stream) {
+  SININN_CHECK_ARG(in && out && B > 0 && C0 > 0 && H > 0 && W > 0, "nhwc_to_unsqueeze2: bad arguments");
+  SININN_CHECK_ARG((H % 4) == 0 && (W % 4) == 0 && aligned16(out), "nhwc_to_unsqueeze2: H and W must be multiples of 4 and the output 16-byte aligned (got %dx%d)", H, W);
+  SININN_CHECK_ARG(B <= 65535 && H / 4 <= 65535 && 16 * C0 <= 192, "nhwc_to_unsqueeze2: batch / height / channels out of range");
+  const int Wo = W / 4;
+  dim3 grid((Wo + SQ_P - 1) / SQ_P, H / 4, B);
+  launch_k(squeeze2_layout_kernel<false>, grid, dim3(256), (size_t)SQ_P * (16 * C0 + 1) * sizeof(float), as_stream(stream), in, out, C0, H, W,
+           static_cast<__nv_bfloat16*>(nullptr), 0, 0);
+  SININN_CHECK_LAUNCH("nhwc_to_unsqueeze2");
   return SININN_OK;
 }
 

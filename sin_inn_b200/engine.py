@@ -93,6 +93,8 @@ FUSE_STORE = os.environ.get("SININN_FUSE_STORE", "0") != "0"
 # A channel permutation next to a coupling block whose adjoining half-step runs as a standalone kernel is folded into that
 # kernel (coupling_apply_permute / coupling_bwd_unpermute): every channel moves once instead of twice
 FOLD_PERM = os.environ.get("SININN_FOLD_PERM", "1") != "0"
+# two squeezes ahead of the first coupling block + the change to channels-last (and back) as one kernel
+FUSE_SQUEEZE2 = os.environ.get("SININN_FUSE_SQUEEZE2", "1") != "0"
 
 TRACE = None     # debugging aid: set to a list to collect (label, trunk copy) after every executed op
 
@@ -1005,6 +1007,9 @@ class Plan:
         if any(o.kind != "resample" for o in self.prefix):
             first = next(i for i, o in enumerate(ops) if o.kind != "resample")
             self.prefix, self.body = ops[:first], ops[first:]
+        # SRF: squeeze, squeeze, first coupling block (archs.py:28-38) -- the two squeezes and the layout change are one kernel
+        self.squeeze2 = (FUSE_SQUEEZE2 and bool(self.body) and len(self.prefix) == 2
+                         and all(o.kind == "resample" and o.mode == 0 for o in self.prefix) and 16 * self.in_dims[0] <= 192)
         self.tail_perm = self.body[-1] if self.body and self.body[-1].kind == "perm" else None
         self.core = self.body[:-1] if self.tail_perm is not None else self.body
         c, h, w = self.in_dims
@@ -1069,6 +1074,26 @@ class Plan:
         if not rev and (x.shape[2] % f or x.shape[3] % f):
             raise SininnError(f"input height/width must be multiples of {f}, got {tuple(x.shape[2:])}")
 
+    def _can_squeeze2(self, t):
+        return self.squeeze2 and t.shape[2] % 4 == 0 and t.shape[3] % 4 == 0 and t.data_ptr() % 16 == 0 and t.is_contiguous()
+
+    def _enter(self, x, hint=None):
+        """Full-resolution NCHW tensor -> channels-last trunk at the first coupling block's level (+ bf16 hint copy)."""
+        if self._can_squeeze2(x):
+            return K.squeeze2_to_nhwc(x, hint)
+        for op in self.prefix:
+            x = op.apply_nchw(x, False)
+        return K.nchw_to_nhwc(x, None, hint)
+
+    def _leave(self, U):
+        """Inverse of _enter: channels-last trunk -> full-resolution NCHW tensor."""
+        if self.squeeze2 and U.is_contiguous():
+            return K.nhwc_to_unsqueeze2(U)
+        y = K.nhwc_to_nchw(U, None)
+        for op in self.prefix[::-1]:
+            y = op.apply_nchw(y, True)
+        return y
+
     def _hint(self, op, rev, ctx):
         """bf16 operand range the next coupling will read first (so the producer can emit it)."""
         if op is None or op.kind != "coupling" or ctx.adt != torch.bfloat16:
@@ -1123,11 +1148,9 @@ class Plan:
         if x.is_cuda and isinstance(x, LatentInput) and x.z is not None and x.z.device != dev:
             raise SininnError("LatentInput: lr and z live on different devices")
         if not rev:
-            for op in self.prefix:
-                x = op.apply_nchw(x, False)
             seq = self.core
             hint = self._hint(seq[0] if seq else None, rev, ctx)
-            U, bf = K.nchw_to_nhwc(x, None, hint)
+            U, bf = self._enter(x, hint)
         else:
             seq = self.core[::-1]
             cmap = self.tail_perm.gather_map(dev, True) if self.tail_perm is not None else None
@@ -1169,10 +1192,7 @@ class Plan:
         if not rev:
             cmap = self.tail_perm.gather_map(dev, False) if self.tail_perm is not None else None
             return K.nhwc_to_nchw(tr.U, cmap)
-        y = K.nhwc_to_nchw(tr.U, None)
-        for op in self.prefix[::-1]:
-            y = op.apply_nchw(y, True)
-        return y
+        return self._leave(tr.U)
 
     # ---- backward from the output ----------------------------------------------------------------
     def backward(self, y, dy, rev, cfg, need_dx=True, stash=None):
@@ -1197,11 +1217,17 @@ class Plan:
             dU, _ = K.nchw_to_nhwc(dy, cmap, None)
             undo = self.core[::-1]
         else:
-            for op in self.prefix:                 # the value pass ended with inverse resamples on NCHW
-                y = op.apply_nchw(y, False)        # re-apply forward map to get back to the trunk
-                dy = op.apply_nchw(dy, True, grad=True)
-            U, _ = K.nchw_to_nhwc(y, None, None)
-            dU, _ = K.nchw_to_nhwc(dy, None, None)
+            # the value pass ended with inverse resamples on NCHW: re-apply the forward map to get back to the trunk (for
+            # the squeeze, the gradient of the inverse map is the forward map too)
+            if self._can_squeeze2(y) and self._can_squeeze2(dy):
+                U, _ = K.squeeze2_to_nhwc(y, None)
+                dU, _ = K.squeeze2_to_nhwc(dy, None)
+            else:
+                for op in self.prefix:
+                    y = op.apply_nchw(y, False)
+                    dy = op.apply_nchw(dy, True, grad=True)
+                U, _ = K.nchw_to_nhwc(y, None, None)
+                dU, _ = K.nchw_to_nhwc(dy, None, None)
             undo = self.core                       # executed order was reversed(core)
         tr = Trunk(U, dU)
         # side stream only on the tensor-core path: its operands are private bf16 copies, while the fp32 path reads views
@@ -1251,9 +1277,12 @@ class Plan:
             return None, ctx.grads
         # 3. gradient back out through the API-side layout change and the NCHW resamples
         if not rev:
-            dx = K.nhwc_to_nchw(tr.dU, None)
-            for op in self.prefix[::-1]:
-                dx = op.apply_nchw(dx, False, grad=True)
+            if self.squeeze2 and tr.dU.is_contiguous():
+                dx = K.nhwc_to_unsqueeze2(tr.dU)       # gradient of the squeeze = its inverse map
+            else:
+                dx = K.nhwc_to_nchw(tr.dU, None)
+                for op in self.prefix[::-1]:
+                    dx = op.apply_nchw(dx, False, grad=True)
         else:
             cmap = self.tail_perm.gather_map(dev, True, grad=True) if self.tail_perm is not None else None
             dx = K.nhwc_to_nchw(tr.dU, cmap)

@@ -205,6 +205,30 @@ def nhwc_to_nchw(x, chan_map=None):
     return out
 
 
+def squeeze2_to_nhwc(x, bf16_range=None):
+    """Two squeezes (resample_nchw mode 0) + nchw_to_nhwc in one pass: [B,C0,H,W] -> ([B,H/4,W/4,16*C0], bf16 copy or None)."""
+    _lib.require_cuda(x)
+    B, c0, H, W = x.shape
+    out = torch.empty(B, H // 4, W // 4, 16 * c0, dtype=torch.float32, device=x.device)
+    bf, b0, b1 = None, 0, 0
+    if bf16_range is not None:
+        b0, b1 = bf16_range
+        bf = torch.empty(B * (H // 4) * (W // 4), b1 - b0, dtype=torch.bfloat16, device=x.device)
+    check(_run("layout", lambda: load().sininn_squeeze2_to_nhwc(x.data_ptr(), out.data_ptr(), B, c0, H, W, _p(bf), b0, b1, stream_ptr()), 1, 0.0,
+               8.0 * x.numel()), "squeeze2_to_nhwc")
+    return out, bf
+
+
+def nhwc_to_unsqueeze2(x):
+    """Inverse of squeeze2_to_nhwc: [B,h,w,16*C0] -> [B,C0,4h,4w]."""
+    _lib.require_cuda(x)
+    B, h, w, c = x.shape
+    out = torch.empty(B, c // 16, 4 * h, 4 * w, dtype=torch.float32, device=x.device)
+    check(_run("layout", lambda: load().sininn_nhwc_to_unsqueeze2(x.data_ptr(), out.data_ptr(), B, c // 16, 4 * h, 4 * w, stream_ptr()), 1, 0.0,
+               8.0 * x.numel()), "nhwc_to_unsqueeze2")
+    return out
+
+
 def permute_nhwc(x, chan_map, bf16_range=None):
     """x: channels-last tensor [..., C]; out[..., i] = x[..., chan_map[i]]."""
     _lib.require_cuda(x)

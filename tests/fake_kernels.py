@@ -55,6 +55,14 @@ def nhwc_to_nchw(x, chan_map=None):
     return x.permute(0, 3, 1, 2).contiguous()
 
 
+def squeeze2_to_nhwc(x, bf16_range=None):
+    return nchw_to_nhwc(resample_nchw(resample_nchw(x, 0, 0), 0, 0), None, bf16_range)
+
+
+def nhwc_to_unsqueeze2(x):
+    return resample_nchw(resample_nchw(nhwc_to_nchw(x, None), 0, 1), 0, 1)
+
+
 def permute_nhwc(x, chan_map, bf16_range=None):
     out = x[..., chan_map.long()].contiguous()
     return out, _bf(out.view(-1, out.shape[-1]), bf16_range)

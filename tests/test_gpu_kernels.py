@@ -53,6 +53,24 @@ def test_resample_nhwc(K, mode, shape):
     assert (xr.cpu() - x).abs().max() <= 1e-6 * x.abs().max()
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 16, 32), (3, 3, 64, 256), (1, 3, 120, 280), (2, 12, 8, 12), (1, 1, 4, 4)])
+def test_two_squeezes_and_layout_change_in_one_pass(K, shape):
+    """squeeze, squeeze, NCHW -> NHWC (the SRF entry, archs.py:28-38) as one kernel == the three separate kernels, bit for
+    bit, with the bf16 operand copy of a channel range; and the inverse map restores the input."""
+    x = rnd(*shape, seed=8).to(DEV)
+    C = 16 * shape[1]
+    hint = (C // 2, C) if (C // 2) % 8 == 0 else None
+    ref, ref_bf = K.nchw_to_nhwc(K.resample_nchw(K.resample_nchw(x, 0, 0), 0, 0), None, hint)
+    got, got_bf = K.squeeze2_to_nhwc(x, hint)
+    assert got.shape == ref.shape and torch.equal(got, ref)
+    if hint:
+        assert torch.equal(got_bf, ref_bf)
+    assert torch.equal(got.cpu(), FK.squeeze2_to_nhwc(x.cpu(), hint)[0])
+    back = K.nhwc_to_unsqueeze2(got)
+    assert torch.equal(back, x)
+    assert torch.equal(back, K.resample_nchw(K.resample_nchw(K.nhwc_to_nchw(ref, None), 0, 1), 0, 1))
+
+
 @pytest.mark.parametrize("C,hw", [(48, (8, 8)), (192, (5, 9)), (7, (3, 11)), (48, (20, 13)), (64, (16, 16)), (72, (9, 15))])
 def test_layout_and_permute(K, C, hw):
     x = rnd(2, C, *hw, seed=3)
