@@ -78,7 +78,7 @@ int sininn_nhwc_to_nchw(const float* in, float* out, int B, int C, int HW, const
                         sininn_stream_t stream);
 /* Two IRevNetDownsampling nodes (mode 0 of sininn_resample_nchw, archs.py:28-38) followed by the NCHW -> NHWC change, as ONE
  * pass:  out[b][i][j][k2 * 4 C0 + k1 * C0 + c] = in[b][c][4 i + 2 (k2 >> 1) + (k1 >> 1)][4 j + 2 (k2 & 1) + (k1 & 1)]
- * (in [B][C0][H][W], out [B][H/4][W/4][16 C0]; H, W multiples of 4), bit-identical to the three separate calls.
+ * (in [B][C0][H][W], out [B][H/4][W/4][16 C0]; H, W multiples of 4, C0 <= 8), bit-identical to the three separate calls.
  * bf16_out (may be NULL): compact bf16 copy of out channels [c0, c1).  sininn_nhwc_to_unsqueeze2 is the inverse map. */
 int sininn_squeeze2_to_nhwc(const float* in, float* out, int B, int C0, int H, int W, void* bf16_out, int c0, int c1,
                             sininn_stream_t stream);

@@ -487,7 +487,7 @@ int sininn_squeeze2_to_nhwc(const float* in, float* out, int B, int C0, int H, i
                             sininn_stream_t stream) {
   SININN_CHECK_ARG(in && out && B > 0 && C0 > 0 && H > 0 && W > 0, "squeeze2_to_nhwc: bad arguments");
   SININN_CHECK_ARG((H % 4) == 0 && (W % 4) == 0 && aligned16(in), "squeeze2_to_nhwc: H and W must be multiples of 4 and the input 16-byte aligned (got %dx%d)", H, W);
-  SININN_CHECK_ARG(B <= 65535 && H / 4 <= 65535 && 16 * C0 <= 192, "squeeze2_to_nhwc: batch / height / channels out of range");
+  SININN_CHECK_ARG(B <= 65535 && H / 4 <= 65535 && 16 * C0 <= 128, "squeeze2_to_nhwc: batch / height / channels out of range");
   if (bf16_out) SININN_CHECK_ARG(0 <= c0 && c0 < c1 && c1 <= 16 * C0, "squeeze2_to_nhwc: bad bf16 channel range");
   const int Wo = W / 4;
   dim3 grid((Wo + SQ_P - 1) / SQ_P, H / 4, B);
@@ -500,7 +500,7 @@ int sininn_squeeze2_to_nhwc(const float* in, float* out, int B, int C0, int H, i
 int sininn_nhwc_to_unsqueeze2(const float* in, float* out, int B, int C0, int H, int W, sininn_stream_t stream) {
   SININN_CHECK_ARG(in && out && B > 0 && C0 > 0 && H > 0 && W > 0, "nhwc_to_unsqueeze2: bad arguments");
   SININN_CHECK_ARG((H % 4) == 0 && (W % 4) == 0 && aligned16(out), "nhwc_to_unsqueeze2: H and W must be multiples of 4 and the output 16-byte aligned (got %dx%d)", H, W);
-  SININN_CHECK_ARG(B <= 65535 && H / 4 <= 65535 && 16 * C0 <= 192, "nhwc_to_unsqueeze2: batch / height / channels out of range");
+  SININN_CHECK_ARG(B <= 65535 && H / 4 <= 65535 && 16 * C0 <= 128, "nhwc_to_unsqueeze2: batch / height / channels out of range");
   const int Wo = W / 4;
   dim3 grid((Wo + SQ_P - 1) / SQ_P, H / 4, B);
   launch_k(squeeze2_layout_kernel<false>, grid, dim3(256), (size_t)SQ_P * (16 * C0 + 1) * sizeof(float), as_stream(stream), in, out, C0, H, W,

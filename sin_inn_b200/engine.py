@@ -1009,7 +1009,7 @@ class Plan:
             self.prefix, self.body = ops[:first], ops[first:]
         # SRF: squeeze, squeeze, first coupling block (archs.py:28-38) -- the two squeezes and the layout change are one kernel
         self.squeeze2 = (FUSE_SQUEEZE2 and bool(self.body) and len(self.prefix) == 2
-                         and all(o.kind == "resample" and o.mode == 0 for o in self.prefix) and 16 * self.in_dims[0] <= 192)
+                         and all(o.kind == "resample" and o.mode == 0 for o in self.prefix) and 16 * self.in_dims[0] <= 128)
         self.tail_perm = self.body[-1] if self.body and self.body[-1].kind == "perm" else None
         self.core = self.body[:-1] if self.tail_perm is not None else self.body
         c, h, w = self.in_dims

@@ -53,7 +53,7 @@ def test_resample_nhwc(K, mode, shape):
     assert (xr.cpu() - x).abs().max() <= 1e-6 * x.abs().max()
 
 
-@pytest.mark.parametrize("shape", [(2, 3, 16, 32), (3, 3, 64, 256), (1, 3, 120, 280), (2, 12, 8, 12), (1, 1, 4, 4)])
+@pytest.mark.parametrize("shape", [(2, 3, 16, 32), (3, 3, 64, 256), (1, 3, 120, 280), (2, 8, 8, 12), (1, 1, 4, 4)])
 def test_two_squeezes_and_layout_change_in_one_pass(K, shape):
     """squeeze, squeeze, NCHW -> NHWC (the SRF entry, archs.py:28-38) as one kernel == the three separate kernels, bit for
     bit, with the bf16 operand copy of a channel range; and the inverse map restores the input."""
