@@ -348,7 +348,17 @@ typedef struct {
    * of the three-term expansions, i.e. the pixel (K) dimension is walked nterms times.  bias_term_mask: bit t set = pair
    * t's dy block enters the bias gradient (each of dh, dm, dl once). */
   int nterms; int x_term_off[6]; int dy_term_off[6]; int bias_term_mask;
+  /* Several convolutions that read the SAME input as ONE problem (tensor-core path, CTA-pair kernel; nseg = 0: off) -- the
+   * DenseBlock of archs.py:74-95, whose conv j reads the first cin_j channels of the growing concatenation x: dy holds their
+   * output gradients side by side ([npix][Cout], Cout = sum of the segments' rows), Cin = the widest cin_j; dw / dbias are
+   * unused.  Segment s owns dy channels [row0, row0 + rows) and receives  dw_s[rows][cin][taps] (+)= ...  (input channels
+   * >= cin are computed and dropped) and, when dbias_s is not NULL,  dbias_s[rows] (+)= sum_p dy[p][row0 + r]. */
+  int nseg;
+  struct { int row0, rows, cin; float* dw; int accumulate; float* dbias; int dbias_accumulate; } seg[8];
 } sininn_wgrad_desc;
+
+/* 1 when the CTA-pair weight-gradient kernel takes this problem (the only kernel that serves nseg > 0) */
+int sininn_wgrad_pair_supported(const sininn_wgrad_desc* d);
 
 size_t sininn_wgrad_workspace_bytes(const sininn_wgrad_desc* d, int tensor_core);
 int sininn_wgrad_simt(const sininn_wgrad_desc* d, sininn_stream_t stream);

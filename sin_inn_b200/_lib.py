@@ -42,6 +42,11 @@ class ConvDesc(C.Structure):
     ]
 
 
+class WgradSegment(C.Structure):
+    _fields_ = [("row0", C.c_int), ("rows", C.c_int), ("cin", C.c_int), ("dw", _vp), ("accumulate", C.c_int),
+                ("dbias", _vp), ("dbias_accumulate", C.c_int)]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
@@ -52,6 +57,7 @@ class WgradDesc(C.Structure):
         ("workspace", _vp), ("workspace_bytes", C.c_size_t),
         ("dbias", _vp), ("dbias_accumulate", C.c_int),
         ("nterms", C.c_int), ("x_term_off", C.c_int * 6), ("dy_term_off", C.c_int * 6), ("bias_term_mask", C.c_int),
+        ("nseg", C.c_int), ("seg", WgradSegment * 8),
     ]
 
 
@@ -146,6 +152,7 @@ SIGNATURES = {
     "sininn_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(WgradDesc), C.c_int]),
     "sininn_wgrad_simt": (C.c_int, [C.POINTER(WgradDesc), _vp]),
     "sininn_wgrad_tc": (C.c_int, [C.POINTER(WgradDesc), _vp]),
+    "sininn_wgrad_pair_supported": (C.c_int, [C.POINTER(WgradDesc)]),
     "sininn_wgrad_group_workspace_bytes": (C.c_size_t, [C.POINTER(WgradDesc), C.c_int]),
     "sininn_wgrad_tc_group": (C.c_int, [C.POINTER(WgradDesc), C.c_int, _vp, C.c_size_t, _vp]),
     "sininn_sqdiff_workspace_bytes": (C.c_size_t, [_c_ll]),

@@ -260,34 +260,52 @@ __global__ void __launch_bounds__(256) cast_slice_kernel(const float* __restrict
   }
 }
 
-template <typename TY, typename TO>
+// VEC = 4: four channels per thread (16 / 8-byte accesses; the launchers check alignment), VEC = 1: any slice
+template <int VEC, typename TY, typename TO>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* d, int d_stride, const TY* __restrict__ y, int y_stride,
                                                       TO* out, int out_stride, long long npix, int L, int act, float slope) {
   pdl_wait();
   pdl_trigger();
-  const long long total = npix * L;
+  const int Lv = L / VEC;
+  const long long total = npix * Lv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     int c;
     long long p;
-    split_index(idx, L, p, c);
-    float g = act_grad(act, slope, to_f32(y[p * y_stride + c]));
-    out[p * out_stride + c] = from_f32<TO>(d[p * d_stride + c] * g);
+    split_index(idx, Lv, p, c);
+    c *= VEC;
+    if (VEC == 4) {
+      const float4 yv = load4(y + p * y_stride + c), dv = load4(d + p * d_stride + c);
+      store4(out + p * out_stride + c, make_float4(dv.x * act_grad(act, slope, yv.x), dv.y * act_grad(act, slope, yv.y),
+                                                   dv.z * act_grad(act, slope, yv.z), dv.w * act_grad(act, slope, yv.w)));
+    } else {
+      float g = act_grad(act, slope, to_f32(y[p * y_stride + c]));
+      out[p * out_stride + c] = from_f32<TO>(d[p * d_stride + c] * g);
+    }
   }
 }
 
-template <typename TA>
+template <int VEC, typename TA>
 __global__ void __launch_bounds__(256) axpy_slice_kernel(float* __restrict__ out, int out_stride, const TA* __restrict__ a,
                                                          int a_stride, long long npix, int L, float alpha) {
   pdl_wait();
   pdl_trigger();
-  const long long total = npix * L;
+  const int Lv = L / VEC;
+  const long long total = npix * Lv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     int c;
     long long p;
-    split_index(idx, L, p, c);
-    out[p * out_stride + c] += alpha * to_f32(a[p * a_stride + c]);
+    split_index(idx, Lv, p, c);
+    c *= VEC;
+    if (VEC == 4) {
+      const float4 av = load4(a + p * a_stride + c);
+      float4 o = load4(out + p * out_stride + c);
+      o.x += alpha * av.x; o.y += alpha * av.y; o.z += alpha * av.z; o.w += alpha * av.w;
+      store4(out + p * out_stride + c, o);
+    } else {
+      out[p * out_stride + c] += alpha * to_f32(a[p * a_stride + c]);
+    }
   }
 }
 
@@ -672,13 +690,18 @@ int sininn_act_bwd(const float* d, int d_stride, const void* y, int y_dtype, int
   SININN_CHECK_ARG(d && y && out && npix > 0 && L > 0, "act_bwd: bad arguments");
   SININN_CHECK_ARG((y_dtype == SININN_F32 || y_dtype == SININN_BF16) && (out_dtype == SININN_F32 || out_dtype == SININN_BF16),
                    "act_bwd: bad dtype");
-  const long long total = npix * L;
+  const int esy = y_dtype == SININN_F32 ? 4 : 2, eso = out_dtype == SININN_F32 ? 4 : 2;
+  const bool v4 = (L % 4) == 0 && (d_stride % 4) == 0 && (y_stride % 4) == 0 && (out_stride % 4) == 0 && aligned16(d) &&
+                  (reinterpret_cast<uintptr_t>(y) % (4 * esy)) == 0 && (reinterpret_cast<uintptr_t>(out) % (4 * eso)) == 0;
+  const long long total = npix * (v4 ? L / 4 : L);
   const int block = 256, grid = grid_for(total, block);
   cudaStream_t st = as_stream(stream);
-#define LAUNCH(TY, TO) launch_k(act_bwd_kernel<TY, TO>, dim3(grid), dim3(block), 0, st, d, d_stride, (const TY*)y, y_stride, (TO*)out, out_stride, npix, L, act, slope)
+#define LAUNCH2(V, TY, TO) launch_k(act_bwd_kernel<V, TY, TO>, dim3(grid), dim3(block), 0, st, d, d_stride, (const TY*)y, y_stride, (TO*)out, out_stride, npix, L, act, slope)
+#define LAUNCH(TY, TO) do { if (v4) LAUNCH2(4, TY, TO); else LAUNCH2(1, TY, TO); } while (0)
   if (y_dtype == SININN_F32) { if (out_dtype == SININN_F32) LAUNCH(float, float); else LAUNCH(float, __nv_bfloat16); }
   else                       { if (out_dtype == SININN_F32) LAUNCH(__nv_bfloat16, float); else LAUNCH(__nv_bfloat16, __nv_bfloat16); }
 #undef LAUNCH
+#undef LAUNCH2
   SININN_CHECK_LAUNCH("act_bwd");
   return SININN_OK;
 }
@@ -687,10 +710,14 @@ int sininn_axpy_slice(float* out, int out_stride, const void* a, int a_dtype, in
                       float alpha, sininn_stream_t stream) {
   SININN_CHECK_ARG(out && a && npix > 0 && L > 0, "axpy_slice: bad arguments");
   SININN_CHECK_ARG(a_dtype == SININN_F32 || a_dtype == SININN_BF16, "axpy_slice: bad dtype");
-  const long long total = npix * L;
+  const int esa = a_dtype == SININN_F32 ? 4 : 2;
+  const bool v4 = (L % 4) == 0 && (out_stride % 4) == 0 && (a_stride % 4) == 0 && aligned16(out) && (reinterpret_cast<uintptr_t>(a) % (4 * esa)) == 0;
+  const long long total = npix * (v4 ? L / 4 : L);
   const int block = 256, grid = grid_for(total, block);
-  if (a_dtype == SININN_F32) launch_k(axpy_slice_kernel<float>, dim3(grid), dim3(block), 0, as_stream(stream), out, out_stride, (const float*)a, a_stride, npix, L, alpha);
-  else launch_k(axpy_slice_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, as_stream(stream), out, out_stride, (const __nv_bfloat16*)a, a_stride, npix, L, alpha);
+#define LAUNCH(V, TA) launch_k(axpy_slice_kernel<V, TA>, dim3(grid), dim3(block), 0, as_stream(stream), out, out_stride, (const TA*)a, a_stride, npix, L, alpha)
+  if (a_dtype == SININN_F32) { if (v4) LAUNCH(4, float); else LAUNCH(1, float); }
+  else                       { if (v4) LAUNCH(4, __nv_bfloat16); else LAUNCH(1, __nv_bfloat16); }
+#undef LAUNCH
   SININN_CHECK_LAUNCH("axpy_slice");
   return SININN_OK;
 }

@@ -369,7 +369,23 @@ struct WgReduceJob {
   float* dw; int accumulate;
   const float* bias_partial; int bias_rows; float* dbias; int dbias_accumulate;
   int block_begin, vec, ru;    // ru: output vectors per thread and pass (RU, or 1 for small problems: more blocks)
+  // merged problems (sininn_wgrad_desc.nseg): output rows [row0, row0 + rows) of segment s go to its own dw / dbias
+  int nseg;
+  struct { int row0, rows, cin; float* dw; int accumulate; float* dbias; int dbias_accumulate; } seg[8];
 };
+
+// destination of gradient entry (co, ci, tap) of a merged problem: NULL if no segment wants it
+__device__ __forceinline__ float* seg_dst(const WgReduceJob& j, int co, int ci, int tap, int& acc) {
+  for (int s = 0; s < j.nseg; ++s) {
+    const int r = co - j.seg[s].row0;
+    if (r >= 0 && r < j.seg[s].rows) {
+      if (ci >= j.seg[s].cin) return nullptr;
+      acc = j.seg[s].accumulate;
+      return j.seg[s].dw + ((long long)r * j.seg[s].cin + ci) * j.taps + tap;
+    }
+  }
+  return nullptr;
+}
 struct WgReduceParams { int njobs; WgReduceJob job[WG_MAX_PROBLEMS + 1]; };     // job[njobs].block_begin = grid size
 
 constexpr int RG = 8;          // split groups (one warp each)
@@ -384,7 +400,17 @@ __device__ __forceinline__ void reduce_job(const WgReduceJob& j, int bid, int nb
       for (int k = ln; k < j.bias_rows; k += 32) s += __ldcs(j.bias_partial + (long long)k * j.Cout + c);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (ln == 0) j.dbias[c] = j.dbias_accumulate ? j.dbias[c] + s : s;
+      if (ln == 0) {
+        if (j.nseg == 0) {
+          j.dbias[c] = j.dbias_accumulate ? j.dbias[c] + s : s;
+        } else {
+          for (int q = 0; q < j.nseg; ++q) {
+            const int r = c - j.seg[q].row0;
+            if (r >= 0 && r < j.seg[q].rows && j.seg[q].dbias != nullptr)
+              j.seg[q].dbias[r] = j.seg[q].dbias_accumulate ? j.seg[q].dbias[r] + s : s;
+          }
+        }
+      }
     }
   }
   const long long per = (long long)j.taps * j.Cw * j.Cn;
@@ -427,20 +453,21 @@ __device__ __forceinline__ void reduce_job(const WgReduceJob& j, int bid, int nb
         const int m = (int)(r % j.Cw);
         const int tap = (int)(r / j.Cw);
         float old[VEC];
+        float* dst[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           const int n = n0 + e;
           const int co = j.wide_is_dy ? m : n, ci = j.wide_is_dy ? n : m;
-          old[e] = j.accumulate ? j.dw[((long long)co * j.Cin + ci) * j.taps + tap] : 0.f;
+          int acc = j.accumulate;
+          dst[e] = j.nseg == 0 ? j.dw + ((long long)co * j.Cin + ci) * j.taps + tap : seg_dst(j, co, ci, tap, acc);
+          old[e] = (acc && dst[e] != nullptr) ? *dst[e] : 0.f;
         }
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           float t = red[0][slot][e];
 #pragma unroll
           for (int qq = 1; qq < RG; ++qq) t += red[qq][slot][e];
-          const int n = n0 + e;
-          const int co = j.wide_is_dy ? m : n, ci = j.wide_is_dy ? n : m;
-          j.dw[((long long)co * j.Cin + ci) * j.taps + tap] = old[e] + t;
+          if (dst[e] != nullptr) *dst[e] = old[e] + t;
         }
       }
     }
@@ -469,6 +496,12 @@ static void reduce_add_job(WgReduceParams& R, const sininn_wgrad_desc* d, const 
   j.Cout = d->Cout; j.Cin = d->Cin;
   j.dw = d->dw; j.accumulate = d->accumulate;
   j.bias_partial = bias_partial; j.bias_rows = bias_rows; j.dbias = d->dbias; j.dbias_accumulate = d->dbias_accumulate;
+  j.nseg = d->nseg;
+  for (int q = 0; q < d->nseg && q < 8; ++q) {
+    j.seg[q].row0 = d->seg[q].row0; j.seg[q].rows = d->seg[q].rows; j.seg[q].cin = d->seg[q].cin;
+    j.seg[q].dw = d->seg[q].dw; j.seg[q].accumulate = d->seg[q].accumulate;
+    j.seg[q].dbias = d->seg[q].dbias; j.seg[q].dbias_accumulate = d->seg[q].dbias_accumulate;
+  }
   j.vec = (j.Cn % 4) == 0 ? 4 : 1;
   const long long per = (long long)d->taps * j.Cw * j.Cn;
   // small problems (the 1x1 convolutions): one output vector per thread, so that the grid still covers the device
@@ -544,6 +577,14 @@ bool wgrad_pair_enabled() {
   return v == 1;
 }
 
+// does the problem ask for a bias gradient (its own, or any segment's of a merged problem)?
+static bool wants_bias(const sininn_wgrad_desc* d) {
+  if (d->nseg == 0) return d->dbias != nullptr;
+  for (int q = 0; q < d->nseg; ++q)
+    if (d->seg[q].dbias != nullptr) return true;
+  return false;
+}
+
 static void set_splits(WgPairPlan& w, long long pairs_budget) {
   long long s = pairs_budget / w.items;                  // one wave of pairs ...
   if (s > w.num_blocks / 4) s = w.num_blocks / 4;        // ... of at least 4 K steps each (partials cost bandwidth)
@@ -603,6 +644,11 @@ static bool plan_wgrad_pair(const sininn_wgrad_desc* d, bool with_bias, WgPairPl
   return true;
 }
 
+bool wgrad_pair_takes(const sininn_wgrad_desc* d) {
+  WgPairPlan w;
+  return plan_wgrad_pair(d, true, w);
+}
+
 size_t wgrad_pair_workspace_bytes(const sininn_wgrad_desc* d) {
   WgPairPlan w;
   if (!plan_wgrad_pair(d, true, w)) return 0;
@@ -619,7 +665,7 @@ int launch_wgrad_pair_group(const sininn_wgrad_desc* ds, int n, void* workspace,
   double work[WG_MAX_PROBLEMS], total = 0.0;
   int items = 0;
   for (int i = 0; i < n; ++i) {
-    if (!plan_wgrad_pair(&ds[i], ds[i].dbias != nullptr, w[i])) return SININN_EUNSUPPORTED;
+    if (!plan_wgrad_pair(&ds[i], wants_bias(&ds[i]), w[i])) return SININN_EUNSUPPORTED;
     work[i] = (double)w[i].num_blocks * w[i].items * w[i].kstep_cycles * (ds[i].nterms > 0 ? ds[i].nterms : 1);
     total += work[i];
     items += w[i].items;
@@ -668,7 +714,7 @@ int launch_wgrad_pair_group(const sininn_wgrad_desc* ds, int n, void* workspace,
     WgPairPlan& wi = w[i];
     set_splits(wi, given[i]);
     const size_t need_w = (size_t)wi.splits * d->taps * d->Cout * d->Cin * sizeof(float);
-    const size_t need_b = d->dbias ? (size_t)wi.splits * d->Cout * sizeof(float) : 0;
+    const size_t need_b = wants_bias(d) ? (size_t)wi.splits * d->Cout * sizeof(float) : 0;
     uint8_t* base = reinterpret_cast<uint8_t*>(workspace) + off;
     off += (need_w + need_b + 255) & ~(size_t)255;
     if (!workspace || off > workspace_bytes) {
@@ -732,12 +778,12 @@ int launch_wgrad_pair_group(const sininn_wgrad_desc* ds, int n, void* workspace,
     p.stages = wi.stages; p.halo_w = wi.halo_w;
     p.stage_bytes = wi.stage_bytes; p.narrow_bytes = wi.narrow_bytes; p.tx_bytes = wi.tx_bytes;
     p.partial = reinterpret_cast<float*>(base);
-    p.bias_mode = d->dbias ? (wi.wide_is_dy ? 1 : 2) : 0;
-    p.bias_partial = d->dbias ? reinterpret_cast<float*>(base + need_w) : nullptr;
+    p.bias_mode = wants_bias(d) ? (wi.wide_is_dy ? 1 : 2) : 0;
+    p.bias_partial = wants_bias(d) ? reinterpret_cast<float*>(base + need_w) : nullptr;
     G.pair_begin[i + 1] = G.pair_begin[i] + wi.items * wi.splits;
     const size_t smem = (size_t)p.stages * p.stage_bytes + WP_ONES_BYTES + sizeof(WgPairBarriers) + 1024;
     if (smem > max_smem) max_smem = smem;
-    reduce_add_job(R, d, p.partial, wi.splits, wi.wide_is_dy, p.bias_partial, d->dbias ? wi.splits : 0, sm_count() * 8 / n);
+    reduce_add_job(R, d, p.partial, wi.splits, wi.wide_is_dy, p.bias_partial, wants_bias(d) ? wi.splits : 0, sm_count() * 8 / n);
   }
   for (int i = n; i < WG_MAX_PROBLEMS; ++i) { G.prob[i] = G.prob[0]; G.pair_begin[i + 1] = G.pair_begin[n]; }
   for (int i = 3 * n; i < 3 * WG_MAX_PROBLEMS; ++i) T.m[i] = T.m[0];

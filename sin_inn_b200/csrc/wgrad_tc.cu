@@ -9,6 +9,7 @@ namespace tc {
 size_t wgrad_pair_workspace_bytes(const sininn_wgrad_desc* d);
 size_t wgrad_pair_group_workspace_bytes(const sininn_wgrad_desc* ds, int n);
 int launch_wgrad_pair_group(const sininn_wgrad_desc* ds, int n, void* workspace, size_t workspace_bytes, cudaStream_t st);
+bool wgrad_pair_takes(const sininn_wgrad_desc* d);
 int launch_reduce_single(const sininn_wgrad_desc* d, cudaStream_t st, const float* partial, int splits, int wide_is_dy,
                          const float* bias_partial, int bias_rows);
 
@@ -336,11 +337,16 @@ size_t sininn_wgrad_group_workspace_bytes(const sininn_wgrad_desc* descs, int n)
   return g > single ? g : single;
 }
 
+int sininn_wgrad_pair_supported(const sininn_wgrad_desc* d) {
+  return (d != nullptr && sininn::tc::wgrad_pair_takes(d)) ? 1 : 0;
+}
+
 int sininn_wgrad_tc_group(const sininn_wgrad_desc* descs, int n, void* workspace, size_t workspace_bytes, sininn_stream_t stream) {
   SININN_CHECK_ARG(descs && n >= 1, "wgrad_tc_group: no problems");
   for (int i = 0; i < n; ++i) {
     const sininn_wgrad_desc* d = &descs[i];
-    SININN_CHECK_ARG(d->x && d->dy && d->dw, "wgrad_tc_group: null pointer in problem %d", i);
+    SININN_CHECK_ARG(d->x && d->dy && (d->dw || d->nseg > 0), "wgrad_tc_group: null pointer in problem %d", i);
+    SININN_CHECK_ARG(d->nseg >= 0 && d->nseg <= 8, "wgrad_tc_group: at most 8 segments");
     SININN_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "wgrad_tc_group: bad shape in problem %d", i);
     SININN_CHECK_ARG(d->taps == 1 || d->taps == 9, "wgrad_tc_group: taps must be 1 or 9");
     SININN_CHECK_ARG(d->x_dtype == SININN_BF16 && d->dy_dtype == SININN_BF16, "wgrad_tc_group: operands must be bf16");
@@ -385,7 +391,7 @@ int sininn_wgrad_tc_group(const sininn_wgrad_desc* descs, int n, void* workspace
 
 int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
   using namespace sininn::tc;
-  SININN_CHECK_ARG(d && d->x && d->dy && d->dw, "wgrad_tc: null pointer");
+  SININN_CHECK_ARG(d && d->x && d->dy && (d->dw || d->nseg > 0), "wgrad_tc: null pointer");
   SININN_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "wgrad_tc: bad shape");
   SININN_CHECK_ARG(d->taps == 1 || d->taps == 9, "wgrad_tc: taps must be 1 or 9");
   SININN_CHECK_ARG(d->x_dtype == SININN_BF16 && d->dy_dtype == SININN_BF16, "wgrad_tc: operands must be bf16");
@@ -396,8 +402,8 @@ int sininn_wgrad_tc(const sininn_wgrad_desc* d, sininn_stream_t stream) {
     const int rc = launch_wgrad_pair_group(d, 1, d->workspace, d->workspace_bytes, as_stream(stream));
     if (rc != SININN_EUNSUPPORTED) return rc;
   }
-  if (d->nterms > 0) {
-    set_error("wgrad_tc: split-operand term lists are only taken by the CTA-pair kernel (wide operand > 128 channels)");
+  if (d->nterms > 0 || d->nseg > 0) {
+    set_error("wgrad_tc: split-operand term lists and merged problems are only taken by the CTA-pair kernel (wide operand > 128 channels)");
     return SININN_EUNSUPPORTED;
   }
   WgradPlan w;

@@ -336,6 +336,8 @@ class RunCtx:
 
 # ----------------------------------------------------------------------------- subnets
 WGRAD_GROUP = max(1, min(4, int(os.environ.get("SININN_WGRAD_GROUP", "4"))))
+# DenseBlock (IRN): the weight gradients of its five convolutions as one problem over the shared concatenation
+MERGE_DENSE_WGRAD = os.environ.get("SININN_MERGE_DENSE_WGRAD", "1") != "0"
 
 
 def flush_param_grads(ctx):
@@ -604,6 +606,7 @@ class DenseSubnet:
         self.gc = self.convs[0].out_channels
         self.cout = self.convs[4].out_channels
         self.ctot = self.cin + 4 * self.gc
+        self._merged_ok = None
 
     def parameters(self):
         out = []
@@ -627,6 +630,17 @@ class DenseSubnet:
                bias=self.convs[4].bias, tensor_core=ctx.tc)
         return out, (cat,)
 
+    def _merge_wgrads(self, ctx, cat):
+        """One weight-gradient problem for all five convolutions (they read prefixes of the same concatenation)?"""
+        if not (MERGE_DENSE_WGRAD and ctx.tc and WGRAD_GROUP > 1 and len(self.convs) <= 8):
+            return False
+        if any(c.bias is None or not c.weight.requires_grad or not c.bias.requires_grad for c in self.convs):
+            return False
+        if self._merged_ok is None:
+            probe = torch.empty(8, _round_up(4 * self.gc + self.cout, 8), dtype=cat.dtype, device=cat.device)
+            self._merged_ok = bool(K.wgrad_merged_supported(cat[:8, :self.ctot], probe[:, :4 * self.gc + self.cout], (1, 1, 8), 9))
+        return self._merged_ok
+
     def bwd(self, ctx, tr, saved, dout, dsrc):
         (cat,) = saved
         dev = cat.device
@@ -634,16 +648,40 @@ class DenseSubnet:
         # cast to the operand dtype (compact, aligned) after the LeakyReLU derivative is applied
         dcat = torch.empty(tr.npix, self.ctot, dtype=torch.float32, device=dev)
         c5 = self.convs[4]
+        merged = self._merge_wgrads(ctx, cat)
+        if merged:
+            # the five output gradients side by side: [g1 | g2 | g3 | g4 | dout], the "dy" of ONE weight-gradient problem
+            # over x = the concatenation (launched when all of them exist) instead of five problems with N = 32
+            gall = torch.empty(tr.npix, _round_up(4 * self.gc + self.cout, 8), dtype=ctx.adt, device=dev)
+            gall[:, 4 * self.gc:4 * self.gc + self.cout].copy_(dout)
         K.conv(dout, ctx.pack(c5.weight, 1), tr.geom, self.ctot, dcat, tensor_core=ctx.tc)
-        _param_grads(ctx, c5, cat[:, :self.ctot], dout, tr.geom, 9)
+        if not merged:
+            _param_grads(ctx, c5, cat[:, :self.ctot], dout, tr.geom, 9)
         for j in (3, 2, 1, 0):
             lo = self.cin + self.gc * j
-            g = torch.empty(tr.npix, self.gc, dtype=ctx.adt, device=dev)
+            g = gall[:, self.gc * j:self.gc * (j + 1)] if merged else torch.empty(tr.npix, self.gc, dtype=ctx.adt, device=dev)
             K.act_bwd(dcat[:, lo:lo + self.gc], cat[:, lo:lo + self.gc], g, ACT_LRELU, self.SLOPE)
             cj = self.convs[j]
             K.conv(g, ctx.pack(cj.weight, 1), tr.geom, lo, dcat[:, :lo], accumulate=True, tensor_core=ctx.tc)
-            _param_grads(ctx, cj, cat[:, :lo], g, tr.geom, 9)
+            if not merged:
+                _param_grads(ctx, cj, cat[:, :lo], g, tr.geom, 9)
         K.axpy_slice(dsrc, dcat[:, :self.cin], 1.0)
+        if merged:
+            segs = []
+            for j, cj in enumerate(self.convs):
+                gw, accw = ctx.grad_out(cj.weight)
+                gb, accb = ctx.grad_out(cj.bias)
+                rows = self.gc if j < 4 else self.cout
+                segs.append((self.gc * j, rows, self.cin + self.gc * j, gw, accw, gb, accb))
+            x, dy = cat[:, :self.ctot], gall[:, :4 * self.gc + self.cout]
+            if ctx.wstream is not None:       # a leaf of the backward pass: next to the data-gradient chain (see _param_grads)
+                ctx.wstream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(ctx.wstream):
+                    K.wgrad_merged(x, dy, tr.geom, 9, segs)
+                cat.record_stream(ctx.wstream)
+                gall.record_stream(ctx.wstream)
+            else:
+                K.wgrad_merged(x, dy, tr.geom, 9, segs)
 
 
 # ----------------------------------------------------------------------------- plan ops

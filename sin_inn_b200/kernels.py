@@ -655,6 +655,47 @@ def wgrad_group(jobs):
           "wgrad_tc_group")
 
 
+def _merged_desc(x, dy, geom, taps, segments):
+    d = WgradDesc()
+    d.B, d.H, d.W = geom
+    d.Cin, d.Cout, d.taps = x.shape[1], dy.shape[1], taps
+    d.x, d.x_dtype, d.x_stride = x.data_ptr(), dtype_code(x), x.stride(0)
+    d.dy, d.dy_dtype, d.dy_stride = dy.data_ptr(), dtype_code(dy), dy.stride(0)
+    d.dw, d.accumulate, d.dbias, d.dbias_accumulate, d.nterms = 0, 0, 0, 0, 0
+    d.workspace, d.workspace_bytes = 0, 0
+    d.nseg = len(segments)
+    for sg, (row0, rows, cin, dw, acc, dbias, dbacc) in zip(d.seg, segments):
+        sg.row0, sg.rows, sg.cin = int(row0), int(rows), int(cin)
+        sg.dw, sg.accumulate = dw.data_ptr(), int(acc)
+        sg.dbias, sg.dbias_accumulate = _p(dbias), int(dbacc)
+    return d
+
+
+def wgrad_merged_supported(x, dy, geom, taps):
+    """Does the CTA-pair weight-gradient kernel take the merged problem (all convolutions of a DenseBlock at once)?"""
+    if x.dtype != torch.bfloat16 or dy.dtype != torch.bfloat16 or x.stride(0) % 8 or dy.stride(0) % 8:
+        return False
+    d = _merged_desc(x, dy, geom, taps, [])
+    return bool(load().sininn_wgrad_pair_supported(C.byref(d)))
+
+
+def wgrad_merged(x, dy, geom, taps, segments):
+    """Weight (+ bias) gradients of several convolutions that read the same input as ONE tensor-core problem (the DenseBlock
+    of archs.py:74-95): x [npix, Cin] the concatenation, dy [npix, sum rows] the output gradients side by side; segments =
+    [(row0, rows, cin, dw, accumulate, dbias or None, dbias_accumulate)]: dw_s[rows][cin][taps] (+)= dy[:, row0:row0+rows]^T x[:, :cin]."""
+    x, dy = _view2d(x), _view2d(dy)
+    if len(segments) > 8:
+        raise _lib.SininnError("wgrad_merged: at most 8 segments")
+    arr = (WgradDesc * 1)()
+    arr[0] = _merged_desc(x, dy, geom, taps, segments)
+    lib = load()
+    ws = _workspace(x.device, "wgrad", lib.sininn_wgrad_group_workspace_bytes(arr, 1))
+    flops = sum(2.0 * geom[0] * geom[1] * geom[2] * rows * cin * taps for _, rows, cin, *_ in segments)
+    tag = lambda: f"{geom[1]}x{geom[2]} merged {x.shape[1]}x{dy.shape[1]} t{taps} ({len(segments)} convs)"
+    check(_run("wgrad", lambda: lib.sininn_wgrad_tc_group(arr, 1, ws.data_ptr(), ws.numel(), stream_ptr()), 2, flops, tag=tag),
+          "wgrad_tc_group(merged)")
+
+
 # ----------------------------------------------------------------------------- caller-side fusions
 def sqdiff(a, b, scale, want_grad=False):
     """scale * sum((a-b)^2) -> 0-dim tensor; optional gradient 2*scale*(a-b)."""

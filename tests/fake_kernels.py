@@ -344,6 +344,15 @@ def wgrad_group(jobs):
         wgrad(x, dy, geom, taps, dw, accumulate=acc, tensor_core=True, dbias=dbias, dbias_accumulate=dbacc)
 
 
+def wgrad_merged_supported(x, dy, geom, taps):
+    return max(x.shape[1], dy.shape[1]) > 128
+
+
+def wgrad_merged(x, dy, geom, taps, segments):
+    for row0, rows, cin, dw, acc, dbias, dbacc in segments:
+        wgrad(x[:, :cin], dy[:, row0:row0 + rows], geom, taps, dw, accumulate=acc, tensor_core=True, dbias=dbias, dbias_accumulate=dbacc)
+
+
 def wgrad(x, dy, geom, taps, dw, accumulate=False, tensor_core=False, dbias=None, dbias_accumulate=False):
     B, H, W = geom
     if dbias is not None:

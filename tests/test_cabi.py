@@ -32,4 +32,5 @@ def test_load_and_version():
 
 def test_struct_layout_matches_header():
     # field order/type drift between the header structs and the ctypes mirrors would corrupt calls silently
-    assert ctypes.sizeof(_lib.ConvDesc) == 200 and ctypes.sizeof(_lib.WgradDesc) == 160
+    assert ctypes.sizeof(_lib.ConvDesc) == 200 and ctypes.sizeof(_lib.WgradDesc) == 544      # (gcc/nvcc sizeof of the header structs)
+    assert ctypes.sizeof(_lib.Subnet1x1Desc) == 216 and ctypes.sizeof(_lib.Subnet1x1BwdDesc) == 208 and ctypes.sizeof(_lib.WgradSegment) == 48

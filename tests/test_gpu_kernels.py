@@ -472,6 +472,38 @@ def test_wgrad_tc_group(K, group):
         assert torch.equal(a[4], b[4]) and torch.equal(a[6], b[6])
 
 
+@pytest.mark.parametrize("cin,cout,geom,accumulate", [(24, 24, (2, 24, 20), False), (84, 108, (1, 16, 24), True), (108, 84, (2, 9, 13), False)])
+def test_wgrad_merged_dense_block(K, cin, cout, geom, accumulate):
+    """The five weight (+ bias) gradients of a DenseBlock (archs.py:74-95) as ONE tensor-core problem over the shared
+    concatenation == five separate problems (torch restatement), incl. accumulation into existing gradients."""
+    B, H, W = geom
+    npix, gc, bf = B * H * W, 32, torch.bfloat16
+    ctot, call = cin + 4 * gc, 4 * gc + cout
+    cat = rnd(npix, (ctot + 7) // 8 * 8, seed=51).to(bf)
+    gall = rnd(npix, (call + 7) // 8 * 8, seed=52).to(bf)
+    segs_ref, segs_dev = [], []
+    for j in range(5):
+        rows, ci = (gc if j < 4 else cout), cin + gc * j
+        dw0, db0 = rnd(rows, ci, 3, 3, seed=60 + j), rnd(rows, seed=70 + j)
+        segs_ref.append((gc * j, rows, ci, dw0.clone(), accumulate, db0.clone(), accumulate))
+        segs_dev.append((gc * j, rows, ci, dw0.clone().to(DEV), accumulate, db0.clone().to(DEV), accumulate))
+    catd, galld = cat.to(DEV), gall.to(DEV)
+    assert K.wgrad_merged_supported(catd[:, :ctot], galld[:, :call], geom, 9)
+    FK.wgrad_merged(cat[:, :ctot], gall[:, :call], geom, 9, segs_ref)
+    K.wgrad_merged(catd[:, :ctot], galld[:, :call], geom, 9, segs_dev)
+    torch.cuda.synchronize()
+    for (r0, rows, ci, dwr, _, dbr, _), (_, _, _, dwd, _, dbd, _) in zip(segs_ref, segs_dev):
+        assert (dwd.cpu() - dwr).abs().max().item() <= 2e-3 * max(1.0, dwr.abs().max().item()), (r0, rows, ci)
+        assert (dbd.cpu() - dbr).abs().max().item() <= 2e-3 * max(1.0, dbr.abs().max().item()), (r0, rows)
+    # deterministic
+    again = [(a, b, c, (torch.zeros_like(d) if not accumulate else segs_ref[i][3].clone().to(DEV) * 0 + d * 0), False, torch.zeros_like(f), False)
+             for i, (a, b, c, d, e, f, g) in enumerate(segs_dev)]
+    again2 = [(a, b, c, torch.zeros_like(d), False, torch.zeros_like(f), False) for (a, b, c, d, e, f, g) in segs_dev]
+    K.wgrad_merged(catd[:, :ctot], galld[:, :call], geom, 9, again)
+    K.wgrad_merged(catd[:, :ctot], galld[:, :call], geom, 9, again2)
+    assert all(torch.equal(x[3], y[3]) and torch.equal(x[5], y[5]) for x, y in zip(again, again2))
+
+
 @pytest.mark.parametrize("cin,hidden,cout,npix", [(24, 256, 48, 128), (24, 256, 48, 20000), (96, 256, 192, 45), (96, 256, 192, 33 * 40),
                                                    (8, 64, 16, 300), (64, 128, 256, 700), (40, 192, 100, 129)])
 @pytest.mark.parametrize("keep", [False, True])
