@@ -277,12 +277,14 @@ def run_ours(args):
         # (2 * pixels * Cin * Cout * taps per launch; the recompute launches inside the backward pass are executed work
         # and are counted as such) / summed CUDA-event time.  The family with the largest share of the step is the one the
         # roofline object describes; every family is listed in roofline.families.
-        tens = {k: prof.get(k, zero) for k in ("conv3x3", "wgrad", "subnet1x1", "conv1x1")}
+        tens = {k: prof.get(k, zero) for k in ("conv3x3", "wgrad", "subnet1x1", "subnet1x1_bwd", "conv1x1")}
         tot_ms = sum(v["ms"] for v in prof.values())
         top = max(tens, key=lambda k: tens[k]["ms"])
         names = {"conv3x3": "conv_tc_pair_kernel (3x3 subnet convolutions: fprop, dgrad; their re-evaluation when activations='recompute')",
                  "wgrad": "wgrad_pair_kernel + wgrad_reduce_kernel (weight and bias gradients, grouped per coupling block)",
                  "subnet1x1": "subnet1x1_fwd_kernel (fused 1x1 subnets: forward, data gradients; re-evaluation when activations='recompute')",
+                 "subnet1x1_bwd": "subnet1x1_bwd_kernel + wgrad_reduce_kernel (fused backward of the level-0 1x1 subnets: hidden activation "
+                                  "re-evaluated on chip, input gradient, both weight / bias gradients; executed FLOPs incl. the re-evaluation)",
                  "conv1x1": "conv_tc_kernel (1x1 convolutions outside the fused kernel)"}
 
         def fam(v):
@@ -374,6 +376,19 @@ def run_ours(args):
                                    "ms_per_step": r0["ms_per_step"], "cores": r0["cores"]}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # The captured step holds graph-captured NCCL work: release it (as the inference leg does) and let every rank get here
+        # before the communicator is torn down -- destroying the communicator under a live graph can block (a multi-rank
+        # run with --no-inference hung at exit in round 2 and ran into its time limit).
+        graphed = feeder = None
+        if "trainer" in locals() and trainer is not None:
+            trainer._graph = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
         dist.destroy_process_group()
 
 
