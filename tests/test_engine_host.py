@@ -276,3 +276,29 @@ def test_stored_and_recomputed_subnet_state_agree(fake_kernels, arch, precision,
     with pytest.raises(E.SininnError):
         net.engine_config = E.EngineConfig(activations="sometimes")
         net(hr.clone().requires_grad_(True))
+
+
+@pytest.mark.parametrize("arch,mode", [("SRF", "store"), ("SRF", "recompute"), ("IRN", "store")])
+def test_engine_level_fusions_do_not_change_results(fake_kernels, monkeypatch, arch, mode):
+    """The engine's peephole fusions -- PermuteRandom folded into the adjoining coupling kernel, the two entry squeezes + layout
+    change as one kernel, a DenseBlock's five weight gradients as one problem, the fused 1x1 subnet backward -- are
+    re-orderings of the same arithmetic: with the torch stand-in kernels the results are identical with and without them."""
+    res = {}
+    for fused in (True, False):
+        for name in ("FOLD_PERM", "FUSE_SQUEEZE2", "MERGE_DENSE_WGRAD", "FUSE_1X1_BWD"):
+            monkeypatch.setattr(E, name, fused)
+        opt, ora, net = _pair(arch, 4, 2 if arch == "SRF" else 1, 10, 16, 32)
+        net.engine_config = E.EngineConfig(precision="bf16", tensor_core=True, activations=mode)
+        hr, lr, z = R.synthetic_batch(opt, 2, 16, 32, seed=5)
+        x = hr.clone().requires_grad_(True)
+        y = net(x)
+        R.reconstruction(y[:, :opt.lr_dims], lr).backward()
+        u = torch.cat((lr, z), 1).requires_grad_(True)
+        xr = net(u, rev=True)
+        R.reconstruction(xr, hr).backward()
+        res[fused] = (y.detach(), xr.detach(), x.grad, u.grad, {n: p.grad.clone() for n, p in net.named_parameters() if p.requires_grad})
+    a, b = res[True], res[False]
+    for i in range(4):
+        assert torch.allclose(a[i], b[i], rtol=0, atol=1e-6 * max(1.0, float(b[i].abs().max()))), i
+    for n, g in a[4].items():
+        assert (g - b[4][n]).norm() <= 2e-2 * max(1e-6, float(g.norm())), n      # (the fused 1x1 backward rounds dh to bf16 like the kernel)
